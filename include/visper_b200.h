@@ -1,0 +1,165 @@
+/*
+ * visper_b200.h — C ABI of libvisper_b200.so, the sm_100a kernel library behind the VisPer-LM
+ * (f.k.a. OLA-VLM) data-parallel training step.
+ *
+ * The reference (SHI-Labs/VisPer-LM @ f7baf3bb) is 100 % Python: it has no FFI of its own, every
+ * FLOP is a call into torch / cuBLAS / flash_attn.  This header therefore declares the native
+ * layer that sits *beneath* the reference's Python operator surface; each entry point names the
+ * reference call site (file:line under /root/reference) whose library call it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all buffers are DEVICE pointers owned by the caller
+ *     (workspaces included); kernels never allocate, never synchronise, never throw;
+ *   - bf16 storage (raw uint16 bit patterns behind `void*`), fp32 accumulation / statistics;
+ *   - `ld*` are row strides in ELEMENTS; matrices are row-major; 16-byte aligned, ld % 8 == 0;
+ *   - `stream` is a cudaStream_t passed as void*; calls are re-entrant per stream;
+ *   - return 0 on success, negative on error; vpb_last_error() gives a thread-local message.
+ */
+#ifndef VISPER_B200_H
+#define VISPER_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPB_ABI_VERSION 1
+
+/* GEMM epilogue activations */
+#define VPB_ACT_NONE 0
+#define VPB_ACT_GELU 1       /* erf GELU — nn.GELU() in mm_projector / FeedForward / build_mlp */
+#define VPB_ACT_QUICK_GELU 2 /* x*sigmoid(1.702x) — CLIP MLP */
+#define VPB_ACT_RELU 3
+
+/* ---- library ------------------------------------------------------------------------------ */
+int vpb_abi_version(void);
+const char* vpb_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t vpb_launch_count(void);
+void vpb_reset_launch_count(void);
+
+/* ---- GEMM: tcgen05 + TMEM + TMA ----------------------------------------------------------
+ * C[M,N] = act(A·Bᵀ + bias) + residual ; optional aux = A·Bᵀ + bias (pre-activation copy).
+ * a_layout 0: A is [M,K] (K contiguous); 1: A is [K,M] (M contiguous).
+ * b_layout 0: B is [N,K] (nn.Linear weight); 1: B is [K,N] (N contiguous).
+ * Replaces every torch.nn.functional.linear / cuBLAS GEMM on the path: HF Llama/Phi-3 q/k/v/o,
+ * gate/up/down, lm_head (ola_llama.py:105,121), CLIP q/k/v/out/fc1/fc2 + patch conv
+ * (clip_encoder.py:56), mm_projector (multimodal_projector/builder.py:56-60), resampler
+ * proj_in/to_q/to_kv/to_out/FF/proj_out (resampler.py:9-16,42-44,181,185,213-222), depth-head
+ * linear_1..3 (aux_heads/da_v2_head.py:450-455) — forward, dgrad (b_layout 1) and wgrad
+ * (a_layout 1, b_layout 1). */
+int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const void* B, int64_t ldb,
+                  int b_layout, void* C, int64_t ldc, int M, int N, int K, int act,
+                  const void* bias, const void* residual, int64_t ldr, void* aux, int64_t ldaux,
+                  void* stream);
+
+/* ---- normalisation -------------------------------------------------------------------------
+ * HF LlamaRMSNorm / Phi3RMSNorm (eps 1e-5) and nn.LayerNorm (CLIP, resampler.py). */
+int vpb_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd,
+                    int M, int D, float eps, void* stream);
+/* dx = rmsnorm'(dy) (+ dres): fuses the residual-stream gradient add */
+int vpb_rmsnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const void* w,
+                    const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
+                    int M, int D, void* stream);
+int vpb_layernorm_fwd(const void* x, int64_t ldx, const void* w, const void* b, void* y,
+                      int64_t ldy, float* mean, float* rstd, int M, int D, float eps, void* stream);
+int vpb_layernorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const void* w,
+                      const float* mean, const float* rstd, const void* dres, int64_t lddres,
+                      void* dx, int64_t lddx, int M, int D, void* stream);
+/* out[n] = sum_m a[m,n] * (b ? (b[m,n]-mean[m])*rstd[m] : 1) — bias / norm-weight gradients */
+int vpb_colsum(const void* a, int64_t lda, const void* b, int64_t ldb, const float* mean,
+               const float* rstd, float* out, int M, int N, void* stream);
+
+/* ---- elementwise ----------------------------------------------------------------------------
+ * RoPE: HF apply_rotary_pos_emb (rotate_half convention), applied in place to `nheads` heads of
+ * the packed QKV buffer; inverse=1 is the backward. SwiGLU: LlamaMLP / Phi3MLP silu(gate)*up on
+ * a packed [M, 2F] gate|up buffer. */
+int vpb_rope_table(float* cos_t, float* sin_t, int max_pos, int head_dim, float theta, void* stream);
+int vpb_rope_inplace(void* x, int64_t ld, int M, int seq_len, const int* pos_ids,
+                     const float* cos_t, const float* sin_t, int nheads, int head_dim, int inverse,
+                     void* stream);
+int vpb_swiglu_fwd(const void* gu, int64_t ldgu, void* h, int64_t ldh, int M, int F, void* stream);
+int vpb_swiglu_bwd(const void* gu, int64_t ldgu, const void* dh, int64_t lddh, void* dgu,
+                   int64_t lddgu, int M, int F, void* stream);
+int vpb_act_bwd(const void* pre, int64_t ldp, const void* dy, int64_t lddy, void* dx, int64_t lddx,
+                int M, int N, int act, void* stream);
+int vpb_axpby(const void* a, const void* b, void* out, float alpha, float beta, int64_t n,
+              void* stream);
+/* out = in * (*scale), scalar read on the device */
+int vpb_scale_dev(const void* in, void* out, const float* scale, int64_t n, void* stream);
+int vpb_transpose(const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, void* stream);
+int vpb_cast_f32_bf16(const float* in, void* out, int64_t n, float scale, void* stream);
+
+/* ---- CLIP patch embedding (clip_encoder.py:56 → HF CLIPVisionEmbeddings) -------------------- */
+int vpb_im2col_patches(const void* images, void* out, int B, int H, int W, int patch, int Kpad,
+                       void* stream);
+int vpb_clip_embed(const void* patch, const void* cls, const void* pos, void* out, int B,
+                   int npatch, int D, void* stream);
+
+/* ---- multimodal splice (ola_arch.py:256-444 prepare_inputs_labels_for_multimodal) -----------
+ * One gather from a host-built index plan replaces the per-sample Python cat loop. */
+int vpb_gather_rows(void* out, int64_t ldo, int nrows, int D, const int* kind, const int* index,
+                    const void* src0, int64_t ld0, const void* src1, int64_t ld1, const void* src2,
+                    int64_t ld2, const void* src3, int64_t ld3, void* stream);
+int vpb_gather_sum_rows(void* out, int64_t ldo, int nslots, int cnt, const int* index,
+                        const void* src, int64_t lds, int D, float scale, void* stream);
+int vpb_scatter_add_rows(float* dst, int64_t ldd, int nrows, const int* index, const void* src,
+                         int64_t lds, int D, void* stream);
+/* task-token pooling param[576,D].view(8,72,D).mean(1) (ola_arch.py:225-228) */
+int vpb_group_mean(const void* in, int64_t ldi, void* out, int64_t ldo, int groups, int gsize,
+                   int D, void* stream);
+int vpb_group_mean_bwd(const void* dout, int64_t ldo, void* din, int64_t ldi, int groups,
+                       int gsize, int D, void* stream);
+
+/* ---- attention ------------------------------------------------------------------------------
+ * Flash attention on packed projections; optional second K/V segment (k2/v2, length sk2) is
+ * appended after the first (PerceiverAttention keys = cat(x, latents), resampler.py:61-62).
+ * lse: [B,H,sq] fp32. delta: [B,H,sq] fp32 workspace for the backward. */
+int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                 const void* k2, int64_t ldk2, const void* v2, int64_t ldv2, void* o, int64_t ldo,
+                 float* lse, int B, int H, int KVH, int sq, int sk, int sk2, int head_dim,
+                 float scale, int causal, void* stream);
+int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                 const void* k2, int64_t ldk2, const void* v2, int64_t ldv2, const void* o,
+                 int64_t ldo, const void* dO, int64_t lddo, const float* lse, float* delta, void* dq,
+                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dk2,
+                 int64_t lddk2, void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk,
+                 int sk2, int head_dim, float scale, int causal, void* stream);
+
+/* ---- next-token cross-entropy (ola_llama.py:121-136) -----------------------------------------
+ * labels: int64 [B,T] UNSHIFTED when shift=1 (row (b,t) is scored against labels[b,t+1]).
+ * vpb_ce_fwd_bwd handles rows row0..row0+R-1 of the flattened [B*T] sequence whose logits sit in
+ * `logits` (bf16, overwritten with gscale*(softmax-onehot)/count when write_grad). */
+int vpb_ce_count(const int64_t* labels, int64_t R, int T, int shift, float* count_out, void* stream);
+int vpb_ce_fwd_bwd(void* logits, int64_t ld, const int64_t* labels, int64_t row0, int R, int V,
+                   int T, int shift, float* row_loss, const float* count, float gscale,
+                   int write_grad, void* stream);
+int vpb_ce_finalize(const float* row_loss, int64_t R, const float* count, float* loss_out,
+                    void* stream);
+
+/* ---- embedding-distillation loss (base_ola_vlm.py:289-320, ola_utils.py:108-125) --------------
+ * pred [B,n], tgt [Bt,n] (all-gathered targets, own rows start at `off`), tau = logit_scale
+ * parameter, mask [B] fp32 or NULL. out4 = {loss, smooth_l1, contrastive, dloss/dtau}.
+ * coef: 2B + B*Bt floats consumed by the backward; stats (optional): B*Bt dots | B |p|² | Bt |t|² | B sl1. */
+int64_t vpb_distill_workspace_floats(int B, int Bt, int64_t n);
+int vpb_distill_loss_fwd(const void* pred, int64_t ldp, const void* tgt, int64_t ldt, int64_t n,
+                         int B, int Bt, int off, const float* tau, const float* mask,
+                         float contrastive_weight, float* workspace, float* out4, float* coef,
+                         float* stats, void* stream);
+int vpb_distill_loss_bwd(const void* pred, int64_t ldp, const void* tgt, int64_t ldt, int64_t n,
+                         int B, int Bt, int off, const float* coef, const float* gout, void* dpred,
+                         int64_t lddp, void* stream);
+
+/* ---- sharded optimizer (HF adamw_torch under DeepSpeed ZeRO-2, scripts/zero2.json) ------------ */
+int vpb_adamw_step(float* master, float* m, float* v, const void* grad, void* param, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                   const float* grad_scale, void* stream);
+int vpb_grad_sumsq(const void* grad, int64_t n, float* workspace, float* out, int accumulate,
+                   void* stream);
+int vpb_clip_coef(const float* sumsq, float max_norm, float extra_scale, float* coef,
+                  float* norm_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VISPER_B200_H */

@@ -1,0 +1,357 @@
+"""GPU unit tests: every C-ABI kernel against a plain torch fp32 restatement of the same op.
+
+Tolerances are bf16-output tolerances: |err| <= atol + rtol*|ref| with rtol ~ 2^-7 unless noted.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(BF).to(dev())
+
+
+def close(got, ref, rtol=1.6e-2, atol=None, name=""):
+    got = got.float()
+    ref = ref.float()
+    if atol is None:
+        atol = 1e-2 * max(ref.abs().max().item(), 1e-6)
+    err = (got - ref).abs()
+    bad = err > (atol + rtol * ref.abs())
+    assert not torch.isnan(got).any(), f"{name}: NaN in output"
+    assert not bad.any(), (
+        f"{name}: {int(bad.sum())}/{bad.numel()} mismatches, max err {err.max().item():.4g}, "
+        f"ref max {ref.abs().max().item():.4g}")
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("al,bl", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 256), (304, 520, 200), (1000, 264, 72),
+                                   (2048, 6144, 1024), (4096, 256, 4096)])
+def test_gemm_layouts(M, N, K, al, bl):
+    from visper_lm_b200 import ops
+    a = rnd(M, K, seed=1)
+    b = rnd(N, K, seed=2)
+    ref = a.float() @ b.float().t()
+    a_in = a if al == 0 else a.t().contiguous()
+    b_in = b if bl == 0 else b.t().contiguous()
+    if (al == 1 and M % 8) or (bl == 1 and N % 8) or (al == 0 and K % 8) or (bl == 0 and K % 8):
+        pytest.skip("stride not 16-byte aligned for this layout")
+    out = ops.gemm(a_in, b_in, a_layout=al, b_layout=bl)
+    torch.cuda.synchronize()
+    close(out, ref, name=f"gemm {M}x{N}x{K} a{al} b{bl}")
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm_epilogues(act):
+    from visper_lm_b200 import ops
+    M, N, K = 520, 776, 320
+    a, b = rnd(M, K, seed=3, scale=0.5), rnd(N, K, seed=4, scale=0.2)
+    bias, res = rnd(N, seed=5), rnd(M, N, seed=6)
+    pre_ref = a.float() @ b.float().t() + bias.float()
+    if act == 1:
+        y = torch.nn.functional.gelu(pre_ref)
+    elif act == 2:
+        y = pre_ref * torch.sigmoid(1.702 * pre_ref)
+    elif act == 3:
+        y = torch.relu(pre_ref)
+    else:
+        y = pre_ref
+    ref = y + res.float()
+    out, pre = ops.gemm(a, b, bias=bias, act=act, residual=res, want_pre=True)
+    torch.cuda.synchronize()
+    close(pre, pre_ref, name="pre-activation")
+    close(out, ref, name=f"epilogue act={act}")
+    # in-place accumulate: residual aliases the output
+    acc = res.clone()
+    ops.gemm(a, b, residual=acc, out=acc)
+    torch.cuda.synchronize()
+    close(acc, a.float() @ b.float().t() + res.float(), name="accumulate")
+
+
+def test_gemm_strided_views():
+    from visper_lm_b200 import ops
+    big = rnd(300, 1024, seed=7)
+    a = big[:, 256:512]            # lda = 1024
+    w = rnd(384, 256, seed=8)
+    outbuf = torch.zeros(300, 1024, dtype=BF, device=dev())
+    ops.gemm(a, w, out=outbuf[:, 128:512])
+    torch.cuda.synchronize()
+    close(outbuf[:, 128:512], a.float() @ w.float().t(), name="strided")
+    assert outbuf[:, :128].abs().max().item() == 0 and outbuf[:, 512:].abs().max().item() == 0
+
+
+# ------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("M,D", [(37, 128), (512, 4096), (100, 3072), (64, 1024)])
+def test_rmsnorm(M, D):
+    from visper_lm_b200 import ops
+    x = rnd(M, D, seed=11).requires_grad_(False)
+    w = (1 + 0.1 * rnd(D, seed=12).float()).to(BF)
+    dy = rnd(M, D, seed=13)
+    dres = rnd(M, D, seed=14)
+    y, rstd = ops.rmsnorm_fwd(x, w, 1e-5)
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    ref.backward(dy.float())
+    close(y, ref, name="rmsnorm fwd")
+    dx = ops.rmsnorm_bwd(dy, x, w, rstd, dres)
+    close(dx, xf.grad + dres.float(), name="rmsnorm bwd")
+    dw = ops.colsum(dy, x, None, rstd, out_dtype=torch.float32)
+    close(dw, wf.grad, rtol=2e-2, name="rmsnorm dw")
+
+
+@pytest.mark.parametrize("M,D", [(50, 64), (300, 1024), (77, 1536)])
+def test_layernorm(M, D):
+    from visper_lm_b200 import ops
+    x = rnd(M, D, seed=21)
+    w = (1 + 0.1 * rnd(D, seed=22).float()).to(BF)
+    b = rnd(D, seed=23, scale=0.1)
+    dy = rnd(M, D, seed=24)
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-5)
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    bf = b.float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (D,), wf, bf, 1e-5)
+    ref.backward(dy.float())
+    close(y, ref, name="ln fwd")
+    dx = ops.layernorm_bwd(dy, x, w, mean, rstd)
+    close(dx, xf.grad, name="ln bwd")
+    close(ops.colsum(dy, x, mean, rstd, out_dtype=torch.float32), wf.grad, rtol=2e-2, name="ln dw")
+    close(ops.colsum(dy, out_dtype=torch.float32), bf.grad, rtol=2e-2, name="ln db")
+
+
+# ------------------------------------------------------------------------------------------- rope / swiglu / act
+def _rope_ref(x, T, hd, theta):
+    # x [M, nh*hd] fp32; HF rotate_half convention
+    M = x.shape[0]
+    nh = x.shape[1] // hd
+    pos = (torch.arange(M, device=x.device) % T).float()
+    inv = 1.0 / (theta ** (torch.arange(0, hd, 2, device=x.device).float() / hd))
+    ang = pos[:, None] * inv[None, :]
+    cos = torch.cat([ang.cos(), ang.cos()], -1)[:, None, :]
+    sin = torch.cat([ang.sin(), ang.sin()], -1)[:, None, :]
+    xv = x.view(M, nh, hd)
+    rot = torch.cat([-xv[..., hd // 2:], xv[..., :hd // 2]], -1)
+    return (xv * cos + rot * sin).reshape(M, nh * hd)
+
+
+@pytest.mark.parametrize("hd,theta", [(128, 500000.0), (96, 10000.0), (32, 10000.0)])
+def test_rope(hd, theta):
+    from visper_lm_b200 import ops
+    T, B, nh_q, nh_kv = 50, 3, 4, 2
+    width = (nh_q + 2 * nh_kv) * hd
+    qkv = rnd(B * T, width, seed=31)
+    orig = qkv.clone()
+    cos, sin = ops.rope_tables(64, hd, theta, dev())
+    ops.rope_(qkv, T, cos, sin, nh_q + nh_kv, hd)
+    ref = _rope_ref(orig[:, :(nh_q + nh_kv) * hd].float(), T, hd, theta)
+    close(qkv[:, :(nh_q + nh_kv) * hd], ref, name="rope fwd")
+    assert torch.equal(qkv[:, (nh_q + nh_kv) * hd:], orig[:, (nh_q + nh_kv) * hd:]), "V must be untouched"
+    ops.rope_(qkv, T, cos, sin, nh_q + nh_kv, hd, inverse=True)
+    close(qkv, orig.float(), name="rope inverse round trip")
+
+
+def test_swiglu_and_act_bwd():
+    from visper_lm_b200 import ops
+    M, F = 130, 512
+    gu = rnd(M, 2 * F, seed=41)
+    dh = rnd(M, F, seed=42)
+    guf = gu.float().requires_grad_(True)
+    ref = torch.nn.functional.silu(guf[:, :F]) * guf[:, F:]
+    ref.backward(dh.float())
+    close(ops.swiglu_fwd(gu), ref, name="swiglu fwd")
+    close(ops.swiglu_bwd(gu, dh), guf.grad, name="swiglu bwd")
+    for act, fn in [(1, torch.nn.functional.gelu), (2, lambda t: t * torch.sigmoid(1.702 * t)),
+                    (3, torch.relu)]:
+        pre = rnd(M, F, seed=43)
+        pf = pre.float().requires_grad_(True)
+        fn(pf).backward(dh.float())
+        close(ops.act_bwd(pre, dh, act), pf.grad, name=f"act_bwd {act}")
+
+
+# ------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, scale, causal):
+    # q [B,H,sq,hd], k/v [B,H,sk,hd] fp32
+    s = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        sq, sk = s.shape[-2:]
+        m = torch.ones(sq, sk, dtype=torch.bool, device=s.device).tril(sk - sq)
+        s = s.masked_fill(~m, float("-inf"))
+    return torch.softmax(s, -1) @ v
+
+
+@pytest.mark.parametrize("B,H,KVH,sq,sk,sk2,hd,causal", [
+    (2, 4, 2, 300, 300, 0, 128, True),
+    (1, 2, 2, 577, 577, 0, 64, False),
+    (2, 4, 4, 200, 200, 0, 96, True),
+    (2, 4, 4, 70, 203, 70, 32, False),
+    (2, 4, 4, 1, 150, 1, 32, False),
+    (2, 4, 2, 130, 130, 0, 32, True),
+    (1, 8, 2, 1024, 1024, 0, 128, True),
+])
+def test_attention_fwd_bwd(B, H, KVH, sq, sk, sk2, hd, causal):
+    from visper_lm_b200 import ops
+    qw, kw = H * hd, KVH * hd
+    qb = rnd(B * sq, qw, seed=51)
+    kvb = rnd(B * sk, 2 * kw, seed=52)
+    kv2 = rnd(B * sk2, 2 * kw, seed=53) if sk2 else None
+    do = rnd(B * sq, qw, seed=54)
+    scale = hd ** -0.5
+    k, v = kvb[:, :kw], kvb[:, kw:]
+    k2 = kv2[:, :kw] if sk2 else None
+    v2 = kv2[:, kw:] if sk2 else None
+    o, lse = ops.attn_fwd(qb, k, v, B, H, KVH, sq, sk, hd, scale, causal, k2=k2, v2=v2, sk2=sk2)
+    torch.cuda.synchronize()
+
+    qf = qb.float().view(B, sq, H, hd).transpose(1, 2).detach().requires_grad_(True)
+    kcat = kvb.float().view(B, sk, 2, KVH, hd)
+    if sk2:
+        kcat = torch.cat([kcat, kv2.float().view(B, sk2, 2, KVH, hd)], 1)
+    kcat = kcat.detach().requires_grad_(True)
+    kf = kcat[:, :, 0].transpose(1, 2).repeat_interleave(H // KVH, 1)
+    vf = kcat[:, :, 1].transpose(1, 2).repeat_interleave(H // KVH, 1)
+    ref = _attn_ref(qf, kf, vf, scale, causal)
+    ref_rows = ref.transpose(1, 2).reshape(B * sq, qw)
+    close(o, ref_rows, name="attn fwd")
+    ref_rows.backward(do.float())
+
+    dq = torch.empty_like(qb)
+    dkv = torch.empty_like(kvb)
+    dkv2 = torch.empty_like(kv2) if sk2 else None
+    ops.attn_bwd(qb, k, v, o, do, lse, dq, dkv[:, :kw], dkv[:, kw:], B, H, KVH, sq, sk, hd, scale,
+                 causal, k2=k2, v2=v2, sk2=sk2, dk2=dkv2[:, :kw] if sk2 else None,
+                 dv2=dkv2[:, kw:] if sk2 else None)
+    torch.cuda.synchronize()
+    close(dq, qf.grad.transpose(1, 2).reshape(B * sq, qw), rtol=3e-2, name="attn dq")
+    g = kcat.grad  # [B, sk+sk2, 2, KVH, hd]
+    close(dkv, g[:, :sk].reshape(B * sk, 2 * kw), rtol=3e-2, name="attn dkv")
+    if sk2:
+        close(dkv2, g[:, sk:].reshape(B * sk2, 2 * kw), rtol=3e-2, name="attn dkv2")
+
+
+# ------------------------------------------------------------------------------------------- losses
+@pytest.mark.parametrize("B,T,V", [(2, 37, 1000), (1, 64, 128256)])
+def test_cross_entropy(B, T, V):
+    from visper_lm_b200 import ops
+    logits = rnd(B * T, V, seed=61, scale=2.0)
+    g = torch.Generator().manual_seed(5)
+    labels = torch.randint(0, V, (B, T), generator=g)
+    labels[:, :5] = -100
+    labels = labels.to(dev())
+    lf = logits.float().view(B, T, V).requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1),
+                                            ignore_index=-100)
+    ref.backward()
+    cnt = ops.ce_count(labels, T)
+    row_loss = torch.empty(B * T, dtype=torch.float32, device=dev())
+    work = logits.clone()
+    ops.ce_fwd_bwd_(work, labels, 0, T, row_loss, cnt)
+    loss = ops.ce_finalize(row_loss, cnt)
+    assert abs(loss.item() - ref.item()) < 2e-4 * max(1.0, abs(ref.item())), (loss.item(), ref.item())
+    close(work, lf.grad.view(B * T, V), rtol=2e-2, atol=1e-2 * lf.grad.abs().max().item(), name="ce grad")
+
+
+@pytest.mark.parametrize("B,Bt,off,n", [(4, 4, 0, 1024), (8, 8, 0, 589824), (3, 12, 6, 8200), (8, 64, 16, 24576)])
+def test_distill_loss(B, Bt, off, n):
+    from visper_lm_b200 import ops
+    pred = rnd(B, n, seed=71)
+    tgt = rnd(Bt, n, seed=72)
+    tgt[off:off + B] = (0.6 * pred.float() + 0.8 * tgt[off:off + B].float()).to(BF)
+    tau = torch.tensor(2.0, device=dev())
+    mask = torch.tensor([1.0, 0.0, 1.0, 1.0, 1.0, 0.0, 1.0, 1.0][:B], device=dev())
+    cw = 0.3
+    pf = pred.float().requires_grad_(True)
+    tf = tgt.float()
+    tauf = tau.clone().requires_grad_(True)
+    sl1 = (torch.nn.functional.smooth_l1_loss(pf, tf[off:off + B], reduction="none") * mask[:, None]).mean()
+    pn = torch.nn.functional.normalize(pf, dim=-1)
+    tn = torch.nn.functional.normalize(tf, dim=-1)
+    logits = pn @ tn.t() * torch.clamp(tauf.exp(), max=100)
+    ce = torch.nn.functional.cross_entropy(logits, torch.arange(B, device=dev()) + off, reduction="none")
+    con = (cw * ce[None, None, :] * mask[:, None, None]).mean()
+    total = sl1 + con
+    total.backward()
+    out4, coef, _ = ops.distill_loss_fwd(pred, tgt, off, tau, mask, cw)
+    got = out4.tolist()
+    for g_, r_, nm in [(got[0], total.item(), "total"), (got[1], sl1.item(), "sl1"), (got[2], con.item(), "con"),
+                       (got[3], tauf.grad.item(), "dtau")]:
+        assert abs(g_ - r_) <= 2e-3 * max(abs(r_), 1e-3) + 1e-6, (nm, g_, r_)
+    gout = torch.tensor(0.5, device=dev())
+    dpred = ops.distill_loss_bwd(pred, tgt, off, coef, gout)
+    close(dpred, 0.5 * pf.grad, rtol=2e-2, atol=2e-2 * pf.grad.abs().max().item() * 0.5, name="distill dpred")
+
+
+# ------------------------------------------------------------------------------------------- misc
+def test_gather_and_pool():
+    from visper_lm_b200 import ops
+    D = 256
+    s0, s1 = rnd(40, D, seed=81), rnd(10, D, seed=82)
+    kind = torch.tensor([0, 1, -1, 0, 1, 0], dtype=torch.int32, device=dev())
+    idx = torch.tensor([3, 9, 0, 39, 0, -1], dtype=torch.int32, device=dev())
+    out = ops.gather_rows(idx, [s0, s1], D, kind=kind)
+    ref = torch.stack([s0[3], s1[9], torch.zeros_like(s0[0]), s0[39], s1[0], torch.zeros_like(s0[0])])
+    assert torch.equal(out, ref)
+    sidx = torch.tensor([[0, 1, -1], [5, 5, 6]], dtype=torch.int32, device=dev())
+    gs = ops.gather_sum_rows(sidx.flatten(), 3, s0, D)
+    close(gs, torch.stack([s0[0].float() + s0[1].float(), 2 * s0[5].float() + s0[6].float()]), name="gather_sum")
+    x = rnd(24, D, seed=83)
+    gm = ops.group_mean(x, 4, 6)
+    close(gm, x.float().view(4, 6, D).mean(1), name="group_mean")
+    close(ops.group_mean_bwd(gm, 4, 6), (gm.float() / 6).repeat_interleave(6, 0), name="group_mean_bwd")
+    dst = torch.zeros(10, D, dtype=torch.float32, device=dev())
+    ops.scatter_add_rows(dst, torch.tensor([1, 1, -1, 7], dtype=torch.int32, device=dev()), s0[:4])
+    close(dst[1], s0[0].float() + s0[1].float(), name="scatter_add")
+    close(dst[7], s0[3].float(), name="scatter_add")
+    t = ops.transpose(s0)
+    assert torch.equal(t, s0.t().contiguous())
+
+
+def test_im2col_clip_embed():
+    from visper_lm_b200 import ops
+    B, H, P, D = 2, 56, 14, 64
+    img = rnd(B, 3, H, H, seed=91)
+    w = rnd(D, 3, P, P, seed=92, scale=0.05)
+    cls, pos = rnd(D, seed=93), rnd((H // P) ** 2 + 1, D, seed=94)
+    K = 3 * P * P
+    kpad = 640
+    cols = ops.im2col_patches(img, P, kpad)
+    wpad = torch.zeros(D, kpad, dtype=BF, device=dev())
+    wpad[:, :K] = w.view(D, K)
+    patch = ops.gemm(cols, wpad)
+    emb = ops.clip_embed(patch, cls, pos, B, (H // P) ** 2)
+    ref = torch.nn.functional.conv2d(img.float(), w.float(), stride=P).flatten(2).transpose(1, 2)
+    ref = torch.cat([cls.float().expand(B, 1, D), ref], 1) + pos.float()[None]
+    close(emb, ref.reshape(-1, D), name="clip embed")
+
+
+def test_adamw_and_clip():
+    from visper_lm_b200 import ops
+    n = 10007
+    p0 = torch.randn(n, device=dev())
+    g = (torch.randn(n, device=dev()) * 0.1).to(BF)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    master, m, v = p0.clone(), torch.zeros(n, device=dev()), torch.zeros(n, device=dev())
+    param = torch.empty(n, dtype=BF, device=dev())
+    ss = ops.grad_sumsq(g)
+    assert abs(ss.item() - g.float().pow(2).sum().item()) < 1e-3 * ss.item()
+    coef, norm = ops.clip_coef(ss, 1.0, 1.0)
+    expect = min(1.0, 1.0 / (g.float().norm().item() + 1e-6))
+    assert abs(coef.item() - expect) < 1e-5
+    for step in range(1, 4):
+        ref_p.grad = g.float() * expect
+        opt.step()
+        ops.adamw_step_(master, m, v, g, param, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, grad_scale=coef)
+    assert (master - ref_p.data).abs().max().item() < 1e-5
+    assert torch.equal(param, master.to(BF))

@@ -1,0 +1,94 @@
+"""Micro-benchmarks of the hot kernels (CUDA events, L2 flushed between iterations).
+Prints one JSON line per case; used to fill profiles/ and DESIGN.md."""
+import json
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from visper_lm_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+BF = torch.bfloat16
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, iters=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm_case(M, N, K, al, bl, name):
+    a = torch.randn((M, K) if al == 0 else (K, M), device=dev).to(BF)
+    b = torch.randn((N, K) if bl == 0 else (K, N), device=dev).to(BF)
+    out = torch.empty(M, N, dtype=BF, device=dev)
+    ms = timeit(lambda: ops.gemm(a, b, a_layout=al, b_layout=bl, out=out))
+    at = a if al == 0 else a.t()
+    bt = b.t() if bl == 0 else b
+    ms_ref = timeit(lambda: torch.matmul(at, bt, out=out))
+    fl = 2.0 * M * N * K
+    print(json.dumps({"kernel": "gemm", "name": name, "M": M, "N": N, "K": K, "a": al, "b": bl,
+                      "ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1),
+                      "cublas_ms": round(ms_ref, 4), "cublas_tflops": round(fl / ms_ref / 1e9, 1)}), flush=True)
+
+
+def attn_case(B, H, KVH, S, hd, causal):
+    qkv = torch.randn(B * S, (H + 2 * KVH) * hd, device=dev).to(BF)
+    q, k, v = qkv[:, :H * hd], qkv[:, H * hd:(H + KVH) * hd], qkv[:, (H + KVH) * hd:]
+    scale = hd ** -0.5
+    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, causal)
+    ms_f = timeit(lambda: ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, causal, out=o))
+    do = torch.randn_like(o)
+    dqkv = torch.empty_like(qkv)
+    dq, dk, dv = dqkv[:, :H * hd], dqkv[:, H * hd:(H + KVH) * hd], dqkv[:, (H + KVH) * hd:]
+    ms_b = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, S, S, hd, scale, causal))
+    fl = 4.0 * B * H * S * S * hd * (0.5 if causal else 1.0)
+    print(json.dumps({"kernel": "attention", "B": B, "H": H, "KVH": KVH, "S": S, "hd": hd, "causal": causal,
+                      "fwd_ms": round(ms_f, 4), "fwd_tflops": round(fl / ms_f / 1e9, 1),
+                      "bwd_ms": round(ms_b, 4), "bwd_tflops": round(2.5 * fl / ms_b / 1e9, 1)}), flush=True)
+
+
+def norm_case(M, D):
+    x = torch.randn(M, D, device=dev).to(BF)
+    w = torch.ones(D, device=dev, dtype=BF)
+    y = torch.empty_like(x)
+    ms = timeit(lambda: ops.rmsnorm_fwd(x, w, 1e-5, out=y))
+    by = 2.0 * M * D * 2
+    print(json.dumps({"kernel": "rmsnorm_fwd", "M": M, "D": D, "ms": round(ms, 4),
+                      "GBps": round(by / ms / 1e6, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    M = 16384
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "gemm"):
+        gemm_case(M, 6144, 4096, 0, 0, "llama qkv fwd")
+        gemm_case(M, 4096, 4096, 0, 0, "llama o fwd")
+        gemm_case(M, 28672, 4096, 0, 0, "llama gate_up fwd")
+        gemm_case(M, 4096, 14336, 0, 0, "llama down fwd")
+        gemm_case(M, 4096, 6144, 0, 1, "llama qkv dgrad")
+        gemm_case(M, 14336, 4096, 0, 1, "llama down dgrad")
+        gemm_case(M, 4096, 28672, 0, 1, "llama gate_up dgrad")
+        gemm_case(4096, 4096, M, 1, 1, "wgrad 4096x4096")
+        gemm_case(8 * 577, 3072, 1024, 0, 0, "clip qkv")
+        gemm_case(8192, 8192, 8192, 0, 0, "square 8192")
+    if which in ("all", "attn"):
+        attn_case(8, 32, 8, 2048, 128, True)
+        attn_case(8, 16, 16, 577, 64, False)
+        attn_case(4, 32, 32, 2048, 96, True)
+    if which in ("all", "norm"):
+        norm_case(16384, 4096)

@@ -1,0 +1,24 @@
+// Library-level plumbing of the C ABI: thread-local error string, launch counter, version.
+#include "common.cuh"
+#include "visper_b200.h"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+namespace vpb {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace vpb
+
+extern "C" int vpb_abi_version(void) { return VPB_ABI_VERSION; }
+extern "C" const char* vpb_last_error(void) { return vpb::g_err; }
+extern "C" int64_t vpb_launch_count(void) { return vpb::g_launches.load(); }
+extern "C" void vpb_reset_launch_count(void) { vpb::g_launches.store(0); }

@@ -1,0 +1,729 @@
+// Flash-attention forward + backward (online softmax, never materialises the S×S matrix).
+// Round-1 implementation on the warp-level tensor path (mma.sync m16n8k16 bf16, ldmatrix,
+// cp.async double buffering, XOR-swizzled shared memory); the tcgen05/TMEM version replaces it
+// in a later round.  Covers every attention on the hot path with one template:
+//   * decoder causal GQA, head_dim 128 (Llama-3) / 96 (Phi-3) — replaces flash_attn_func selected
+//     by attn_implementation="flash_attention_2" (/root/reference/ola_vlm/train/ola_vlm_train_mem.py:5)
+//   * CLIP ViT-L patch attention, 16 heads × 64, S = 577, non-causal (clip_encoder.py:56)
+//   * PerceiverAttention of the embedding-predictor heads, 4 heads × 32, queries = latents,
+//     keys = cat(context, latents) given as TWO key/value segments so the concat is never built
+//     (/root/reference/ola_vlm/model/multimodal_projector/resampler.py:46-75)
+// Q/K/V/O are addressed in place inside packed row-major projections: row = b*seq + i,
+// head h at columns [h*HD, (h+1)*HD).
+#include "common.cuh"
+#include "visper_b200.h"
+
+namespace vpb {
+
+struct AttnParams {
+  const bf16 *q, *k, *v, *k2, *v2;
+  bf16* o;
+  float* lse;  // [B,H,sq] natural-log LSE of the scaled scores
+  int64_t ldq, ldk, ldv, ldk2, ldv2, ldo;
+  int B, H, KVH, sq, sk, sk2;
+  float scale;
+  // backward only
+  const bf16* dO;
+  int64_t lddo;
+  const float* delta;  // [B,H,sq]
+  bf16 *dq, *dk, *dv, *dk2, *dv2;
+  int64_t lddq, lddk, lddv, lddk2, lddv2;
+};
+
+template <int HD>
+struct Cfg {
+  static constexpr int HDP = (HD == 96) ? 128 : HD;  // padded smem row (elements)
+  static constexpr int CPR = HDP / 8;                 // 16-byte chunks per smem row
+  static constexpr int KS = HD / 16;                  // k-steps over head_dim
+  static constexpr int ND = HD / 8;                   // 8-wide n-blocks over head_dim
+};
+
+template <int CPR>
+__device__ __forceinline__ int swz(int row, int chunk) {
+  if (CPR >= 8) return chunk ^ (row & 7);
+  return chunk ^ ((row >> 1) & 3);
+}
+template <int CPR>
+__device__ __forceinline__ uint32_t saddr(uint32_t base, int row, int chunk) {
+  return base + (uint32_t)((row * CPR + swz<CPR>(row, chunk)) * 16);
+}
+
+// cp.async a [ROWS x HD] tile (rows >= rows_valid zero-filled) into swizzled shared memory
+template <int ROWS, int HD, int NT>
+__device__ __forceinline__ void load_tile(uint32_t sbase, const bf16* g, int64_t ld, int rows_valid) {
+  constexpr int CPR = Cfg<HD>::CPR;
+  constexpr int CH = HD / 8;
+  for (int idx = threadIdx.x; idx < ROWS * CH; idx += NT) {
+    const int r = idx / CH, c = idx - r * CH;
+    const bool ok = r < rows_valid;
+    cp_async16(saddr<CPR>(sbase, r, c), ok ? (const void*)(g + (int64_t)r * ld + c * 8) : (const void*)g, ok);
+  }
+}
+
+// A fragment (16 rows starting at r0, k-step ks) from a row-major [rows][HD] tile
+template <int CPR>
+__device__ __forceinline__ void ld_a(uint32_t* f, uint32_t sbase, int r0, int ks, int lane) {
+  ldsm_x4(f, saddr<CPR>(sbase, r0 + (lane & 15), 2 * ks + (lane >> 4)));
+}
+// B fragments for n-blocks nb, nb+1 (tile rows = n), k-step ks: f = {b0(nb), b1(nb), b0(nb+1), b1(nb+1)}
+template <int CPR>
+__device__ __forceinline__ void ld_b(uint32_t* f, uint32_t sbase, int nb, int ks, int lane) {
+  const int id = lane >> 3;
+  ldsm_x4(f, saddr<CPR>(sbase, (nb + (id >> 1)) * 8 + (lane & 7), 2 * ks + (id & 1)));
+}
+// B fragments from a tile whose rows are the contraction index: rows kk*16..+16, column chunks nd, nd+1
+template <int CPR>
+__device__ __forceinline__ void ld_bt(uint32_t* f, uint32_t sbase, int kk, int nd, int lane) {
+  const int id = lane >> 3;
+  ldsm_x4_t(f, saddr<CPR>(sbase, kk * 16 + (id & 1) * 8 + (lane & 7), nd + (id >> 1)));
+}
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(256)
+attn_fwd_kernel(const AttnParams p) {
+  using C = Cfg<HD>;
+  constexpr int CPR = C::CPR, KS = C::KS, ND = C::ND, HDP = C::HDP;
+  constexpr int BMQ = 128, BN = 64, NT = 256;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK0 = sQ + BMQ * HDP * 2;
+  const uint32_t sV0 = sK0 + 2 * BN * HDP * 2;
+
+  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.H / p.KVH);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = qt * BMQ;
+  const int off = p.sk - p.sq;  // causal diagonal offset
+
+  int n1 = (p.sk + BN - 1) / BN;
+  int n2 = (p.sk2 + BN - 1) / BN;
+  if (CAUSAL) {
+    int kv_end = q0 + BMQ + off;
+    if (kv_end > p.sk) kv_end = p.sk;
+    if (kv_end < 0) kv_end = 0;
+    n1 = (kv_end + BN - 1) / BN;
+    n2 = 0;
+  }
+  const int ntiles = n1 + n2;
+
+  const bf16* qg = p.q + ((int64_t)b * p.sq + q0) * p.ldq + h * HD;
+  {
+    int rv = p.sq - q0;
+    load_tile<BMQ, HD, NT>(sQ, qg, p.ldq, rv < BMQ ? rv : BMQ);
+  }
+  auto issue_kv = [&](int jt, int buf) {
+    const bool seg2 = jt >= n1;
+    const int j0 = (seg2 ? jt - n1 : jt) * BN;
+    const int len = seg2 ? p.sk2 : p.sk;
+    const int64_t ldk = seg2 ? p.ldk2 : p.ldk, ldv = seg2 ? p.ldv2 : p.ldv;
+    const bf16* kg = (seg2 ? p.k2 : p.k) + ((int64_t)b * len + j0) * ldk + kvh * HD;
+    const bf16* vg = (seg2 ? p.v2 : p.v) + ((int64_t)b * len + j0) * ldv + kvh * HD;
+    int rv = len - j0;
+    if (rv > BN) rv = BN;
+    load_tile<BN, HD, NT>(sK0 + buf * BN * HDP * 2, kg, ldk, rv);
+    load_tile<BN, HD, NT>(sV0 + buf * BN * HDP * 2, vg, ldv, rv);
+  };
+  if (ntiles > 0) issue_kv(0, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  uint32_t qf[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) ld_a<CPR>(qf[ks], sQ, warp * 16, ks, lane);
+
+  float o[ND][4];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+  const float sl2 = p.scale * LOG2E;
+
+  for (int jt = 0; jt < ntiles; ++jt) {
+    const int buf = jt & 1;
+    if (jt + 1 < ntiles) {
+      issue_kv(jt + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint32_t sK = sK0 + buf * BN * HDP * 2, sV = sV0 + buf * BN * HDP * 2;
+
+    float s[BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int nb = 0; nb < BN / 8; nb += 2) {
+        uint32_t bf[4];
+        ld_b<CPR>(bf, sK, nb, ks, lane);
+        mma16816(s[nb], qf[ks], bf);
+        mma16816(s[nb + 1], qf[ks], bf + 2);
+      }
+    }
+    // masking (boundary tiles only)
+    const bool seg2 = jt >= n1;
+    const int j0 = (seg2 ? jt - n1 : jt) * BN;
+    const int len = seg2 ? p.sk2 : p.sk;
+    const bool need_mask = (j0 + BN > len) || (CAUSAL && (j0 + BN - 1 > q0 + off));
+    if (need_mask) {
+#pragma unroll
+      for (int nb = 0; nb < BN / 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = j0 + nb * 8 + 2 * t + (e & 1);
+          const int i = q0 + warp * 16 + g + (e >> 1) * 8;
+          const bool ok = (j < len) && (!CAUSAL || j <= i + off);
+          if (!ok) s[nb][e] = -INFINITY;
+        }
+      }
+    }
+    // online softmax
+    float mnew[2], alpha[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float mx = mrow[r];
+#pragma unroll
+      for (int nb = 0; nb < BN / 8; ++nb) mx = fmaxf(mx, fmaxf(s[nb][2 * r], s[nb][2 * r + 1]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mnew[r] = mx;
+      const float base = (mx == -INFINITY) ? 0.f : mx;
+      alpha[r] = exp2f((mrow[r] - base) * sl2);  // mrow = -inf → 0
+      mrow[r] = mx;
+      lrow[r] *= alpha[r];
+      const float mb = base * sl2;
+#pragma unroll
+      for (int nb = 0; nb < BN / 8; ++nb) {
+        const float p0 = exp2f(s[nb][2 * r] * sl2 - mb);
+        const float p1 = exp2f(s[nb][2 * r + 1] * sl2 - mb);
+        s[nb][2 * r] = p0;
+        s[nb][2 * r + 1] = p1;
+        lrow[r] += p0 + p1;
+      }
+    }
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) {
+      o[nd][0] *= alpha[0];
+      o[nd][1] *= alpha[0];
+      o[nd][2] *= alpha[1];
+      o[nd][3] *= alpha[1];
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < BN / 16; ++kk) {
+      uint32_t pf[4];
+      pf[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+      pf[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+      pf[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pf[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nd = 0; nd < ND; nd += 2) {
+        uint32_t vf[4];
+        ld_bt<CPR>(vf, sV, kk, nd, lane);
+        mma16816(o[nd], pf, vf);
+        mma16816(o[nd + 1], pf, vf + 2);
+      }
+    }
+    __syncthreads();
+  }
+
+  // finalize: normalise, stage through sQ (each warp owns its 16 rows), coalesced 16-byte stores
+  float inv[2], lse[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float l = lrow[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    inv[r] = l > 0.f ? 1.f / l : 0.f;
+    lse[r] = (l > 0.f) ? mrow[r] * p.scale + logf(l) : -INFINITY;
+  }
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) {
+    const int r0 = warp * 16 + g;
+    uint32_t a0 = saddr<CPR>(sQ, r0, nd) + t * 4;
+    uint32_t a1 = saddr<CPR>(sQ, r0 + 8, nd) + t * 4;
+    uint32_t v0 = pack2(o[nd][0] * inv[0], o[nd][1] * inv[0]);
+    uint32_t v1 = pack2(o[nd][2] * inv[1], o[nd][3] * inv[1]);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0), "r"(v0));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1), "r"(v1));
+  }
+  __syncwarp();
+  bf16* og = p.o + ((int64_t)b * p.sq + q0) * p.ldo + h * HD;
+  for (int idx = lane; idx < 16 * ND; idx += 32) {
+    const int r = warp * 16 + idx / ND, c = idx % ND;
+    if (q0 + r < p.sq) {
+      uint4 val;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                   : "r"(saddr<CPR>(sQ, r, c)));
+      stg16(og + (int64_t)r * p.ldo + c * 8, val);
+    }
+  }
+  if (p.lse && t == 0) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = q0 + warp * 16 + g + r * 8;
+      if (i < p.sq) p.lse[((int64_t)b * p.H + h) * p.sq + i] = lse[r];
+    }
+  }
+}
+
+// =============================================================================================
+// backward
+// =============================================================================================
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ o, int64_t ldo, const bf16* __restrict__ dO, int64_t lddo,
+                  float* __restrict__ delta, int B, int H, int sq, int HD) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t idx = (int64_t)blockIdx.x * 8 + warp;  // over B*sq*H
+  if (idx >= (int64_t)B * sq * H) return;
+  const int h = (int)(idx % H);
+  const int64_t row = idx / H;  // b*sq + i
+  float acc = 0.f;
+  for (int c = lane; c < HD / 8; c += 32) {
+    float a[8], d[8];
+    unpack8(ldg16(o + row * ldo + h * HD + c * 8), a);
+    unpack8(ldg16(dO + row * lddo + h * HD + c * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += a[j] * d[j];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const int b = (int)(row / sq), i = (int)(row % sq);
+    delta[((int64_t)b * H + h) * sq + i] = acc;
+  }
+}
+
+// dK, dV for one 64-row key tile of one kv head (all query heads of its GQA group, all query tiles)
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(128)
+attn_bwd_dkdv_kernel(const AttnParams p) {
+  using C = Cfg<HD>;
+  constexpr int CPR = C::CPR, KS = C::KS, ND = C::ND, HDP = C::HDP;
+  constexpr int BKV = 64, BQ = (HD > 64) ? 32 : 64, NT = 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sK = smem_u32(smem);
+  const uint32_t sV = sK + BKV * HDP * 2;
+  const uint32_t sQ = sV + BKV * HDP * 2;
+  const uint32_t sdO = sQ + BQ * HDP * 2;
+  float* sLse = reinterpret_cast<float*>(smem + (2 * BKV + 2 * BQ) * HDP * 2);
+  float* sDelta = sLse + BQ;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n1 = (p.sk + BKV - 1) / BKV;
+  const bool seg2 = (int)blockIdx.x >= n1;
+  const int kv0 = (seg2 ? blockIdx.x - n1 : blockIdx.x) * BKV;
+  const int len = seg2 ? p.sk2 : p.sk;
+  const int kvh = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.KVH;
+  const int off = p.sk - p.sq;
+  const int64_t ldk = seg2 ? p.ldk2 : p.ldk, ldv = seg2 ? p.ldv2 : p.ldv;
+  const bf16* kg = (seg2 ? p.k2 : p.k) + ((int64_t)b * len + kv0) * ldk + kvh * HD;
+  const bf16* vg = (seg2 ? p.v2 : p.v) + ((int64_t)b * len + kv0) * ldv + kvh * HD;
+  int kv_valid = len - kv0;
+  if (kv_valid > BKV) kv_valid = BKV;
+  load_tile<BKV, HD, NT>(sK, kg, ldk, kv_valid);
+  load_tile<BKV, HD, NT>(sV, vg, ldv, kv_valid);
+  cp_async_commit();
+
+  float dk[ND][4], dv[ND][4];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+  }
+  const float sl2 = p.scale * LOG2E;
+  const int nq_tiles = (p.sq + BQ - 1) / BQ;
+  int qt_begin = 0;
+  if (CAUSAL) {
+    int first = kv0 - off;  // first query row that can see key kv0
+    if (first < 0) first = 0;
+    qt_begin = first / BQ;
+  }
+
+  for (int hq = kvh * G; hq < (kvh + 1) * G; ++hq) {
+    for (int qt = qt_begin; qt < nq_tiles; ++qt) {
+      const int q0 = qt * BQ;
+      __syncthreads();  // previous tile fully consumed
+      int q_valid = p.sq - q0;
+      if (q_valid > BQ) q_valid = BQ;
+      load_tile<BQ, HD, NT>(sQ, p.q + ((int64_t)b * p.sq + q0) * p.ldq + hq * HD, p.ldq, q_valid);
+      load_tile<BQ, HD, NT>(sdO, p.dO + ((int64_t)b * p.sq + q0) * p.lddo + hq * HD, p.lddo, q_valid);
+      cp_async_commit();
+      for (int i = threadIdx.x; i < BQ; i += NT) {
+        const bool ok = i < q_valid;
+        const int64_t li = ((int64_t)b * p.H + hq) * p.sq + q0 + i;
+        sLse[i] = ok ? p.lse[li] * LOG2E : 0.f;
+        sDelta[i] = ok ? p.delta[li] : 0.f;
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+
+      // S^T = K_w Q^T and dP^T = V_w dO^T : [16 kv rows x BQ]
+      float st[BQ / 8][4], dpt[BQ / 8][4];
+#pragma unroll
+      for (int i = 0; i < BQ / 8; ++i) {
+        st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+        dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t kf[4], vf[4];
+        ld_a<CPR>(kf, sK, warp * 16, ks, lane);
+        ld_a<CPR>(vf, sV, warp * 16, ks, lane);
+#pragma unroll
+        for (int nb = 0; nb < BQ / 8; nb += 2) {
+          uint32_t bq[4], bo[4];
+          ld_b<CPR>(bq, sQ, nb, ks, lane);
+          ld_b<CPR>(bo, sdO, nb, ks, lane);
+          mma16816(st[nb], kf, bq);
+          mma16816(st[nb + 1], kf, bq + 2);
+          mma16816(dpt[nb], vf, bo);
+          mma16816(dpt[nb + 1], vf, bo + 2);
+        }
+      }
+      // P^T and dS^T (in place: st ← P^T, dpt ← dS^T)
+#pragma unroll
+      for (int nb = 0; nb < BQ / 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int qc = nb * 8 + 2 * t + (e & 1);
+          const int kr = warp * 16 + g + (e >> 1) * 8;
+          const bool ok = (qc < q_valid) && (kr < kv_valid) && (!CAUSAL || kv0 + kr <= q0 + qc + off);
+          const float pv = ok ? exp2f(st[nb][e] * sl2 - sLse[qc]) : 0.f;
+          st[nb][e] = pv;
+          dpt[nb][e] = pv * (dpt[nb][e] - sDelta[qc]);
+        }
+      }
+      // dV += P^T dO ; dK += dS^T Q   (contraction over the BQ query rows)
+#pragma unroll
+      for (int kk = 0; kk < BQ / 16; ++kk) {
+        uint32_t pf[4], sf[4];
+        pf[0] = pack2(st[2 * kk][0], st[2 * kk][1]);
+        pf[1] = pack2(st[2 * kk][2], st[2 * kk][3]);
+        pf[2] = pack2(st[2 * kk + 1][0], st[2 * kk + 1][1]);
+        pf[3] = pack2(st[2 * kk + 1][2], st[2 * kk + 1][3]);
+        sf[0] = pack2(dpt[2 * kk][0], dpt[2 * kk][1]);
+        sf[1] = pack2(dpt[2 * kk][2], dpt[2 * kk][3]);
+        sf[2] = pack2(dpt[2 * kk + 1][0], dpt[2 * kk + 1][1]);
+        sf[3] = pack2(dpt[2 * kk + 1][2], dpt[2 * kk + 1][3]);
+#pragma unroll
+        for (int nd = 0; nd < ND; nd += 2) {
+          uint32_t f1[4], f2[4];
+          ld_bt<CPR>(f1, sdO, kk, nd, lane);
+          ld_bt<CPR>(f2, sQ, kk, nd, lane);
+          mma16816(dv[nd], pf, f1);
+          mma16816(dv[nd + 1], pf, f1 + 2);
+          mma16816(dk[nd], sf, f2);
+          mma16816(dk[nd + 1], sf, f2 + 2);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // stage dK through sQ/sdO? BQ may be 32 rows only — use sK (dK) and sV (dV): all reads are done.
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) {
+    const int r0 = warp * 16 + g;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr<CPR>(sK, r0, nd) + t * 4),
+                 "r"(pack2(dk[nd][0] * p.scale, dk[nd][1] * p.scale)));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr<CPR>(sK, r0 + 8, nd) + t * 4),
+                 "r"(pack2(dk[nd][2] * p.scale, dk[nd][3] * p.scale)));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr<CPR>(sV, r0, nd) + t * 4),
+                 "r"(pack2(dv[nd][0], dv[nd][1])));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr<CPR>(sV, r0 + 8, nd) + t * 4),
+                 "r"(pack2(dv[nd][2], dv[nd][3])));
+  }
+  __syncwarp();
+  const int64_t lddk = seg2 ? p.lddk2 : p.lddk, lddv = seg2 ? p.lddv2 : p.lddv;
+  bf16* dkg = (seg2 ? p.dk2 : p.dk) + ((int64_t)b * len + kv0) * lddk + kvh * HD;
+  bf16* dvg = (seg2 ? p.dv2 : p.dv) + ((int64_t)b * len + kv0) * lddv + kvh * HD;
+  for (int idx = lane; idx < 16 * ND; idx += 32) {
+    const int r = warp * 16 + idx / ND, c = idx % ND;
+    if (r < kv_valid) {
+      uint4 a, d;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                   : "r"(saddr<CPR>(sK, r, c)));
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w)
+                   : "r"(saddr<CPR>(sV, r, c)));
+      stg16(dkg + (int64_t)r * lddk + c * 8, a);
+      stg16(dvg + (int64_t)r * lddv + c * 8, d);
+    }
+  }
+}
+
+// dQ for one 64-row query tile of one head
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const AttnParams p) {
+  using C = Cfg<HD>;
+  constexpr int CPR = C::CPR, KS = C::KS, ND = C::ND, HDP = C::HDP;
+  constexpr int BQ = 64, BKV = (HD > 64) ? 32 : 64, NT = 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sdO = sQ + BQ * HDP * 2;
+  const uint32_t sK = sdO + BQ * HDP * 2;
+  const uint32_t sV = sK + BKV * HDP * 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.H / p.KVH);
+  const int q0 = qt * BQ;
+  const int off = p.sk - p.sq;
+  int q_valid = p.sq - q0;
+  if (q_valid > BQ) q_valid = BQ;
+
+  load_tile<BQ, HD, NT>(sQ, p.q + ((int64_t)b * p.sq + q0) * p.ldq + h * HD, p.ldq, q_valid);
+  load_tile<BQ, HD, NT>(sdO, p.dO + ((int64_t)b * p.sq + q0) * p.lddo + h * HD, p.lddo, q_valid);
+  cp_async_commit();
+
+  float lse2[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = warp * 16 + g + r * 8;
+    const bool ok = i < q_valid;
+    const int64_t li = ((int64_t)b * p.H + h) * p.sq + q0 + i;
+    lse2[r] = ok ? p.lse[li] * LOG2E : 0.f;
+    dl[r] = ok ? p.delta[li] : 0.f;
+  }
+
+  int n1 = (p.sk + BKV - 1) / BKV;
+  int n2 = (p.sk2 + BKV - 1) / BKV;
+  if (CAUSAL) {
+    int kv_end = q0 + BQ + off;
+    if (kv_end > p.sk) kv_end = p.sk;
+    if (kv_end < 0) kv_end = 0;
+    n1 = (kv_end + BKV - 1) / BKV;
+    n2 = 0;
+  }
+  float dq[ND][4];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  const float sl2 = p.scale * LOG2E;
+
+  for (int jt = 0; jt < n1 + n2; ++jt) {
+    const bool seg2 = jt >= n1;
+    const int j0 = (seg2 ? jt - n1 : jt) * BKV;
+    const int len = seg2 ? p.sk2 : p.sk;
+    const int64_t ldk = seg2 ? p.ldk2 : p.ldk, ldv = seg2 ? p.ldv2 : p.ldv;
+    int kv_valid = len - j0;
+    if (kv_valid > BKV) kv_valid = BKV;
+    __syncthreads();
+    load_tile<BKV, HD, NT>(sK, (seg2 ? p.k2 : p.k) + ((int64_t)b * len + j0) * ldk + kvh * HD, ldk, kv_valid);
+    load_tile<BKV, HD, NT>(sV, (seg2 ? p.v2 : p.v) + ((int64_t)b * len + j0) * ldv + kvh * HD, ldv, kv_valid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    float s[BKV / 8][4], dp[BKV / 8][4];
+#pragma unroll
+    for (int i = 0; i < BKV / 8; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t qf[4], of[4];
+      ld_a<CPR>(qf, sQ, warp * 16, ks, lane);
+      ld_a<CPR>(of, sdO, warp * 16, ks, lane);
+#pragma unroll
+      for (int nb = 0; nb < BKV / 8; nb += 2) {
+        uint32_t bk[4], bv[4];
+        ld_b<CPR>(bk, sK, nb, ks, lane);
+        ld_b<CPR>(bv, sV, nb, ks, lane);
+        mma16816(s[nb], qf, bk);
+        mma16816(s[nb + 1], qf, bk + 2);
+        mma16816(dp[nb], of, bv);
+        mma16816(dp[nb + 1], of, bv + 2);
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < BKV / 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int jc = nb * 8 + 2 * t + (e & 1);
+        const int r = e >> 1;
+        const int i = warp * 16 + g + r * 8;
+        const bool ok = (i < q_valid) && (jc < kv_valid) && (!CAUSAL || j0 + jc <= q0 + i + off);
+        const float pv = ok ? exp2f(s[nb][e] * sl2 - lse2[r]) : 0.f;
+        s[nb][e] = pv * (dp[nb][e] - dl[r]);  // dS
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < BKV / 16; ++kk) {
+      uint32_t sf[4];
+      sf[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+      sf[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+      sf[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      sf[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nd = 0; nd < ND; nd += 2) {
+        uint32_t kf[4];
+        ld_bt<CPR>(kf, sK, kk, nd, lane);
+        mma16816(dq[nd], sf, kf);
+        mma16816(dq[nd + 1], sf, kf + 2);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) {
+    const int r0 = warp * 16 + g;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr<CPR>(sQ, r0, nd) + t * 4),
+                 "r"(pack2(dq[nd][0] * p.scale, dq[nd][1] * p.scale)));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr<CPR>(sQ, r0 + 8, nd) + t * 4),
+                 "r"(pack2(dq[nd][2] * p.scale, dq[nd][3] * p.scale)));
+  }
+  __syncwarp();
+  bf16* dqg = p.dq + ((int64_t)b * p.sq + q0) * p.lddq + h * HD;
+  for (int idx = lane; idx < 16 * ND; idx += 32) {
+    const int r = warp * 16 + idx / ND, c = idx % ND;
+    if (r < q_valid) {
+      uint4 a;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                   : "r"(saddr<CPR>(sQ, r, c)));
+      stg16(dqg + (int64_t)r * p.lddq + c * 8, a);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int HD, bool CAUSAL>
+static int launch_fwd(const AttnParams& p, cudaStream_t st) {
+  constexpr int HDP = Cfg<HD>::HDP;
+  constexpr int SMEM = (128 + 4 * 64) * HDP * 2;
+  auto kern = attn_fwd_kernel<HD, CAUSAL>;
+  static bool cfg = false;
+  if (!cfg) {
+    VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    cfg = true;
+  }
+  dim3 grid((p.sq + 127) / 128, p.H, p.B);
+  kern<<<grid, 256, SMEM, st>>>(p);
+  VPB_LAUNCH_OK();
+  return 0;
+}
+template <int HD, bool CAUSAL>
+static int launch_bwd(const AttnParams& p, cudaStream_t st) {
+  constexpr int HDP = Cfg<HD>::HDP;
+  constexpr int BSMALL = (HD > 64) ? 32 : 64;
+  {
+    constexpr int SMEM = (2 * 64 + 2 * BSMALL) * HDP * 2 + 2 * BSMALL * 4;
+    auto kern = attn_bwd_dkdv_kernel<HD, CAUSAL>;
+    static bool cfg = false;
+    if (!cfg) {
+      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      cfg = true;
+    }
+    dim3 grid((p.sk + 63) / 64 + (p.sk2 + 63) / 64, p.KVH, p.B);
+    kern<<<grid, 128, SMEM, st>>>(p);
+    VPB_LAUNCH_OK();
+  }
+  {
+    constexpr int SMEM = (2 * 64 + 2 * BSMALL) * HDP * 2;
+    auto kern = attn_bwd_dq_kernel<HD, CAUSAL>;
+    static bool cfg = false;
+    if (!cfg) {
+      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      cfg = true;
+    }
+    dim3 grid((p.sq + 63) / 64, p.H, p.B);
+    kern<<<grid, 128, SMEM, st>>>(p);
+    VPB_LAUNCH_OK();
+  }
+  return 0;
+}
+
+static int check_attn(const AttnParams& p, int HD) {
+  VPB_CHECK(HD == 32 || HD == 64 || HD == 96 || HD == 128, "attention: unsupported head_dim %d", HD);
+  VPB_CHECK(p.B > 0 && p.H > 0 && p.KVH > 0 && p.H % p.KVH == 0 && p.sq > 0 && p.sk > 0 && p.sk2 >= 0,
+            "attention: bad shape B=%d H=%d KVH=%d sq=%d sk=%d sk2=%d", p.B, p.H, p.KVH, p.sq, p.sk, p.sk2);
+  VPB_CHECK(p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0 && p.ldo % 8 == 0,
+            "attention: row strides must be multiples of 8 elements");
+  return 0;
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+#define DISPATCH_HD(HDv, CAUSALv, FN, ...)                                  \
+  do {                                                                      \
+    if (CAUSALv) {                                                          \
+      switch (HDv) {                                                        \
+        case 32: return FN<32, true>(__VA_ARGS__);                          \
+        case 64: return FN<64, true>(__VA_ARGS__);                          \
+        case 96: return FN<96, true>(__VA_ARGS__);                          \
+        default: return FN<128, true>(__VA_ARGS__);                         \
+      }                                                                     \
+    } else {                                                                \
+      switch (HDv) {                                                        \
+        case 32: return FN<32, false>(__VA_ARGS__);                         \
+        case 64: return FN<64, false>(__VA_ARGS__);                         \
+        case 96: return FN<96, false>(__VA_ARGS__);                         \
+        default: return FN<128, false>(__VA_ARGS__);                        \
+      }                                                                     \
+    }                                                                       \
+  } while (0)
+
+extern "C" int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                            int64_t ldv, const void* k2, int64_t ldk2, const void* v2, int64_t ldv2,
+                            void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk,
+                            int sk2, int head_dim, float scale, int causal, void* stream) {
+  AttnParams p = {};
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
+  p.k2 = (const bf16*)k2; p.v2 = (const bf16*)v2;
+  p.o = (bf16*)o; p.lse = lse;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldk2 = ldk2; p.ldv2 = ldv2; p.ldo = ldo;
+  p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk; p.sk2 = k2 ? sk2 : 0;
+  p.scale = scale;
+  if (check_attn(p, head_dim)) return -1;
+  VPB_CHECK(!(causal && p.sk2 > 0), "attention: causal with a second key segment is not supported");
+  DISPATCH_HD(head_dim, causal, launch_fwd, p, (cudaStream_t)stream);
+}
+
+extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                            int64_t ldv, const void* k2, int64_t ldk2, const void* v2, int64_t ldv2,
+                            const void* o, int64_t ldo, const void* dO, int64_t lddo,
+                            const float* lse, float* delta, void* dq, int64_t lddq, void* dk,
+                            int64_t lddk, void* dv, int64_t lddv, void* dk2, int64_t lddk2,
+                            void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk, int sk2,
+                            int head_dim, float scale, int causal, void* stream) {
+  AttnParams p = {};
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
+  p.k2 = (const bf16*)k2; p.v2 = (const bf16*)v2;
+  p.lse = const_cast<float*>(lse);
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldk2 = ldk2; p.ldv2 = ldv2; p.ldo = ldo;
+  p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk; p.sk2 = k2 ? sk2 : 0;
+  p.scale = scale;
+  p.dO = (const bf16*)dO; p.lddo = lddo; p.delta = delta;
+  p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.dk2 = (bf16*)dk2; p.dv2 = (bf16*)dv2;
+  p.lddq = lddq; p.lddk = lddk; p.lddv = lddv; p.lddk2 = lddk2; p.lddv2 = lddv2;
+  if (check_attn(p, head_dim)) return -1;
+  VPB_CHECK(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "attention bwd: strides");
+  VPB_CHECK(!(causal && p.sk2 > 0), "attention: causal with a second key segment is not supported");
+  const int64_t nrows = (int64_t)B * sq * H;
+  attn_delta_kernel<<<(int)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)o, ldo, (const bf16*)dO, lddo, delta, B, H, sq, head_dim);
+  VPB_LAUNCH_OK();
+  DISPATCH_HD(head_dim, causal, launch_bwd, p, (cudaStream_t)stream);
+}

@@ -1,0 +1,363 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA (128B swizzle) → shared memory ring →
+// tcgen05.mma (accumulators in TMEM, double buffered) → tcgen05.ld epilogue with fused
+// bias / activation / residual.  One CTA per SM, 192 threads:
+//   warp 0   : TMA producer (one elected lane)
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2-5: epilogue (TMEM lane quarter = warp_idx % 4)
+//
+// C[M,N] = epilogue( A · Bᵀ ) with fp32 accumulation, bf16 in / bf16 out.
+//   a_layout 0: A stored [M,K], K contiguous ("K-major")      1: A stored [K,M], M contiguous
+//   b_layout 0: B stored [N,K], K contiguous (nn.Linear weight) 1: B stored [K,N], N contiguous
+// so that forward (x·Wᵀ: 0/0), dgrad (dY·W: 0/1) and wgrad (dYᵀ·X: 1/1) all run without
+// materialising a transpose — the MN-major cases are expressed in the UMMA descriptors.
+//
+// Replaces the cuBLAS calls behind every F.linear on the reference hot path
+// (HF modeling_llama/phi3/clip → torch.nn.functional.linear).
+#include "common.cuh"
+#include "visper_b200.h"
+
+namespace vpb {
+
+struct GemmArgs {
+  bf16* C;
+  int64_t ldc;
+  const bf16* bias;  // [N] or null
+  const bf16* res;   // [M,N] residual added after the activation, or null
+  int64_t ldr;
+  bf16* aux;  // optional copy of the pre-activation (bias added), for activation backward
+  int64_t ldaux;
+  int M, N, K;
+  int act;  // VPB_ACT_*
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GROUP_M = 16;
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  switch (act) {
+    case VPB_ACT_GELU:
+      return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    case VPB_ACT_QUICK_GELU:
+      return x / (1.f + __expf(-1.702f * x));
+    case VPB_ACT_RELU:
+      return fmaxf(x, 0.f);
+    default:
+      return x;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (512 or 256 columns)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (args.M + BM - 1) / BM;
+  const int num_n = (args.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (args.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile order: groups of GROUP_M row-blocks swept over all column-blocks, so one wave of
+  // 148 CTAs shares a ~2048-row A panel and a ~2300-row B panel in L2.
+  auto decode_tile = [&](int t, int& mb, int& nb) {
+    const int per_group = GROUP_M * num_n;
+    const int g = t / per_group;
+    const int first_m = g * GROUP_M;
+    const int gsize = min(GROUP_M, num_m - first_m);
+    const int r = t - g * per_group;
+    mb = first_m + r % gsize;
+    nb = r / gsize;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int mb, nb;
+        decode_tile(t, mb, nb);
+        const int m0 = mb * BM, n0 = nb * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d(sa + c * 8192, &tmA, &full[s], m0 + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * 8192, &tmB, &full[s], n0 + c * 64, kb * BK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // descriptor start-address increment (16-byte units) per UMMA_K = 16 slice
+      constexpr uint32_t A_KADV = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      constexpr uint32_t B_KADV = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      uint32_t it = 0, tile_iter = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_iter) {
+        const uint32_t acc = tile_iter & 1;
+        const uint32_t acc_ph = (tile_iter >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t adesc = A_MN ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc(sb, 8192, 1024) : make_smem_desc(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * A_KADV), bdesc + (uint64_t)(k * B_KADV), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // frees the smem slot when these MMAs retire
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete → epilogue
+      }
+    }
+  } else {
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    uint32_t tile_iter = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_iter) {
+      int mb, nb;
+      decode_tile(t, mb, nb);
+      const uint32_t acc = tile_iter & 1;
+      const uint32_t acc_ph = (tile_iter >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const int row = mb * BM + quarter * 32 + lane;
+      const bool row_ok = row < args.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      bf16* crow = args.C + (int64_t)row * args.ldc;
+      const bf16* rrow = args.res ? args.res + (int64_t)row * args.ldr : nullptr;
+      bf16* xrow = args.aux ? args.aux + (int64_t)row * args.ldaux : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n_base = nb * BN + c * 32;
+        if (n_base >= args.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n_base + g * 8;
+          if (n + 8 <= args.N) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+            if (args.bias) {
+              float b[8];
+              unpack8(ldg16(args.bias + n), b);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += b[j];
+            }
+            if (row_ok) {
+              if (xrow) stg16(xrow + n, pack8(v));
+              if (args.act != VPB_ACT_NONE) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], args.act);
+              }
+              if (rrow) {
+                float q[8];
+                unpack8(*reinterpret_cast<const uint4*>(rrow + n), q);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += q[j];
+              }
+              stg16(crow + n, pack8(v));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows `ld` elements apart.
+int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                 uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  VPB_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  VPB_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
+  VPB_CHECK((ld * 2) % 16 == 0, "TMA row stride must be a multiple of 16 bytes (ld=%llu)",
+            (unsigned long long)ld);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VPB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return 0;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
+                       cudaStream_t stream) {
+  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const int tiles = ((args.M + BM - 1) / BM) * ((args.N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 192, SMEM, stream>>>(tmA, tmB, args);
+  VPB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+
+extern "C" int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const void* B, int64_t ldb,
+                             int b_layout, void* C, int64_t ldc, int M, int N, int K, int act,
+                             const void* bias, const void* residual, int64_t ldr, void* aux,
+                             int64_t ldaux, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VPB_CHECK(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  VPB_CHECK(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+  VPB_CHECK(ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+            "gemm: C must be 16-byte aligned with ldc %% 8 == 0");
+  VPB_CHECK(!residual || (ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0),
+            "gemm: residual alignment");
+  VPB_CHECK(!aux || (ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0),
+            "gemm: aux alignment");
+  VPB_CHECK(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias alignment");
+  VPB_CHECK(act >= VPB_ACT_NONE && act <= VPB_ACT_RELU, "gemm: unknown activation %d", act);
+
+  const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
+  const bool bn256 = tiles256 >= num_sms() && N >= 256;
+  const int BN = bn256 ? 256 : 128;
+
+  CUtensorMap tmA, tmB;
+  if (a_layout == 0) {
+    if (make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return -1;
+  } else {
+    if (make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK)) return -1;
+  }
+  if (b_layout == 0) {
+    if (make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN)) return -1;
+  } else {
+    if (make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK)) return -1;
+  }
+  GemmArgs args;
+  args.C = static_cast<bf16*>(C);
+  args.ldc = ldc;
+  args.bias = static_cast<const bf16*>(bias);
+  args.res = static_cast<const bf16*>(residual);
+  args.ldr = ldr;
+  args.aux = static_cast<bf16*>(aux);
+  args.ldaux = ldaux;
+  args.M = M;
+  args.N = N;
+  args.K = K;
+  args.act = act;
+
+  const int key = (bn256 ? 4 : 0) | (a_layout ? 2 : 0) | (b_layout ? 1 : 0);
+  switch (key) {
+    case 0: return launch_gemm<128, false, false>(tmA, tmB, args, stream);
+    case 1: return launch_gemm<128, false, true>(tmA, tmB, args, stream);
+    case 2: return launch_gemm<128, true, false>(tmA, tmB, args, stream);
+    case 3: return launch_gemm<128, true, true>(tmA, tmB, args, stream);
+    case 4: return launch_gemm<256, false, false>(tmA, tmB, args, stream);
+    case 5: return launch_gemm<256, false, true>(tmA, tmB, args, stream);
+    case 6: return launch_gemm<256, true, false>(tmA, tmB, args, stream);
+    default: return launch_gemm<256, true, true>(tmA, tmB, args, stream);
+  }
+}

@@ -1,0 +1,105 @@
+// Sharded-optimizer kernels for the ZeRO-2 step: fused AdamW over a flat fp32 master shard with
+// bf16 gradient in / bf16 parameter out, deterministic grad-norm reduction and clip coefficient
+// computed on the device (no host sync in the step).
+//
+// Reference semantics: torch.optim.AdamW as built by HF Trainer (optim="adamw_torch",
+// /root/reference/ola_vlm/train/ola_vlm_train.py:124; llava_trainer.py:890-995 create_optimizer)
+// wrapped by DeepSpeed ZeRO-2 (scripts/zero2.json), grads averaged over ranks.
+#include "common.cuh"
+#include "visper_b200.h"
+
+namespace vpb {
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ master, float* __restrict__ m, float* __restrict__ v,
+             const bf16* __restrict__ grad, bf16* __restrict__ param, int64_t n, float lr,
+             float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+             const float* __restrict__ grad_scale) {
+  const float gs = grad_scale ? *grad_scale : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float g = __bfloat162float(grad[i]) * gs;
+    float p = master[i];
+    p *= (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * g;
+    const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p -= (lr / bc1) * (mi / denom);
+    master[i] = p;
+    param[i] = __float2bfloat16(p);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sumsq_partial_kernel(const bf16* __restrict__ g, int64_t n, float* __restrict__ partial) {
+  __shared__ float red[33];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __bfloat162float(g[i]);
+    s += x * x;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(256)
+sumsq_final_kernel(const float* __restrict__ partial, int np, float* __restrict__ out,
+                   int accumulate) {
+  __shared__ float red[33];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s += partial[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = accumulate ? *out + s : s;
+}
+
+// coef = extra_scale * min(1, max_norm / (sqrt(sumsq * extra_scale²) + 1e-6))  (max_norm<=0: no clip)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float extra_scale,
+                                 float* __restrict__ coef, float* __restrict__ norm_out) {
+  const float norm = sqrtf(*sumsq) * extra_scale;
+  float c = 1.f;
+  if (max_norm > 0.f) c = fminf(1.f, max_norm / (norm + 1e-6f));
+  *coef = c * extra_scale;
+  if (norm_out) *norm_out = norm;
+}
+
+}  // namespace vpb
+
+using namespace vpb;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" int vpb_adamw_step(float* master, float* m, float* v, const void* grad, void* param,
+                              int64_t n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int step, const float* grad_scale, void* stream) {
+  VPB_CHECK(n > 0 && step >= 1, "adamw: n=%lld step=%d", (long long)n, step);
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adamw_kernel<<<(int)blocks, 256, 0, ST(stream)>>>(master, m, v, (const bf16*)grad, (bf16*)param, n,
+                                                    lr, beta1, beta2, eps, weight_decay, bc1,
+                                                    sqrtf(bc2), grad_scale);
+  VPB_LAUNCH_OK();
+  return 0;
+}
+
+// workspace: >= 1024 floats
+extern "C" int vpb_grad_sumsq(const void* grad, int64_t n, float* workspace, float* out,
+                              int accumulate, void* stream) {
+  VPB_CHECK(n > 0, "grad_sumsq: n=%lld", (long long)n);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  sumsq_partial_kernel<<<(int)blocks, 256, 0, ST(stream)>>>((const bf16*)grad, n, workspace);
+  VPB_LAUNCH_OK();
+  sumsq_final_kernel<<<1, 256, 0, ST(stream)>>>(workspace, (int)blocks, out, accumulate);
+  VPB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vpb_clip_coef(const float* sumsq, float max_norm, float extra_scale, float* coef,
+                             float* norm_out, void* stream) {
+  clip_coef_kernel<<<1, 1, 0, ST(stream)>>>(sumsq, max_norm, extra_scale, coef, norm_out);
+  VPB_LAUNCH_OK();
+  return 0;
+}
