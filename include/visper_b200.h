@@ -105,6 +105,9 @@ int vpb_gather_sum_rows(void* out, int64_t ldo, int nslots, int cnt, const int* 
                         const void* src, int64_t lds, int D, float scale, void* stream);
 int vpb_scatter_add_rows(float* dst, int64_t ldd, int nrows, const int* index, const void* src,
                          int64_t lds, int D, void* stream);
+/* dst[index[r]] += src[r] (bf16; indices unique per call) */
+int vpb_add_rows(void* dst, int64_t ldd, int nrows, const int* index, const void* src, int64_t lds,
+                 int D, void* stream);
 /* task-token pooling param[576,D].view(8,72,D).mean(1) (ola_arch.py:225-228) */
 int vpb_group_mean(const void* in, int64_t ldi, void* out, int64_t ldo, int groups, int gsize,
                    int D, void* stream);

@@ -212,6 +212,15 @@ def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True
         model.img_gen_loss_weight = 0.5
         model.img_seg_loss_weight = 0.5
         model.img_depth_loss_weight = 0.5
+    if distill and cfg["depth_dim"] != 1024:
+        # the frozen DPT decoder ("next" row) is hard-wired to 1024 channels; its
+        # output only feeds the logging-only `depth_preds` field, so tiny configs stub it out.
+        class _NoDPT(torch.nn.Module):
+            def forward(self, feats):
+                f = feats[0][0]
+                return torch.zeros(f.shape[0], 336, 336, dtype=f.dtype, device=f.device)
+
+        model.da_v2_head = _NoDPT()
     model = model.float().eval()  # no dropout anywhere on the path; eval() only disables HF ckpt hooks
     if seed_fn is not None:
         with torch.no_grad():

@@ -1,0 +1,88 @@
+"""CPU tests (no GPU): the oracle restatement against the golden vectors of the unmodified
+reference, the reference itself when /root/reference is present, and the state-dict ABI."""
+import pytest
+import torch
+
+from parity_utils import configs, restate
+
+GOLDEN = __import__("pathlib").Path(__file__).parent / "golden"
+CASES = [("tiny_llama_dsg", "TINY_LLAMA", True), ("tiny_llama_dsg_padded", "TINY_LLAMA", True),
+         ("tiny_phi3_dsg", "TINY_PHI3", True), ("tiny_llama_ntp", "TINY_LLAMA", False)]
+
+
+def _state(fx):
+    return {n: restate.seeded_param(n, s) for n, s in fx["state_spec"].items()}
+
+
+@pytest.mark.parametrize("name,cfg_name,distill", CASES)
+def test_oracle_matches_golden(name, cfg_name, distill):
+    fx = torch.load(GOLDEN / f"{name}.pt")
+    cfg = getattr(configs, cfg_name)
+    sd = {k: v.requires_grad_(k in fx["grads"]) for k, v in _state(fx).items()}
+    batch = configs.synthetic_batch(cfg, fx["B"], fx["n_text"], seed=fx["seed"], distill=distill,
+                                    pad_rows=fx["pad_rows"])
+    pub = restate.forward_step(sd, cfg, batch, distill=distill, zero_masks_like_reference=True)
+    assert abs(pub["loss"].item() - fx["loss_as_published"]) < 1e-5
+    out = restate.forward_step(sd, cfg, batch, distill=distill, zero_masks_like_reference=False)
+    assert abs(out["text_loss"].item() - fx["text_loss"]) < 1e-5
+    assert abs(out["loss"].item() - fx["loss_live"]) < 2e-5, (out["loss"].item(), fx["loss_live"])
+    assert torch.allclose(out["logits"][:, ::16, ::8], fx["logits_sub"], atol=2e-5)
+    for a, b in zip(out["hidden_states"], fx["hidden_sub"]):
+        assert torch.allclose(a[..., ::32, ::8], b, atol=3e-5)
+    if distill:
+        for task in ("depth", "seg", "gen"):
+            for (l, s1, c), (rl, rs1, rc) in zip(out[f"{task}_losses"], fx["emb_losses_live"][task]):
+                assert abs(l.item() - rl) < 1e-5 and abs(s1.item() - rs1) < 1e-5 and abs(c.item() - rc) < 1e-5
+    out["loss"].backward()
+    for n, g in fx["grads"].items():
+        mine = sd[n].grad
+        if g["norm"] == 0.0:
+            assert mine is None or mine.norm().item() < 1e-7, n
+            continue
+        assert abs(mine.norm().item() - g["norm"]) <= 1e-4 * g["norm"] + 1e-7, n
+        assert torch.allclose(mine.flatten()[:16], g["head"], atol=1e-5 + 1e-4 * g["norm"]), n
+
+
+def test_depth_heads_linear_2_3_get_no_gradient():
+    """Reference quirk (Appendix A): only features[0] is supervised."""
+    fx = torch.load(GOLDEN / "tiny_llama_dsg.pt")
+    live = {n for n, g in fx["grads"].items() if g["norm"] > 0.0}
+    assert not any("linear_2" in n or "linear_3" in n for n in live)
+    assert any("linear_1" in n for n in live)
+    assert any("linear_2" in n for n in fx["state_spec"])
+
+
+@pytest.mark.parametrize("name,cfg_name,distill", [c for c in CASES if c[0] != "tiny_llama_dsg_padded"])
+def test_state_dict_abi(name, cfg_name, distill):
+    from parity_utils import build_product
+
+    fx = torch.load(GOLDEN / f"{name}.pt")
+    model = build_product(getattr(configs, cfg_name), distill, None)
+    mine = {n: tuple(p.shape) for n, p in model.named_parameters()}
+    assert mine == fx["state_spec"]
+
+
+def test_oracle_matches_live_reference():
+    """Only where the reference tree is mounted (this container): run the unmodified classes."""
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("/root/reference not mounted")
+    cfg = configs.TINY_LLAMA
+    model = ref_shim.build_reference_model(cfg, "llama", True, seed_fn=restate.seeded_param)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = configs.synthetic_batch(cfg, 2, 40)
+    ref_shim.install_synthetic_teachers(model, batch["targets"])
+    masks = {k: v.clone() for k, v in batch["masks"].items()}
+    with torch.no_grad():
+        out = model(input_ids=batch["input_ids"], labels=batch["labels"], attention_mask=batch["attention_mask"],
+                    images=batch["images"], pil_images=[None] * 2, depth_mask=masks["depth"],
+                    seg_mask=masks["seg"], gen_mask=masks["gen"])
+        mine = restate.forward_step(sd, cfg, batch, distill=True, zero_masks_like_reference=True)
+    assert abs(out.loss.item() - mine["loss"].item()) < 1e-5
+    assert torch.allclose(out.logits, mine["logits"], atol=3e-5)
+    for a, b in zip(out.hidden_states, mine["hidden_states"]):
+        assert torch.allclose(a, b, atol=3e-5)
+    assert torch.allclose(out.depth_embs[0][0][0], mine["depth_embs"][0][0], atol=3e-5)
+    assert torch.allclose(out.seg_embs[1], mine["seg_embs"][1], atol=3e-5)
+    assert torch.allclose(out.image_embs[0], mine["gen_embs"][0], atol=3e-5)

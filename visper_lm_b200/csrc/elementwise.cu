@@ -290,6 +290,23 @@ scatter_add_rows_kernel(float* __restrict__ dst, int64_t ldd, const int* __restr
   }
 }
 
+// dst[index[r]] += src[r]  (bf16, indices unique within one call; index < 0 skipped)
+__global__ void __launch_bounds__(128)
+add_rows_kernel(bf16* __restrict__ dst, int64_t ldd, const int* __restrict__ index,
+                const bf16* __restrict__ src, int64_t lds, int D) {
+  const int r = blockIdx.x;
+  const int idx = index[r];
+  if (idx < 0) return;
+  for (int v = threadIdx.x; v < (D >> 3); v += blockDim.x) {
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const uint4*>(dst + (int64_t)idx * ldd + v * 8), a);
+    unpack8(ldg16_stream(src + (int64_t)r * lds + v * 8), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    stg16(dst + (int64_t)idx * ldd + v * 8, pack8(a));
+  }
+}
+
 // in [groups*gsize, D] → out [groups, D] mean over consecutive gsize rows (task-token pooling,
 // ola_arch.py:225-228) ; backward broadcasts dout/gsize.
 __global__ void __launch_bounds__(128)
@@ -475,6 +492,14 @@ extern "C" int vpb_scatter_add_rows(float* dst, int64_t ldd, int nrows, const in
                                     const void* src, int64_t lds, int D, void* stream) {
   VPB_CHECK(D % 8 == 0 && nrows > 0, "scatter_add_rows: bad shape");
   scatter_add_rows_kernel<<<nrows, 128, 0, ST(stream)>>>(dst, ldd, index, (const bf16*)src, lds, D);
+  VPB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vpb_add_rows(void* dst, int64_t ldd, int nrows, const int* index, const void* src,
+                            int64_t lds, int D, void* stream) {
+  VPB_CHECK(D % 8 == 0 && nrows > 0, "add_rows: bad shape");
+  add_rows_kernel<<<nrows, 128, 0, ST(stream)>>>((bf16*)dst, ldd, index, (const bf16*)src, lds, D);
   VPB_LAUNCH_OK();
   return 0;
 }

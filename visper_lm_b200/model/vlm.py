@@ -1,0 +1,681 @@
+"""B200-native stand-ins for the reference's model classes, behind the same Python surface:
+
+  OlaLlavaLlamaForCausalLM / OlaLlavaPhi3ForCausalLM   (ola_vlm/model/language_model/ola_llama.py:58,
+                                                         ola_phi3.py:58 — NTP + distillation heads)
+  LlavaLlamaForCausalLM / LlavaPhi3ForCausalLM         (llava_llama.py:51, llava_phi3.py — NTP only)
+
+forward(...) takes the collator's batch and returns an object with .loss, .logits,
+.hidden_states, .image_embs / .seg_embs / .depth_embs / .depth_preds like OlaCausalLLMOutputWithPast
+(ola_llama.py:36-44).  prepare_inputs_labels_for_multimodal keeps the reference signature
+(ola_arch.py:256-259) but is sync-free on the device: the splice is planned on the host from the
+token ids and executed as one gather kernel.
+
+Out of scope here (SURVEY.md §8f "next" rows): the frozen teachers (targets are supplied by the
+caller or by overriding _get_dav2_feats/_get_seg_targets/_get_gen_feats, the same hooks the
+reference has at base_ola_vlm.py:323,347,382), the frozen DPT decoder behind `depth_preds`,
+generation, wandb logging.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import autograd as A
+from .. import ops
+from ..ops import ACT_GELU, ACT_NONE, BF16
+from . import modules as M
+
+IGNORE_INDEX = -100
+IMAGE_TOKEN_INDEX = -200
+
+
+# ------------------------------------------------------------------------------------------------ config
+class VisperConfig:
+    """Attribute bag with the HF-style names the reference reads (hidden_size, vocab_size, …) plus
+    the aux-head injection of ola_vlm/train/ola_vlm_train.py:1149-1229."""
+
+    model_type = "visper"
+
+    def __init__(self, family="llama", vocab_size=128256, hidden_size=4096, intermediate_size=14336,
+                 num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8,
+                 max_position_embeddings=4096, rope_theta=500000.0, rms_norm_eps=1e-5,
+                 vision=None, mm_projector_type="mlp2x_gelu", mm_vision_select_layer=-2,
+                 mm_vision_select_feature="patch", tokenizer_model_max_length=4096,
+                 tokenizer_padding_side="right", **extra):
+        self.family = family
+        self.vocab_size = vocab_size
+        self.hidden_size = hidden_size
+        self.intermediate_size = intermediate_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.num_key_value_heads = num_key_value_heads
+        self.max_position_embeddings = max_position_embeddings
+        self.rope_theta = rope_theta
+        self.rms_norm_eps = rms_norm_eps
+        self.vision = vision or dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24,
+                                     num_attention_heads=16, image_size=336, patch_size=14)
+        self.mm_vision_tower = "openai/clip-vit-large-patch14-336"
+        self.mm_hidden_size = self.vision["hidden_size"]
+        self.mm_projector_type = mm_projector_type
+        self.mm_vision_select_layer = mm_vision_select_layer
+        self.mm_vision_select_feature = mm_vision_select_feature
+        self.tokenizer_model_max_length = tokenizer_model_max_length
+        self.tokenizer_padding_side = tokenizer_padding_side
+        self.use_return_dict = True
+        self.output_hidden_states = False
+        self.zero_masks_like_reference = False  # off for training value
+        self.materialize_logits = False         # .logits only on request while training
+        self.num_task_tokens = 0
+        for k, v in extra.items():
+            setattr(self, k, v)
+
+    def inject_aux(self, mode="gen-depth-seg", layer_indices="d18-20_s10-18_g12-20",
+                   loss_weights="d0.5_s0.5_g0.5", num_task_tokens=8, contrastive_loss_weight=0.3,
+                   gen_dim=1024, seg_dim=1536, depth_dim=1024, pass_text_to_aux=True,
+                   use_contrastive=True):
+        """The string DSLs of --layer_indices / --loss_weights (ola_vlm_train.py:1159-1194)."""
+        import re
+
+        li = {"d": "0", "s": "0", "g": "0"}
+        for m in re.findall(r"[a-zA-Z]\d+(?:-\d+)?", layer_indices):
+            li[m[0]] = m[1:]
+        lw = {"d": 0.5, "s": 0.5, "g": 0.5}
+        for m in re.findall(r"[a-zA-Z]\d+\.\d+", loss_weights):
+            lw[m[0]] = float(m[1:])
+
+        def head(prefix, nt, od, key):
+            return {"depth": 1, "dim_head": 32, "num_heads": 4, "num_tokens": nt, "output_dim": od,
+                    "ff_mult": 1, f"{prefix}_layer_indices": li[key], f"{prefix}_loss_weight": lw[key]}
+
+        self.aux_mode = mode
+        self.contrastive_loss_weight = contrastive_loss_weight
+        self.num_task_tokens = num_task_tokens
+        self.task_token_format = "emb"
+        self.pass_text_to_aux = pass_text_to_aux
+        self.use_contrastive = use_contrastive
+        self.use_ce = False
+        self.sample_tokens = False
+        self.image_gen = head("img", 1, gen_dim, "g")
+        self.image_seg = head("seg", 576, seg_dim, "s")
+        self.image_seg["seg_teacher"] = "oneformer"
+        self.image_depth = head("depth", 576, depth_dim, "d")
+        return self
+
+
+class OlaLlavaLlamaConfig(VisperConfig):
+    model_type = "ola_llama"
+
+
+class OlaLlavaPhi3Config(VisperConfig):
+    model_type = "ola_phi3"
+
+
+class LlavaConfig(VisperConfig):
+    model_type = "llava_llama"
+
+
+class LlavaPhi3Config(VisperConfig):
+    model_type = "llava_phi3"
+
+
+@dataclass
+class OlaCausalLLMOutputWithPast:
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+    past_key_values: Optional[tuple] = None
+    hidden_states: Optional[tuple] = None
+    attentions: Optional[tuple] = None
+    image_embs: Optional[list] = None
+    seg_embs: Optional[list] = None
+    depth_embs: Optional[list] = None
+    depth_preds: Optional[list] = None
+    # extras (not in the reference's dataclass): the loss components as tensors instead of the
+    # wandb logging done inside the reference's forward (ola_llama.py:146-168)
+    text_loss: Optional[torch.Tensor] = None
+    loss_terms: Optional[dict] = None
+
+    def __getitem__(self, k):
+        if isinstance(k, str):
+            return getattr(self, k)
+        return tuple(v for v in (self.loss, self.logits, self.past_key_values, self.hidden_states)
+                     if v is not None)[k]
+
+
+# ------------------------------------------------------------------------------------------------ splice plan
+class SplicePlan:
+    """Host-built index plan for prepare_inputs_labels_for_multimodal (ola_arch.py:337-444)."""
+
+    def __init__(self, input_ids, labels, attention_mask, n_img_tok, task_rows, max_len, pad_side):
+        ids = input_ids.numpy() if isinstance(input_ids, torch.Tensor) else np.asarray(input_ids)
+        B = ids.shape[0]
+        am = np.ones_like(ids, dtype=bool) if attention_mask is None else attention_mask.numpy().astype(bool)
+        lab = np.full_like(ids, IGNORE_INDEX) if labels is None else labels.numpy()
+        kinds, idxs, labs = [], [], []
+        img_slot = 0
+        for b in range(B):
+            cid, clab = ids[b][am[b]], lab[b][am[b]]
+            pos = np.nonzero(cid == IMAGE_TOKEN_INDEX)[0]
+            if len(pos) == 0:
+                kinds.append(np.zeros(len(cid), np.int32))
+                idxs.append(cid.astype(np.int32))
+                labs.append(clab)
+                img_slot += 1  # ola_arch.py:354 consumes an image slot without using it
+                continue
+            k_parts, i_parts, l_parts = [], [], []
+            bounds = [-1] + pos.tolist() + [len(cid)]
+            for i in range(len(bounds) - 1):
+                seg = slice(bounds[i] + 1, bounds[i + 1])
+                n = bounds[i + 1] - bounds[i] - 1
+                k_parts.append(np.zeros(n, np.int32))
+                i_parts.append(cid[seg].astype(np.int32))
+                l_parts.append(clab[seg])
+                if i < len(pos):
+                    k_parts.append(np.full(n_img_tok, 1, np.int32))
+                    i_parts.append(np.arange(img_slot * n_img_tok, (img_slot + 1) * n_img_tok, dtype=np.int32))
+                    l_parts.append(np.full(n_img_tok, IGNORE_INDEX, clab.dtype))
+                    img_slot += 1
+                    if task_rows:
+                        k_parts.append(np.full(task_rows, 2, np.int32))
+                        i_parts.append(np.arange(task_rows, dtype=np.int32))
+                        l_parts.append(np.full(task_rows, IGNORE_INDEX, clab.dtype))
+            kinds.append(np.concatenate(k_parts))
+            idxs.append(np.concatenate(i_parts))
+            labs.append(np.concatenate(l_parts))
+        if max_len is not None:
+            kinds = [k[:max_len] for k in kinds]
+            idxs = [i[:max_len] for i in idxs]
+            labs = [l[:max_len] for l in labs]
+        T = max(len(k) for k in kinds)
+        if pad_side != "right":
+            raise NotImplementedError("left padding is not on the training path (tokenizer padding_side='right')")
+        self.B, self.T = B, T
+        self.n_images = img_slot
+        kind = np.full((B, T), -1, np.int32)
+        index = np.full((B, T), -1, np.int32)
+        out_lab = np.full((B, T), IGNORE_INDEX, np.int64)
+        mask = np.zeros((B, T), bool)
+        for b in range(B):
+            n = len(kinds[b])
+            kind[b, :n], index[b, :n], out_lab[b, :n], mask[b, :n] = kinds[b], idxs[b], labs[b], True
+        flat_kind, flat_index = kind.reshape(-1), index.reshape(-1)
+        rows = np.arange(B * T, dtype=np.int32)
+        inv_img = np.full(img_slot * n_img_tok, -1, np.int32)
+        sel = flat_kind == 1
+        inv_img[flat_index[sel]] = rows[sel]
+        inv_task = None
+        if task_rows:
+            inv_task = np.full((task_rows, B), -1, np.int32)
+            sel = np.nonzero(flat_kind == 2)[0]
+            # at most one image (→ one task block) per sample contributes per column; extra images
+            # of a multi-image sample add further columns
+            cols = {}
+            for r in sel:
+                s = flat_index[r]
+                c = cols.get(s, 0)
+                if c >= inv_task.shape[1]:
+                    inv_task = np.concatenate([inv_task, np.full((task_rows, 1), -1, np.int32)], 1)
+                inv_task[s, c] = r
+                cols[s] = c + 1
+        embed_scatter = np.where(flat_kind == 0, flat_index, -1).astype(np.int32)
+        self.np = dict(kind=flat_kind, index=flat_index, inv_img=inv_img, inv_task=inv_task,
+                       embed_scatter=embed_scatter, labels=out_lab, mask=mask)
+        self.all_valid = bool(mask.all())
+
+    def to(self, device):
+        n = self.np
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+        self.kind, self.index = t(n["kind"]), t(n["index"])
+        self.inv_img, self.embed_scatter = t(n["inv_img"]), t(n["embed_scatter"])
+        self.inv_task = t(n["inv_task"])
+        if n["inv_task"] is not None:
+            self.B_cols = n["inv_task"].shape[1]
+        self.labels = t(n["labels"])
+        self.mask = t(n["mask"])
+        return self
+
+
+class HeadPlan:
+    """Token selection of forward_emb_predictor (base_ola_vlm.py:413-443) as gather indices."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, B, T, S, nt, order, task, pass_text, n_latents, heads, device):
+        key = (B, T, S, nt, tuple(order), task, pass_text, n_latents, heads, str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(B, T, S, nt, order, task, pass_text, n_latents, heads, device)
+        return cls._cache[key]
+
+    def __init__(self, B, T, S, nt, order, task, pass_text, n_latents, heads, device):
+        k = order.index(task)
+        t0 = S + 576 + nt * k
+        end = S + 576 + nt * len(order)
+        if nt == 0 or T < 600:
+            cols = np.arange(T) if pass_text else np.arange(S + 576)
+        else:
+            parts = [np.arange(S + 576), np.arange(t0, t0 + nt)]
+            if pass_text:
+                parts.append(np.arange(end, T))
+            cols = np.concatenate(parts)
+        nk = len(cols)
+        ctx = (np.arange(B)[:, None] * T + cols[None, :]).astype(np.int32)  # [B, nk]
+        inv_ctx = np.full(B * T, -1, np.int32)
+        inv_ctx[ctx.reshape(-1)] = np.arange(B * nk, dtype=np.int32)
+        self.B, self.nk, self.nt, self.heads = B, nk, nt, heads
+        dev = device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a.astype(np.int32))).to(dev)
+        self.ctx_index, self.inv_ctx = t(ctx.reshape(-1)), t(inv_ctx)
+        if task == "gen":
+            # latents = the 8 hidden states of this task's tokens INSIDE inp_tokens
+            # (base_ola_vlm.py:439: inp_tokens[:, S+576 : S+576+nt]), mean-pooled to 1 query
+            lat_cols = cols[S + 576:S + 576 + nt]
+            gi = (np.arange(B)[:, None] * T + lat_cols[None, :])
+            self.gen_index = t(gi.reshape(-1))
+            self.nq = 1
+            self.lat_index = self.inv_lat = None
+        else:
+            self.nq = n_latents
+            self.lat_index = t(np.tile(np.arange(n_latents), B))
+            # inv_lat[r, b] = row of (b, r) inside the latent block
+            self.inv_lat = t((np.arange(n_latents)[:, None] + np.arange(B)[None, :] * n_latents).reshape(-1))
+            self.gen_index = None
+
+
+# ------------------------------------------------------------------------------------------------ model
+class VisperModel(nn.Module):
+    """OlaLlavaLlamaModel / OlaLlavaPhi3Model (ola_llama.py:51-55 + OlaLlavaMetaModel ola_arch.py:35-94)."""
+
+    def __init__(self, config, device=None):
+        super().__init__()
+        self.config = config
+        D = config.hidden_size
+        self.embed_tokens = M.Weight((config.vocab_size, D), None, device)
+        self.layers = nn.ModuleList([M.DecoderLayer(config, device) for _ in range(config.num_hidden_layers)])
+        self.norm = M.Norm(D, False, device)
+        self.vision_tower = M.CLIPVisionTower(config.vision, config.mm_vision_select_layer,
+                                              config.mm_vision_select_feature, device)
+        self.mm_projector = M.Seq(_0=M.Linear(config.mm_hidden_size, D, True, device),
+                                  _2=M.Linear(D, D, True, device))
+        self.aux_tokens = "depth-seg-gen"
+        self.token_order = ["depth", "seg", "gen"]
+        self.num_task_tokens = 0
+        self._device = device
+        if getattr(config, "num_task_tokens", 0) and hasattr(config, "aux_mode"):
+            self.initialize_special_tokens(config)
+
+    def get_vision_tower(self):
+        return self.vision_tower
+
+    def get_special_tokens(self):
+        return (getattr(self, "special_depth_tokens", None), getattr(self, "special_seg_tokens", None),
+                getattr(self, "special_gen_tokens", None))
+
+    def initialize_special_tokens(self, config):
+        """ola_arch.py:67-94"""
+        self.num_task_tokens = config.num_task_tokens
+        self.task_token_format = getattr(config, "task_token_format", "emb")
+        self.aux_tokens = config.aux_mode
+        self.token_order = config.aux_mode.split("-")
+        D = config.hidden_size
+        if self.num_task_tokens > 0:
+            if "depth" in config.aux_mode:
+                assert config.image_depth["num_tokens"] % self.num_task_tokens == 0
+                self.special_depth_tokens = M._param(config.image_depth["num_tokens"], D, device=self._device)
+            if "seg" in config.aux_mode:
+                assert config.image_seg["num_tokens"] % self.num_task_tokens == 0
+                self.special_seg_tokens = M._param(config.image_seg["num_tokens"], D, device=self._device)
+            if "gen" in config.aux_mode:
+                self.special_gen_tokens = M._param(self.num_task_tokens, D, device=self._device)
+
+    def initialize_vision_modules(self, model_args=None, fsdp=None):
+        return  # tower + projector are built in __init__ (config.mm_vision_tower is always set here)
+
+
+class VisperForCausalLM(nn.Module):
+    """Shared implementation; the four public classes below only pick family / distillation."""
+
+    family = "llama"
+    distill = True
+    config_class = VisperConfig
+
+    def __init__(self, config, device=None):
+        super().__init__()
+        config.family = self.family
+        self.config = config
+        self.steps = 0
+        self.model = VisperModel(config, device)
+        self.vocab_size = config.vocab_size
+        if self.family == "phi3":
+            self.NUM_SYS_TOKENS = 13  # ola_phi3.py:68
+        else:
+            self.NUM_SYS_TOKENS = 26 if self.vocab_size < 128000 else 38  # ola_llama.py:65-68
+        self.lm_head = M.Linear(config.hidden_size, config.vocab_size, False, device)
+        self._device = device
+        if self.distill and hasattr(config, "image_gen"):
+            self.init_heads(config)
+
+    # ---- reference accessors ---------------------------------------------------------------
+    def get_model(self):
+        return self.model
+
+    def get_vision_tower(self):
+        return self.model.get_vision_tower()
+
+    @property
+    def depth_tokens(self):
+        return self.model.get_special_tokens()[0]
+
+    @property
+    def seg_tokens(self):
+        return self.model.get_special_tokens()[1]
+
+    @property
+    def gen_tokens(self):
+        return self.model.get_special_tokens()[2]
+
+    @property
+    def num_task_tokens(self):
+        return self.model.num_task_tokens
+
+    @property
+    def token_order(self):
+        return self.model.token_order
+
+    @property
+    def device(self):
+        return self.lm_head.weight.device
+
+    def init_target_models(self, config):
+        """Frozen teachers are OUT OF SCOPE: targets come from the caller."""
+        return
+
+    def _layer_loss_weight(self, cfgd, prefix):
+        idx = [int(i) - 1 for i in cfgd[f"{prefix}_layer_indices"].split("-")]  # base_ola_vlm.py:97-102
+        return idx, cfgd[f"{prefix}_loss_weight"]
+
+    def init_heads(self, config):
+        """base_ola_vlm.py:104-168 (task-token heads only: num_task_tokens > 0)."""
+        dev = self._device
+        self.mode = getattr(config, "aux_mode", "gen-depth-seg")
+        self.pass_text_to_aux_head = getattr(config, "pass_text_to_aux", True)
+        self.contrastive_loss_weight = config.contrastive_loss_weight
+        assert config.num_task_tokens > 0, "only the TaskToken* heads are on the shipped training path"
+        D = config.hidden_size
+        use_con = getattr(config, "use_contrastive", True)
+        if "gen" in self.mode:
+            self.img_layer_indices, self.img_gen_loss_weight = self._layer_loss_weight(config.image_gen, "img")
+            self.gen_logit_scale = nn.Parameter(torch.tensor(2.0, device=dev)) if use_con else None
+            self.image_gen_heads = nn.ModuleList([M.TaskTokenGenHead(config.image_gen, D, dev)
+                                                  for _ in self.img_layer_indices])
+        if "depth" in self.mode:
+            self.depth_layer_indices, self.img_depth_loss_weight = self._layer_loss_weight(config.image_depth, "depth")
+            self.depth_logit_scale = nn.Parameter(torch.tensor(2.0, device=dev)) if use_con else None
+            self.use_intermediate_depth = config.image_depth.get("use_intermediate_depth", True)
+            self.image_depth_heads = nn.ModuleList([
+                M.TaskTokenDepthHead(config.image_depth, D, self.use_intermediate_depth, dev)
+                for _ in self.depth_layer_indices])
+        if "seg" in self.mode:
+            self.seg_layer_indices, self.img_seg_loss_weight = self._layer_loss_weight(config.image_seg, "seg")
+            self.seg_logit_scale = nn.Parameter(torch.tensor(2.0, device=dev)) if use_con else None
+            self.image_seg_heads = nn.ModuleList([M.OneFormerTaskTokenSegHead(config.image_seg, D, dev)
+                                                  for _ in self.seg_layer_indices])
+
+    # ---- weights -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def init_weights(self, seed_fn=None, std=0.02, seed=0):
+        """Random init (HF std=0.02 style) or deterministic by-name init (tests: seed_fn(name, shape))."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for name, p in self.named_parameters():
+            if seed_fn is not None:
+                p.copy_(seed_fn(name, tuple(p.shape)).to(p.dtype))
+                continue
+            last = name.split(".")[-1]
+            if name.endswith("logit_scale"):
+                p.fill_(2.0)
+            elif last == "bias":
+                p.zero_()
+            elif last == "weight" and p.dim() == 1:
+                p.fill_(1.0)
+            elif "special_" in name:
+                p.normal_(0.0, 1.0)
+            else:
+                p.normal_(0.0, std)
+        return self
+
+    # ---- the multimodal splice ---------------------------------------------------------------
+    def encode_images(self, images):
+        """ola_arch.py:187-190 — frozen tower (no grad) then the trainable mlp2x_gelu projector."""
+        feats = self.get_vision_tower()(images)
+        pj = self.model.mm_projector
+        h = A.linear(feats, pj[0].weight, pj[0].bias, ACT_GELU)
+        return A.linear(h, pj[2].weight, pj[2].bias, ACT_NONE)
+
+    def _task_rows(self):
+        """append_special_tokens (ola_arch.py:224-254): pooled rows in token_order."""
+        nt = self.num_task_tokens
+        if not (self.distill and nt):
+            return None
+        rows = []
+        for task in self.token_order:
+            tok = {"depth": self.depth_tokens, "seg": self.seg_tokens, "gen": self.gen_tokens}[task]
+            if tok is None or task not in self.model.aux_tokens:
+                continue
+            if task == "gen":
+                rows.append(tok)
+            else:
+                rows.append(A.GroupMeanFn.apply(tok, nt, tok.shape[0] // nt))
+        return torch.cat(rows, 0) if rows else None
+
+    def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask,
+                                             past_key_values, labels, images, image_sizes=None):
+        """Same signature / return tuple as ola_arch.py:256-259,444."""
+        if self.get_vision_tower() is None or images is None or input_ids.shape[1] == 1:
+            return input_ids, position_ids, attention_mask, past_key_values, None, labels
+        if isinstance(images, (list, tuple)) or images.dim() == 5:
+            images = torch.cat([im.unsqueeze(0) if im.dim() == 3 else im for im in images], 0)
+        dev = self.device
+        image_features = self.encode_images(images.to(dev, non_blocking=True))  # [n_img*576, D]
+        n_tok = self.get_vision_tower().num_patches
+        task_rows = self._task_rows()
+        cpu = lambda t: None if t is None else (t.cpu() if t.is_cuda else t)
+        plan = SplicePlan(cpu(input_ids), cpu(labels), cpu(attention_mask), n_tok,
+                          0 if task_rows is None else task_rows.shape[0],
+                          getattr(self.config, "tokenizer_model_max_length", None),
+                          getattr(self.config, "tokenizer_padding_side", "right")).to(dev)
+        if task_rows is None:
+            task_rows_in = image_features[:0]
+        else:
+            task_rows_in = task_rows
+        embeds = A.SpliceFn.apply(self.model.embed_tokens.weight, image_features, task_rows_in, plan)
+        B, T = plan.B, plan.T
+        self._last_plan = plan
+        new_labels = plan.labels if labels is not None else None
+        new_mask = plan.mask.to(attention_mask.dtype) if attention_mask is not None else None
+        return None, None if position_ids is None else position_ids, new_mask, past_key_values, \
+            embeds.view(B, T, -1), new_labels
+
+    # ---- decoder -----------------------------------------------------------------------------
+    def _decoder(self, inputs_embeds):
+        cfg = self.config
+        B, T, D = inputs_embeds.shape
+        H, KVH = cfg.num_attention_heads, cfg.num_key_value_heads
+        hd = D // H
+        cos, sin = ops.rope_tables(max(cfg.max_position_embeddings, T), hd, cfg.rope_theta, inputs_embeds.device)
+        meta = SimpleNamespace(B=B, T=T, H=H, KVH=KVH, hd=hd, eps=cfg.rms_norm_eps, cos=cos, sin=sin,
+                               pos_ids=None)
+        x = inputs_embeds.reshape(B * T, D)
+        if x.dtype != BF16:
+            x = x.to(BF16)
+        states = [x]
+        for layer in self.model.layers:
+            x = layer.run(x, meta)
+            states.append(x)
+        states[-1] = A.RMSNormFn.apply(x, self.model.norm.weight, cfg.rms_norm_eps)
+        return states
+
+    # ---- teachers (hooks kept for drop-in monkeypatching; OUT OF SCOPE by default) --------------
+    def _get_dav2_feats(self, pil_images, device):
+        raise NotImplementedError("frozen depth teacher is out of scope: pass distill_targets=")
+
+    def _get_seg_targets(self, pil_images, seg_preds):
+        raise NotImplementedError("frozen seg teacher is out of scope: pass distill_targets=")
+
+    def _get_gen_feats(self, pil_images, device):
+        raise NotImplementedError("frozen gen teacher is out of scope: pass distill_targets=")
+
+    def _targets(self, task, pil_images, distill_targets, device):
+        if distill_targets is not None:
+            return distill_targets.get(task)
+        if pil_images is None:
+            return None
+        if task == "depth":
+            return self._get_dav2_feats(pil_images, device)[0][0][0]
+        if task == "seg":
+            return self._get_seg_targets(pil_images, None)
+        return self._get_gen_feats(pil_images, device)
+
+    def _gather_targets(self, tgt_flat):
+        """dist_collect (ola_utils.py:96-106): targets carry no grad → plain NCCL all-gather, once
+        per task per step."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            out = torch.empty((dist.get_world_size() * tgt_flat.shape[0], tgt_flat.shape[1]),
+                              dtype=tgt_flat.dtype, device=tgt_flat.device)
+            dist.all_gather_into_tensor(out, tgt_flat)
+            return out, dist.get_rank() * tgt_flat.shape[0]
+        return tgt_flat, 0
+
+    def _emb_loss(self, pred_flat, mask, tgt_all, off, logit_scale):
+        """base_ola_vlm.py:289-320 → (loss, sl1, contrastive) as a 3-vector."""
+        tau = logit_scale.float().reshape(1)
+        m = None if mask is None else mask.float().contiguous()
+        return A.DistillLossFn.apply(pred_flat, tgt_all, tau, m, off, float(self.contrastive_loss_weight))
+
+    def _distill(self, states, B, T, pil_images, masks, distill_targets):
+        cfg = self.config
+        dev = states[0].device
+        layer_states = states[1:]
+        S, nt = self.NUM_SYS_TOKENS, self.num_task_tokens
+        out = dict(depth_embs=[], seg_embs=[], image_embs=[], depth_preds=[], terms={})
+        total = None
+        spec = [("depth", "depth", "image_depth_heads", "depth_layer_indices", "img_depth_loss_weight",
+                 "depth_logit_scale", self.depth_tokens, "depth_embs"),
+                ("seg", "seg", "image_seg_heads", "seg_layer_indices", "img_seg_loss_weight",
+                 "seg_logit_scale", self.seg_tokens, "seg_embs"),
+                ("gen", "gen", "image_gen_heads", "img_layer_indices", "img_gen_loss_weight",
+                 "gen_logit_scale", self.gen_tokens, "image_embs")]
+        for task, key, heads_name, idx_name, w_name, scale_name, special, out_name in spec:
+            if task not in self.mode or T <= S:
+                continue
+            heads = getattr(self, heads_name)
+            weight = getattr(self, w_name)
+            tgt = self._targets(task, pil_images, distill_targets, dev)
+            tgt_all = off = None
+            if tgt is not None:
+                tgt = tgt.to(dev, BF16)
+                if task == "seg":  # [B,C,24,24] → token-major [B,576,C] to match the head's layout
+                    Bc, C = tgt.shape[0], tgt.shape[1]
+                    tflat = torch.empty((Bc, 576 * C), dtype=BF16, device=dev)
+                    tgt = tgt.contiguous()
+                    for b in range(Bc):
+                        ops.transpose(tgt[b].view(C, 576), out=tflat[b].view(576, C))
+                    tgt_flat = tflat
+                else:
+                    tgt_flat = tgt.reshape(tgt.shape[0], -1).contiguous()
+                tgt_all, off = self._gather_targets(tgt_flat)
+            mask = masks.get(task)
+            for i, idx in enumerate(getattr(self, idx_name)):
+                head = heads[i]
+                n_lat = 1 if task == "gen" else special.shape[0]
+                plan = HeadPlan.get(B, T, S, nt, self.token_order, task, self.pass_text_to_aux_head,
+                                    n_lat, head.projector.heads, dev)
+                e = head.projector.run(layer_states[idx], None if task == "gen" else special, plan)
+                if task == "depth":
+                    feats = [(head.mlp(k, e).view(B, plan.nq, -1), None) for k in (1, 2, 3)] \
+                        if head.use_intermediate_depth else []
+                    feats.append((e.view(B, plan.nq, -1), None))
+                    out[out_name].append(feats)
+                    pred = feats[0][0]  # base_ola_vlm.py:369 supervises features[0] only
+                elif task == "seg":
+                    ev = e.view(B, plan.nq, -1)
+                    side = int(math.sqrt(plan.nq))
+                    out[out_name].append(ev.permute(0, 2, 1).unflatten(2, (side, side)))
+                    pred = ev
+                else:
+                    pred = e.view(B, plan.nq, -1)
+                    out[out_name].append(pred)
+                if mask is not None and cfg.zero_masks_like_reference:
+                    mask.zero_()  # base_ola_vlm.py:472-473, 498-499, 525-526
+                if tgt_all is not None:
+                    l3 = self._emb_loss(pred.reshape(B, -1), mask, tgt_all, off, getattr(self, scale_name))
+                    out["terms"].setdefault(task, []).append(l3)
+                    total = l3[0] * weight if total is None else total + l3[0] * weight
+        out["total"] = total
+        return out
+
+    # ---- forward -----------------------------------------------------------------------------
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                inputs_embeds=None, labels=None, use_cache=None, output_attentions=None,
+                output_hidden_states=None, images=None, image_sizes=None, return_dict=None,
+                pil_images=None, gen_mask=None, seg_mask=None, depth_mask=None, **kwargs):
+        """Keyword surface of ola_llama.py:190-209 (llava_llama.py:73-91 for the NTP-only classes)."""
+        distill_targets = kwargs.pop("distill_targets", None)
+        if inputs_embeds is None:
+            (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds,
+             labels) = self.prepare_inputs_labels_for_multimodal(
+                input_ids, position_ids, attention_mask, past_key_values, labels, images, image_sizes)
+        if inputs_embeds is None:
+            inputs_embeds = ops.gather_rows(input_ids.reshape(-1).to(torch.int32),
+                                            [self.model.embed_tokens.weight], self.config.hidden_size
+                                            ).view(*input_ids.shape, -1)
+        B, T, D = inputs_embeds.shape
+        states = self._decoder(inputs_embeds)
+        hidden = states[-1]
+        loss = text_loss = logits = None
+        if labels is not None:
+            labels = labels.to(hidden.device).contiguous()
+            V = self.config.vocab_size
+            chunk = max(1024, min(B * T, (1 << 31) // V))
+            text_loss = A.LMHeadCEFn.apply(hidden, self.lm_head.weight, labels, T, chunk)
+        if labels is None or self.config.materialize_logits:
+            with torch.no_grad():
+                logits = A.lm_head_logits(hidden.detach(), self.lm_head.weight).view(B, T, -1)
+        d = None
+        if self.distill and hasattr(self, "mode"):
+            d = self._distill(states, B, T, pil_images,
+                              {"depth": depth_mask, "seg": seg_mask, "gen": gen_mask}, distill_targets)
+        if text_loss is not None:
+            loss = text_loss if (d is None or d["total"] is None) else text_loss + d["total"]
+        hs = tuple(s.view(B, T, D) for s in states)
+        if self.steps is not None:
+            self.steps += 1
+        out = OlaCausalLLMOutputWithPast(
+            loss=loss, logits=logits, past_key_values=None, hidden_states=hs, attentions=None,
+            image_embs=d["image_embs"] if d else None, seg_embs=d["seg_embs"] if d else None,
+            depth_embs=d["depth_embs"] if d else None, depth_preds=d["depth_preds"] if d else None,
+            text_loss=text_loss, loss_terms=d["terms"] if d else None)
+        if return_dict is False:
+            return tuple(v for v in (loss, logits, hs) if v is not None)
+        return out
+
+
+class OlaLlavaLlamaForCausalLM(VisperForCausalLM):
+    family, distill, config_class = "llama", True, OlaLlavaLlamaConfig
+
+
+class OlaLlavaPhi3ForCausalLM(VisperForCausalLM):
+    family, distill, config_class = "phi3", True, OlaLlavaPhi3Config
+
+
+class LlavaLlamaForCausalLM(VisperForCausalLM):
+    family, distill, config_class = "llama", False, LlavaConfig
+
+
+class LlavaPhi3ForCausalLM(VisperForCausalLM):
+    family, distill, config_class = "phi3", False, LlavaPhi3Config

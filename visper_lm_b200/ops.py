@@ -66,11 +66,13 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None
     return (out, pre) if want_pre else out
 
 
-def transpose(x):
+def transpose(x, out=None):
     R, C = x.shape
-    out = torch.empty((C, R), dtype=BF16, device=x.device)
+    if out is None:
+        out = torch.empty((C, R), dtype=BF16, device=x.device)
     pi, ldi = _rows(x)
-    _chk(_L().vpb_transpose(pi, ldi, out.data_ptr(), R, R, C, _stream()), "transpose")
+    po, ldo = _rows(out)
+    _chk(_L().vpb_transpose(pi, ldi, po, ldo, R, C, _stream()), "transpose")
     return out
 
 
@@ -86,14 +88,15 @@ def rmsnorm_fwd(x, w, eps, out=None):
     return y, rstd
 
 
-def rmsnorm_bwd(dy, x, w, rstd, dres=None):
+def rmsnorm_bwd(dy, x, w, rstd, dres=None, out=None):
     M, D = x.shape
-    dx = torch.empty((M, D), dtype=BF16, device=x.device)
+    dx = out if out is not None else torch.empty((M, D), dtype=BF16, device=x.device)
     pdy, lddy = _rows(dy)
     px, ldx = _rows(x)
     pr, ldr = _rows(dres) if dres is not None else (0, 0)
+    pdx, lddx = _rows(dx)
     _chk(_L().vpb_rmsnorm_bwd(pdy, lddy, px, ldx, w.data_ptr(), rstd.data_ptr(), pr, ldr,
-                              dx.data_ptr(), D, M, D, _stream()), "rmsnorm_bwd")
+                              pdx, lddx, M, D, _stream()), "rmsnorm_bwd")
     return dx
 
 
@@ -109,14 +112,15 @@ def layernorm_fwd(x, w, b, eps, out=None):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, w, mean, rstd, dres=None):
+def layernorm_bwd(dy, x, w, mean, rstd, dres=None, out=None):
     M, D = x.shape
-    dx = torch.empty((M, D), dtype=BF16, device=x.device)
+    dx = out if out is not None else torch.empty((M, D), dtype=BF16, device=x.device)
     pdy, lddy = _rows(dy)
     px, ldx = _rows(x)
     pr, ldr = _rows(dres) if dres is not None else (0, 0)
+    pdx, lddx = _rows(dx)
     _chk(_L().vpb_layernorm_bwd(pdy, lddy, px, ldx, w.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                pr, ldr, dx.data_ptr(), D, M, D, _stream()), "layernorm_bwd")
+                                pr, ldr, pdx, lddx, M, D, _stream()), "layernorm_bwd")
     return dx
 
 
@@ -265,11 +269,21 @@ def scatter_add_rows(dst_f32, index, src):
     return dst_f32
 
 
-def group_mean(x, groups, gsize):
+def add_rows_(dst, index, src):
+    n, D = src.shape
+    pd, ldd = _rows(dst)
+    ps, lds = _rows(src)
+    _chk(_L().vpb_add_rows(pd, ldd, n, index.data_ptr(), ps, lds, D, _stream()), "add_rows")
+    return dst
+
+
+def group_mean(x, groups, gsize, out=None):
     D = x.shape[1]
-    out = torch.empty((groups, D), dtype=BF16, device=x.device)
+    if out is None:
+        out = torch.empty((groups, D), dtype=BF16, device=x.device)
     px, ldx = _rows(x)
-    _chk(_L().vpb_group_mean(px, ldx, out.data_ptr(), D, groups, gsize, D, _stream()), "group_mean")
+    po, ldo = _rows(out)
+    _chk(_L().vpb_group_mean(px, ldx, po, ldo, groups, gsize, D, _stream()), "group_mean")
     return out
 
 
