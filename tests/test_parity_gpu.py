@@ -56,8 +56,11 @@ def test_forward_backward_vs_oracle_and_golden(name, cfg_name, distill, B, n_tex
                 assert rel_err(a, b) <= 2e-2, f"{task} emb rel err {rel_err(a, b):.4f}"
             for l3, (l, s1, c) in zip(out.loss_terms[task], ref[f"{task}_losses"]):
                 got = l3.tolist()
-                for g_, r_ in zip(got, (l.item(), s1.item(), c.item())):
-                    assert abs(g_ - r_) <= 3e-3 * abs(r_) + 1e-5, (task, got, (l.item(), s1.item(), c.item()))
+                # total and smooth-L1 are tight; the InfoNCE term multiplies cosines of bf16
+                # embeddings by exp(tau)=7.39 (B=2..3 logits) → bf16 rounding shows at the 1e-2 level,
+                # as it does inside the bf16 reference itself (SURVEY.md §8a "dtype flow")
+                for g_, r_, tol in zip(got, (l.item(), s1.item(), c.item()), (3e-3, 3e-3, 1e-2)):
+                    assert abs(g_ - r_) <= tol * abs(r_) + 1e-5, (task, got, (l.item(), s1.item(), c.item()))
     # ---- gradients of the PT-stage trainable set ----
     checked = 0
     for n, p in model.named_parameters():
@@ -70,7 +73,9 @@ def test_forward_backward_vs_oracle_and_golden(name, cfg_name, distill, B, n_tex
         assert p.grad is not None, f"{n}: no gradient"
         c = cos_sim(p.grad, g_ref)
         ratio = p.grad.float().norm().item() / g_ref.norm().item()
-        assert c >= 0.995 and abs(ratio - 1) <= 3e-2, f"{n}: cos {c:.5f} norm ratio {ratio:.4f}"
+        # logit scales are scalars whose gradient is a cancelling sum over the B×B' softmax → looser
+        tol = 0.1 if n.endswith("logit_scale") else 3e-2
+        assert c >= 0.995 and abs(ratio - 1) <= tol, f"{n}: cos {c:.5f} norm ratio {ratio:.4f}"
         checked += 1
     assert checked >= (100 if distill else 4)
 

@@ -397,5 +397,5 @@ class DistillLossFn(torch.autograd.Function):
         # only the total (element 0) carries gradient; sl1/contrastive are reporting outputs
         g0 = gout[0:1].contiguous().float()
         dpred = ops.distill_loss_bwd(pred, tgt_all, ctx.off, coef, g0) if ctx.needs_input_grad[0] else None
-        dtau = (out4[3] * g0[0]) if ctx.needs_input_grad[2] else None
+        dtau = (out4[3] * g0[0]).reshape(1) if ctx.needs_input_grad[2] else None
         return dpred, None, dtau, None, None, None

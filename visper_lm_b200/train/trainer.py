@@ -1,0 +1,296 @@
+"""Data-parallel trainer for the hot path: the reference's `LLaVATrainer` constructor / `train()` /
+`training_step` surface (ola_vlm/train/llava_trainer.py:217, ola_vlm_train.py:1299-1310) over a
+B200-native step — one process per GPU, NCCL over NVLink for the three collectives of ZeRO-2
+(scripts/zero2.json): gradient reduce-scatter, sharded fused AdamW on fp32 masters, bf16 parameter
+all-gather.  HF Trainer / accelerate / DeepSpeed are not used (and not installed here).
+
+Step semantics follow SURVEY.md §8a "Optimizer/step semantics": AdamW β=(0.9,0.999) eps 1e-8,
+weight-decay / lr groups of create_optimizer (llava_trainer.py:890-995), cosine schedule with linear
+warm-up, loss = rank-local batch mean, gradients averaged over ranks, optional global-norm clip.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import time
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..ops import BF16
+
+
+@dataclass
+class TrainingArguments:
+    """Subset of HF TrainingArguments + the reference's extras (ola_vlm_train.py:122-155) that the
+    step itself consumes."""
+    output_dir: str = "./checkpoints"
+    per_device_train_batch_size: int = 8
+    gradient_accumulation_steps: int = 1
+    learning_rate: float = 1e-3
+    weight_decay: float = 0.0
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_epsilon: float = 1e-8
+    max_grad_norm: float = 1.0
+    warmup_ratio: float = 0.03
+    lr_scheduler_type: str = "cosine"
+    num_train_epochs: float = 1.0
+    max_steps: int = -1
+    logging_steps: int = 1
+    save_steps: int = 200
+    bf16: bool = True
+    mm_projector_lr: Optional[float] = None
+    mm_vision_lr: Optional[float] = None
+    group_by_modality_length: bool = False
+    model_max_length: int = 4096
+    dataloader_num_workers: int = 0
+    zero_stage: int = 2
+    seed: int = 42
+
+
+def cosine_with_warmup(step, total, warmup):
+    """HF get_cosine_schedule_with_warmup multiplier."""
+    if step < warmup:
+        return step / max(1, warmup)
+    prog = (step - warmup) / max(1, total - warmup)
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
+
+
+class Zero2Optimizer:
+    """ZeRO-2: every rank holds all bf16 parameters (one flat buffer) and the full bf16 gradient
+    buffer; fp32 master weights and Adam moments exist only for the rank's 1/N shard.
+
+    groups: list of (predicate(name) -> bool, lr_scale, weight_decay); first match wins."""
+
+    ALIGN = 8
+
+    def __init__(self, named_params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 max_grad_norm=1.0, groups=None, process_group=None):
+        self.named = [(n, p) for n, p in named_params if p.requires_grad]
+        assert self.named, "no trainable parameters"
+        self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
+        self.pg = process_group
+        self.world = dist.get_world_size(self.pg) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(self.pg) if dist.is_initialized() else 0
+        dev = self.named[0][1].device
+        groups = groups or [(lambda n: True, 1.0, weight_decay)]
+        # layout: parameters sorted by group so each group is one contiguous range
+        order = []
+        for gi, (pred, _, _) in enumerate(groups):
+            for n, p in self.named:
+                if not any(n == o[0] for o in order) and pred(n) and \
+                        not any(g[0](n) for g in groups[:gi]):
+                    order.append((n, p, gi))
+        self.named = [(n, p) for n, p, _ in order]
+        offs, off = [], 0
+        self.group_ranges = []
+        cur_g, g_start = order[0][2], 0
+        for n, p, gi in order:
+            if gi != cur_g:
+                self.group_ranges.append((g_start, off, cur_g))
+                cur_g, g_start = gi, off
+            offs.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.group_ranges.append((g_start, off, cur_g))
+        self.groups = groups
+        chunk = self.world * 1024
+        self.total = (off + chunk - 1) // chunk * chunk
+        self.offsets = offs
+        self.flat_p = torch.zeros(self.total, dtype=BF16, device=dev)
+        self.flat_g = torch.zeros(self.total, dtype=BF16, device=dev)
+        with torch.no_grad():
+            for (n, p), o in zip(self.named, offs):
+                view = self.flat_p[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view  # parameters now live in the flat buffer (dtype becomes bf16)
+        self.shard = self.total // self.world
+        s0 = self.rank * self.shard
+        self.s0, self.s1 = s0, s0 + self.shard
+        self.master = self.flat_p[s0:s0 + self.shard].float()
+        self.m = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.g_shard = torch.zeros(self.shard, dtype=BF16, device=dev) if self.world > 1 else None
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        self.last_grad_norm = None
+
+    def zero_grad(self):
+        for _, p in self.named:
+            p.grad = None
+
+    def _pack_grads(self):
+        for (n, p), o in zip(self.named, self.offsets):
+            dst = self.flat_g[o:o + p.numel()]
+            if p.grad is None:
+                dst.zero_()
+                continue
+            g = p.grad
+            if g.dtype == BF16 and g.is_contiguous() and g.numel() % 8 == 0:
+                ops.axpby(g.reshape(-1), None, 1.0, 0.0, out=dst)
+            else:
+                dst.copy_(g.reshape(-1))
+
+    def step(self, lr_mult=1.0):
+        self.step_count += 1
+        self._pack_grads()
+        if self.world > 1:
+            dist.reduce_scatter_tensor(self.g_shard, self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+            g = self.g_shard
+        else:
+            g = self.flat_g
+        ops.grad_sumsq(g, out=self.sumsq)
+        if self.world > 1:
+            dist.all_reduce(self.sumsq, group=self.pg)
+        # gradients are SUMS over ranks here → average with 1/world inside the clip coefficient
+        coef, norm = ops.clip_coef(self.sumsq, self.max_grad_norm or 0.0, 1.0 / self.world)
+        self.last_grad_norm = norm
+        for (a, b, gi) in self.group_ranges:
+            lo, hi = max(a, self.s0), min(b, self.s1)
+            if lo >= hi:
+                continue
+            _, lr_scale, wd = self.groups[gi]
+            sl = slice(lo - self.s0, hi - self.s0)
+            ops.adamw_step_(self.master[sl], self.m[sl], self.v[sl], g[sl], self.flat_p[lo:hi],
+                            self.lr * lr_scale * lr_mult, self.betas[0], self.betas[1], self.eps, wd,
+                            self.step_count, grad_scale=coef)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.flat_p, self.flat_p[self.s0:self.s1], group=self.pg)
+
+    def state_dict(self):
+        return {"step": self.step_count, "master": self.master, "m": self.m, "v": self.v,
+                "rank": self.rank, "world": self.world}
+
+
+def _no_decay(name):
+    return name.endswith(".bias") or "norm" in name or "layernorm" in name
+
+
+class LLaVATrainer:
+    """Constructor and entry points of ola_vlm/train/llava_trainer.py:217 (HF Trainer subclass)."""
+
+    def __init__(self, model=None, tokenizer=None, args: TrainingArguments = None, train_dataset=None,
+                 eval_dataset=None, data_collator=None, **kwargs):
+        self.model = model
+        self.tokenizer = tokenizer
+        self.args = args or TrainingArguments()
+        self.train_dataset = train_dataset
+        self.eval_dataset = eval_dataset
+        self.data_collator = data_collator
+        self.deepspeed = None
+        self.optimizer = None
+        self.state = {"global_step": 0, "log_history": []}
+        self.is_dist = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size() if self.is_dist else 1
+        self.rank = dist.get_rank() if self.is_dist else 0
+        self.total_steps = None
+        self._pinned = {}
+
+    # -- optimizer groups: decay / no-decay × projector-lr (llava_trainer.py:903-976) ---------------
+    def create_optimizer(self):
+        if self.optimizer is not None:
+            return self.optimizer
+        a = self.args
+        groups = []
+        if a.mm_projector_lr is not None:
+            scale = a.mm_projector_lr / a.learning_rate
+            groups.append((lambda n: "mm_projector" in n and not _no_decay(n), scale, a.weight_decay))
+            groups.append((lambda n: "mm_projector" in n and _no_decay(n), scale, 0.0))
+        groups.append((lambda n: not _no_decay(n), 1.0, a.weight_decay))
+        groups.append((lambda n: True, 1.0, 0.0))
+        self.optimizer = Zero2Optimizer(self.model.named_parameters(), a.learning_rate,
+                                        (a.adam_beta1, a.adam_beta2), a.adam_epsilon, a.weight_decay,
+                                        a.max_grad_norm, groups)
+        return self.optimizer
+
+    # -- one optimisation step on a HOST batch (collator output) ------------------------------------
+    def _to_device(self, batch):
+        dev = self.model.device
+        out = {}
+        for k, v in batch.items():
+            if isinstance(v, torch.Tensor):
+                if k in ("input_ids", "labels", "attention_mask"):
+                    out[k] = v  # consumed on the host by the splice planner
+                else:
+                    if not v.is_pinned():
+                        buf = self._pinned.get(k)
+                        if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+                            buf = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                            self._pinned[k] = buf
+                        buf.copy_(v)
+                        v = buf
+                    out[k] = v.to(dev, non_blocking=True)
+            elif isinstance(v, dict):
+                out[k] = {kk: vv.to(dev, non_blocking=True) for kk, vv in v.items()}
+            else:
+                out[k] = v
+        return out
+
+    def training_step(self, model, inputs):
+        """HF Trainer.training_step semantics (llava_trainer.py:357-381 is a dead verbatim copy):
+        forward → loss → backward; returns the detached loss tensor (no host sync)."""
+        inputs = self._to_device(inputs)
+        out = model(**inputs)
+        loss = out.loss
+        loss.backward()
+        return loss.detach(), out
+
+    def step(self, inputs):
+        opt = self.create_optimizer()
+        opt.zero_grad()
+        loss, out = self.training_step(self.model, inputs)
+        a = self.args
+        total = self.total_steps or max(1, a.max_steps)
+        warm = math.ceil(total * a.warmup_ratio)
+        mult = cosine_with_warmup(self.state["global_step"], total, warm) if a.lr_scheduler_type == "cosine" else 1.0
+        if self.total_steps is None and a.max_steps <= 0:
+            mult = 1.0
+        opt.step(lr_mult=mult)
+        self.state["global_step"] += 1
+        return loss, out
+
+    def _batches(self):
+        a = self.args
+        n = len(self.train_dataset)
+        per_rank = n // self.world
+        idx = list(range(self.rank * per_rank, (self.rank + 1) * per_rank))  # contiguous split by rank
+        B = a.per_device_train_batch_size
+        for i in range(0, len(idx) - B + 1, B):
+            yield self.data_collator([self.train_dataset[j] for j in idx[i:i + B]])
+
+    def train(self, resume_from_checkpoint=None):
+        a = self.args
+        n = len(self.train_dataset) // self.world // a.per_device_train_batch_size
+        self.total_steps = a.max_steps if a.max_steps > 0 else int(n * a.num_train_epochs)
+        self.create_optimizer()
+        t0 = time.time()
+        last = None
+        done = 0
+        while done < self.total_steps:
+            for batch in self._batches():
+                loss, _ = self.step(batch)
+                done += 1
+                if done % a.logging_steps == 0:
+                    last = float(loss)  # the only host sync, outside forward (cf. ola_llama.py:146-168)
+                    self.state["log_history"].append({"step": done, "loss": last})
+                if done >= self.total_steps:
+                    break
+        return {"global_step": done, "training_loss": last, "train_runtime": time.time() - t0}
+
+    # -- checkpoint surface (minimal; adapter-only save as in llava_trainer.py:997-1016)
+    def save_state(self):
+        os.makedirs(self.args.output_dir, exist_ok=True)
+        if self.rank == 0:
+            with open(os.path.join(self.args.output_dir, "trainer_state.json"), "w") as f:
+                json.dump(self.state, f)
+
+    def _save(self, output_dir=None, state_dict=None):
+        output_dir = output_dir or self.args.output_dir
+        os.makedirs(output_dir, exist_ok=True)
+        if self.rank == 0:
+            sd = state_dict or {k: v.detach().cpu() for k, v in self.model.named_parameters() if v.requires_grad}
+            torch.save(sd, os.path.join(output_dir, "mm_projector.bin"))
