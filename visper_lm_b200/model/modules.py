@@ -258,7 +258,11 @@ class CLIPVisionTower(nn.Module):
         """images [B,3,H,W] (any float dtype) → [B*npatch, D] rows (B-major), bf16."""
         vm = self.vision_tower.vision_model
         cfg = self.config
-        images = images.to(device=self.device, dtype=BF16).contiguous()
+        images = images.to(device=self.device, non_blocking=True).contiguous()
+        if images.dtype == torch.float32:
+            images = ops.cast_bf16(images)
+        elif images.dtype != BF16:
+            images = images.to(BF16)
         B = images.shape[0]
         D, Hh = cfg.hidden_size, cfg.num_attention_heads
         hd = D // Hh

@@ -40,6 +40,23 @@ def _chk(status, what):
 
 
 # --------------------------------------------------------------------------------------------- GEMM
+class GemmTimer:
+    """CUDA-event timing of every GEMM launch on the launching stream (bench.py's live roofline)."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e, _ in self.records)
+        fl = sum(f for _, _, f in self.records)
+        return {"launches": len(self.records), "ms": ms, "flops": fl,
+                "tflops": (fl / ms / 1e9) if ms > 0 else None}
+
+
+GEMM_TIMER = None
+
+
 def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None, out=None,
          want_pre=False):
     """C = act(A·Bᵀ + bias) + residual.  a_layout/b_layout as in include/visper_b200.h."""
@@ -61,8 +78,15 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None
     pc, ldc = _rows(out)
     pr, ldr = _rows(residual) if residual is not None else (0, 0)
     px, ldx = _rows(pre) if pre is not None else (0, 0)
+    timer = GEMM_TIMER
+    if timer is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _chk(_L().vpb_gemm_bf16(pa, lda, a_layout, pb, ldb, b_layout, pc, ldc, M, N, K, act, _p(bias),
                             pr, ldr, px, ldx, _stream()), "gemm")
+    if timer is not None:
+        ev1.record()
+        timer.records.append((ev0, ev1, 2.0 * M * N * K))
     return (out, pre) if want_pre else out
 
 

@@ -215,6 +215,8 @@ class LLaVATrainer:
             if isinstance(v, torch.Tensor):
                 if k in ("input_ids", "labels", "attention_mask"):
                     out[k] = v  # consumed on the host by the splice planner
+                elif v.is_cuda:
+                    out[k] = v
                 else:
                     if not v.is_pinned():
                         buf = self._pinned.get(k)
@@ -225,7 +227,7 @@ class LLaVATrainer:
                         v = buf
                     out[k] = v.to(dev, non_blocking=True)
             elif isinstance(v, dict):
-                out[k] = {kk: vv.to(dev, non_blocking=True) for kk, vv in v.items()}
+                out[k] = {kk: (vv if vv.is_cuda else vv.to(dev, non_blocking=True)) for kk, vv in v.items()}
             else:
                 out[k] = v
         return out
