@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "phi3-mini", "tiny"])
     ap.add_argument("--layers", type=int, default=None, help="override decoder depth (debug only; reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-input leg")
+    ap.add_argument("--profile", action="store_true",
+                    help="bracket the timed device leg with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--cpu-baseline-layers", type=int, default=1)
     return ap.parse_args()
 
@@ -347,11 +350,18 @@ def run_b200(args):
         clocks.start()
     lib.reset_launch_count()
     ops.GEMM_TIMER = ops.GemmTimer()
+    if args.profile:
+        torch.cuda.profiler.start()
     ms_dev, loss_dev = timed(devb, args.steps, read_loss=False)
+    if args.profile:
+        torch.cuda.profiler.stop()
     gemm_stats = ops.GEMM_TIMER.summary()
     ops.GEMM_TIMER = None
     launches = lib.launch_count()
-    ms_e2e, loss_e2e = timed(pinned, args.steps, read_loss=True)
+    if args.no_e2e:
+        ms_e2e, loss_e2e = ms_dev, loss_dev
+    else:
+        ms_e2e, loss_e2e = timed(pinned, args.steps, read_loss=True)
     clk = clocks.stop() if rank == 0 else None
 
     samples = B * world * args.steps

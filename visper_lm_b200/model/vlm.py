@@ -288,6 +288,19 @@ class HeadPlan:
             self.gen_index = None
 
 
+def gather_targets(tgt_flat, group=None):
+    """dist_collect (ola_utils.py:96-106) for the InfoNCE negatives: all-gather of the rank-local
+    targets [B, n] → ([world·B, n], offset of the local rows = rank·B, cf. ola_utils.py:111).
+    Targets carry no gradient, so a plain collective suffices (no backward collective)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        out = torch.empty((world * tgt_flat.shape[0], tgt_flat.shape[1]), dtype=tgt_flat.dtype,
+                          device=tgt_flat.device)
+        dist.all_gather_into_tensor(out, tgt_flat.contiguous(), group=group)
+        return out, dist.get_rank(group) * tgt_flat.shape[0]
+    return tgt_flat, 0
+
+
 # ------------------------------------------------------------------------------------------------ model
 class VisperModel(nn.Module):
     """OlaLlavaLlamaModel / OlaLlavaPhi3Model (ola_llama.py:51-55 + OlaLlavaMetaModel ola_arch.py:35-94)."""
@@ -544,12 +557,7 @@ class VisperForCausalLM(nn.Module):
     def _gather_targets(self, tgt_flat):
         """dist_collect (ola_utils.py:96-106): targets carry no grad → plain NCCL all-gather, once
         per task per step."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            out = torch.empty((dist.get_world_size() * tgt_flat.shape[0], tgt_flat.shape[1]),
-                              dtype=tgt_flat.dtype, device=tgt_flat.device)
-            dist.all_gather_into_tensor(out, tgt_flat)
-            return out, dist.get_rank() * tgt_flat.shape[0]
-        return tgt_flat, 0
+        return gather_targets(tgt_flat)
 
     def _emb_loss(self, pred_flat, mask, tgt_all, off, logit_scale):
         """base_ola_vlm.py:289-320 → (loss, sl1, contrastive) as a 3-vector."""
