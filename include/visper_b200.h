@@ -37,6 +37,10 @@ const char* vpb_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t vpb_launch_count(void);
 void vpb_reset_launch_count(void);
+/* process-wide kernel-selection switches (testing / A-B timing): key VPB_OPT_*, value 0/1 */
+#define VPB_OPT_ATTN_LEGACY_FWD 0 /* 1: force the mma.sync attention forward */
+#define VPB_OPT_ATTN_LEGACY_BWD 1 /* 1: force the mma.sync attention backward */
+int vpb_set_option(int key, int value);
 
 /* ---- GEMM: tcgen05 + TMEM + TMA ----------------------------------------------------------
  * C[M,N] = act(A·Bᵀ + bias) + residual ; optional aux = A·Bᵀ + bias (pre-activation copy).

@@ -240,6 +240,24 @@ def test_attention_fwd_bwd(B, H, KVH, sq, sk, sk2, hd, causal):
         close(dkv2, g[:, sk:].reshape(B * sk2, 2 * kw), rtol=3e-2, name="attn dkv2")
 
 
+@pytest.mark.parametrize("B,H,KVH,sq,sk,causal", [(2, 8, 2, 2048, 2048, True), (1, 4, 4, 333, 333, True),
+                                                   (2, 4, 2, 200, 520, False), (1, 4, 1, 128, 128, True)])
+def test_attention_tcgen05_matches_legacy(B, H, KVH, sq, sk, causal):
+    """hd=128 forward: the tcgen05/TMEM kernel against the mma.sync kernel (both vs torch above)."""
+    from visper_lm_b200 import ops
+    hd = 128
+    q = rnd(B * sq, H * hd, seed=55)
+    kv = rnd(B * sk, 2 * KVH * hd, seed=56)
+    k, v = kv[:, :KVH * hd], kv[:, KVH * hd:]
+    ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 1)
+    o_ref, lse_ref = ops.attn_fwd(q, k, v, B, H, KVH, sq, sk, hd, hd ** -0.5, causal)
+    ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
+    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, sq, sk, hd, hd ** -0.5, causal)
+    torch.cuda.synchronize()
+    close(o, o_ref, name="tc fwd vs legacy")
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+
+
 # ------------------------------------------------------------------------------------------- losses
 @pytest.mark.parametrize("B,T,V", [(2, 37, 1000), (1, 64, 128256)])
 def test_cross_entropy(B, T, V):

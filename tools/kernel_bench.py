@@ -88,6 +88,11 @@ if __name__ == "__main__":
         gemm_case(8192, 8192, 8192, 0, 0, "square 8192")
     if which in ("all", "attn"):
         attn_case(8, 32, 8, 2048, 128, True)
+        ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 1)
+        ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 1)
+        attn_case(8, 32, 8, 2048, 128, True)
+        ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
+        ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
         attn_case(8, 16, 16, 577, 64, False)
         attn_case(4, 32, 32, 2048, 96, True)
     if which in ("all", "norm"):

@@ -16,9 +16,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<int> g_options[16];
+int get_option(int key) { return (key >= 0 && key < 16) ? g_options[key].load() : 0; }
 }  // namespace vpb
 
 extern "C" int vpb_abi_version(void) { return VPB_ABI_VERSION; }
 extern "C" const char* vpb_last_error(void) { return vpb::g_err; }
 extern "C" int64_t vpb_launch_count(void) { return vpb::g_launches.load(); }
 extern "C" void vpb_reset_launch_count(void) { vpb::g_launches.store(0); }
+extern "C" int vpb_set_option(int key, int value) {
+  if (key < 0 || key >= 16) return -1;
+  vpb::g_options[key].store(value);
+  return 0;
+}

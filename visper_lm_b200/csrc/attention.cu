@@ -664,6 +664,11 @@ static int check_attn(const AttnParams& p, int HD) {
 
 }  // namespace vpb
 
+namespace vpb {
+int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk, float scale,
+                int causal, cudaStream_t st);
+}
 using namespace vpb;
 
 #define DISPATCH_HD(HDv, CAUSALv, FN, ...)                                  \
@@ -698,6 +703,11 @@ extern "C" int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   p.scale = scale;
   if (check_attn(p, head_dim)) return -1;
   VPB_CHECK(!(causal && p.sk2 > 0), "attention: causal with a second key segment is not supported");
+  if (head_dim == 128 && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_FWD) &&
+      (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(v) & 15) == 0)
+    return attn_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, KVH, sq, sk, scale, causal,
+                       (cudaStream_t)stream);
   DISPATCH_HD(head_dim, causal, launch_fwd, p, (cudaStream_t)stream);
 }
 

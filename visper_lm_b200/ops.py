@@ -34,6 +34,13 @@ def _rows(t: torch.Tensor):
     return t.data_ptr(), t.stride(0)
 
 
+OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD = 0, 1
+
+
+def set_option(key, value):
+    _chk(_L().vpb_set_option(int(key), int(value)), "set_option")
+
+
 def _chk(status, what):
     if status != 0:
         _lib.check(status, what)
