@@ -668,6 +668,10 @@ namespace vpb {
 int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk, float scale,
                 int causal, cudaStream_t st);
+int attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                const void* dO, int64_t lddo, const float* lse, const float* delta, void* dq,
+                int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int KVH,
+                int sq, int sk, float scale, int causal, cudaStream_t st);
 }
 using namespace vpb;
 
@@ -735,5 +739,10 @@ extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t l
   attn_delta_kernel<<<(int)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)o, ldo, (const bf16*)dO, lddo, delta, B, H, sq, head_dim);
   VPB_LAUNCH_OK();
+  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  if (head_dim == 128 && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_BWD) && al16(q) && al16(k) &&
+      al16(v) && al16(dO))
+    return attn_bwd_tc(q, ldq, k, ldk, v, ldv, dO, lddo, lse, delta, dq, lddq, dk, lddk, dv, lddv, B,
+                       H, KVH, sq, sk, scale, causal, (cudaStream_t)stream);
   DISPATCH_HD(head_dim, causal, launch_bwd, p, (cudaStream_t)stream);
 }

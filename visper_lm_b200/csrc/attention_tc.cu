@@ -281,6 +281,533 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   return 0;
 }
 
+// =============================================================================================
+// backward (head_dim 128)
+// =============================================================================================
+struct AttnTcBwdParams {
+  const float* lse;    // [B,H,sq] natural log
+  const float* delta;  // [B,H,sq] rowsum(dO*O)
+  bf16 *dq, *dk, *dv;
+  int64_t lddq, lddk, lddv;
+  int B, H, KVH, sq, sk;
+  float scale;
+};
+
+namespace tcb {
+constexpr int HD = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+// ---- dK/dV kernel: 128-key tile per CTA, 64-query tiles streamed ----
+constexpr int A_BKV = 128, A_BQ = 64, A_ST = 3;
+constexpr int A_OFF_K = 0, A_OFF_V = 32768;
+constexpr int A_OFF_QD = 65536;              // stage s: Q (16 KB) then dO (16 KB)
+constexpr int A_OFF_P = A_OFF_QD + A_ST * 32768;   // P^T  [128 keys x 64 queries] 16 KB
+constexpr int A_OFF_DS = A_OFF_P + 16384;          // dS^T 16 KB
+constexpr int A_OFF_LD = A_OFF_DS + 16384;         // [2][2][64] floats: lse*log2e | delta
+constexpr int A_OFF_BAR = A_OFF_LD + 1024;
+constexpr int A_SMEM = A_OFF_BAR + 256 + 1024;
+// ---- dQ kernel: 128-query tile per CTA, 64-key tiles streamed ----
+constexpr int B_BQ = 128, B_BKV = 64, B_ST = 3;
+constexpr int B_OFF_Q = 0, B_OFF_DO = 32768;
+constexpr int B_OFF_KV = 65536;              // stage s: K (16 KB) then V (16 KB)
+constexpr int B_OFF_DS = B_OFF_KV + B_ST * 32768;  // dS [128 queries x 64 keys] 16 KB
+constexpr int B_OFF_BAR = B_OFF_DS + 16384;
+constexpr int B_SMEM = B_OFF_BAR + 256 + 1024;
+}  // namespace tcb
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// dK_j = scale * sum_i dS_ij^T Q_i ,  dV_j = sum_i P_ij^T dO_i   (sum over the GQA group's heads too)
+template <bool CAUSAL>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                        const AttnTcBwdParams p) {
+  using namespace tcb;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qd_full = bars + 1;    // [3]
+  uint64_t* qd_empty = bars + 4;   // [3]
+  uint64_t* sd_full = bars + 7;    // [2]
+  uint64_t* pds_full = bars + 9;
+  uint64_t* pds_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* ld_buf = reinterpret_cast<float*>(smem + A_OFF_LD);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * A_BKV;
+  const int kvh = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.KVH;
+  const int off = p.sk - p.sq;
+  const int nq_tiles = (p.sq + A_BQ - 1) / A_BQ;
+  int qt_begin = 0;
+  if (CAUSAL) {
+    int first = kv0 - off;
+    if (first < 0) first = 0;
+    qt_begin = first / A_BQ;
+    if (qt_begin > nq_tiles) qt_begin = nq_tiles;
+  }
+  const int nper = nq_tiles - qt_begin;
+  const int nit = G * nper;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < A_ST; ++i) {
+      mbar_init(&qd_full[i], 1);
+      mbar_init(&qd_empty[i], 1);
+    }
+    mbar_init(&sd_full[0], 1);
+    mbar_init(&sd_full[1], 1);
+    mbar_init(pds_full, 4);
+    mbar_init(pds_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t TM_S = tmem_base;         // S^T[2]  : 2 x 64 columns
+  const uint32_t TM_DP = tmem_base + 128;  // dP^T[2] : 2 x 64 columns
+  const uint32_t TM_DV = tmem_base + 256;  // 128 columns
+  const uint32_t TM_DK = tmem_base + 384;  // 128 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 65536);
+      const int krow = b * p.sk + kv0;
+      tma_load_2d(smem + A_OFF_K, &tmK, kv_full, kvh * HD, krow);
+      tma_load_2d(smem + A_OFF_K + 16384, &tmK, kv_full, kvh * HD + 64, krow);
+      tma_load_2d(smem + A_OFF_V, &tmV, kv_full, kvh * HD, krow);
+      tma_load_2d(smem + A_OFF_V + 16384, &tmV, kv_full, kvh * HD + 64, krow);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it % A_ST;
+        const int hq = kvh * G + it / nper;
+        const int qrow = b * p.sq + (qt_begin + it % nper) * A_BQ;
+        mbar_wait(&qd_empty[st], ((it / A_ST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qd_full[st], 32768);
+        uint8_t* sq_ = smem + A_OFF_QD + st * 32768;
+        tma_load_2d(sq_, &tmQ, &qd_full[st], hq * HD, qrow);
+        tma_load_2d(sq_ + 8192, &tmQ, &qd_full[st], hq * HD + 64, qrow);
+        tma_load_2d(sq_ + 16384, &tmDO, &qd_full[st], hq * HD, qrow);
+        tma_load_2d(sq_ + 24576, &tmDO, &qd_full[st], hq * HD + 64, qrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nit > 0) {
+      constexpr uint32_t idesc_sd = make_idesc_bf16(128, A_BQ, 0, 0);   // [128 keys x 64 queries]
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, 0, 1);    // A K-major, B MN-major
+      const uint32_t k_addr = smem_u32(smem + A_OFF_K), v_addr = smem_u32(smem + A_OFF_V);
+      const uint32_t p_addr = smem_u32(smem + A_OFF_P), ds_addr = smem_u32(smem + A_OFF_DS);
+      auto issue_sd = [&](int it) {
+        const int st = it % A_ST, sb = it & 1;
+        mbar_wait(&qd_full[st], (it / A_ST) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + A_OFF_QD + st * 32768);
+        const uint32_t do_addr = q_addr + 16384;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;  // K / V tiles: 128-row chunks
+          const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;   // Q / dO tiles: 64-row chunks
+          umma_bf16(TM_S + sb * A_BQ, make_smem_desc(k_addr + oa, 16, 1024),
+                    make_smem_desc(q_addr + ob, 16, 1024), idesc_sd, k != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;
+          const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;
+          umma_bf16(TM_DP + sb * A_BQ, make_smem_desc(v_addr + oa, 16, 1024),
+                    make_smem_desc(do_addr + ob, 16, 1024), idesc_sd, k != 0);
+        }
+        umma_commit(&sd_full[sb]);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sd(0);
+      for (int it = 0; it < nit; ++it) {
+        if (it + 1 < nit) issue_sd(it + 1);
+        mbar_wait(pds_full, it & 1);
+        tc_fence_after();
+        const int st = it % A_ST;
+        const uint32_t q_addr = smem_u32(smem + A_OFF_QD + st * 32768);
+        const uint32_t do_addr = q_addr + 16384;
+#pragma unroll
+        for (int k = 0; k < A_BQ / 16; ++k) {  // contraction over the 64 queries
+          umma_bf16(TM_DV, make_smem_desc(p_addr + k * 32, 16, 1024),
+                    make_smem_desc(do_addr + k * 2048, 8192, 1024), idesc_acc, (it | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < A_BQ / 16; ++k) {
+          umma_bf16(TM_DK, make_smem_desc(ds_addr + k * 32, 16, 1024),
+                    make_smem_desc(q_addr + k * 2048, 8192, 1024), idesc_acc, (it | k) != 0);
+        }
+        umma_commit(pds_empty);
+        umma_commit(&qd_empty[st]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // key row within the tile
+    const int tid = threadIdx.x - 64;     // 0..127 among the softmax warps
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    const bool key_ok = kv0 + row < p.sk;
+    uint8_t* prow = smem + A_OFF_P + row * 128;
+    uint8_t* dsrow = smem + A_OFF_DS + row * 128;
+    for (int it = 0; it < nit; ++it) {
+      const int sb = it & 1;
+      const int hq = kvh * G + it / nper;
+      const int q0 = (qt_begin + it % nper) * A_BQ;
+      // stage lse*log2e / delta of the 64 queries (double buffered by iteration parity)
+      {
+        float* buf = ld_buf + sb * 128;
+        const int c = tid & 63;
+        const bool ok = q0 + c < p.sq;
+        const int64_t li = ((int64_t)b * p.H + hq) * p.sq + q0 + c;
+        if (tid < 64) buf[c] = ok ? p.lse[li] * LOG2E : 0.f;
+        else buf[64 + c] = ok ? p.delta[li] : 0.f;
+      }
+      mbar_wait(&sd_full[sb], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[64], d[64];
+      tmem_ld32(TM_S + lane_addr + sb * A_BQ, s);
+      tmem_ld32(TM_S + lane_addr + sb * A_BQ + 32, s + 32);
+      tmem_ld32(TM_DP + lane_addr + sb * A_BQ, d);
+      tmem_ld32(TM_DP + lane_addr + sb * A_BQ + 32, d + 32);
+      named_bar_sync(1, 128);  // lse/delta staged
+      tmem_ld_wait();
+      const float* lbuf = ld_buf + sb * 128;
+      const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
+                             (CAUSAL && (kv0 + A_BKV - 1 > q0 + off));
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float pv = exp2f(__uint_as_float(s[c]) * sl2 - lbuf[c]);
+        if (need_mask) {
+          const bool ok = (q0 + c < p.sq) && key_ok && (!CAUSAL || kv0 + row <= q0 + c + off);
+          pv = ok ? pv : 0.f;
+        }
+        const float dsv = pv * (__uint_as_float(d[c]) - lbuf[64 + c]);
+        s[c] = __float_as_uint(pv);
+        d[c] = __float_as_uint(dsv);
+      }
+      if (it > 0) {
+        mbar_wait(pds_empty, (it - 1) & 1);  // previous dV/dK MMAs finished reading P^T / dS^T
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float a[8], g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[i] = __uint_as_float(s[u * 8 + i]);
+          g[i] = __uint_as_float(d[u * 8 + i]);
+        }
+        const int so = (u ^ (row & 7)) << 4;
+        *reinterpret_cast<uint4*>(prow + so) = pack8(a);
+        *reinterpret_cast<uint4*>(dsrow + so) = pack8(g);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    // epilogue
+    if (nit > 0) {
+      mbar_wait(pds_empty, (nit - 1) & 1);
+      tc_fence_after();
+    }
+    bf16* dkrow = p.dk + ((int64_t)b * p.sk + kv0 + row) * p.lddk + kvh * HD;
+    bf16* dvrow = p.dv + ((int64_t)b * p.sk + kv0 + row) * p.lddv + kvh * HD;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t a[32], g[32];
+      if (nit > 0) {
+        tmem_ld32(TM_DK + lane_addr + c * 32, a);
+        tmem_ld32(TM_DV + lane_addr + c * 32, g);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = g[i] = 0;
+      }
+      if (key_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float x[8], y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            x[i] = __uint_as_float(a[q * 8 + i]) * p.scale;
+            y[i] = __uint_as_float(g[q * 8 + i]);
+          }
+          stg16(dkrow + c * 32 + q * 8, pack8(x));
+          stg16(dvrow + c * 32 + q * 8, pack8(y));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// dQ_i = scale * sum_j dS_ij K_j
+template <bool CAUSAL>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                      const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                      const AttnTcBwdParams p) {
+  using namespace tcb;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [3]
+  uint64_t* kv_empty = bars + 4;  // [3]
+  uint64_t* sd_full = bars + 7;   // [2]
+  uint64_t* ds_full = bars + 9;
+  uint64_t* ds_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.H / p.KVH);
+  const int q0 = qt * B_BQ;
+  const int off = p.sk - p.sq;
+  int kv_end = p.sk;
+  if (CAUSAL) {
+    kv_end = q0 + B_BQ + off;
+    if (kv_end > p.sk) kv_end = p.sk;
+    if (kv_end < 0) kv_end = 0;
+  }
+  const int nit = (kv_end + B_BKV - 1) / B_BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < B_ST; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(&sd_full[0], 1);
+    mbar_init(&sd_full[1], 1);
+    mbar_init(ds_full, 4);
+    mbar_init(ds_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t TM_S = tmem_base;         // S[2]  : 2 x 64
+  const uint32_t TM_DP = tmem_base + 128;  // dP[2] : 2 x 64
+  const uint32_t TM_DQ = tmem_base + 256;  // 128
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 65536);
+      const int qrow = b * p.sq + q0;
+      tma_load_2d(smem + B_OFF_Q, &tmQ, q_full, h * HD, qrow);
+      tma_load_2d(smem + B_OFF_Q + 16384, &tmQ, q_full, h * HD + 64, qrow);
+      tma_load_2d(smem + B_OFF_DO, &tmDO, q_full, h * HD, qrow);
+      tma_load_2d(smem + B_OFF_DO + 16384, &tmDO, q_full, h * HD + 64, qrow);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it % B_ST;
+        const int krow = b * p.sk + it * B_BKV;
+        mbar_wait(&kv_empty[st], ((it / B_ST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 32768);
+        uint8_t* sk_ = smem + B_OFF_KV + st * 32768;
+        tma_load_2d(sk_, &tmK, &kv_full[st], kvh * HD, krow);
+        tma_load_2d(sk_ + 8192, &tmK, &kv_full[st], kvh * HD + 64, krow);
+        tma_load_2d(sk_ + 16384, &tmV, &kv_full[st], kvh * HD, krow);
+        tma_load_2d(sk_ + 24576, &tmV, &kv_full[st], kvh * HD + 64, krow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nit > 0) {
+      constexpr uint32_t idesc_sd = make_idesc_bf16(128, B_BKV, 0, 0);  // [128 queries x 64 keys]
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 0, 1);
+      const uint32_t q_addr = smem_u32(smem + B_OFF_Q), do_addr = smem_u32(smem + B_OFF_DO);
+      const uint32_t ds_addr = smem_u32(smem + B_OFF_DS);
+      auto issue_sd = [&](int it) {
+        const int st = it % B_ST, sb = it & 1;
+        mbar_wait(&kv_full[st], (it / B_ST) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem + B_OFF_KV + st * 32768);
+        const uint32_t v_addr = k_addr + 16384;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;
+          const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;
+          umma_bf16(TM_S + sb * B_BKV, make_smem_desc(q_addr + oa, 16, 1024),
+                    make_smem_desc(k_addr + ob, 16, 1024), idesc_sd, k != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;
+          const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;
+          umma_bf16(TM_DP + sb * B_BKV, make_smem_desc(do_addr + oa, 16, 1024),
+                    make_smem_desc(v_addr + ob, 16, 1024), idesc_sd, k != 0);
+        }
+        umma_commit(&sd_full[sb]);
+      };
+      mbar_wait(q_full, 0);
+      issue_sd(0);
+      for (int it = 0; it < nit; ++it) {
+        if (it + 1 < nit) issue_sd(it + 1);
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+        const int st = it % B_ST;
+        const uint32_t k_addr = smem_u32(smem + B_OFF_KV + st * 32768);
+#pragma unroll
+        for (int k = 0; k < B_BKV / 16; ++k) {  // contraction over the 64 keys
+          umma_bf16(TM_DQ, make_smem_desc(ds_addr + k * 32, 16, 1024),
+                    make_smem_desc(k_addr + k * 2048, 8192, 1024), idesc_dq, (it | k) != 0);
+        }
+        umma_commit(ds_empty);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // query row within the tile
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    const bool row_ok = q0 + row < p.sq;
+    const int64_t li = ((int64_t)b * p.H + h) * p.sq + q0 + row;
+    const float lse2 = row_ok ? p.lse[li] * LOG2E : 0.f;
+    const float dl = row_ok ? p.delta[li] : 0.f;
+    uint8_t* dsrow = smem + B_OFF_DS + row * 128;
+    for (int it = 0; it < nit; ++it) {
+      const int sb = it & 1;
+      const int j0 = it * B_BKV;
+      mbar_wait(&sd_full[sb], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t s[64], d[64];
+      tmem_ld32(TM_S + lane_addr + sb * B_BKV, s);
+      tmem_ld32(TM_S + lane_addr + sb * B_BKV + 32, s + 32);
+      tmem_ld32(TM_DP + lane_addr + sb * B_BKV, d);
+      tmem_ld32(TM_DP + lane_addr + sb * B_BKV + 32, d + 32);
+      tmem_ld_wait();
+      const bool need_mask = !row_ok || (j0 + B_BKV > p.sk) || (CAUSAL && (j0 + B_BKV - 1 > q0 + off));
+      const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float pv = exp2f(__uint_as_float(s[c]) * sl2 - lse2);
+        if (need_mask) pv = (row_ok && j0 + c <= lim) ? pv : 0.f;
+        d[c] = __float_as_uint(pv * (__uint_as_float(d[c]) - dl));
+      }
+      if (it > 0) mbar_wait(ds_empty, (it - 1) & 1);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = __uint_as_float(d[u * 8 + i]);
+        *reinterpret_cast<uint4*>(dsrow + ((u ^ (row & 7)) << 4)) = pack8(g);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    if (nit > 0) {
+      mbar_wait(ds_empty, (nit - 1) & 1);
+      tc_fence_after();
+    }
+    bf16* dqrow = p.dq + ((int64_t)b * p.sq + q0 + row) * p.lddq + h * HD;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t a[32];
+      if (nit > 0) {
+        tmem_ld32(TM_DQ + lane_addr + c * 32, a);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = 0;
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(a[q * 8 + i]) * p.scale;
+          stg16(dqrow + c * 32 + q * 8, pack8(x));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool CAUSAL>
+static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                         int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
+                         cudaStream_t st) {
+  using namespace tcb;
+  const uint64_t qcols = (uint64_t)p.H * HD, kcols = (uint64_t)p.KVH * HD;
+  const uint64_t qrows = (uint64_t)p.B * p.sq, krows = (uint64_t)p.B * p.sk;
+  {
+    CUtensorMap tmQ, tmDO, tmK, tmV;
+    if (make_tmap_2d(&tmQ, q, qcols, qrows, (uint64_t)ldq, 64, A_BQ)) return -1;
+    if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, A_BQ)) return -1;
+    if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, A_BKV)) return -1;
+    if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, A_BKV)) return -1;
+    auto kern = attn_bwd_dkdv_tc_kernel<CAUSAL>;
+    static bool cfg = false;
+    if (!cfg) {
+      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
+      cfg = true;
+    }
+    dim3 grid((p.sk + A_BKV - 1) / A_BKV, p.KVH, p.B);
+    kern<<<grid, 192, A_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
+    VPB_LAUNCH_OK();
+  }
+  {
+    CUtensorMap tmQ, tmDO, tmK, tmV;
+    if (make_tmap_2d(&tmQ, q, qcols, qrows, (uint64_t)ldq, 64, B_BQ)) return -1;
+    if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, B_BQ)) return -1;
+    if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, B_BKV)) return -1;
+    if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, B_BKV)) return -1;
+    auto kern = attn_bwd_dq_tc_kernel<CAUSAL>;
+    static bool cfg = false;
+    if (!cfg) {
+      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+      cfg = true;
+    }
+    dim3 grid((p.sq + B_BQ - 1) / B_BQ, p.H, p.B);
+    kern<<<grid, 192, B_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
+    VPB_LAUNCH_OK();
+  }
+  return 0;
+}
+
+// entry used by vpb_attn_bwd (attention.cu) after the delta kernel, head_dim 128, one K/V segment
+int attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                const void* dO, int64_t lddo, const float* lse, const float* delta, void* dq,
+                int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int KVH,
+                int sq, int sk, float scale, int causal, cudaStream_t st) {
+  AttnTcBwdParams p;
+  p.lse = lse; p.delta = delta;
+  p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
+  p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk;
+  p.scale = scale;
+  return causal ? launch_bwd_tc<true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)
+                : launch_bwd_tc<false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+}
+
 // entry used by vpb_attn_fwd (attention.cu) for head_dim 128, single K/V segment
 int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk, float scale,
