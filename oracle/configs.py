@@ -12,6 +12,19 @@ TINY_LLAMA = dict(
 
 TINY_PHI3 = dict(TINY_LLAMA, family="phi3", kv_heads=4, rope_theta=10000.0, num_sys_tokens=13)
 
+# real layer WIDTHS (Llama-3-8B / Phi-3-mini / CLIP-ViT-L dims, all three head widths) at reduced depth
+# and vocabulary: exercises the production kernel shapes (hd 128 GQA 32/8, hd 96, K=14336, dim-4096
+# depth head) while the fp32 CPU oracle still finishes in seconds.
+WIDE_LLAMA = dict(
+    family="llama", vocab=8192, hidden=4096, inter=14336, layers=2, heads=32, kv_heads=8, max_pos=1024,
+    rope_theta=500000.0, vis_hidden=1024, vis_inter=4096, vis_layers=3, vis_heads=16, image_size=336,
+    patch_size=14, gen_dim=1024, seg_dim=1536, depth_dim=1024, depth_layers="1-2", seg_layers="1-2",
+    gen_layers="1-2", aux_mode="gen-depth-seg", num_task_tokens=8, num_sys_tokens=26,
+    tokenizer_model_max_length=1024)
+
+WIDE_PHI3 = dict(WIDE_LLAMA, family="phi3", hidden=3072, inter=8192, heads=32, kv_heads=32,
+                 rope_theta=10000.0, num_sys_tokens=13)
+
 LLAMA3_8B = dict(
     family="llama", vocab=128256, hidden=4096, inter=14336, layers=32, heads=32, kv_heads=8,
     max_pos=4096, rope_theta=500000.0, vis_hidden=1024, vis_inter=4096, vis_layers=24, vis_heads=16,

@@ -33,3 +33,21 @@ def test_product_never_imports_oracle():
     root = pathlib.Path(lib.__file__).resolve().parent
     for f in root.rglob("*.py"):
         assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read_text(), re.M), f
+
+
+def test_reference_module_paths_resolve():
+    """ola_vlm.model / ola_vlm.train.llava_trainer export the names the reference's train() imports."""
+    import importlib
+    import sys
+
+    for k in [k for k in sys.modules if k == "ola_vlm" or k.startswith("ola_vlm.")]:
+        del sys.modules[k]  # the oracle shim may have registered namespace stubs in this process
+    m = importlib.import_module("ola_vlm.model")
+    for name in ("OlaLlavaLlamaForCausalLM", "OlaLlavaPhi3ForCausalLM", "LlavaLlamaForCausalLM",
+                 "LlavaPhi3ForCausalLM", "OlaLlavaLlamaConfig", "LlavaConfig"):
+        assert hasattr(m, name)
+    assert m.OlaLlavaLlamaConfig.model_type == "ola_llama" and m.LlavaConfig.model_type == "llava_llama"
+    t = importlib.import_module("ola_vlm.train.llava_trainer")
+    assert hasattr(t, "LLaVATrainer")
+    for k in [k for k in sys.modules if k == "ola_vlm" or k.startswith("ola_vlm.")]:
+        del sys.modules[k]

@@ -7,7 +7,8 @@ from parity_utils import configs, restate
 
 GOLDEN = __import__("pathlib").Path(__file__).parent / "golden"
 CASES = [("tiny_llama_dsg", "TINY_LLAMA", True), ("tiny_llama_dsg_padded", "TINY_LLAMA", True),
-         ("tiny_phi3_dsg", "TINY_PHI3", True), ("tiny_llama_ntp", "TINY_LLAMA", False)]
+         ("tiny_phi3_dsg", "TINY_PHI3", True), ("tiny_llama_ntp", "TINY_LLAMA", False),
+         ("wide_llama_dsg", "WIDE_LLAMA", True), ("wide_phi3_dsg", "WIDE_PHI3", True)]
 
 
 def _state(fx):
@@ -52,7 +53,7 @@ def test_depth_heads_linear_2_3_get_no_gradient():
     assert any("linear_2" in n for n in fx["state_spec"])
 
 
-@pytest.mark.parametrize("name,cfg_name,distill", [c for c in CASES if c[0] != "tiny_llama_dsg_padded"])
+@pytest.mark.parametrize("name,cfg_name,distill", [c for c in CASES if c[0].startswith("tiny") and c[0] != "tiny_llama_dsg_padded"])
 def test_state_dict_abi(name, cfg_name, distill):
     from parity_utils import build_product
 

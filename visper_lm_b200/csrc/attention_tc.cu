@@ -34,12 +34,18 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_KV = TILE_BYTES;                   // stage s: K at OFF_KV + s*2*TILE, V right after
 constexpr int OFF_P = OFF_KV + 4 * TILE_BYTES;
 constexpr int OFF_BAR = OFF_P + TILE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int OFF_X = OFF_BAR + 256;  // softmax exchange: 768 floats
+constexpr int SMEM_BYTES = OFF_X + 3072 + 1024;
+constexpr int THREADS = 320;  // TMA warp + MMA warp + 8 softmax warps
 constexpr float LOG2E = 1.4426950408889634f;
 }  // namespace tc
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <bool CAUSAL>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using namespace tc;
@@ -79,7 +85,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -147,40 +153,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
+    // 8 softmax warps: warp pair (w, w+4) shares the 32 TMEM lanes of quarter w&3 and splits the
+    // 128 key columns in two halves, so every SM sub-partition runs two softmax warps.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
     float m_used = -INFINITY, l = 0.f;
-    uint8_t* prow = smem + OFF_P + row * 128;
+    uint8_t* prow = smem + OFF_P + half * CHUNK_BYTES + row * 128;
+    float* xchg = reinterpret_cast<float*>(smem + OFF_X);  // [2 parity][2 half][128 rows] + [2][128]
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j & 1;
       mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t r[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(TM_S + lane_addr + sb * BN + c * 32, r + c * 32);
+      uint32_t r[64];
+      tmem_ld32(TM_S + lane_addr + sb * BN + half * 64, r);
+      tmem_ld32(TM_S + lane_addr + sb * BN + half * 64 + 32, r + 32);
       tmem_ld_wait();
-      const int j0 = j * BN;
-      const bool need_mask = (j0 + BN > p.sk) || (CAUSAL && (j0 + BN - 1 > q0 + off));
-      float mx = -INFINITY;
+      const int j0 = j * BN + half * 64;
+      const bool need_mask = (j * BN + BN > p.sk) || (CAUSAL && (j * BN + BN - 1 > q0 + off));
+      float mx = -INFINITY;  // max of the RAW scores; scaled once (scale > 0)
       if (need_mask) {
         const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;  // last visible key
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
-          float v = __uint_as_float(r[c]) * sl2;
-          if (j0 + c > lim) v = -INFINITY;
-          r[c] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
+        for (int c = 0; c < 64; ++c) {
+          if (j0 + c > lim) r[c] = 0xff800000u;  // -inf
+          mx = fmaxf(mx, __uint_as_float(r[c]));
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
-          const float v = __uint_as_float(r[c]) * sl2;
-          r[c] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
-        }
+        for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
       }
+      xchg[(sb * 2 + half) * 128 + row] = mx;
+      named_bar_sync(1, 256);
+      mx = fmaxf(mx, xchg[(sb * 2 + (half ^ 1)) * 128 + row]) * sl2;
       // lazy rescale: keep the old reference max unless the new one is > 2^8 larger
       const bool upd = mx > m_used + 8.f;
       float alpha = 1.f;
@@ -194,13 +201,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         if (__any_sync(0xffffffffu, upd)) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
-            tmem_ld32(TM_O + lane_addr + c * 32, o);
+            tmem_ld32(TM_O + lane_addr + half * 64 + c * 32, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(TM_O + lane_addr + c * 32, o);
+            tmem_st32(TM_O + lane_addr + half * 64 + c * 32, o);
           }
           tmem_st_wait();
         }
@@ -208,16 +215,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float mb = (m_used == -INFINITY) ? 0.f : m_used;
       float sum = 0.f;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {  // 16-byte units of 8 keys
+      for (int u = 0; u < 8; ++u) {  // 16-byte units of 8 keys
         float pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          pv[i] = exp2f(__uint_as_float(r[u * 8 + i]) - mb);
+          pv[i] = ex2_approx(fmaf(__uint_as_float(r[u * 8 + i]), sl2, -mb));
           sum += pv[i];
         }
-        const uint4 packed = pack8(pv);
-        const int chunk = u >> 3, uu = u & 7;
-        *reinterpret_cast<uint4*>(prow + chunk * CHUNK_BYTES + ((uu ^ (row & 7)) << 4)) = packed;
+        *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) << 4)) = pack8(pv);
       }
       l += sum;
       fence_proxy_async();  // generic-proxy smem writes → visible to the tensor-core (async) proxy
@@ -225,19 +230,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: O / l → bf16 → global, LSE
+    // epilogue: combine the two half-row sums, O / l → bf16 → global, LSE
+    float* lx = xchg + 512;
+    lx[half * 128 + row] = l;
+    named_bar_sync(1, 256);
+    l += lx[(half ^ 1) * 128 + row];
     const bool row_ok = q0 + row < p.sq;
     if (ntiles > 0) {
       mbar_wait(pv_done, (ntiles - 1) & 1);
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    bf16* orow = p.o + ((int64_t)b * p.sq + q0 + row) * p.ldo + h * HD;
+    bf16* orow = p.o + ((int64_t)b * p.sq + q0 + row) * p.ldo + h * HD + half * 64;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
       if (ntiles > 0) {
-        tmem_ld32(TM_O + lane_addr + c * 32, o);
+        tmem_ld32(TM_O + lane_addr + half * 64 + c * 32, o);
         tmem_ld_wait();
       } else {
 #pragma unroll
@@ -253,7 +262,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
-    if (p.lse && row_ok)
+    if (p.lse && row_ok && half == 0)
       p.lse[((int64_t)b * p.H + h) * p.sq + q0 + row] =
           l > 0.f ? m_used * 0.6931471805599453f + logf(l) : -INFINITY;
   }
@@ -276,7 +285,7 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
     cfg = true;
   }
   dim3 grid((p.sq + tc::BM - 1) / tc::BM, p.H, p.B);
-  kern<<<grid, 192, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
   VPB_LAUNCH_OK();
   return 0;
 }
@@ -314,13 +323,9 @@ constexpr int B_OFF_BAR = B_OFF_DS + 16384;
 constexpr int B_SMEM = B_OFF_BAR + 256 + 1024;
 }  // namespace tcb
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 // dK_j = scale * sum_i dS_ij^T Q_i ,  dV_j = sum_i P_ij^T dO_i   (sum over the GQA group's heads too)
 template <bool CAUSAL>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                         const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                         const AttnTcBwdParams p) {
@@ -366,7 +371,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     mbar_init(&sd_full[0], 1);
     mbar_init(&sd_full[1], 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, 8);
     mbar_init(pds_empty, 1);
     fence_barrier_init();
   }
@@ -454,8 +459,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else {
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;     // which 32 of the 64 query columns this warp handles
     const int row = quarter * 32 + lane;  // key row within the tile
-    const int tid = threadIdx.x - 64;     // 0..127 among the softmax warps
+    const int tid = threadIdx.x - 64;     // 0..255 among the softmax warps
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
     const bool key_ok = kv0 + row < p.sk;
@@ -466,7 +472,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const int hq = kvh * G + it / nper;
       const int q0 = (qt_begin + it % nper) * A_BQ;
       // stage lse*log2e / delta of the 64 queries (double buffered by iteration parity)
-      {
+      if (tid < 128) {
         float* buf = ld_buf + sb * 128;
         const int c = tid & 63;
         const bool ok = q0 + c < p.sq;
@@ -476,39 +482,45 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       mbar_wait(&sd_full[sb], (it >> 1) & 1);
       tc_fence_after();
-      uint32_t s[64], d[64];
-      tmem_ld32(TM_S + lane_addr + sb * A_BQ, s);
-      tmem_ld32(TM_S + lane_addr + sb * A_BQ + 32, s + 32);
-      tmem_ld32(TM_DP + lane_addr + sb * A_BQ, d);
-      tmem_ld32(TM_DP + lane_addr + sb * A_BQ + 32, d + 32);
-      named_bar_sync(1, 128);  // lse/delta staged
+      uint32_t s[32], d[32];
+      tmem_ld32(TM_S + lane_addr + sb * A_BQ + half * 32, s);
+      tmem_ld32(TM_DP + lane_addr + sb * A_BQ + half * 32, d);
+      named_bar_sync(1, 256);  // lse/delta staged
       tmem_ld_wait();
       const float* lbuf = ld_buf + sb * 128;
       const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
                              (CAUSAL && (kv0 + A_BKV - 1 > q0 + off));
+      const float4* l4 = reinterpret_cast<const float4*>(lbuf) + half * 8;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float pv = exp2f(__uint_as_float(s[c]) * sl2 - lbuf[c]);
-        if (need_mask) {
-          const bool ok = (q0 + c < p.sq) && key_ok && (!CAUSAL || kv0 + row <= q0 + c + off);
-          pv = ok ? pv : 0.f;
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 ls = l4[c4], dl4 = l4[16 + c4];
+        const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c4 * 4 + e;
+          float pv = ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e]));
+          if (need_mask) {
+            const int qc = q0 + half * 32 + c;
+            const bool ok = (qc < p.sq) && key_ok && (!CAUSAL || kv0 + row <= qc + off);
+            pv = ok ? pv : 0.f;
+          }
+          const float dsv = pv * (__uint_as_float(d[c]) - dlv[e]);
+          s[c] = __float_as_uint(pv);
+          d[c] = __float_as_uint(dsv);
         }
-        const float dsv = pv * (__uint_as_float(d[c]) - lbuf[64 + c]);
-        s[c] = __float_as_uint(pv);
-        d[c] = __float_as_uint(dsv);
       }
       if (it > 0) {
         mbar_wait(pds_empty, (it - 1) & 1);  // previous dV/dK MMAs finished reading P^T / dS^T
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         float a[8], g[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           a[i] = __uint_as_float(s[u * 8 + i]);
           g[i] = __uint_as_float(d[u * 8 + i]);
         }
-        const int so = (u ^ (row & 7)) << 4;
+        const int so = ((half * 4 + u) ^ (row & 7)) << 4;
         *reinterpret_cast<uint4*>(prow + so) = pack8(a);
         *reinterpret_cast<uint4*>(dsrow + so) = pack8(g);
       }
@@ -517,7 +529,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
     }
-    // epilogue
+    // epilogue: each warp of a pair writes 64 of the 128 head-dim columns
     if (nit > 0) {
       mbar_wait(pds_empty, (nit - 1) & 1);
       tc_fence_after();
@@ -525,7 +537,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     bf16* dkrow = p.dk + ((int64_t)b * p.sk + kv0 + row) * p.lddk + kvh * HD;
     bf16* dvrow = p.dv + ((int64_t)b * p.sk + kv0 + row) * p.lddv + kvh * HD;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
       uint32_t a[32], g[32];
       if (nit > 0) {
         tmem_ld32(TM_DK + lane_addr + c * 32, a);
@@ -557,7 +570,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
 // dQ_i = scale * sum_j dS_ij K_j
 template <bool CAUSAL>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                       const AttnTcBwdParams p) {
@@ -600,7 +613,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     mbar_init(&sd_full[0], 1);
     mbar_init(&sd_full[1], 1);
-    mbar_init(ds_full, 4);
+    mbar_init(ds_full, 8);
     mbar_init(ds_empty, 1);
     fence_barrier_init();
   }
@@ -680,6 +693,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else {
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;     // which 32 of the 64 key columns this warp handles
     const int row = quarter * 32 + lane;  // query row within the tile
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
@@ -693,27 +707,25 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int j0 = it * B_BKV;
       mbar_wait(&sd_full[sb], (it >> 1) & 1);
       tc_fence_after();
-      uint32_t s[64], d[64];
-      tmem_ld32(TM_S + lane_addr + sb * B_BKV, s);
-      tmem_ld32(TM_S + lane_addr + sb * B_BKV + 32, s + 32);
-      tmem_ld32(TM_DP + lane_addr + sb * B_BKV, d);
-      tmem_ld32(TM_DP + lane_addr + sb * B_BKV + 32, d + 32);
+      uint32_t s[32], d[32];
+      tmem_ld32(TM_S + lane_addr + sb * B_BKV + half * 32, s);
+      tmem_ld32(TM_DP + lane_addr + sb * B_BKV + half * 32, d);
       tmem_ld_wait();
       const bool need_mask = !row_ok || (j0 + B_BKV > p.sk) || (CAUSAL && (j0 + B_BKV - 1 > q0 + off));
       const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float pv = exp2f(__uint_as_float(s[c]) * sl2 - lse2);
-        if (need_mask) pv = (row_ok && j0 + c <= lim) ? pv : 0.f;
+      for (int c = 0; c < 32; ++c) {
+        float pv = ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lse2));
+        if (need_mask) pv = (row_ok && j0 + half * 32 + c <= lim) ? pv : 0.f;
         d[c] = __float_as_uint(pv * (__uint_as_float(d[c]) - dl));
       }
       if (it > 0) mbar_wait(ds_empty, (it - 1) & 1);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         float g[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = __uint_as_float(d[u * 8 + i]);
-        *reinterpret_cast<uint4*>(dsrow + ((u ^ (row & 7)) << 4)) = pack8(g);
+        *reinterpret_cast<uint4*>(dsrow + (((half * 4 + u) ^ (row & 7)) << 4)) = pack8(g);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -726,7 +738,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     bf16* dqrow = p.dq + ((int64_t)b * p.sq + q0 + row) * p.lddq + h * HD;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = half * 2 + cc;
       uint32_t a[32];
       if (nit > 0) {
         tmem_ld32(TM_DQ + lane_addr + c * 32, a);
@@ -771,7 +784,7 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
       cfg = true;
     }
     dim3 grid((p.sk + A_BKV - 1) / A_BKV, p.KVH, p.B);
-    kern<<<grid, 192, A_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
+    kern<<<grid, 320, A_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
     VPB_LAUNCH_OK();
   }
   {
@@ -787,7 +800,7 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
       cfg = true;
     }
     dim3 grid((p.sq + B_BQ - 1) / B_BQ, p.H, p.B);
-    kern<<<grid, 192, B_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
+    kern<<<grid, 320, B_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
     VPB_LAUNCH_OK();
   }
   return 0;
