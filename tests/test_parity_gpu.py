@@ -137,3 +137,33 @@ def test_logits_on_request_and_tuple_return():
     tup = model(input_ids=batch["input_ids"], labels=batch["labels"], attention_mask=batch["attention_mask"],
                 images=batch["images"].to(DEV), return_dict=False)
     assert isinstance(tup, tuple) and abs(tup[0].item() - out.loss.item()) < 1e-6
+
+
+@pytest.mark.parametrize("cfg_name", ["TINY_LLAMA", "TINY_PHI3"])
+def test_full_finetune_gradients(cfg_name):
+    """IFT regime (finetune.sh): every LLM / projector weight trainable, NTP only — checks the wgrad
+    paths of DecoderLayerFn / LMHeadCEFn / SpliceFn (embedding scatter-add) against oracle autograd.
+    The tower stays frozen (clip_encoder.py:32-33,47 @torch.no_grad)."""
+    cfg = getattr(configs, cfg_name)
+    model = build_product(cfg, False, DEV)
+    for n, p in model.named_parameters():
+        p.requires_grad_("vision_tower" not in n)
+    batch = round_batch(configs.synthetic_batch(cfg, 2, 40, seed=77, distill=False, pad_rows=1))
+    out = run_product(model, batch, False, DEV)
+    out.loss.backward()
+    torch.cuda.synchronize()
+    sd = {k: v.requires_grad_("vision_tower" not in k) for k, v in oracle_state(model).items()}
+    ref = restate.forward_step(sd, dict(cfg), batch, distill=False)
+    ref["loss"].backward()
+    assert abs(out.loss.item() - ref["loss"].item()) <= 2e-3 * abs(ref["loss"].item())
+    checked = 0
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        g_ref = sd[n].grad
+        assert p.grad is not None and g_ref is not None, n
+        c = cos_sim(p.grad, g_ref)
+        ratio = p.grad.float().norm().item() / max(g_ref.norm().item(), 1e-12)
+        assert c >= 0.99 and abs(ratio - 1) <= 4e-2, f"{n}: cos {c:.5f} norm ratio {ratio:.4f}"
+        checked += 1
+    assert checked >= 30

@@ -72,6 +72,30 @@ def norm_case(M, D):
                       "GBps": round(by / ms / 1e6, 1)}), flush=True)
 
 
+def attn_profile(B=8, H=32, KVH=8, S=2048, hd=128):
+    """Per-kernel device times of one attention fwd+bwd via torch.profiler (CUPTI)."""
+    from torch.profiler import ProfilerActivity, profile
+    qkv = torch.randn(B * S, (H + 2 * KVH) * hd, device=dev).to(BF)
+    q, k, v = qkv[:, :H * hd], qkv[:, H * hd:(H + KVH) * hd], qkv[:, (H + KVH) * hd:]
+    scale = hd ** -0.5
+    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, True)
+    do = torch.randn_like(o)
+    dqkv = torch.empty_like(qkv)
+    dq, dk, dv = dqkv[:, :H * hd], dqkv[:, H * hd:(H + KVH) * hd], dqkv[:, (H + KVH) * hd:]
+    for _ in range(2):
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, S, S, hd, scale, True)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, True, out=o)
+            ops.attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, S, S, hd, scale, True)
+        torch.cuda.synchronize()
+    for e in prof.key_averages():
+        if e.device_time_total > 0:
+            print(json.dumps({"kernel": e.key[:60], "calls": e.count,
+                              "avg_us": round(e.device_time_total / e.count, 1)}), flush=True)
+
+
 if __name__ == "__main__":
     M = 16384
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -95,5 +119,7 @@ if __name__ == "__main__":
         ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
         attn_case(8, 16, 16, 577, 64, False)
         attn_case(4, 32, 32, 2048, 96, True)
+    if which == "attnprof":
+        attn_profile()
     if which in ("all", "norm"):
         norm_case(16384, 4096)

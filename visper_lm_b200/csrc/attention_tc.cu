@@ -196,6 +196,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         m_used = mx;
         l *= alpha;
       }
+      // exponentials first (registers only) so they overlap the PV MMA of the previous tile
+      const float mb = (m_used == -INFINITY) ? 0.f : m_used;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float pv = ex2_approx(fmaf(__uint_as_float(r[c]), sl2, -mb));
+        sum += pv;
+        r[c] = __float_as_uint(pv);
+      }
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} finished: O and the P buffer are ours
         tc_fence_after();
@@ -212,16 +221,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tmem_st_wait();
         }
       }
-      const float mb = (m_used == -INFINITY) ? 0.f : m_used;
-      float sum = 0.f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {  // 16-byte units of 8 keys
         float pv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          pv[i] = ex2_approx(fmaf(__uint_as_float(r[u * 8 + i]), sl2, -mb));
-          sum += pv[i];
-        }
+        for (int i = 0; i < 8; ++i) pv[i] = __uint_as_float(r[u * 8 + i]);
         *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) << 4)) = pack8(pv);
       }
       l += sum;
