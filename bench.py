@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--seq", type=int, default=2048, help="embedded sequence length T")
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "phi3-mini", "tiny"])
     ap.add_argument("--layers", type=int, default=None, help="override decoder depth (debug only; reported)")
+    ap.add_argument("--torch-profile", action="store_true",
+                    help="diagnostic: torch.profiler over 2 device-leg steps, prints kernel totals and busy time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-input leg")
     ap.add_argument("--profile", action="store_true",
@@ -345,6 +347,27 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         trainer.step(fresh(devb))
     sync_all()
+    if args.torch_profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        sync_all()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            t0 = time.perf_counter()
+            for _ in range(2):
+                trainer.step(fresh(devb))
+            t_cpu = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            t_all = time.perf_counter() - t0
+        evs = [e for e in prof.key_averages() if e.device_time_total > 0]
+        busy = sum(e.device_time_total for e in evs) / 1e3
+        print(json.dumps({"profile_steps": 2, "cpu_enqueue_ms": t_cpu * 1e3, "wall_ms": t_all * 1e3,
+                          "gpu_busy_ms": busy}), flush=True)
+        for e in sorted(evs, key=lambda e: -e.device_time_total)[:25]:
+            print(json.dumps({"kernel": e.key[:70], "calls": e.count, "total_ms": round(e.device_time_total / 1e3, 2)}),
+                  flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()

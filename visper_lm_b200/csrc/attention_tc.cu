@@ -31,9 +31,10 @@ constexpr int BM = 128, BN = 128, HD = 128;
 constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 64-column chunks of [128 rows x 128 B]
 constexpr int CHUNK_BYTES = 16384;
 constexpr int OFF_Q = 0;
-constexpr int OFF_KV = TILE_BYTES;                   // stage s: K at OFF_KV + s*2*TILE, V right after
-constexpr int OFF_P = OFF_KV + 4 * TILE_BYTES;
-constexpr int OFF_BAR = OFF_P + TILE_BYTES;
+constexpr int KST = 3, VST = 2;                      // K ring runs ahead of the V ring
+constexpr int OFF_K = TILE_BYTES;                    // K stage s at OFF_K + s*TILE
+constexpr int OFF_V = OFF_K + KST * TILE_BYTES;      // V stage s at OFF_V + s*TILE
+constexpr int OFF_BAR = OFF_V + VST * TILE_BYTES;
 constexpr int OFF_X = OFF_BAR + 256;  // softmax exchange: 768 floats
 constexpr int SMEM_BYTES = OFF_X + 3072 + 1024;
 constexpr int THREADS = 320;  // TMA warp + MMA warp + 8 softmax warps
@@ -54,12 +55,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    // [2]
-  uint64_t* p_full = bars + 7;
-  uint64_t* pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [2]
+  uint64_t* v_empty = bars + 9;   // [2]
+  uint64_t* s_full = bars + 11;   // [2]
+  uint64_t* p_full = bars + 13;
+  uint64_t* pv_done = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy tiles first
@@ -80,9 +83,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+    for (int i = 0; i < KST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < VST; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
     mbar_init(p_full, 8);
@@ -102,17 +109,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive_expect_tx(q_full, TILE_BYTES);
       tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * HD, b * p.sq + q0);
       tma_load_2d(smem + OFF_Q + CHUNK_BYTES, &tmQ, q_full, h * HD + 64, b * p.sq + q0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        uint8_t* sk = smem + OFF_KV + s * 2 * TILE_BYTES;
-        uint8_t* sv = sk + TILE_BYTES;
+      auto load_k = [&](int j) {
+        const int s = j % KST;
+        mbar_wait(&k_empty[s], ((j / KST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+        uint8_t* sk = smem + OFF_K + s * TILE_BYTES;
         const int row = b * p.sk + j * BN;
-        tma_load_2d(sk, &tmK, &kv_full[s], kvh * HD, row);
-        tma_load_2d(sk + CHUNK_BYTES, &tmK, &kv_full[s], kvh * HD + 64, row);
-        tma_load_2d(sv, &tmV, &kv_full[s], kvh * HD, row);
-        tma_load_2d(sv + CHUNK_BYTES, &tmV, &kv_full[s], kvh * HD + 64, row);
+        tma_load_2d(sk, &tmK, &k_full[s], kvh * HD, row);
+        tma_load_2d(sk + CHUNK_BYTES, &tmK, &k_full[s], kvh * HD + 64, row);
+      };
+      if (ntiles > 0) load_k(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) load_k(j + 1);  // K runs one tile ahead of V
+        const int s = j % VST;
+        mbar_wait(&v_empty[s], ((j / VST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+        uint8_t* sv = smem + OFF_V + s * TILE_BYTES;
+        const int row = b * p.sk + j * BN;
+        tma_load_2d(sv, &tmV, &v_full[s], kvh * HD, row);
+        tma_load_2d(sv + CHUNK_BYTES, &tmV, &v_full[s], kvh * HD + 64, row);
       }
     }
   } else if (warp == 1) {
@@ -120,36 +135,36 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(BM, HD, 0, 1);
       const uint32_t sq_addr = smem_u32(smem + OFF_Q);
-      const uint32_t sp_addr = smem_u32(smem + OFF_P);
       auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        const int s = j % KST, sb = j & 1;
+        mbar_wait(&k_full[s], (j / KST) & 1);
         tc_fence_after();
-        const uint32_t sk_addr = smem_u32(smem + OFF_KV + s * 2 * TILE_BYTES);
+        const uint32_t sk_addr = smem_u32(smem + OFF_K + s * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           const uint32_t o = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
-          umma_bf16(TM_S + s * BN, make_smem_desc(sq_addr + o, 16, 1024),
+          umma_bf16(TM_S + sb * BN, make_smem_desc(sq_addr + o, 16, 1024),
                     make_smem_desc(sk_addr + o, 16, 1024), idesc_s, k != 0);
         }
-        umma_commit(&s_full[s]);
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[s]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_s(j + 1);
+        mbar_wait(&v_full[j % VST], (j / VST) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t sv_addr = smem_u32(smem + OFF_KV + (j & 1) * 2 * TILE_BYTES + TILE_BYTES);
+        const uint32_t sv_addr = smem_u32(smem + OFF_V + (j % VST) * TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < BN / 16; ++k) {
-          const uint32_t oa = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;  // P: K-major over keys
-          umma_bf16(TM_O, make_smem_desc(sp_addr + oa, 16, 1024),
-                    make_smem_desc(sv_addr + k * 2048, CHUNK_BYTES, 1024), idesc_pv,
-                    (j | k) != 0);
+          // A = P_j in TMEM, written by the softmax warps over the first 64 columns of S[j&1]
+          umma_bf16_ts(TM_O, TM_S + (j & 1) * BN + k * 8,
+                       make_smem_desc(sv_addr + k * 2048, CHUNK_BYTES, 1024), idesc_pv, (j | k) != 0);
         }
         umma_commit(pv_done);
-        umma_commit(&kv_empty[j & 1]);
+        umma_commit(&v_empty[j % VST]);
       }
     }
   } else {
@@ -161,7 +176,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
     float m_used = -INFINITY, l = 0.f;
-    uint8_t* prow = smem + OFF_P + half * CHUNK_BYTES + row * 128;
     float* xchg = reinterpret_cast<float*>(smem + OFF_X);  // [2 parity][2 half][128 rows] + [2][128]
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j & 1;
@@ -173,18 +187,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld_wait();
       const int j0 = j * BN + half * 64;
       const bool need_mask = (j * BN + BN > p.sk) || (CAUSAL && (j * BN + BN - 1 > q0 + off));
-      float mx = -INFINITY;  // max of the RAW scores; scaled once (scale > 0)
       if (need_mask) {
         const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;  // last visible key
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
+        for (int c = 0; c < 64; ++c)
           if (j0 + c > lim) r[c] = 0xff800000u;  // -inf
-          mx = fmaxf(mx, __uint_as_float(r[c]));
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
       }
+      // max of the RAW scores (scaled once, scale > 0); four independent chains for ILP
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(r[c + e]));
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       xchg[(sb * 2 + half) * 128 + row] = mx;
       named_bar_sync(1, 256);
       mx = fmaxf(mx, xchg[(sb * 2 + (half ^ 1)) * 128 + row]) * sl2;
@@ -198,38 +214,39 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       // exponentials first (registers only) so they overlap the PV MMA of the previous tile
       const float mb = (m_used == -INFINITY) ? 0.f : m_used;
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float pv = ex2_approx(fmaf(__uint_as_float(r[c]), sl2, -mb));
-        sum += pv;
-        r[c] = __float_as_uint(pv);
-      }
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} finished: O and the P buffer are ours
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, upd)) {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(TM_O + lane_addr + half * 64 + c * 32, o);
-            tmem_ld_wait();
+      for (int c = 0; c < 64; c += 4) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(TM_O + lane_addr + half * 64 + c * 32, o);
-          }
-          tmem_st_wait();
+        for (int e = 0; e < 4; ++e) {
+          const float pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
+          sum4[e] += pv;
+          r[c + e] = __float_as_uint(pv);
         }
       }
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (j > 0 && __any_sync(0xffffffffu, upd)) {
+        mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} finished: O may be rescaled
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(TM_O + lane_addr + half * 64 + c * 32, o);
+          tmem_ld_wait();
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {  // 16-byte units of 8 keys
-        float pv[8];
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(TM_O + lane_addr + half * 64 + c * 32, o);
+        }
+      }
+      // P_j (bf16 pairs) overwrites this thread pair's own scores in TMEM: columns [0,64) of S[sb]
+      {
+        uint32_t w[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pv[i] = __uint_as_float(r[u * 8 + i]);
-        *reinterpret_cast<uint4*>(prow + ((u ^ (row & 7)) << 4)) = pack8(pv);
+        for (int i = 0; i < 32; ++i) w[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+        tmem_st32(TM_S + lane_addr + sb * BN + half * 32, w);
+        tmem_st_wait();
       }
       l += sum;
-      fence_proxy_async();  // generic-proxy smem writes → visible to the tensor-core (async) proxy
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -533,7 +550,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
     }
-    // epilogue: each warp of a pair writes 64 of the 128 head-dim columns
+    // epilogue: each of the four warps sharing a lane quarter writes 32 of the 128 head-dim columns
     if (nit > 0) {
       mbar_wait(pds_empty, (nit - 1) & 1);
       tc_fence_after();
