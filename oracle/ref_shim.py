@@ -108,10 +108,6 @@ def load():
     return out
 
 
-class _ExplicitCLIP:
-    """Serves output_hidden_states with an explicit layer loop (SURVEY.md §0.9a hazard)."""
-
-
 def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True, seed_fn=None):
     """Instantiate the reference's own OlaLlava*/Llava* class on a (tiny or full) config.
 
@@ -134,8 +130,8 @@ def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True
         tower = CLIPVisionModel(vis_cfg)
         tower.requires_grad_(False)
 
-        orig_forward = tower.forward
-
+        # explicit layer loop: the hook-based hidden-state capture of transformers 5.x double-registers
+        # on the nested tower after the first full-model forward
         def explicit_forward(pixel_values, output_hidden_states=False, **kw):
             vm = tower.vision_model
             hs = vm.embeddings(pixel_values)

@@ -115,15 +115,18 @@ class DecoderLayerFn(torch.autograd.Function):
         nig = ctx.needs_input_grad
         g = [None] * 11
 
+        def dgrad(dy, w, wt):  # dY·W: K-major frozen copy Wᵀ when available, else MN-major descriptor
+            return ops.gemm(dy, wt) if wt is not None else ops.gemm(dy, w, b_layout=1)
+
         # ---- MLP: x3 = x2 + down(swiglu(gate_up(rmsnorm(x2)))) ----
-        dh = ops.gemm(dx3, wd, b_layout=1)
+        dh = dgrad(dx3, wd, meta.wdT)
         if nig[9]:
             hh = ops.swiglu_fwd(gu)
             g[9] = ops.gemm(dx3, hh, a_layout=1, b_layout=1)
             del hh
         dgu = ops.swiglu_bwd(gu, dh)
         del dh
-        dn2 = ops.gemm(dgu, wgu, b_layout=1)
+        dn2 = dgrad(dgu, wgu, meta.wguT)
         if nig[7] or nig[8]:
             h2, _ = ops.rmsnorm_fwd(x2, n2, eps)
             dwgu = ops.gemm(dgu, h2, a_layout=1, b_layout=1)
@@ -139,7 +142,7 @@ class DecoderLayerFn(torch.autograd.Function):
         del dn2
 
         # ---- attention: x2 = x + o_proj(attn(rope(qkv(rmsnorm(x))))) ----
-        do = ops.gemm(dx2, wo, b_layout=1)
+        do = dgrad(dx2, wo, meta.woT)
         if nig[5]:
             g[5] = ops.gemm(dx2, o, a_layout=1, b_layout=1)
         dqkv = torch.empty_like(qkv)
@@ -147,7 +150,7 @@ class DecoderLayerFn(torch.autograd.Function):
                      dqkv[:, qw:qw + kw], dqkv[:, qw + kw:], B, H, KVH, T, T, hd, hd ** -0.5, True)
         del do
         ops.rope_(dqkv, T, meta.cos, meta.sin, H + KVH, hd, inverse=True, pos_ids=meta.pos_ids)
-        dn1 = ops.gemm(dqkv, wqkv, b_layout=1)
+        dn1 = dgrad(dqkv, wqkv, meta.wqkvT)
         if nig[2] or nig[3] or nig[4]:
             h1, _ = ops.rmsnorm_fwd(x, n1, eps)
             dwqkv = ops.gemm(dqkv, h1, a_layout=1, b_layout=1)
@@ -172,7 +175,7 @@ class LMHeadCEFn(torch.autograd.Function):
     the forward pass and only scaled by grad_output in backward."""
 
     @staticmethod
-    def forward(ctx, hidden, w, labels, T, chunk_rows):
+    def forward(ctx, hidden, w, labels, T, chunk_rows, wt=None):
         M, D = hidden.shape
         V = w.shape[0]
         dev = hidden.device
@@ -189,7 +192,10 @@ class LMHeadCEFn(torch.autograd.Function):
             ops.gemm(hidden[r0:r1], w, out=lg)
             ops.ce_fwd_bwd_(lg, labels, r0, T, row_loss, count, 1.0, need_dh or need_dw, shift=True)
             if need_dh:
-                ops.gemm(lg, w, b_layout=1, out=dh[r0:r1])
+                if wt is not None:
+                    ops.gemm(lg, wt, out=dh[r0:r1])
+                else:
+                    ops.gemm(lg, w, b_layout=1, out=dh[r0:r1])
             if need_dw:
                 if dw is None:
                     dw = ops.gemm(lg, hidden[r0:r1], a_layout=1, b_layout=1)
@@ -205,7 +211,7 @@ class LMHeadCEFn(torch.autograd.Function):
         gout = gout.contiguous().float()
         gh = ops.scale_dev(dh, gout) if dh is not None else None
         gw = ops.scale_dev(dw, gout) if dw is not None else None
-        return gh, gw, None, None, None
+        return gh, gw, None, None, None, None
 
 
 def lm_head_logits(hidden, w):

@@ -83,6 +83,26 @@ class FusedRows:
         return self.fused
 
 
+class FrozenTranspose:
+    """K-major copy Wᵀ of a FROZEN weight for the dgrad GEMM (dY·W): trades HBM capacity (the PT stage
+    freezes the whole LLM) for the faster K-major B operand.  Trainable weights use
+    the MN-major descriptor path instead (no copy to keep in sync)."""
+
+    def __init__(self):
+        self.key = None
+        self.wt = None
+
+    def get(self, w):
+        if w.requires_grad:
+            return None
+        key = (w.data_ptr(), w._version, tuple(w.shape))
+        if self.key != key:
+            with torch.no_grad():
+                self.wt = ops.transpose(w.detach())
+            self.key = key
+        return self.wt
+
+
 # ------------------------------------------------------------------------------------------------ decoder
 class Attention(nn.Module):
     def __init__(self, cfg, device):
@@ -122,6 +142,9 @@ class DecoderLayer(nn.Module):
             a, m = self.self_attn, self.mlp
             self._qkv = FusedRows([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight])
             self._gu = FusedRows([m.gate_proj.weight, m.up_proj.weight])
+        self._t = [FrozenTranspose() for _ in range(4)]
+        # measured on B200: no gain inside the (power-capped) step, costs +14 GB → off by default
+        self.use_frozen_transposes = False
 
     def run(self, x, meta_base):
         a, m = self.self_attn, self.mlp
@@ -134,6 +157,16 @@ class DecoderLayer(nn.Module):
             wg, wu = m.gate_proj.weight, m.up_proj.weight
         meta = SimpleNamespace(**vars(meta_base))
         meta.wqkv, meta.wgu = wqkv.detach(), wgu.detach()
+        meta.wqkvT = meta.woT = meta.wguT = meta.wdT = None
+        if self.use_frozen_transposes and torch.is_grad_enabled():
+            frozen_qkv = not (wq.requires_grad or (wk is not None and (wk.requires_grad or wv.requires_grad)))
+            frozen_gu = not (wg.requires_grad or (wu is not None and wu.requires_grad))
+            if frozen_qkv:
+                meta.wqkvT = self._t[0].get(meta.wqkv)
+            meta.woT = self._t[1].get(a.o_proj.weight)
+            if frozen_gu:
+                meta.wguT = self._t[2].get(meta.wgu)
+            meta.wdT = self._t[3].get(m.down_proj.weight)
         return A.DecoderLayerFn.apply(x, self.input_layernorm.weight, wq, wk, wv, a.o_proj.weight,
                                       self.post_attention_layernorm.weight, wg, wu, m.down_proj.weight,
                                       meta)

@@ -650,7 +650,11 @@ class VisperForCausalLM(nn.Module):
             labels = labels.to(hidden.device).contiguous()
             V = self.config.vocab_size
             chunk = max(1024, min(B * T, (1 << 31) // V))
-            text_loss = A.LMHeadCEFn.apply(hidden, self.lm_head.weight, labels, T, chunk)
+            if not hasattr(self, "_lm_head_t"):
+                self._lm_head_t = M.FrozenTranspose()
+            wt = (self._lm_head_t.get(self.lm_head.weight)
+                  if (torch.is_grad_enabled() and getattr(self.config, "frozen_transposes", False)) else None)
+            text_loss = A.LMHeadCEFn.apply(hidden, self.lm_head.weight, labels, T, chunk, wt)
         if labels is None or self.config.materialize_logits:
             with torch.no_grad():
                 logits = A.lm_head_logits(hidden.detach(), self.lm_head.weight).view(B, T, -1)
