@@ -57,6 +57,18 @@ int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const void* B, int64
                   const void* bias, const void* residual, int64_t ldr, void* aux, int64_t ldaux,
                   void* stream);
 
+/* Fused SwiGLU epilogues of the MLP GEMMs (HF LlamaMLP / Phi3MLP: down(silu(gate(x))·up(x)),
+ * called through ola_llama.py:105).  Wgu is the fused [2F, K] gate|up weight (gate rows first).
+ * fwd: gu[M,2F] = A·Wguᵀ (stored when gu != NULL, needed by the backward) and h[M,F] = silu(g)·u in
+ *      one launch; F % 128 == 0.
+ * bwd: dgu[M,2F] = swiglu'(gu) ∘ (dY·W), W = down_proj weight: b_layout 1 → [K, F] as stored by
+ *      nn.Linear (read MN-major), b_layout 0 → a K-major transposed copy [F, K]. */
+int vpb_gemm_swiglu_fwd(const void* A, int64_t lda, const void* Wgu, int64_t ldw, void* gu,
+                        int64_t ldgu, void* h, int64_t ldh, int M, int F, int K, void* stream);
+int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, int64_t ldw, int b_layout,
+                        const void* gu, int64_t ldgu, void* dgu, int64_t lddgu, int M, int F, int K,
+                        void* stream);
+
 /* ---- normalisation -------------------------------------------------------------------------
  * HF LlamaRMSNorm / Phi3RMSNorm (eps 1e-5) and nn.LayerNorm (CLIP, resampler.py). */
 int vpb_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd,

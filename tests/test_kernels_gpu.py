@@ -91,6 +91,32 @@ def test_gemm_strided_views():
     assert outbuf[:, :128].abs().max().item() == 0 and outbuf[:, 512:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("M,F,K", [(200, 128, 64), (1000, 384, 200), (2048, 1792, 512), (4096, 14336, 256)])
+def test_gemm_swiglu_fused(M, F, K):
+    """SwiGLU in the GEMM epilogues: bit-identical to the separate GEMM + swiglu kernels."""
+    from visper_lm_b200 import ops
+    x = rnd(M, K, seed=31, scale=0.5)
+    wgu = rnd(2 * F, K, seed=32, scale=0.2)
+    wd = rnd(K, F, seed=33, scale=0.2)       # down_proj [D, F]
+    dy = rnd(M, K, seed=34)
+    gu_ref = ops.gemm(x, wgu)
+    h_ref = ops.swiglu_fwd(gu_ref)
+    h, gu = ops.gemm_swiglu_fwd(x, wgu)
+    torch.cuda.synchronize()
+    assert torch.equal(gu, gu_ref), "fused gate|up differs from the plain GEMM"
+    assert torch.equal(h, h_ref), "fused silu(g)*u differs from swiglu_fwd"
+    g, u = gu.float()[:, :F], gu.float()[:, F:]
+    close(h, torch.nn.functional.silu(g) * u, name="swiglu fwd vs torch")
+    h2, none = ops.gemm_swiglu_fwd(x, wgu, want_gu=False)
+    assert none is None and torch.equal(h2, h_ref)
+    dgu_ref = ops.swiglu_bwd(gu_ref, ops.gemm(dy, wd, b_layout=1))
+    dgu = ops.gemm_swiglu_bwd(dy, wd, gu, b_layout=1)
+    dgu_t = ops.gemm_swiglu_bwd(dy, wd.t().contiguous(), gu, b_layout=0)
+    torch.cuda.synchronize()
+    assert torch.equal(dgu, dgu_ref), "fused swiglu backward (MN-major W) differs"
+    assert torch.equal(dgu_t, dgu_ref), "fused swiglu backward (K-major Wt) differs"
+
+
 # ------------------------------------------------------------------------------------------- norms
 @pytest.mark.parametrize("M,D", [(37, 128), (512, 4096), (100, 3072), (64, 1024)])
 def test_rmsnorm(M, D):

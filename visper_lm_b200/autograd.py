@@ -93,9 +93,12 @@ class DecoderLayerFn(torch.autograd.Function):
                               hd ** -0.5, True)
         x2 = ops.gemm(o, wo, residual=x)
         h2, rstd2 = ops.rmsnorm_fwd(x2, n2, eps)
-        gu = ops.gemm(h2, wgu)
+        if ops.FUSE_SWIGLU and wgu.shape[0] % 256 == 0:
+            hh, gu = ops.gemm_swiglu_fwd(h2, wgu)  # SwiGLU in the GEMM epilogue
+        else:
+            gu = ops.gemm(h2, wgu)
+            hh = ops.swiglu_fwd(gu)
         del h2
-        hh = ops.swiglu_fwd(gu)
         x3 = ops.gemm(hh, wd, residual=x2)
         ctx.meta = meta
         ctx.split_qkv = wk is not None
@@ -119,13 +122,17 @@ class DecoderLayerFn(torch.autograd.Function):
             return ops.gemm(dy, wt) if wt is not None else ops.gemm(dy, w, b_layout=1)
 
         # ---- MLP: x3 = x2 + down(swiglu(gate_up(rmsnorm(x2)))) ----
-        dh = dgrad(dx3, wd, meta.wdT)
         if nig[9]:
             hh = ops.swiglu_fwd(gu)
             g[9] = ops.gemm(dx3, hh, a_layout=1, b_layout=1)
             del hh
-        dgu = ops.swiglu_bwd(gu, dh)
-        del dh
+        if ops.FUSE_SWIGLU:  # dgrad of down_proj with the SwiGLU derivative in its epilogue
+            dgu = (ops.gemm_swiglu_bwd(dx3, meta.wdT, gu, b_layout=0) if meta.wdT is not None
+                   else ops.gemm_swiglu_bwd(dx3, wd, gu, b_layout=1))
+        else:
+            dh = dgrad(dx3, wd, meta.wdT)
+            dgu = ops.swiglu_bwd(gu, dh)
+            del dh
         dn2 = dgrad(dgu, wgu, meta.wguT)
         if nig[7] or nig[8]:
             h2, _ = ops.rmsnorm_fwd(x2, n2, eps)
@@ -175,13 +182,22 @@ class LMHeadCEFn(torch.autograd.Function):
     the forward pass and only scaled by grad_output in backward."""
 
     @staticmethod
-    def forward(ctx, hidden, w, labels, T, chunk_rows, wt=None):
-        M, D = hidden.shape
+    def forward(ctx, hidden, w, labels, T, chunk_rows, wt=None, compact=None):
+        M_full, D = hidden.shape
         V = w.shape[0]
         dev = hidden.device
         need_dh = hidden.requires_grad
         need_dw = w.requires_grad
-        count = ops.ce_count(labels, T, shift=True)
+        shift = True
+        inv = None
+        if compact is not None:
+            # score only the rows whose shifted label is not -100 (host-built index, no sync):
+            # the others add nothing to the loss or to any gradient
+            rows, labels, inv, _ = compact
+            hidden = ops.gather_rows(rows, [hidden], D)
+            shift, T = False, 1
+        M = hidden.shape[0]
+        count = ops.ce_count(labels, T, shift=shift)
         row_loss = torch.empty((M,), dtype=torch.float32, device=dev)
         dh = torch.empty((M, D), dtype=BF16, device=dev) if need_dh else None
         dw = None
@@ -190,7 +206,7 @@ class LMHeadCEFn(torch.autograd.Function):
             r1 = min(M, r0 + chunk_rows)
             lg = logits[: r1 - r0]
             ops.gemm(hidden[r0:r1], w, out=lg)
-            ops.ce_fwd_bwd_(lg, labels, r0, T, row_loss, count, 1.0, need_dh or need_dw, shift=True)
+            ops.ce_fwd_bwd_(lg, labels, r0, T, row_loss, count, 1.0, need_dh or need_dw, shift=shift)
             if need_dh:
                 if wt is not None:
                     ops.gemm(lg, wt, out=dh[r0:r1])
@@ -202,6 +218,8 @@ class LMHeadCEFn(torch.autograd.Function):
                 else:
                     ops.gemm(lg, hidden[r0:r1], a_layout=1, b_layout=1, residual=dw, out=dw)
         loss = ops.ce_finalize(row_loss, count)
+        if inv is not None and dh is not None:
+            dh = ops.gather_rows(inv, [dh], D)  # back to all rows; unscored rows get zero gradient
         ctx.save_for_backward(dh, dw)
         return loss
 
@@ -211,7 +229,7 @@ class LMHeadCEFn(torch.autograd.Function):
         gout = gout.contiguous().float()
         gh = ops.scale_dev(dh, gout) if dh is not None else None
         gw = ops.scale_dev(dw, gout) if dw is not None else None
-        return gh, gw, None, None, None, None
+        return gh, gw, None, None, None, None, None
 
 
 def lm_head_logits(hidden, w):

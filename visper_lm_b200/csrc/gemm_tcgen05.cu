@@ -28,7 +28,17 @@ struct GemmArgs {
   int64_t ldaux;
   int M, N, K;
   int act;  // VPB_ACT_*
+  int F;    // SwiGLU epilogues: width of one half of the packed gate|up buffer
 };
+
+// Epilogue variants.  EPI_SWIGLU_FWD: the B tile is 128 gate rows + 128 up rows of the fused
+// gate|up weight, so accumulator columns [0,128) / [128,256) hold gate / up of the SAME 128 output
+// columns; the epilogue writes h = silu(g)·u to C and (optionally) the bf16 g|u pair to aux.
+// EPI_SWIGLU_BWD: the accumulator is dh = dY·W_down; the epilogue reads the saved g|u from aux and
+// writes d_gate | d_up to C.  Both replace a full extra pass over [M, 2F] in HBM.
+constexpr int EPI_STD = 0;
+constexpr int EPI_SWIGLU_FWD = 1;
+constexpr int EPI_SWIGLU_BWD = 2;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -47,7 +57,7 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EPI = EPI_STD>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
@@ -70,7 +80,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int lane = threadIdx.x & 31;
 
   const int num_m = (args.M + BM - 1) / BM;
-  const int num_n = (args.N + BN - 1) / BN;
+  constexpr int BNO = (EPI == EPI_SWIGLU_FWD) ? BN / 2 : BN;  // output columns per tile
+  const int num_n = (args.N + BNO - 1) / BNO;
   const int num_tiles = num_m * num_n;
   const int num_kb = (args.K + BK - 1) / BK;
 
@@ -111,7 +122,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int mb, nb;
         decode_tile(t, mb, nb);
-        const int m0 = mb * BM, n0 = nb * BN;
+        const int m0 = mb * BM, n0 = nb * BNO;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -126,7 +137,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             for (int c = 0; c < BM / 64; ++c)
               tma_load_2d(sa + c * 8192, &tmA, &full[s], m0 + c * 64, kb * BK);
           }
-          if constexpr (!B_MN) {
+          if constexpr (EPI == EPI_SWIGLU_FWD) {
+            static_assert(EPI != EPI_SWIGLU_FWD || (!B_MN && BN == 256), "swiglu fwd: K-major B, BN 256");
+            tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);                       // gate rows
+            tma_load_2d(sb + BNO * BK * 2, &tmB, &full[s], kb * BK, args.F + n0);  // up rows
+          } else if constexpr (!B_MN) {
             tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
           } else {
 #pragma unroll
@@ -184,6 +199,78 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       bf16* crow = args.C + (int64_t)row * args.ldc;
       const bf16* rrow = args.res ? args.res + (int64_t)row * args.ldr : nullptr;
       bf16* xrow = args.aux ? args.aux + (int64_t)row * args.ldaux : nullptr;
+      if constexpr (EPI == EPI_SWIGLU_FWD) {
+#pragma unroll 1
+        for (int c = 0; c < BNO / 32; ++c) {
+          const int n_base = nb * BNO + c * 32;
+          uint32_t rg[32], ru[32];
+          tmem_ld32(taddr + c * 32, rg);
+          tmem_ld32(taddr + BNO + c * 32, ru);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = n_base + g * 8;
+              float gv[8], uv[8], o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                gv[j] = __uint_as_float(rg[g * 8 + j]);
+                uv[j] = __uint_as_float(ru[g * 8 + j]);
+              }
+              // round to bf16 first: h is then bit-identical to swiglu_fwd_kernel on the stored g|u
+              const uint4 pg = pack8(gv), pu = pack8(uv);
+              if (xrow) {
+                stg16(xrow + n, pg);
+                stg16(xrow + args.F + n, pu);
+              }
+              unpack8(pg, gv);
+              unpack8(pu, uv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = gv[j] / (1.f + __expf(-gv[j])) * uv[j];
+              stg16(crow + n, pack8(o));
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_SWIGLU_BWD) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n_base = nb * BN + c * 32;
+          if (n_base >= args.N) break;  // warp-uniform
+          uint4 lg[4], lu[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n_base + g * 8;
+            if (row_ok && n + 8 <= args.N) {
+              lg[g] = ldg16_stream(xrow + n);
+              lu[g] = ldg16_stream(xrow + args.F + n);
+            }
+          }
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n_base + g * 8;
+            if (row_ok && n + 8 <= args.N) {
+              float d[8], gv[8], uv[8], dg[8], du[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d[j] = __uint_as_float(r[g * 8 + j]);
+              unpack8(pack8(d), d);  // dh rounded to bf16 as the unfused dgrad GEMM would store it
+              unpack8(lg[g], gv);
+              unpack8(lu[g], uv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float sg = 1.f / (1.f + __expf(-gv[j]));
+                const float silu = gv[j] * sg;
+                du[j] = d[j] * silu;
+                dg[j] = d[j] * uv[j] * (sg + silu * (1.f - sg));
+              }
+              stg16(crow + n, pack8(dg));
+              stg16(crow + args.F + n, pack8(du));
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n_base = nb * BN + c * 32;
@@ -220,6 +307,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             }
           }
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -283,18 +371,19 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EPI = EPI_STD>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
                        cudaStream_t stream) {
   constexpr int STAGES = (BN == 256) ? 4 : 6;
   constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
     VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  const int tiles = ((args.M + BM - 1) / BM) * ((args.N + BN - 1) / BN);
+  constexpr int BNO = (EPI == EPI_SWIGLU_FWD) ? BN / 2 : BN;
+  const int tiles = ((args.M + BM - 1) / BM) * ((args.N + BNO - 1) / BNO);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, 192, SMEM, stream>>>(tmA, tmB, args);
   VPB_LAUNCH_OK();
@@ -348,6 +437,7 @@ extern "C" int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const voi
   args.N = N;
   args.K = K;
   args.act = act;
+  args.F = 0;
 
   const int key = (bn256 ? 4 : 0) | (a_layout ? 2 : 0) | (b_layout ? 1 : 0);
   switch (key) {
@@ -360,4 +450,68 @@ extern "C" int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const voi
     case 6: return launch_gemm<256, true, false>(tmA, tmB, args, stream);
     default: return launch_gemm<256, true, true>(tmA, tmB, args, stream);
   }
+}
+
+// gu[M,2F] = A·Wguᵀ (optional store) and h[M,F] = silu(gate)·up in ONE launch.
+extern "C" int vpb_gemm_swiglu_fwd(const void* A, int64_t lda, const void* Wgu, int64_t ldw,
+                                   void* gu, int64_t ldgu, void* h, int64_t ldh, int M, int F,
+                                   int K, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VPB_CHECK(M > 0 && F > 0 && K > 0, "gemm_swiglu_fwd: empty problem M=%d F=%d K=%d", M, F, K);
+  VPB_CHECK(F % 128 == 0, "gemm_swiglu_fwd: F=%d must be a multiple of 128", F);
+  VPB_CHECK(ldh % 8 == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0, "gemm_swiglu_fwd: h alignment");
+  VPB_CHECK(!gu || (ldgu % 8 == 0 && (reinterpret_cast<uintptr_t>(gu) & 15) == 0),
+            "gemm_swiglu_fwd: gu alignment");
+  CUtensorMap tmA, tmB;
+  if (make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return -1;
+  if (make_tmap_2d(&tmB, Wgu, (uint64_t)K, (uint64_t)(2 * (int64_t)F), (uint64_t)ldw, BK, 128)) return -1;
+  GemmArgs args;
+  args.C = static_cast<bf16*>(h);
+  args.ldc = ldh;
+  args.bias = nullptr;
+  args.res = nullptr;
+  args.ldr = 0;
+  args.aux = static_cast<bf16*>(gu);
+  args.ldaux = ldgu;
+  args.M = M;
+  args.N = F;
+  args.K = K;
+  args.act = VPB_ACT_NONE;
+  args.F = F;
+  return launch_gemm<256, false, false, EPI_SWIGLU_FWD>(tmA, tmB, args, stream);
+}
+
+// dgu[M,2F] = swiglu'(gu) ∘ (dY·W) where W is the down projection: b_layout 1 → W is [K=D, F]
+// (the nn.Linear weight read MN-major), b_layout 0 → W is a K-major transposed copy [F, D].
+extern "C" int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, int64_t ldw,
+                                   int b_layout, const void* gu, int64_t ldgu, void* dgu,
+                                   int64_t lddgu, int M, int F, int K, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VPB_CHECK(M > 0 && F > 0 && K > 0, "gemm_swiglu_bwd: empty problem M=%d F=%d K=%d", M, F, K);
+  VPB_CHECK(F % 8 == 0, "gemm_swiglu_bwd: F=%d must be a multiple of 8", F);
+  VPB_CHECK(gu && dgu && ldgu % 8 == 0 && lddgu % 8 == 0 &&
+                (reinterpret_cast<uintptr_t>(gu) & 15) == 0 && (reinterpret_cast<uintptr_t>(dgu) & 15) == 0,
+            "gemm_swiglu_bwd: gu/dgu alignment");
+  CUtensorMap tmA, tmB;
+  if (make_tmap_2d(&tmA, dY, (uint64_t)K, (uint64_t)M, (uint64_t)lddy, BK, BM)) return -1;
+  if (b_layout == 0) {
+    if (make_tmap_2d(&tmB, W, (uint64_t)K, (uint64_t)F, (uint64_t)ldw, BK, 256)) return -1;
+  } else {
+    if (make_tmap_2d(&tmB, W, (uint64_t)F, (uint64_t)K, (uint64_t)ldw, 64, BK)) return -1;
+  }
+  GemmArgs args;
+  args.C = static_cast<bf16*>(dgu);
+  args.ldc = lddgu;
+  args.bias = nullptr;
+  args.res = nullptr;
+  args.ldr = 0;
+  args.aux = const_cast<bf16*>(static_cast<const bf16*>(gu));
+  args.ldaux = ldgu;
+  args.M = M;
+  args.N = F;
+  args.K = K;
+  args.act = VPB_ACT_NONE;
+  args.F = F;
+  if (b_layout == 0) return launch_gemm<256, false, false, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
+  return launch_gemm<256, false, true, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
 }

@@ -227,6 +227,23 @@ class SplicePlan:
         self.np = dict(kind=flat_kind, index=flat_index, inv_img=inv_img, inv_task=inv_task,
                        embed_scatter=embed_scatter, labels=out_lab, mask=mask)
         self.all_valid = bool(mask.all())
+        # Rows that carry a next-token target (shifted label != -100): lm_head + CE run on these
+        # only — ignored rows contribute neither loss nor gradient (ola_llama.py:126-136).
+        shifted = np.full((B, T), IGNORE_INDEX, np.int64)
+        shifted[:, :-1] = out_lab[:, 1:]
+        shifted = shifted.reshape(-1)
+        valid = np.nonzero(shifted != IGNORE_INDEX)[0].astype(np.int32)
+        inv = np.full(B * T, -1, np.int32)
+        inv[valid] = np.arange(len(valid), dtype=np.int32)
+        self.np.update(ce_rows=valid, ce_targets=shifted[valid], ce_inv=inv)
+        self.n_ce_rows = int(len(valid))
+
+    def ce_compaction(self):
+        """(rows, targets, inverse, n) device index tensors for the label-carrying rows, or None when
+        compaction would not pay (nearly every row is scored, or none is)."""
+        if self.n_ce_rows == 0 or self.n_ce_rows > 0.9 * self.B * self.T:
+            return None
+        return self.ce_rows, self.ce_targets, self.ce_inv, self.n_ce_rows
 
     def to(self, device):
         n = self.np
@@ -238,6 +255,7 @@ class SplicePlan:
             self.B_cols = n["inv_task"].shape[1]
         self.labels = t(n["labels"])
         self.mask = t(n["mask"])
+        self.ce_rows, self.ce_targets, self.ce_inv = t(n["ce_rows"]), t(n["ce_targets"]), t(n["ce_inv"])
         return self
 
 
@@ -647,14 +665,19 @@ class VisperForCausalLM(nn.Module):
         hidden = states[-1]
         loss = text_loss = logits = None
         if labels is not None:
-            labels = labels.to(hidden.device).contiguous()
+            if labels.device != hidden.device or not labels.is_contiguous():
+                labels = labels.to(hidden.device).contiguous()
             V = self.config.vocab_size
             chunk = max(1024, min(B * T, (1 << 31) // V))
             if not hasattr(self, "_lm_head_t"):
                 self._lm_head_t = M.FrozenTranspose()
             wt = (self._lm_head_t.get(self.lm_head.weight)
                   if (torch.is_grad_enabled() and getattr(self.config, "frozen_transposes", False)) else None)
-            text_loss = A.LMHeadCEFn.apply(hidden, self.lm_head.weight, labels, T, chunk, wt)
+            plan = getattr(self, "_last_plan", None)
+            compact = (plan.ce_compaction() if (plan is not None and labels is plan.labels
+                                                and getattr(self.config, "skip_ignored_ce_rows", True))
+                       else None)
+            text_loss = A.LMHeadCEFn.apply(hidden, self.lm_head.weight, labels, T, chunk, wt, compact)
         if labels is None or self.config.materialize_logits:
             with torch.no_grad():
                 logits = A.lm_head_logits(hidden.detach(), self.lm_head.weight).view(B, T, -1)

@@ -7,6 +7,7 @@ only the allocator / stream provider; there is no torch compute and no CPU fallb
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -95,6 +96,60 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None
         ev1.record()
         timer.records.append((ev0, ev1, 2.0 * M * N * K))
     return (out, pre) if want_pre else out
+
+
+# A/B switch for the fused SwiGLU GEMM epilogues (VPB_FUSE_SWIGLU=0 selects the separate kernels)
+FUSE_SWIGLU = os.environ.get("VPB_FUSE_SWIGLU", "1") != "0"
+
+
+def _timed(flops):
+    timer = GEMM_TIMER
+    if timer is None:
+        return None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    return timer, ev0, ev1, flops
+
+
+def _timed_end(t):
+    if t is not None:
+        timer, ev0, ev1, flops = t
+        ev1.record()
+        timer.records.append((ev0, ev1, flops))
+
+
+def gemm_swiglu_fwd(a, wgu, want_gu=True):
+    """(h, gu): gu[M,2F] = a·wguᵀ (None unless want_gu) and h[M,F] = silu(gate)·up, one launch."""
+    M, K = a.shape
+    F2, Kb = wgu.shape
+    F = F2 // 2
+    assert K == Kb and F % 128 == 0
+    h = torch.empty((M, F), dtype=BF16, device=a.device)
+    gu = torch.empty((M, F2), dtype=BF16, device=a.device) if want_gu else None
+    pa, lda = _rows(a)
+    pw, ldw = _rows(wgu)
+    pg, ldg = _rows(gu) if gu is not None else (0, 0)
+    t = _timed(2.0 * M * F2 * K)
+    _chk(_L().vpb_gemm_swiglu_fwd(pa, lda, pw, ldw, pg, ldg, h.data_ptr(), F, M, F, K, _stream()),
+         "gemm_swiglu_fwd")
+    _timed_end(t)
+    return h, gu
+
+
+def gemm_swiglu_bwd(dy, w, gu, b_layout=1):
+    """dgu[M,2F] = swiglu'(gu) ∘ (dy·W); w is down_proj [D,F] (b_layout 1) or its transpose [F,D]."""
+    M, K = dy.shape
+    F = gu.shape[1] // 2
+    assert (w.shape == (K, F)) if b_layout == 1 else (w.shape == (F, K)), (w.shape, K, F)
+    dgu = torch.empty((M, 2 * F), dtype=BF16, device=dy.device)
+    pd, ldd = _rows(dy)
+    pw, ldw = _rows(w)
+    pg, ldg = _rows(gu)
+    t = _timed(2.0 * M * F * K)
+    _chk(_L().vpb_gemm_swiglu_bwd(pd, ldd, pw, ldw, b_layout, pg, ldg, dgu.data_ptr(), 2 * F, M, F, K,
+                                  _stream()), "gemm_swiglu_bwd")
+    _timed_end(t)
+    return dgu
 
 
 def transpose(x, out=None):
