@@ -126,7 +126,7 @@ class DecoderLayerFn(torch.autograd.Function):
             hh = ops.swiglu_fwd(gu)
             g[9] = ops.gemm(dx3, hh, a_layout=1, b_layout=1)
             del hh
-        if ops.FUSE_SWIGLU:  # dgrad of down_proj with the SwiGLU derivative in its epilogue
+        if ops.FUSE_SWIGLU_BWD:  # dgrad of down_proj with the SwiGLU derivative in its epilogue
             dgu = (ops.gemm_swiglu_bwd(dx3, meta.wdT, gu, b_layout=0) if meta.wdT is not None
                    else ops.gemm_swiglu_bwd(dx3, wd, gu, b_layout=1))
         else:

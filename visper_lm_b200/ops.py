@@ -98,8 +98,11 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None
     return (out, pre) if want_pre else out
 
 
-# A/B switch for the fused SwiGLU GEMM epilogues (VPB_FUSE_SWIGLU=0 selects the separate kernels)
+# A/B switches for the fused SwiGLU GEMM epilogues (0 selects the separate kernels).  Measured in
+# the Llama-3-8B step (call A, r01): the forward fusion is a small win, the backward one loses to
+# the separate kernel because its row-strided g|u reads are DRAM-unfriendly.
 FUSE_SWIGLU = os.environ.get("VPB_FUSE_SWIGLU", "1") != "0"
+FUSE_SWIGLU_BWD = os.environ.get("VPB_FUSE_SWIGLU_BWD", "0") != "0"
 
 
 def _timed(flops):
