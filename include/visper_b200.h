@@ -40,6 +40,7 @@ void vpb_reset_launch_count(void);
 /* process-wide kernel-selection switches (testing / A-B timing): key VPB_OPT_*, value 0/1 */
 #define VPB_OPT_ATTN_LEGACY_FWD 0 /* 1: force the mma.sync attention forward */
 #define VPB_OPT_ATTN_LEGACY_BWD 1 /* 1: force the mma.sync attention backward */
+#define VPB_OPT_ATTN_TC_BWD_V1 2   /* 1: tcgen05 attention backward without the ping-pong groups */
 int vpb_set_option(int key, int value);
 
 /* ---- GEMM: tcgen05 + TMEM + TMA ----------------------------------------------------------

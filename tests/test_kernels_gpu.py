@@ -284,6 +284,49 @@ def test_attention_tcgen05_matches_legacy(B, H, KVH, sq, sk, causal):
     assert (lse - lse_ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("B,H,KVH,sq,sk,causal", [
+    (2, 8, 2, 2048, 2048, True), (1, 4, 4, 333, 333, True), (2, 4, 2, 200, 520, False),
+    (1, 4, 1, 128, 128, True), (1, 8, 8, 1100, 1100, True), (2, 4, 2, 130, 700, True),
+    (1, 2, 1, 64, 64, False), (1, 4, 2, 1537, 1537, False)])
+def test_attention_tc_backward_v2_matches_v1_and_torch(B, H, KVH, sq, sk, causal):
+    """hd=128 backward: ping-pong (v2) tcgen05 kernels against the v1 tcgen05 kernels and torch."""
+    from visper_lm_b200 import ops
+    hd = 128
+    qw, kw = H * hd, KVH * hd
+    q = rnd(B * sq, qw, seed=57)
+    kv = rnd(B * sk, 2 * kw, seed=58)
+    do = rnd(B * sq, qw, seed=59)
+    k, v = kv[:, :kw], kv[:, kw:]
+    scale = hd ** -0.5
+    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, sq, sk, hd, scale, causal)
+
+    def bwd():
+        dq = torch.zeros_like(q)
+        dkv = torch.zeros_like(kv)
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dkv[:, :kw], dkv[:, kw:], B, H, KVH, sq, sk, hd, scale, causal)
+        torch.cuda.synchronize()
+        return dq, dkv
+
+    ops.set_option(ops.OPT_ATTN_TC_BWD_V1, 1)
+    try:
+        dq1, dkv1 = bwd()
+    finally:
+        ops.set_option(ops.OPT_ATTN_TC_BWD_V1, 0)
+    dq2, dkv2 = bwd()
+    dq2b, dkv2b = bwd()
+    assert torch.equal(dq2, dq2b) and torch.equal(dkv2, dkv2b), "v2 backward is not deterministic"
+    close(dq2, dq1, rtol=2e-2, name="dq v2 vs v1")
+    close(dkv2, dkv1, rtol=2e-2, name="dkv v2 vs v1")
+    qf = q.float().view(B, sq, H, hd).transpose(1, 2).detach().requires_grad_(True)
+    kvf = kv.float().view(B, sk, 2, KVH, hd).detach().requires_grad_(True)
+    kf = kvf[:, :, 0].transpose(1, 2).repeat_interleave(H // KVH, 1)
+    vf = kvf[:, :, 1].transpose(1, 2).repeat_interleave(H // KVH, 1)
+    ref = _attn_ref(qf, kf, vf, scale, causal).transpose(1, 2).reshape(B * sq, qw)
+    ref.backward(do.float())
+    close(dq2, qf.grad.transpose(1, 2).reshape(B * sq, qw), rtol=3e-2, name="dq v2 vs torch")
+    close(dkv2, kvf.grad.reshape(B * sk, 2 * kw), rtol=3e-2, name="dkv v2 vs torch")
+
+
 # ------------------------------------------------------------------------------------------- losses
 @pytest.mark.parametrize("B,T,V", [(2, 37, 1000), (1, 64, 128256)])
 def test_cross_entropy(B, T, V):

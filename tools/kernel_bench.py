@@ -120,6 +120,11 @@ if __name__ == "__main__":
         attn_case(8, 16, 16, 577, 64, False)
         attn_case(4, 32, 32, 2048, 96, True)
     if which == "attnprof":
+        print(json.dumps({"variant": "tc backward v2 (ping-pong)"}), flush=True)
         attn_profile()
+        ops.set_option(ops.OPT_ATTN_TC_BWD_V1, 1)
+        print(json.dumps({"variant": "tc backward v1"}), flush=True)
+        attn_profile()
+        ops.set_option(ops.OPT_ATTN_TC_BWD_V1, 0)
     if which in ("all", "norm"):
         norm_case(16384, 4096)

@@ -131,23 +131,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && ntiles > 0) {
+    if (ntiles > 0) {  // warp-uniform loop, one elected lane issues (descriptors stay uniform)
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(BM, HD, 0, 1);
-      const uint32_t sq_addr = smem_u32(smem + OFF_Q);
+      const uint64_t q_desc = make_smem_desc(smem_u32(smem + OFF_Q), 16, 1024);
+      const uint64_t k_desc0 = make_smem_desc(smem_u32(smem + OFF_K), 16, 1024);
+      const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + OFF_V), CHUNK_BYTES, 1024);  // MN-major
       auto issue_s = [&](int j) {
         const int s = j % KST, sb = j & 1;
         mbar_wait(&k_full[s], (j / KST) & 1);
         tc_fence_after();
-        const uint32_t sk_addr = smem_u32(smem + OFF_K + s * TILE_BYTES);
+        if (leader) {
+          const uint64_t k_desc = desc_adv(k_desc0, s * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t o = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
-          umma_bf16(TM_S + sb * BN, make_smem_desc(sq_addr + o, 16, 1024),
-                    make_smem_desc(sk_addr + o, 16, 1024), idesc_s, k != 0);
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint32_t o = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
+            umma_bf16(TM_S + sb * BN, desc_adv(q_desc, o), desc_adv(k_desc, o), idesc_s, k != 0);
+          }
+          umma_commit(&s_full[sb]);
+          umma_commit(&k_empty[s]);
         }
-        umma_commit(&s_full[sb]);
-        umma_commit(&k_empty[s]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -156,15 +160,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&v_full[j % VST], (j / VST) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t sv_addr = smem_u32(smem + OFF_V + (j % VST) * TILE_BYTES);
+        if (leader) {
+          const uint64_t v_desc = desc_adv(v_desc0, (j % VST) * TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k) {
-          // A = P_j in TMEM, written by the softmax warps over the first 64 columns of S[j&1]
-          umma_bf16_ts(TM_O, TM_S + (j & 1) * BN + k * 8,
-                       make_smem_desc(sv_addr + k * 2048, CHUNK_BYTES, 1024), idesc_pv, (j | k) != 0);
+          for (int k = 0; k < BN / 16; ++k) {
+            // A = P_j in TMEM, written by the softmax warps over the first 64 columns of S[j&1]
+            umma_bf16_ts(TM_O, TM_S + (j & 1) * BN + k * 8, desc_adv(v_desc, k * 2048), idesc_pv,
+                         (j | k) != 0);
+          }
+          umma_commit(pv_done);
+          umma_commit(&v_empty[j % VST]);
         }
-        umma_commit(pv_done);
-        umma_commit(&v_empty[j % VST]);
       }
     }
   } else {
@@ -519,17 +525,22 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = c4 * 4 + e;
-          float pv = ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e]));
-          if (need_mask) {
-            const int qc = q0 + half * 32 + c;
-            const bool ok = (qc < p.sq) && key_ok && (!CAUSAL || kv0 + row <= qc + off);
-            pv = ok ? pv : 0.f;
-          }
-          const float dsv = pv * (__uint_as_float(d[c]) - dlv[e]);
-          s[c] = __float_as_uint(pv);
-          d[c] = __float_as_uint(dsv);
+          s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e])));
+          d[c] = __float_as_uint(__uint_as_float(d[c]) - dlv[e]);
         }
       }
+      if (need_mask) {  // ONE warp-uniform branch per tile (a per-element branch costs 3 control
+                        // instructions + a branch-resolve stall per score: r01 ncu source view)
+        // visible queries are qc >= first_q; everything is masked for an out-of-range key row
+        const int first_q = key_ok ? (CAUSAL ? kv0 + row - off : 0) : 0x7fffffff;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int qc = q0 + half * 32 + c;
+          if (qc < first_q || qc >= p.sq) s[c] = 0u;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) d[c] = __float_as_uint(__uint_as_float(s[c]) * __uint_as_float(d[c]));
       if (it > 0) {
         mbar_wait(pds_empty, (it - 1) & 1);  // previous dV/dK MMAs finished reading P^T / dS^T
       }
@@ -735,11 +746,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const bool need_mask = !row_ok || (j0 + B_BKV > p.sk) || (CAUSAL && (j0 + B_BKV - 1 > q0 + off));
       const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float pv = ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lse2));
-        if (need_mask) pv = (row_ok && j0 + half * 32 + c <= lim) ? pv : 0.f;
-        d[c] = __float_as_uint(pv * (__uint_as_float(d[c]) - dl));
+      for (int c = 0; c < 32; ++c) s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lse2)));
+      if (need_mask) {  // one warp-uniform branch, not one per score
+        const int vis = row_ok ? lim - (j0 + half * 32) : -1;  // last visible column of this chunk
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c > vis) s[c] = 0u;
       }
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        d[c] = __float_as_uint(__uint_as_float(s[c]) * (__uint_as_float(d[c]) - dl));
       if (it > 0) mbar_wait(ds_empty, (it - 1) & 1);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -785,8 +801,590 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// =============================================================================================
+// backward v2: ping-pong softmax groups
+// =============================================================================================
+// The v1 kernels above run ONE softmax group per CTA, so every iteration is a serial chain
+// (S/dP MMA → TMEM load → exp / dS → smem → dV/dK MMA) and the tensor pipe idles ~65 % of the time
+// (profiles/r01_ncu_attn_tc_8warp.csv).  v2 splits the 8 softmax warps into two groups of 4 (one
+// warp per TMEM lane quarter) that work on ALTERNATE iterations with their own S/dP TMEM buffers
+// and their own P/dS shared-memory buffers, releases the S/dP buffers as soon as they are in
+// registers (s_free), and lets the single MMA thread POLL (mbarrier.test_wait) for whichever of
+// "next S/dP" / "next accumulate" is ready instead of issuing in a fixed order.  lse/delta of a
+// query tile are prefetched one iteration ahead.  The dQ kernel additionally pairs a heavy and a
+// light causal query tile in one CTA (balanced work, half the prologues) with dQ double-buffered
+// in TMEM.
+namespace tcb2 {
+constexpr int HD = 128;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int A_BKV = 128, A_BQ = 64, A_ST = 3;
+constexpr int A_OFF_K = 0, A_OFF_V = 32768;
+constexpr int A_OFF_QD = 65536;                      // stage s: Q (16 KB) then dO (16 KB)
+constexpr int A_OFF_PDS = A_OFF_QD + A_ST * 32768;   // group g: P^T (16 KB) then dS^T (16 KB)
+constexpr int A_OFF_LD = A_OFF_PDS + 2 * 32768;      // [2 groups][2 parity][64 lse | 64 delta] floats
+constexpr int A_OFF_BAR = A_OFF_LD + 2048;
+constexpr int A_SMEM = A_OFF_BAR + 256;              // 231 680 B: needs the 1024-aligned base
+constexpr int B_BQ = 128, B_BKV = 64, B_ST = 3;
+constexpr int B_OFF_Q = 0, B_OFF_DO = 32768;
+constexpr int B_OFF_KV = 65536;                      // stage s: K (16 KB) then V (16 KB)
+constexpr int B_OFF_DS = B_OFF_KV + B_ST * 32768;    // group g: dS [128 queries x 64 keys] 16 KB
+constexpr int B_OFF_BAR = B_OFF_DS + 2 * 16384;
+constexpr int B_SMEM = B_OFF_BAR + 256;
+}  // namespace tcb2
+
+__device__ __forceinline__ void poll_guard(uint32_t& spins, bool did) {
+  if (did) {
+    spins = 0;
+  } else if (++spins > (1u << 28)) {
+    printf("[vpb] attention MMA issuer starved (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+    __trap();
+  }
+}
+
 template <bool CAUSAL>
-static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                         const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                         const AttnTcBwdParams p) {
+  using namespace tcb2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_OFF_BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qd_full = bars + 1;     // [3]
+  uint64_t* qd_empty = bars + 4;    // [3]
+  uint64_t* sd_full = bars + 7;     // [2] S^T/dP^T of buffer b complete
+  uint64_t* s_free = bars + 9;      // [2] group b has its S^T/dP^T in registers
+  uint64_t* pds_full = bars + 11;   // [2] group b wrote P^T/dS^T
+  uint64_t* pds_empty = bars + 13;  // [2] dV/dK MMAs reading buffer b retired
+  uint64_t* all_done = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* ld_buf = reinterpret_cast<float*>(smem + A_OFF_LD);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * A_BKV;
+  const int kvh = blockIdx.y, b = blockIdx.z;
+  const int G = p.H / p.KVH;
+  const int off = p.sk - p.sq;
+  const int nq_tiles = (p.sq + A_BQ - 1) / A_BQ;
+  int qt_begin = 0;
+  if (CAUSAL) {
+    int first = kv0 - off;
+    if (first < 0) first = 0;
+    qt_begin = first / A_BQ;
+    if (qt_begin > nq_tiles) qt_begin = nq_tiles;
+  }
+  const int nper = nq_tiles - qt_begin;
+  const int nit = G * nper;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("[vpb] dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < A_ST; ++i) {
+      mbar_init(&qd_full[i], 1);
+      mbar_init(&qd_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sd_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&pds_full[i], 4);
+      mbar_init(&pds_empty[i], 1);
+    }
+    mbar_init(all_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t TM_S = tmem_base;         // S^T[2]  : 2 x 64 columns
+  const uint32_t TM_DP = tmem_base + 128;  // dP^T[2] : 2 x 64 columns
+  const uint32_t TM_DV = tmem_base + 256;  // 128 columns
+  const uint32_t TM_DK = tmem_base + 384;  // 128 columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 65536);
+      const int krow = b * p.sk + kv0;
+      tma_load_2d(smem + A_OFF_K, &tmK, kv_full, kvh * HD, krow);
+      tma_load_2d(smem + A_OFF_K + 16384, &tmK, kv_full, kvh * HD + 64, krow);
+      tma_load_2d(smem + A_OFF_V, &tmV, kv_full, kvh * HD, krow);
+      tma_load_2d(smem + A_OFF_V + 16384, &tmV, kv_full, kvh * HD + 64, krow);
+      for (int it = 0; it < nit; ++it) {
+        const int st = it % A_ST;
+        const int hq = kvh * G + it / nper;
+        const int qrow = b * p.sq + (qt_begin + it % nper) * A_BQ;
+        mbar_wait(&qd_empty[st], ((it / A_ST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qd_full[st], 32768);
+        uint8_t* sq_ = smem + A_OFF_QD + st * 32768;
+        tma_load_2d(sq_, &tmQ, &qd_full[st], hq * HD, qrow);
+        tma_load_2d(sq_ + 8192, &tmQ, &qd_full[st], hq * HD + 64, qrow);
+        tma_load_2d(sq_ + 16384, &tmDO, &qd_full[st], hq * HD, qrow);
+        tma_load_2d(sq_ + 24576, &tmDO, &qd_full[st], hq * HD + 64, qrow);
+      }
+    }
+  } else if (warp == 1) {
+    // The whole warp runs this loop (warp-uniform control flow keeps the descriptor arithmetic on
+    // the uniform datapath — the issuing thread's own instruction stream was the limiter when the
+    // descriptors were rebuilt per MMA inside an `if (lane == 0)` region); one elected lane issues.
+    if (nit > 0) {
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_sd = make_idesc_bf16(128, A_BQ, 0, 0);   // [128 keys x 64 queries]
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, HD, 0, 1);    // A K-major, B MN-major
+      const uint64_t k_desc = make_smem_desc(smem_u32(smem + A_OFF_K), 16, 1024);
+      const uint64_t v_desc = make_smem_desc(smem_u32(smem + A_OFF_V), 16, 1024);
+      const uint64_t q_desc0 = make_smem_desc(smem_u32(smem + A_OFF_QD), 16, 1024);       // K-major view
+      const uint64_t q_mn0 = make_smem_desc(smem_u32(smem + A_OFF_QD), 8192, 1024);      // MN-major view
+      const uint64_t p_desc0 = make_smem_desc(smem_u32(smem + A_OFF_PDS), 16, 1024);
+      mbar_wait(kv_full, 0);
+      int n_sd = 0, n_acc = 0;
+      uint32_t spins = 0;
+      while (n_acc < nit) {
+        bool did = false;
+        if (n_sd < nit) {
+          const int sb = n_sd & 1, st = n_sd % A_ST;
+          bool ok = (n_sd < 2) || mbar_test(&s_free[sb], ((n_sd >> 1) - 1) & 1);
+          ok = ok && mbar_test(&qd_full[st], (n_sd / A_ST) & 1);
+          if (ok) {
+            tc_fence_after();
+            if (leader) {
+              const uint64_t q_desc = desc_adv(q_desc0, st * 32768);
+              const uint64_t do_desc = desc_adv(q_desc, 16384);
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k) {
+                const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;  // K / V tiles: 128-row chunks
+                const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;   // Q / dO tiles: 64-row chunks
+                umma_bf16(TM_S + sb * A_BQ, desc_adv(k_desc, oa), desc_adv(q_desc, ob), idesc_sd, k != 0);
+              }
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k) {
+                const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;
+                const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;
+                umma_bf16(TM_DP + sb * A_BQ, desc_adv(v_desc, oa), desc_adv(do_desc, ob), idesc_sd, k != 0);
+              }
+              umma_commit(&sd_full[sb]);
+            }
+            ++n_sd;
+            did = true;
+          }
+        }
+        if (n_acc < n_sd && mbar_test(&pds_full[n_acc & 1], (n_acc >> 1) & 1)) {
+          tc_fence_after();
+          const int st = n_acc % A_ST;
+          if (leader) {
+            const uint64_t q_mn = desc_adv(q_mn0, st * 32768);
+            const uint64_t do_mn = desc_adv(q_mn, 16384);
+            const uint64_t p_desc = desc_adv(p_desc0, (n_acc & 1) * 32768);
+            const uint64_t ds_desc = desc_adv(p_desc, 16384);
+#pragma unroll
+            for (int k = 0; k < A_BQ / 16; ++k) {  // contraction over the 64 queries
+              umma_bf16(TM_DV, desc_adv(p_desc, k * 32), desc_adv(do_mn, k * 2048), idesc_acc,
+                        (n_acc | k) != 0);
+            }
+#pragma unroll
+            for (int k = 0; k < A_BQ / 16; ++k) {
+              umma_bf16(TM_DK, desc_adv(ds_desc, k * 32), desc_adv(q_mn, k * 2048), idesc_acc,
+                        (n_acc | k) != 0);
+            }
+            umma_commit(&pds_empty[n_acc & 1]);
+            umma_commit(&qd_empty[st]);
+          }
+          ++n_acc;
+          did = true;
+        }
+        poll_guard(spins, did);
+      }
+      if (leader) umma_commit(all_done);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int g = (warp - 2) >> 2;        // softmax group: iterations it ≡ g (mod 2)
+    const int row = quarter * 32 + lane;  // key row within the tile == TMEM lane
+    const int gtid = threadIdx.x - 64 - g * 128;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    const bool key_ok = kv0 + row < p.sk;
+    uint8_t* prow = smem + A_OFF_PDS + g * 32768 + row * 128;
+    uint8_t* dsrow = prow + 16384;
+    float* lbase = ld_buf + g * 256;
+    auto fetch = [&](int it) -> float {  // this thread's share of the tile's lse*log2e | delta
+      const int hq = kvh * G + it / nper;
+      const int c = gtid & 63;
+      const int q = (qt_begin + it % nper) * A_BQ + c;
+      if (q >= p.sq) return 0.f;
+      const int64_t li = ((int64_t)b * p.H + hq) * p.sq + q;
+      return gtid < 64 ? p.lse[li] * LOG2E : p.delta[li];
+    };
+    float pre = (g < nit) ? fetch(g) : 0.f;
+    int k = 0;
+    for (int it = g; it < nit; it += 2, ++k) {
+      float* lbuf = lbase + (k & 1) * 128;
+      lbuf[gtid] = pre;
+      if (it + 2 < nit) pre = fetch(it + 2);  // in flight during this iteration
+      named_bar_sync(1 + g, 128);
+      const int q0 = (qt_begin + it % nper) * A_BQ;
+      const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
+                             (CAUSAL && (kv0 + A_BKV - 1 > q0 + off));
+      mbar_wait(&sd_full[g], k & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {  // two chunks of 32 query columns
+        uint32_t s[32], d[32];
+        tmem_ld32(TM_S + lane_addr + g * A_BQ + hc * 32, s);
+        tmem_ld32(TM_DP + lane_addr + g * A_BQ + hc * 32, d);
+        tmem_ld_wait();
+        if (hc == 1) {  // S^T/dP^T of this buffer are in registers: the next S/dP MMA may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[g]);
+        }
+        const float4* l4 = reinterpret_cast<const float4*>(lbuf) + hc * 8;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 ls = l4[c4], dl4 = l4[16 + c4];
+          const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e])));
+            d[c] = __float_as_uint(__uint_as_float(d[c]) - dlv[e]);
+          }
+        }
+        if (need_mask) {  // one warp-uniform branch per chunk, never one per score
+          const int first_q = key_ok ? (CAUSAL ? kv0 + row - off : 0) : 0x7fffffff;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int qc = q0 + hc * 32 + c;
+            if (qc < first_q || qc >= p.sq) s[c] = 0u;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) d[c] = __float_as_uint(__uint_as_float(s[c]) * __uint_as_float(d[c]));
+        if (hc == 0 && k > 0) mbar_wait(&pds_empty[g], (k - 1) & 1);  // dV/dK of it-2 read this buffer
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float a[8], gg[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            a[i] = __uint_as_float(s[u * 8 + i]);
+            gg[i] = __uint_as_float(d[u * 8 + i]);
+          }
+          const int so = ((hc * 4 + u) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + so) = pack8(a);
+          *reinterpret_cast<uint4*>(dsrow + so) = pack8(gg);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[g]);
+    }
+    if (nit > 0) {
+      mbar_wait(all_done, 0);
+      tc_fence_after();
+    }
+    bf16* dkrow = p.dk + ((int64_t)b * p.sk + kv0 + row) * p.lddk + kvh * HD;
+    bf16* dvrow = p.dv + ((int64_t)b * p.sk + kv0 + row) * p.lddv + kvh * HD;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = g * 2 + cc;
+      uint32_t a[32], gg[32];
+      if (nit > 0) {
+        tmem_ld32(TM_DK + lane_addr + c * 32, a);
+        tmem_ld32(TM_DV + lane_addr + c * 32, gg);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = gg[i] = 0;
+      }
+      if (key_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float x[8], y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            x[i] = __uint_as_float(a[q * 8 + i]) * p.scale;
+            y[i] = __uint_as_float(gg[q * 8 + i]);
+          }
+          stg16(dkrow + c * 32 + q * 8, pack8(x));
+          stg16(dvrow + c * 32 + q * 8, pack8(y));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// dQ_i = scale * sum_j dS_ij K_j — two query tiles (heavy + light) per CTA, ping-pong groups
+template <bool CAUSAL>
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                       const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                       const AttnTcBwdParams p) {
+  using namespace tcb2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;    // [3]
+  uint64_t* kv_empty = bars + 5;   // [3]
+  uint64_t* sd_full = bars + 8;    // [2]
+  uint64_t* s_free = bars + 10;    // [2]
+  uint64_t* ds_full = bars + 12;   // [2]
+  uint64_t* ds_empty = bars + 14;  // [2]
+  uint64_t* tile_done = bars + 16; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.H / p.KVH);
+  const int off = p.sk - p.sq;
+  const int nqt = (p.sq + B_BQ - 1) / B_BQ;
+  // tile 0 = the heavier (later) query tile, tile 1 = its mirror image
+  int qt[2] = {nqt - 1 - (int)blockIdx.x, (int)blockIdx.x};
+  const int ntl = (qt[0] != qt[1]) ? 2 : 1;
+  int nit[2] = {0, 0};
+  for (int t = 0; t < ntl; ++t) {
+    int kv_end = p.sk;
+    if (CAUSAL) {
+      kv_end = qt[t] * B_BQ + B_BQ + off;
+      if (kv_end > p.sk) kv_end = p.sk;
+    }
+    nit[t] = (kv_end + B_BKV - 1) / B_BKV;  // >= 1: the launcher guarantees sk >= sq for causal
+  }
+  const int total = nit[0] + nit[1];
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("[vpb] dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < B_ST; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sd_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&ds_full[i], 4);
+      mbar_init(&ds_empty[i], 1);
+      mbar_init(&tile_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t TM_S = tmem_base;         // S[2]  : 2 x 64
+  const uint32_t TM_DP = tmem_base + 128;  // dP[2] : 2 x 64
+  const uint32_t TM_DQ = tmem_base + 256;  // dQ[2] : 2 x 128 (one per query tile)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int t = 0; t < ntl; ++t) {
+        if (t > 0) mbar_wait(q_empty, 0);  // every S/dP MMA of tile 0 retired: Q/dO smem is free
+        mbar_arrive_expect_tx(q_full, 65536);
+        const int qrow = b * p.sq + qt[t] * B_BQ;
+        tma_load_2d(smem + B_OFF_Q, &tmQ, q_full, h * HD, qrow);
+        tma_load_2d(smem + B_OFF_Q + 16384, &tmQ, q_full, h * HD + 64, qrow);
+        tma_load_2d(smem + B_OFF_DO, &tmDO, q_full, h * HD, qrow);
+        tma_load_2d(smem + B_OFF_DO + 16384, &tmDO, q_full, h * HD + 64, qrow);
+        for (int it = 0; it < nit[t]; ++it, ++n) {
+          const int st = n % B_ST;
+          const int krow = b * p.sk + it * B_BKV;
+          mbar_wait(&kv_empty[st], ((n / B_ST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[st], 32768);
+          uint8_t* sk_ = smem + B_OFF_KV + st * 32768;
+          tma_load_2d(sk_, &tmK, &kv_full[st], kvh * HD, krow);
+          tma_load_2d(sk_ + 8192, &tmK, &kv_full[st], kvh * HD + 64, krow);
+          tma_load_2d(sk_ + 16384, &tmV, &kv_full[st], kvh * HD, krow);
+          tma_load_2d(sk_ + 24576, &tmV, &kv_full[st], kvh * HD + 64, krow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    {  // warp-uniform issue loop, one elected lane issues (see the dK/dV kernel)
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_sd = make_idesc_bf16(128, B_BKV, 0, 0);  // [128 queries x 64 keys]
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 0, 1);
+      const uint64_t q_desc = make_smem_desc(smem_u32(smem + B_OFF_Q), 16, 1024);
+      const uint64_t do_desc = make_smem_desc(smem_u32(smem + B_OFF_DO), 16, 1024);
+      const uint64_t kv_desc0 = make_smem_desc(smem_u32(smem + B_OFF_KV), 16, 1024);    // K-major view
+      const uint64_t kv_mn0 = make_smem_desc(smem_u32(smem + B_OFF_KV), 8192, 1024);   // MN-major view
+      const uint64_t ds_desc0 = make_smem_desc(smem_u32(smem + B_OFF_DS), 16, 1024);
+      int n_sd = 0, n_dq = 0;
+      uint32_t spins = 0;
+      while (n_dq < total) {
+        bool did = false;
+        if (n_sd < total) {
+          const int t = n_sd < nit[0] ? 0 : 1;
+          const int i = n_sd - (t ? nit[0] : 0);
+          const int sb = n_sd & 1, st = n_sd % B_ST;
+          bool ok = (n_sd < 2) || mbar_test(&s_free[sb], ((n_sd >> 1) - 1) & 1);
+          ok = ok && mbar_test(&kv_full[st], (n_sd / B_ST) & 1);
+          if (ok && i == 0) ok = mbar_test(q_full, t);
+          if (ok) {
+            tc_fence_after();
+            if (leader) {
+              const uint64_t k_desc = desc_adv(kv_desc0, st * 32768);
+              const uint64_t v_desc = desc_adv(k_desc, 16384);
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k) {
+                const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;
+                const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;
+                umma_bf16(TM_S + sb * B_BKV, desc_adv(q_desc, oa), desc_adv(k_desc, ob), idesc_sd, k != 0);
+              }
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k) {
+                const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;
+                const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;
+                umma_bf16(TM_DP + sb * B_BKV, desc_adv(do_desc, oa), desc_adv(v_desc, ob), idesc_sd, k != 0);
+              }
+              umma_commit(&sd_full[sb]);
+              if (i == nit[t] - 1) umma_commit(q_empty);  // last reader of this tile's Q / dO
+            }
+            ++n_sd;
+            did = true;
+          }
+        }
+        if (n_dq < n_sd && mbar_test(&ds_full[n_dq & 1], (n_dq >> 1) & 1)) {
+          tc_fence_after();
+          const int t = n_dq < nit[0] ? 0 : 1;
+          const int i = n_dq - (t ? nit[0] : 0);
+          const int st = n_dq % B_ST;
+          if (leader) {
+            const uint64_t k_mn = desc_adv(kv_mn0, st * 32768);
+            const uint64_t ds_desc = desc_adv(ds_desc0, (n_dq & 1) * 16384);
+#pragma unroll
+            for (int k = 0; k < B_BKV / 16; ++k) {  // contraction over the 64 keys
+              umma_bf16(TM_DQ + t * HD, desc_adv(ds_desc, k * 32), desc_adv(k_mn, k * 2048), idesc_dq,
+                        (i | k) != 0);
+            }
+            umma_commit(&ds_empty[n_dq & 1]);
+            umma_commit(&kv_empty[st]);
+            if (i == nit[t] - 1) umma_commit(&tile_done[t]);
+          }
+          ++n_dq;
+          did = true;
+        }
+        poll_guard(spins, did);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int g = (warp - 2) >> 2;        // softmax group: running iterations n ≡ g (mod 2)
+    const int row = quarter * 32 + lane;  // query row within a tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    float lse2[2] = {0.f, 0.f}, dl[2] = {0.f, 0.f};
+    bool row_ok[2] = {false, false};
+    for (int t = 0; t < ntl; ++t) {
+      row_ok[t] = qt[t] * B_BQ + row < p.sq;
+      if (row_ok[t]) {
+        const int64_t li = ((int64_t)b * p.H + h) * p.sq + qt[t] * B_BQ + row;
+        lse2[t] = p.lse[li] * LOG2E;
+        dl[t] = p.delta[li];
+      }
+    }
+    uint8_t* dsrow = smem + B_OFF_DS + g * 16384 + row * 128;
+    int k = 0;
+    for (int n = g; n < total; n += 2, ++k) {
+      const int t = n < nit[0] ? 0 : 1;
+      const int it = n - (t ? nit[0] : 0);
+      const int q0 = qt[t] * B_BQ;
+      const int j0 = it * B_BKV;
+      const bool rok = t ? row_ok[1] : row_ok[0];
+      const float l2 = t ? lse2[1] : lse2[0];
+      const float dlt = t ? dl[1] : dl[0];
+      const bool need_mask = !rok || (j0 + B_BKV > p.sk) || (CAUSAL && (j0 + B_BKV - 1 > q0 + off));
+      const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
+      mbar_wait(&sd_full[g], k & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t s[32], d[32];
+        tmem_ld32(TM_S + lane_addr + g * B_BKV + hc * 32, s);
+        tmem_ld32(TM_DP + lane_addr + g * B_BKV + hc * 32, d);
+        tmem_ld_wait();
+        if (hc == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[g]);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
+        if (need_mask) {  // one warp-uniform branch per chunk, never one per score
+          const int vis = rok ? lim - (j0 + hc * 32) : -1;  // last visible column of this chunk
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c > vis) s[c] = 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          d[c] = __float_as_uint(__uint_as_float(s[c]) * (__uint_as_float(d[c]) - dlt));
+        if (hc == 0 && k > 0) mbar_wait(&ds_empty[g], (k - 1) & 1);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float gg[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gg[i] = __uint_as_float(d[u * 8 + i]);
+          *reinterpret_cast<uint4*>(dsrow + (((hc * 4 + u) ^ (row & 7)) << 4)) = pack8(gg);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[g]);
+    }
+    // epilogue: both query tiles' dQ sit in TMEM; the 8 warps split the 128 head-dim columns
+    for (int t = 0; t < ntl; ++t) {
+      mbar_wait(&tile_done[t], 0);
+      tc_fence_after();
+      bf16* dqrow = p.dq + ((int64_t)b * p.sq + qt[t] * B_BQ + row) * p.lddq + h * HD;
+      const bool rok = t ? row_ok[1] : row_ok[0];
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = g * 2 + cc;
+        uint32_t a[32];
+        tmem_ld32(TM_DQ + t * HD + lane_addr + c * 32, a);
+        tmem_ld_wait();
+        if (rok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(a[q * 8 + i]) * p.scale;
+            stg16(dqrow + c * 32 + q * 8, pack8(x));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool CAUSAL>
+static int launch_bwd_tc_v1(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
                          cudaStream_t st) {
   using namespace tcb;
@@ -825,6 +1423,59 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
     VPB_LAUNCH_OK();
   }
   return 0;
+}
+
+template <bool CAUSAL>
+static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                            int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
+                            cudaStream_t st) {
+  using namespace tcb2;
+  const uint64_t qcols = (uint64_t)p.H * HD, kcols = (uint64_t)p.KVH * HD;
+  const uint64_t qrows = (uint64_t)p.B * p.sq, krows = (uint64_t)p.B * p.sk;
+  {
+    CUtensorMap tmQ, tmDO, tmK, tmV;
+    if (make_tmap_2d(&tmQ, q, qcols, qrows, (uint64_t)ldq, 64, A_BQ)) return -1;
+    if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, A_BQ)) return -1;
+    if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, A_BKV)) return -1;
+    if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, A_BKV)) return -1;
+    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL>;
+    static bool cfg = false;
+    if (!cfg) {
+      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
+      cfg = true;
+    }
+    dim3 grid((p.sk + A_BKV - 1) / A_BKV, p.KVH, p.B);
+    kern<<<grid, 320, A_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
+    VPB_LAUNCH_OK();
+  }
+  {
+    CUtensorMap tmQ, tmDO, tmK, tmV;
+    if (make_tmap_2d(&tmQ, q, qcols, qrows, (uint64_t)ldq, 64, B_BQ)) return -1;
+    if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, B_BQ)) return -1;
+    if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, B_BKV)) return -1;
+    if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, B_BKV)) return -1;
+    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL>;
+    static bool cfg = false;
+    if (!cfg) {
+      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+      cfg = true;
+    }
+    const int nqt = (p.sq + B_BQ - 1) / B_BQ;
+    dim3 grid((nqt + 1) / 2, p.H, p.B);
+    kern<<<grid, 320, B_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
+    VPB_LAUNCH_OK();
+  }
+  return 0;
+}
+
+template <bool CAUSAL>
+static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                         int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
+                         cudaStream_t st) {
+  // v2 assumes every query tile sees at least one key tile (sk >= sq when causal)
+  if (get_option(VPB_OPT_ATTN_TC_BWD_V1) || (CAUSAL && p.sk < p.sq))
+    return launch_bwd_tc_v1<CAUSAL>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+  return launch_bwd_tc_v2<CAUSAL>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
 }
 
 // entry used by vpb_attn_bwd (attention.cu) after the delta kernel, head_dim 128, one K/V segment

@@ -152,11 +152,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // warp-uniform loop (descriptor arithmetic on the uniform datapath), one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      // descriptor start-address increment (16-byte units) per UMMA_K = 16 slice
-      constexpr uint32_t A_KADV = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
-      constexpr uint32_t B_KADV = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      // descriptor start-address increment (bytes) per UMMA_K = 16 slice
+      constexpr uint32_t A_KADV = A_MN ? 16 * 128 : 16 * 2;
+      constexpr uint32_t B_KADV = B_MN ? 16 * 128 : 16 * 2;
+      const uint32_t s0 = smem_u32(smem);
+      const uint64_t adesc0 = A_MN ? make_smem_desc(s0, 8192, 1024) : make_smem_desc(s0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(s0 + A_BYTES, 8192, 1024) : make_smem_desc(s0 + A_BYTES, 16, 1024);
       uint32_t it = 0, tile_iter = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_iter) {
         const uint32_t acc = tile_iter & 1;
@@ -169,18 +173,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
-          const uint64_t adesc = A_MN ? make_smem_desc(sa, 8192, 1024) : make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = B_MN ? make_smem_desc(sb, 8192, 1024) : make_smem_desc(sb, 16, 1024);
+          if (leader) {
+            const uint64_t adesc = desc_adv(adesc0, s * STAGE_BYTES);
+            const uint64_t bdesc = desc_adv(bdesc0, s * STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16(d_tmem, adesc + (uint64_t)(k * A_KADV), bdesc + (uint64_t)(k * B_KADV), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16(d_tmem, desc_adv(adesc, k * A_KADV), desc_adv(bdesc, k * B_KADV), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);  // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty[s]);  // frees the smem slot when these MMAs retire
         }
-        umma_commit(&tfull[acc]);  // accumulator complete → epilogue
+        if (leader) umma_commit(&tfull[acc]);  // accumulator complete → epilogue
       }
     }
   } else {
