@@ -52,6 +52,32 @@ def test_gemm_layouts(M, N, K, al, bl):
     close(out, ref, name=f"gemm {M}x{N}x{K} a{al} b{bl}")
 
 
+@pytest.mark.parametrize("al,bl", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(4096, 4096, 512), (2304, 5000, 328), (2000, 8192, 1024), (16384, 6144, 256)])
+def test_gemm_cta_pair_matches_single_cta(M, N, K, al, bl):
+    """cta_group::2 kernel (two CTAs per 256x256 tile) against the 1-CTA kernel: same K order, so
+    bit-identical; both against torch.  Shapes include ragged M / N edges."""
+    from visper_lm_b200 import ops
+    if (al == 1 and M % 8) or (bl == 1 and N % 8):
+        pytest.skip("stride not 16-byte aligned for this layout")
+    a = rnd(M, K, seed=41)
+    b = rnd(N, K, seed=42)
+    bias, res = rnd(N, seed=43), rnd(M, N, seed=44)
+    a_in = a if al == 0 else a.t().contiguous()
+    b_in = b if bl == 0 else b.t().contiguous()
+    ops.set_option(ops.OPT_GEMM_1CTA, 1)
+    try:
+        ref1 = ops.gemm(a_in, b_in, a_layout=al, b_layout=bl, bias=bias, act=1, residual=res)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_GEMM_1CTA, 0)
+    out = ops.gemm(a_in, b_in, a_layout=al, b_layout=bl, bias=bias, act=1, residual=res)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref1), f"pair kernel differs from 1-CTA kernel: {(out.float() - ref1.float()).abs().max().item()}"
+    ref = torch.nn.functional.gelu(a.float() @ b.float().t() + bias.float()) + res.float()
+    close(out, ref, name=f"pair gemm {M}x{N}x{K} a{al} b{bl}")
+
+
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 def test_gemm_epilogues(act):
     from visper_lm_b200 import ops

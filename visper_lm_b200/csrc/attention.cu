@@ -282,27 +282,46 @@ attn_fwd_kernel(const AttnParams p) {
 // backward
 // =============================================================================================
 // delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+// One warp per (b,i) row, HD/8 lanes per head (128-bit coalesced loads of both tensors), all index
+// arithmetic in 32 bits and hoisted out of the head loop (the first version spent its time in
+// 64-bit div/mod: ALU-bound at 81 % issue-slot use for an HBM-bound reduction).
+template <int LPH>  // lanes per head = HD / 8 (4, 8, 12→16 padded, 16)
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, int64_t ldo, const bf16* __restrict__ dO, int64_t lddo,
                   float* __restrict__ delta, int B, int H, int sq, int HD) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t idx = (int64_t)blockIdx.x * 8 + warp;  // over B*sq*H
-  if (idx >= (int64_t)B * sq * H) return;
-  const int h = (int)(idx % H);
-  const int64_t row = idx / H;  // b*sq + i
-  float acc = 0.f;
-  for (int c = lane; c < HD / 8; c += 32) {
-    float a[8], d[8];
-    unpack8(ldg16(o + row * ldo + h * HD + c * 8), a);
-    unpack8(ldg16(dO + row * lddo + h * HD + c * 8), d);
+  const int row = blockIdx.x * 8 + warp;  // b*sq + i
+  if (row >= B * sq) return;
+  const int b = row / sq, i = row - b * sq;
+  constexpr int HPW = 32 / LPH;  // heads per warp pass
+  const int sub = lane / LPH, l = lane % LPH;
+  const bool lane_ok = l * 8 < HD;
+  const bf16* orow = o + (int64_t)row * ldo + l * 8;
+  const bf16* drow = dO + (int64_t)row * lddo + l * 8;
+  float* dout = delta + (int64_t)b * H * sq + i;
+#pragma unroll 4
+  for (int h0 = 0; h0 < H; h0 += HPW) {
+    const int h = h0 + sub;
+    float acc = 0.f;
+    if (h < H && lane_ok) {
+      float a[8], d[8];
+      unpack8(ldg16_stream(orow + h * HD), a);
+      unpack8(ldg16_stream(drow + h * HD), d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc += a[j] * d[j];
+      for (int j = 0; j < 8; ++j) acc = fmaf(a[j], d[j], acc);
+    }
+#pragma unroll
+    for (int s = LPH / 2; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (l == 0 && h < H) dout[(int64_t)h * sq] = acc;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const int b = (int)(row / sq), i = (int)(row % sq);
-    delta[((int64_t)b * H + h) * sq + i] = acc;
-  }
+}
+
+static void launch_delta(const bf16* o, int64_t ldo, const bf16* dO, int64_t lddo, float* delta, int B,
+                         int H, int sq, int HD, cudaStream_t st) {
+  const int grid = (B * sq + 7) / 8;
+  if (HD <= 32) attn_delta_kernel<4><<<grid, 256, 0, st>>>(o, ldo, dO, lddo, delta, B, H, sq, HD);
+  else if (HD <= 64) attn_delta_kernel<8><<<grid, 256, 0, st>>>(o, ldo, dO, lddo, delta, B, H, sq, HD);
+  else attn_delta_kernel<16><<<grid, 256, 0, st>>>(o, ldo, dO, lddo, delta, B, H, sq, HD);
 }
 
 // dK, dV for one 64-row key tile of one kv head (all query heads of its GQA group, all query tiles)
@@ -735,9 +754,8 @@ extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t l
   if (check_attn(p, head_dim)) return -1;
   VPB_CHECK(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "attention bwd: strides");
   VPB_CHECK(!(causal && p.sk2 > 0), "attention: causal with a second key segment is not supported");
-  const int64_t nrows = (int64_t)B * sq * H;
-  attn_delta_kernel<<<(int)((nrows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)o, ldo, (const bf16*)dO, lddo, delta, B, H, sq, head_dim);
+  VPB_CHECK((int64_t)B * sq < (1ll << 31), "attention bwd: B*sq too large");
+  launch_delta((const bf16*)o, ldo, (const bf16*)dO, lddo, delta, B, H, sq, head_dim, (cudaStream_t)stream);
   VPB_LAUNCH_OK();
   auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
   if (head_dim == 128 && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_BWD) && al16(q) && al16(k) &&

@@ -824,7 +824,7 @@ constexpr int A_OFF_PDS = A_OFF_QD + A_ST * 32768;   // group g: P^T (16 KB) the
 constexpr int A_OFF_LD = A_OFF_PDS + 2 * 32768;      // [2 groups][2 parity][64 lse | 64 delta] floats
 constexpr int A_OFF_BAR = A_OFF_LD + 2048;
 constexpr int A_SMEM = A_OFF_BAR + 256;              // 231 680 B: needs the 1024-aligned base
-constexpr int B_BQ = 128, B_BKV = 64, B_ST = 3;
+constexpr int B_BQ = 128, B_BKV = 64, B_ST = 4;
 constexpr int B_OFF_Q = 0, B_OFF_DO = 32768;
 constexpr int B_OFF_KV = 65536;                      // stage s: K (16 KB) then V (16 KB)
 constexpr int B_OFF_DS = B_OFF_KV + B_ST * 32768;    // group g: dS [128 queries x 64 keys] 16 KB
@@ -861,8 +861,13 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   float* ld_buf = reinterpret_cast<float*>(smem + A_OFF_LD);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * A_BKV;
-  const int kvh = blockIdx.y, b = blockIdx.z;
+  // CTAs are dispatched in linear blockIdx order; with causal masking the early key tiles carry the
+  // most work, so the linear id is re-read as (key tile major, (kv head, batch) minor): every SM
+  // starts on heavy tiles and the tail of the grid is made of the lightest ones.
+  const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int nhb = gridDim.y * gridDim.z;
+  const int kv0 = (lin / nhb) * A_BKV;
+  const int kvh = (lin % nhb) % gridDim.y, b = (lin % nhb) / gridDim.y;
   const int G = p.H / p.KVH;
   const int off = p.sk - p.sq;
   const int nq_tiles = (p.sq + A_BQ - 1) / A_BQ;
@@ -1034,17 +1039,21 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                              (CAUSAL && (kv0 + A_BKV - 1 > q0 + off));
       mbar_wait(&sd_full[g], k & 1);
       tc_fence_after();
-#pragma unroll 1
+      // all 64 S^T / dP^T columns go to registers first, so the buffer is handed back to the MMA
+      // issuer (S/dP of iteration it+2) before any of the exp / dS work starts
+      uint32_t sall[64], dall[64];
+      tmem_ld32(TM_S + lane_addr + g * A_BQ, sall);
+      tmem_ld32(TM_S + lane_addr + g * A_BQ + 32, sall + 32);
+      tmem_ld32(TM_DP + lane_addr + g * A_BQ, dall);
+      tmem_ld32(TM_DP + lane_addr + g * A_BQ + 32, dall + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);
+#pragma unroll
       for (int hc = 0; hc < 2; ++hc) {  // two chunks of 32 query columns
-        uint32_t s[32], d[32];
-        tmem_ld32(TM_S + lane_addr + g * A_BQ + hc * 32, s);
-        tmem_ld32(TM_DP + lane_addr + g * A_BQ + hc * 32, d);
-        tmem_ld_wait();
-        if (hc == 1) {  // S^T/dP^T of this buffer are in registers: the next S/dP MMA may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[g]);
-        }
+        uint32_t* s = sall + hc * 32;
+        uint32_t* d = dall + hc * 32;
         const float4* l4 = reinterpret_cast<const float4*>(lbuf) + hc * 8;
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
@@ -1135,14 +1144,14 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;    // [3]
-  uint64_t* kv_empty = bars + 5;   // [3]
-  uint64_t* sd_full = bars + 8;    // [2]
-  uint64_t* s_free = bars + 10;    // [2]
-  uint64_t* ds_full = bars + 12;   // [2]
-  uint64_t* ds_empty = bars + 14;  // [2]
-  uint64_t* tile_done = bars + 16; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* kv_full = bars + 2;    // [4]
+  uint64_t* kv_empty = bars + 6;   // [4]
+  uint64_t* sd_full = bars + 10;   // [2]
+  uint64_t* s_free = bars + 12;    // [2]
+  uint64_t* ds_full = bars + 14;   // [2]
+  uint64_t* ds_empty = bars + 16;  // [2]
+  uint64_t* tile_done = bars + 18; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -1318,36 +1327,35 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
       mbar_wait(&sd_full[g], k & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int hc = 0; hc < 2; ++hc) {
-        uint32_t s[32], d[32];
-        tmem_ld32(TM_S + lane_addr + g * B_BKV + hc * 32, s);
-        tmem_ld32(TM_DP + lane_addr + g * B_BKV + hc * 32, d);
-        tmem_ld_wait();
-        if (hc == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[g]);
-        }
+      // all 64 S / dP columns go to registers first, so the buffer is handed back to the MMA
+      // issuer (S/dP of iteration n+2) before any of the exp / dS work starts
+      uint32_t s[64], d[64];
+      tmem_ld32(TM_S + lane_addr + g * B_BKV, s);
+      tmem_ld32(TM_S + lane_addr + g * B_BKV + 32, s + 32);
+      tmem_ld32(TM_DP + lane_addr + g * B_BKV, d);
+      tmem_ld32(TM_DP + lane_addr + g * B_BKV + 32, d + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
-        if (need_mask) {  // one warp-uniform branch per chunk, never one per score
-          const int vis = rok ? lim - (j0 + hc * 32) : -1;  // last visible column of this chunk
+      for (int c = 0; c < 64; ++c) s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
+      if (need_mask) {  // one warp-uniform branch per tile, never one per score
+        const int vis = rok ? lim - j0 : -1;  // last visible column of this tile
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c > vis) s[c] = 0u;
-        }
+        for (int c = 0; c < 64; ++c)
+          if (c > vis) s[c] = 0u;
+      }
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          d[c] = __float_as_uint(__uint_as_float(s[c]) * (__uint_as_float(d[c]) - dlt));
-        if (hc == 0 && k > 0) mbar_wait(&ds_empty[g], (k - 1) & 1);
+      for (int c = 0; c < 64; ++c)
+        d[c] = __float_as_uint(__uint_as_float(s[c]) * (__uint_as_float(d[c]) - dlt));
+      if (k > 0) mbar_wait(&ds_empty[g], (k - 1) & 1);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float gg[8];
+      for (int u = 0; u < 8; ++u) {
+        float gg[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gg[i] = __uint_as_float(d[u * 8 + i]);
-          *reinterpret_cast<uint4*>(dsrow + (((hc * 4 + u) ^ (row & 7)) << 4)) = pack8(gg);
-        }
+        for (int i = 0; i < 8; ++i) gg[i] = __uint_as_float(d[u * 8 + i]);
+        *reinterpret_cast<uint4*>(dsrow + ((u ^ (row & 7)) << 4)) = pack8(gg);
       }
       fence_proxy_async();
       tc_fence_before();

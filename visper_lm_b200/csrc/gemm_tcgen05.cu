@@ -57,6 +57,127 @@ __device__ __forceinline__ float act_apply(float x, int act) {
   }
 }
 
+// Epilogue of one accumulator tile for one warp: thread `lane` owns output row `row` and walks
+// the BN fp32 accumulator columns at TMEM address `taddr` (lane quarter already applied).
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_t taddr, int row, int nb) {
+  constexpr int BNO = (EPI == EPI_SWIGLU_FWD) ? BN / 2 : BN;
+  const bool row_ok = row < args.M;
+  bf16* crow = args.C + (int64_t)row * args.ldc;
+  const bf16* rrow = args.res ? args.res + (int64_t)row * args.ldr : nullptr;
+  bf16* xrow = args.aux ? args.aux + (int64_t)row * args.ldaux : nullptr;
+  if constexpr (EPI == EPI_SWIGLU_FWD) {
+#pragma unroll 1
+    for (int c = 0; c < BNO / 32; ++c) {
+      const int n_base = nb * BNO + c * 32;
+      uint32_t rg[32], ru[32];
+      tmem_ld32(taddr + c * 32, rg);
+      tmem_ld32(taddr + BNO + c * 32, ru);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n_base + g * 8;
+          float gv[8], uv[8], o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            gv[j] = __uint_as_float(rg[g * 8 + j]);
+            uv[j] = __uint_as_float(ru[g * 8 + j]);
+          }
+          // round to bf16 first: h is then bit-identical to swiglu_fwd_kernel on the stored g|u
+          const uint4 pg = pack8(gv), pu = pack8(uv);
+          if (xrow) {
+            stg16(xrow + n, pg);
+            stg16(xrow + args.F + n, pu);
+          }
+          unpack8(pg, gv);
+          unpack8(pu, uv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = gv[j] / (1.f + __expf(-gv[j])) * uv[j];
+          stg16(crow + n, pack8(o));
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_SWIGLU_BWD) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int n_base = nb * BN + c * 32;
+      if (n_base >= args.N) break;  // warp-uniform
+      uint4 lg[4], lu[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n_base + g * 8;
+        if (row_ok && n + 8 <= args.N) {
+          lg[g] = ldg16_stream(xrow + n);
+          lu[g] = ldg16_stream(xrow + args.F + n);
+        }
+      }
+      uint32_t r[32];
+      tmem_ld32(taddr + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n_base + g * 8;
+        if (row_ok && n + 8 <= args.N) {
+          float d[8], gv[8], uv[8], dg[8], du[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = __uint_as_float(r[g * 8 + j]);
+          unpack8(pack8(d), d);  // dh rounded to bf16 as the unfused dgrad GEMM would store it
+          unpack8(lg[g], gv);
+          unpack8(lu[g], uv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float sg = 1.f / (1.f + __expf(-gv[j]));
+            const float silu = gv[j] * sg;
+            du[j] = d[j] * silu;
+            dg[j] = d[j] * uv[j] * (sg + silu * (1.f - sg));
+          }
+          stg16(crow + n, pack8(dg));
+          stg16(crow + args.F + n, pack8(du));
+        }
+      }
+    }
+  } else {
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int n_base = nb * BN + c * 32;
+    if (n_base >= args.N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n = n_base + g * 8;
+      if (n + 8 <= args.N) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+        if (args.bias) {
+          float b[8];
+          unpack8(ldg16(args.bias + n), b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += b[j];
+        }
+        if (row_ok) {
+          if (xrow) stg16(xrow + n, pack8(v));
+          if (args.act != VPB_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], args.act);
+          }
+          if (rrow) {
+            float q[8];
+            unpack8(*reinterpret_cast<const uint4*>(rrow + n), q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += q[j];
+          }
+          stg16(crow + n, pack8(v));
+        }
+      }
+    }
+  }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI = EPI_STD>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -197,122 +318,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       const uint32_t acc_ph = (tile_iter >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
-      const int row = mb * BM + quarter * 32 + lane;
-      const bool row_ok = row < args.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-      bf16* crow = args.C + (int64_t)row * args.ldc;
-      const bf16* rrow = args.res ? args.res + (int64_t)row * args.ldr : nullptr;
-      bf16* xrow = args.aux ? args.aux + (int64_t)row * args.ldaux : nullptr;
-      if constexpr (EPI == EPI_SWIGLU_FWD) {
-#pragma unroll 1
-        for (int c = 0; c < BNO / 32; ++c) {
-          const int n_base = nb * BNO + c * 32;
-          uint32_t rg[32], ru[32];
-          tmem_ld32(taddr + c * 32, rg);
-          tmem_ld32(taddr + BNO + c * 32, ru);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = n_base + g * 8;
-              float gv[8], uv[8], o[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                gv[j] = __uint_as_float(rg[g * 8 + j]);
-                uv[j] = __uint_as_float(ru[g * 8 + j]);
-              }
-              // round to bf16 first: h is then bit-identical to swiglu_fwd_kernel on the stored g|u
-              const uint4 pg = pack8(gv), pu = pack8(uv);
-              if (xrow) {
-                stg16(xrow + n, pg);
-                stg16(xrow + args.F + n, pu);
-              }
-              unpack8(pg, gv);
-              unpack8(pu, uv);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = gv[j] / (1.f + __expf(-gv[j])) * uv[j];
-              stg16(crow + n, pack8(o));
-            }
-          }
-        }
-      } else if constexpr (EPI == EPI_SWIGLU_BWD) {
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n_base = nb * BN + c * 32;
-          if (n_base >= args.N) break;  // warp-uniform
-          uint4 lg[4], lu[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n_base + g * 8;
-            if (row_ok && n + 8 <= args.N) {
-              lg[g] = ldg16_stream(xrow + n);
-              lu[g] = ldg16_stream(xrow + args.F + n);
-            }
-          }
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n_base + g * 8;
-            if (row_ok && n + 8 <= args.N) {
-              float d[8], gv[8], uv[8], dg[8], du[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) d[j] = __uint_as_float(r[g * 8 + j]);
-              unpack8(pack8(d), d);  // dh rounded to bf16 as the unfused dgrad GEMM would store it
-              unpack8(lg[g], gv);
-              unpack8(lu[g], uv);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float sg = 1.f / (1.f + __expf(-gv[j]));
-                const float silu = gv[j] * sg;
-                du[j] = d[j] * silu;
-                dg[j] = d[j] * uv[j] * (sg + silu * (1.f - sg));
-              }
-              stg16(crow + n, pack8(dg));
-              stg16(crow + args.F + n, pack8(du));
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n_base = nb * BN + c * 32;
-        if (n_base >= args.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n_base + g * 8;
-          if (n + 8 <= args.N) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-            if (args.bias) {
-              float b[8];
-              unpack8(ldg16(args.bias + n), b);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += b[j];
-            }
-            if (row_ok) {
-              if (xrow) stg16(xrow + n, pack8(v));
-              if (args.act != VPB_ACT_NONE) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], args.act);
-              }
-              if (rrow) {
-                float q[8];
-                unpack8(*reinterpret_cast<const uint4*>(rrow + n), q);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += q[j];
-              }
-              stg16(crow + n, pack8(v));
-            }
-          }
-        }
-      }
-      }
+      gemm_epilogue_tile<BN, EPI>(args, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN,
+                                  mb * BM + quarter * 32 + lane, nb);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -322,6 +329,175 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster compute one 256 x 256 tile.
+//   * each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), so a
+//     stage is 32 KB (6-deep ring) instead of 48 KB and every B byte is fetched and held once per
+//     pair — a third less TMA / shared-memory traffic per FLOP than the 1-CTA kernel;
+//   * both producers' TMA loads complete on the LEADER's "full" barrier; the leader's single MMA
+//     thread issues tcgen05.mma.cta_group::2 (M = 256: 128 TMEM lanes in each CTA) and its commits
+//     multicast to the "empty" / "accumulator full" barriers of both CTAs;
+//   * each CTA's four epilogue warps drain their own TMEM half; the accumulator-free barrier lives
+//     in the leader and counts the epilogue warps of both CTAs (remote mbarrier.arrive).
+// ----------------------------------------------------------------------------------------------
+constexpr int PAIR_BN = 256;
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_GROUP_M = 8;  // 8 x 256 rows per L2 panel
+
+template <bool A_MN, bool B_MN, int EPI = EPI_STD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+                         const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
+  constexpr int BN = PAIR_BN, STAGES = PAIR_STAGES;
+  constexpr int A_BYTES = BM * BK * 2;        // this CTA's 128 rows of A
+  constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the B tile
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int BNO = (EPI == EPI_SWIGLU_FWD) ? BN / 2 : BN;  // output columns per tile
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // used in the leader
+  uint64_t* empty = full + STAGES;   // per CTA: the pair's MMAs have consumed this CTA's stage
+  uint64_t* tfull = empty + STAGES;  // per CTA: accumulator stage complete
+  uint64_t* tempty = tfull + 2;      // leader: both CTAs' epilogues drained the stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool is_leader_cta = rank == 0;
+
+  const int num_m = (args.M + 2 * BM - 1) / (2 * BM);
+  const int num_n = (args.N + BNO - 1) / BNO;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (args.K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("[vpb] dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode_tile = [&](int t, int& mb, int& nb) {
+    const int per_group = PAIR_GROUP_M * num_n;
+    const int g = t / per_group;
+    const int first_m = g * PAIR_GROUP_M;
+    const int gsize = min(PAIR_GROUP_M, num_m - first_m);
+    const int r = t - g * per_group;
+    mb = first_m + r % gsize;
+    nb = r / gsize;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int mb, nb;
+        decode_tile(t, mb, nb);
+        const int m0 = mb * 2 * BM + (int)rank * BM;
+        int nrow;  // first of this CTA's 128 B rows
+        if constexpr (EPI == EPI_SWIGLU_FWD) nrow = (rank == 0 ? 0 : args.F) + nb * BNO;
+        else nrow = nb * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (is_leader_cta) mbar_arrive_expect_tx(&full[s], 2 * STAGE_BYTES);  // both CTAs' bytes
+          const uint32_t fbar = mapa_u32(&full[s], 0);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d_pair(sa, &tmA, fbar, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * 8192, &tmA, fbar, m0 + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(sb, &tmB, fbar, kb * BK, nrow);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 128; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, fbar, nrow + c * 64, kb * BK);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (is_leader_cta) {  // warp-uniform loop, one elected lane issues for the pair
+      const bool leader = elect_one();
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t A_KADV = A_MN ? 16 * 128 : 16 * 2;
+      constexpr uint32_t B_KADV = B_MN ? 16 * 128 : 16 * 2;
+      const uint32_t s0 = smem_u32(smem);
+      const uint64_t adesc0 = A_MN ? make_smem_desc(s0, 8192, 1024) : make_smem_desc(s0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? make_smem_desc(s0 + A_BYTES, 8192, 1024) : make_smem_desc(s0 + A_BYTES, 16, 1024);
+      uint32_t it = 0, tile_iter = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_iter) {
+        const uint32_t acc = tile_iter & 1;
+        const uint32_t acc_ph = (tile_iter >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t adesc = desc_adv(adesc0, s * STAGE_BYTES);
+            const uint64_t bdesc = desc_adv(bdesc0, s * STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16_pair(d_tmem, desc_adv(adesc, k * A_KADV), desc_adv(bdesc, k * B_KADV), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(&empty[s], 3);  // frees the stage in both CTAs
+          }
+        }
+        if (leader) umma_commit_pair(&tfull[acc], 3);  // accumulator complete in both CTAs
+      }
+    }
+  } else {
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    uint32_t tile_iter = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++tile_iter) {
+      int mb, nb;
+      decode_tile(t, mb, nb);
+      const uint32_t acc = tile_iter & 1;
+      const uint32_t acc_ph = (tile_iter >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      gemm_epilogue_tile<BN, EPI>(args, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN,
+                                  mb * 2 * BM + (int)rank * BM + quarter * 32 + lane, nb);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading this CTA's smem / signalling its barriers
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -394,6 +570,41 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   return 0;
 }
 
+
+template <bool A_MN, bool B_MN, int EPI = EPI_STD>
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
+                            cudaStream_t stream) {
+  constexpr int SMEM = PAIR_STAGES * (BM * BK * 2 + (PAIR_BN / 2) * BK * 2) + 256;
+  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  constexpr int BNO = (EPI == EPI_SWIGLU_FWD) ? PAIR_BN / 2 : PAIR_BN;
+  const int tiles = ((args.M + 2 * BM - 1) / (2 * BM)) * ((args.N + BNO - 1) / BNO);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  kern<<<grid, 192, SMEM, stream>>>(tmA, tmB, args);
+  VPB_LAUNCH_OK();
+  return 0;
+}
+
+// CTA pairs win on large problems (less TMA / shared-memory traffic per FLOP); on small ones the
+// coarser 256 x 256 tiles can quantise into more waves than the 1-CTA kernel, so compare the two
+// wave efficiencies (measured: CLIP QKV M=4616 N=3072 is 3.08 pair waves vs exactly 3 single waves).
+static bool use_pair(int M, int N) {
+  if (get_option(VPB_OPT_GEMM_1CTA)) return false;
+  if (N < 256 || M < 256) return false;
+  const int pairs = num_sms() / 2, sms = num_sms();
+  const int64_t tp = (int64_t)((M + 255) / 256) * ((N + 255) / 256);
+  if (tp < pairs) return false;
+  const int64_t t1 = (int64_t)((M + 127) / 128) * ((N + 255) / 256);
+  const double eff_p = (double)tp / (double)(((tp + pairs - 1) / pairs) * pairs);
+  const double eff_1 = (double)t1 / (double)(((t1 + sms - 1) / sms) * sms);
+  return eff_p + 0.05 >= eff_1;
+}
+
 }  // namespace vpb
 
 using namespace vpb;
@@ -416,7 +627,8 @@ extern "C" int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const voi
 
   const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
   const bool bn256 = tiles256 >= num_sms() && N >= 256;
-  const int BN = bn256 ? 256 : 128;
+  const bool pair = use_pair(M, N);
+  const int BN = pair ? 128 : (bn256 ? 256 : 128);  // B rows per TMA box (a pair CTA loads half a tile)
 
   CUtensorMap tmA, tmB;
   if (a_layout == 0) {
@@ -443,6 +655,14 @@ extern "C" int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const voi
   args.act = act;
   args.F = 0;
 
+  if (pair) {
+    switch ((a_layout ? 2 : 0) | (b_layout ? 1 : 0)) {
+      case 0: return launch_gemm_pair<false, false>(tmA, tmB, args, stream);
+      case 1: return launch_gemm_pair<false, true>(tmA, tmB, args, stream);
+      case 2: return launch_gemm_pair<true, false>(tmA, tmB, args, stream);
+      default: return launch_gemm_pair<true, true>(tmA, tmB, args, stream);
+    }
+  }
   const int key = (bn256 ? 4 : 0) | (a_layout ? 2 : 0) | (b_layout ? 1 : 0);
   switch (key) {
     case 0: return launch_gemm<128, false, false>(tmA, tmB, args, stream);
@@ -482,6 +702,7 @@ extern "C" int vpb_gemm_swiglu_fwd(const void* A, int64_t lda, const void* Wgu, 
   args.K = K;
   args.act = VPB_ACT_NONE;
   args.F = F;
+  if (use_pair(M, 2 * F)) return launch_gemm_pair<false, false, EPI_SWIGLU_FWD>(tmA, tmB, args, stream);
   return launch_gemm<256, false, false, EPI_SWIGLU_FWD>(tmA, tmB, args, stream);
 }
 
@@ -498,8 +719,9 @@ extern "C" int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, 
             "gemm_swiglu_bwd: gu/dgu alignment");
   CUtensorMap tmA, tmB;
   if (make_tmap_2d(&tmA, dY, (uint64_t)K, (uint64_t)M, (uint64_t)lddy, BK, BM)) return -1;
+  const bool pair = use_pair(M, F);
   if (b_layout == 0) {
-    if (make_tmap_2d(&tmB, W, (uint64_t)K, (uint64_t)F, (uint64_t)ldw, BK, 256)) return -1;
+    if (make_tmap_2d(&tmB, W, (uint64_t)K, (uint64_t)F, (uint64_t)ldw, BK, pair ? 128 : 256)) return -1;
   } else {
     if (make_tmap_2d(&tmB, W, (uint64_t)F, (uint64_t)K, (uint64_t)ldw, 64, BK)) return -1;
   }
@@ -516,6 +738,10 @@ extern "C" int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, 
   args.K = K;
   args.act = VPB_ACT_NONE;
   args.F = F;
+  if (pair) {
+    if (b_layout == 0) return launch_gemm_pair<false, false, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
+    return launch_gemm_pair<false, true, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
+  }
   if (b_layout == 0) return launch_gemm<256, false, false, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
   return launch_gemm<256, false, true, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
 }

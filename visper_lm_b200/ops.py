@@ -35,7 +35,7 @@ def _rows(t: torch.Tensor):
     return t.data_ptr(), t.stride(0)
 
 
-OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD, OPT_ATTN_TC_BWD_V1 = 0, 1, 2
+OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD, OPT_ATTN_TC_BWD_V1, OPT_GEMM_1CTA = 0, 1, 2, 3
 
 
 def set_option(key, value):
