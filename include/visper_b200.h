@@ -64,12 +64,16 @@ int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const void* B, int64
  * fwd: gu[M,2F] = A·Wguᵀ (stored when gu != NULL, needed by the backward) and h[M,F] = silu(g)·u in
  *      one launch; F % 128 == 0.
  * bwd: dgu[M,2F] = swiglu'(gu) ∘ (dY·W), W = down_proj weight: b_layout 1 → [K, F] as stored by
- *      nn.Linear (read MN-major), b_layout 0 → a K-major transposed copy [F, K]. */
+ *      nn.Linear (read MN-major), b_layout 0 → a K-major transposed copy [F, K].
+ * gu_tiled 1: g|u is kept in the tile-major layout [M/128][F/32][128 rows][32 gate | 32 up]
+ *      (ceil(M/128)*128*2F elements, ldgu ignored) that makes the row-owning epilogue threads touch
+ *      whole 128-byte lines; only the two fused kernels read it. */
 int vpb_gemm_swiglu_fwd(const void* A, int64_t lda, const void* Wgu, int64_t ldw, void* gu,
-                        int64_t ldgu, void* h, int64_t ldh, int M, int F, int K, void* stream);
-int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, int64_t ldw, int b_layout,
-                        const void* gu, int64_t ldgu, void* dgu, int64_t lddgu, int M, int F, int K,
+                        int64_t ldgu, int gu_tiled, void* h, int64_t ldh, int M, int F, int K,
                         void* stream);
+int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, int64_t ldw, int b_layout,
+                        const void* gu, int64_t ldgu, int gu_tiled, void* dgu, int64_t lddgu, int M,
+                        int F, int K, void* stream);
 
 /* ---- normalisation -------------------------------------------------------------------------
  * HF LlamaRMSNorm / Phi3RMSNorm (eps 1e-5) and nn.LayerNorm (CLIP, resampler.py). */

@@ -117,7 +117,8 @@ def test_gemm_strided_views():
     assert outbuf[:, :128].abs().max().item() == 0 and outbuf[:, 512:].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("M,F,K", [(200, 128, 64), (1000, 384, 200), (2048, 1792, 512), (4096, 14336, 256)])
+@pytest.mark.parametrize("M,F,K", [(200, 128, 64), (1000, 384, 200), (2048, 1792, 512), (4096, 14336, 256),
+                                   (2100, 3584, 320)])
 def test_gemm_swiglu_fused(M, F, K):
     """SwiGLU in the GEMM epilogues: bit-identical to the separate GEMM + swiglu kernels."""
     from visper_lm_b200 import ops
@@ -141,6 +142,11 @@ def test_gemm_swiglu_fused(M, F, K):
     torch.cuda.synchronize()
     assert torch.equal(dgu, dgu_ref), "fused swiglu backward (MN-major W) differs"
     assert torch.equal(dgu_t, dgu_ref), "fused swiglu backward (K-major Wt) differs"
+    # tile-major g|u (what the frozen-LLM step saves): same h, same gradients
+    h3, gut = ops.gemm_swiglu_fwd(x, wgu, tiled=True)
+    dgu3 = ops.gemm_swiglu_bwd(dy, wd, gut, b_layout=1, tiled=True, F=F)
+    torch.cuda.synchronize()
+    assert torch.equal(h3, h_ref) and torch.equal(dgu3, dgu_ref), "tile-major g|u path differs"
 
 
 # ------------------------------------------------------------------------------------------- norms

@@ -62,6 +62,27 @@ def attn_case(B, H, KVH, S, hd, causal):
                       "bwd_ms": round(ms_b, 4), "bwd_tflops": round(2.5 * fl / ms_b / 1e9, 1)}), flush=True)
 
 
+def swiglu_case(M=16384, D=4096, F=14336):
+    x = (torch.randn(M, D, device=dev) * 0.5).to(BF)
+    wgu = (torch.randn(2 * F, D, device=dev) * 0.02).to(BF)
+    wd = (torch.randn(D, F, device=dev) * 0.02).to(BF)
+    dy = torch.randn(M, D, device=dev).to(BF)
+    gu = ops.gemm(x, wgu)
+    _, gut = ops.gemm_swiglu_fwd(x, wgu, tiled=True)
+    res = {"kernel": "swiglu_mlp", "M": M, "D": D, "F": F}
+    res["fwd_gemm_ms"] = round(timeit(lambda: ops.gemm(x, wgu, out=gu)), 4)
+    res["fwd_swiglu_ms"] = round(timeit(lambda: ops.swiglu_fwd(gu)), 4)
+    res["fwd_fused_rowmajor_ms"] = round(timeit(lambda: ops.gemm_swiglu_fwd(x, wgu)), 4)
+    res["fwd_fused_tiled_ms"] = round(timeit(lambda: ops.gemm_swiglu_fwd(x, wgu, tiled=True)), 4)
+    res["fwd_fused_nogu_ms"] = round(timeit(lambda: ops.gemm_swiglu_fwd(x, wgu, want_gu=False)), 4)
+    dh = ops.gemm(dy, wd, b_layout=1)
+    res["bwd_gemm_ms"] = round(timeit(lambda: ops.gemm(dy, wd, b_layout=1, out=dh)), 4)
+    res["bwd_swiglu_ms"] = round(timeit(lambda: ops.swiglu_bwd(gu, dh)), 4)
+    res["bwd_fused_rowmajor_ms"] = round(timeit(lambda: ops.gemm_swiglu_bwd(dy, wd, gu, b_layout=1)), 4)
+    res["bwd_fused_tiled_ms"] = round(timeit(lambda: ops.gemm_swiglu_bwd(dy, wd, gut, b_layout=1, tiled=True, F=F)), 4)
+    print(json.dumps(res), flush=True)
+
+
 def norm_case(M, D):
     x = torch.randn(M, D, device=dev).to(BF)
     w = torch.ones(D, device=dev, dtype=BF)
@@ -126,5 +147,7 @@ if __name__ == "__main__":
         print(json.dumps({"variant": "tc backward v1"}), flush=True)
         attn_profile()
         ops.set_option(ops.OPT_ATTN_TC_BWD_V1, 0)
+    if which in ("all", "swiglu"):
+        swiglu_case()
     if which in ("all", "norm"):
         norm_case(16384, 4096)

@@ -93,8 +93,11 @@ class DecoderLayerFn(torch.autograd.Function):
                               hd ** -0.5, True)
         x2 = ops.gemm(o, wo, residual=x)
         h2, rstd2 = ops.rmsnorm_fwd(x2, n2, eps)
+        # g|u is saved tile-major when only the fused backward will read it (down_proj frozen)
+        gu_tiled = (ops.FUSE_SWIGLU and ops.FUSE_SWIGLU_BWD and wgu.shape[0] % 256 == 0
+                    and not wd.requires_grad)
         if ops.FUSE_SWIGLU and wgu.shape[0] % 256 == 0:
-            hh, gu = ops.gemm_swiglu_fwd(h2, wgu)  # SwiGLU in the GEMM epilogue
+            hh, gu = ops.gemm_swiglu_fwd(h2, wgu, tiled=gu_tiled)  # SwiGLU in the GEMM epilogue
         else:
             gu = ops.gemm(h2, wgu)
             hh = ops.swiglu_fwd(gu)
@@ -103,6 +106,8 @@ class DecoderLayerFn(torch.autograd.Function):
         ctx.meta = meta
         ctx.split_qkv = wk is not None
         ctx.split_gu = wu is not None
+        ctx.gu_tiled = gu_tiled
+        ctx.F = wgu.shape[0] // 2
         ctx.save_for_backward(x, n1, wo, n2, wd, rstd1, qkv, o, lse, x2, rstd2, gu)
         return x3
 
@@ -113,7 +118,7 @@ class DecoderLayerFn(torch.autograd.Function):
         B, T, H, KVH, hd, eps = meta.B, meta.T, meta.H, meta.KVH, meta.hd, meta.eps
         wqkv, wgu = meta.wqkv, meta.wgu
         qw, kw = H * hd, KVH * hd
-        F = gu.shape[1] // 2
+        F = ctx.F
         dx3 = dx3.contiguous()
         nig = ctx.needs_input_grad
         g = [None] * 11
@@ -126,9 +131,10 @@ class DecoderLayerFn(torch.autograd.Function):
             hh = ops.swiglu_fwd(gu)
             g[9] = ops.gemm(dx3, hh, a_layout=1, b_layout=1)
             del hh
-        if ops.FUSE_SWIGLU_BWD:  # dgrad of down_proj with the SwiGLU derivative in its epilogue
-            dgu = (ops.gemm_swiglu_bwd(dx3, meta.wdT, gu, b_layout=0) if meta.wdT is not None
-                   else ops.gemm_swiglu_bwd(dx3, wd, gu, b_layout=1))
+        if ctx.gu_tiled:  # dgrad of down_proj with the SwiGLU derivative in its epilogue
+            dgu = (ops.gemm_swiglu_bwd(dx3, meta.wdT, gu, b_layout=0, tiled=True, F=F)
+                   if meta.wdT is not None
+                   else ops.gemm_swiglu_bwd(dx3, wd, gu, b_layout=1, tiled=True, F=F))
         else:
             dh = dgrad(dx3, wd, meta.wdT)
             dgu = ops.swiglu_bwd(gu, dh)

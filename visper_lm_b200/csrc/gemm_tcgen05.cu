@@ -29,7 +29,16 @@ struct GemmArgs {
   int M, N, K;
   int act;  // VPB_ACT_*
   int F;    // SwiGLU epilogues: width of one half of the packed gate|up buffer
+  int aux_tiled;  // SwiGLU epilogues: g|u saved in the tile-major layout (see gu_tiled_ptr)
 };
+
+// Tile-major layout of the saved gate|up activations: [M/128 row blocks][F/32 chunks][128 rows]
+// [32 gate | 32 up] bf16.  The epilogue thread that owns a row touches one contiguous 128-byte
+// line per chunk and a warp touches 4 KB contiguous, in the forward store and in the backward load
+// alike (the row-major layout makes both 64-byte pieces at a 2F-element stride).
+__device__ __forceinline__ bf16* gu_tiled_ptr(bf16* base, int F, int row, int chunk) {
+  return base + ((int64_t)((row >> 7) * (F >> 5) + chunk) * 128 + (row & 127)) * 64;
+}
 
 // Epilogue variants.  EPI_SWIGLU_FWD: the B tile is 128 gate rows + 128 up rows of the fused
 // gate|up weight, so accumulator columns [0,128) / [128,256) hold gate / up of the SAME 128 output
@@ -86,9 +95,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
           }
           // round to bf16 first: h is then bit-identical to swiglu_fwd_kernel on the stored g|u
           const uint4 pg = pack8(gv), pu = pack8(uv);
-          if (xrow) {
-            stg16(xrow + n, pg);
-            stg16(xrow + args.F + n, pu);
+          if (args.aux) {
+            if (args.aux_tiled) {
+              bf16* t = gu_tiled_ptr(args.aux, args.F, row, n_base >> 5);
+              stg16(t + g * 8, pg);
+              stg16(t + 32 + g * 8, pu);
+            } else {
+              stg16(xrow + n, pg);
+              stg16(xrow + args.F + n, pu);
+            }
           }
           unpack8(pg, gv);
           unpack8(pu, uv);
@@ -108,8 +123,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
       for (int g = 0; g < 4; ++g) {
         const int n = n_base + g * 8;
         if (row_ok && n + 8 <= args.N) {
-          lg[g] = ldg16_stream(xrow + n);
-          lu[g] = ldg16_stream(xrow + args.F + n);
+          if (args.aux_tiled) {
+            const bf16* t = gu_tiled_ptr(args.aux, args.F, row, n_base >> 5);
+            lg[g] = ldg16_stream(t + g * 8);
+            lu[g] = ldg16_stream(t + 32 + g * 8);
+          } else {
+            lg[g] = ldg16_stream(xrow + n);
+            lu[g] = ldg16_stream(xrow + args.F + n);
+          }
         }
       }
       uint32_t r[32];
@@ -654,6 +675,7 @@ extern "C" int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const voi
   args.K = K;
   args.act = act;
   args.F = 0;
+  args.aux_tiled = 0;
 
   if (pair) {
     switch ((a_layout ? 2 : 0) | (b_layout ? 1 : 0)) {
@@ -678,8 +700,8 @@ extern "C" int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const voi
 
 // gu[M,2F] = A·Wguᵀ (optional store) and h[M,F] = silu(gate)·up in ONE launch.
 extern "C" int vpb_gemm_swiglu_fwd(const void* A, int64_t lda, const void* Wgu, int64_t ldw,
-                                   void* gu, int64_t ldgu, void* h, int64_t ldh, int M, int F,
-                                   int K, void* stream_) {
+                                   void* gu, int64_t ldgu, int gu_tiled, void* h, int64_t ldh,
+                                   int M, int F, int K, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VPB_CHECK(M > 0 && F > 0 && K > 0, "gemm_swiglu_fwd: empty problem M=%d F=%d K=%d", M, F, K);
   VPB_CHECK(F % 128 == 0, "gemm_swiglu_fwd: F=%d must be a multiple of 128", F);
@@ -702,6 +724,7 @@ extern "C" int vpb_gemm_swiglu_fwd(const void* A, int64_t lda, const void* Wgu, 
   args.K = K;
   args.act = VPB_ACT_NONE;
   args.F = F;
+  args.aux_tiled = gu_tiled;
   if (use_pair(M, 2 * F)) return launch_gemm_pair<false, false, EPI_SWIGLU_FWD>(tmA, tmB, args, stream);
   return launch_gemm<256, false, false, EPI_SWIGLU_FWD>(tmA, tmB, args, stream);
 }
@@ -709,11 +732,12 @@ extern "C" int vpb_gemm_swiglu_fwd(const void* A, int64_t lda, const void* Wgu, 
 // dgu[M,2F] = swiglu'(gu) ∘ (dY·W) where W is the down projection: b_layout 1 → W is [K=D, F]
 // (the nn.Linear weight read MN-major), b_layout 0 → W is a K-major transposed copy [F, D].
 extern "C" int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, int64_t ldw,
-                                   int b_layout, const void* gu, int64_t ldgu, void* dgu,
-                                   int64_t lddgu, int M, int F, int K, void* stream_) {
+                                   int b_layout, const void* gu, int64_t ldgu, int gu_tiled,
+                                   void* dgu, int64_t lddgu, int M, int F, int K, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VPB_CHECK(M > 0 && F > 0 && K > 0, "gemm_swiglu_bwd: empty problem M=%d F=%d K=%d", M, F, K);
   VPB_CHECK(F % 8 == 0, "gemm_swiglu_bwd: F=%d must be a multiple of 8", F);
+  VPB_CHECK(!gu_tiled || F % 32 == 0, "gemm_swiglu_bwd: tiled g|u needs F %% 32 == 0 (F=%d)", F);
   VPB_CHECK(gu && dgu && ldgu % 8 == 0 && lddgu % 8 == 0 &&
                 (reinterpret_cast<uintptr_t>(gu) & 15) == 0 && (reinterpret_cast<uintptr_t>(dgu) & 15) == 0,
             "gemm_swiglu_bwd: gu/dgu alignment");
@@ -738,6 +762,7 @@ extern "C" int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, 
   args.K = K;
   args.act = VPB_ACT_NONE;
   args.F = F;
+  args.aux_tiled = gu_tiled;
   if (pair) {
     if (b_layout == 0) return launch_gemm_pair<false, false, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
     return launch_gemm_pair<false, true, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);

@@ -99,8 +99,9 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None
 
 
 # A/B switches for the fused SwiGLU GEMM epilogues (0 selects the separate kernels).  Measured in
-# the Llama-3-8B step (call A, r01): the forward fusion is a small win, the backward one loses to
-# the separate kernel because its row-strided g|u reads are DRAM-unfriendly.
+# the Llama-3-8B step, same box, alternating runs (profiles/r01_swiglu_fusion_ab.txt): the forward
+# fusion wins ~1.7 % of the step; the backward fusion (with the tile-major g|u layout) wins 0.4 ms
+# per layer in isolation but is a wash inside the power-capped step, so it stays off by default.
 FUSE_SWIGLU = os.environ.get("VPB_FUSE_SWIGLU", "1") != "0"
 FUSE_SWIGLU_BWD = os.environ.get("VPB_FUSE_SWIGLU_BWD", "0") != "0"
 
@@ -121,36 +122,40 @@ def _timed_end(t):
         timer.records.append((ev0, ev1, flops))
 
 
-def gemm_swiglu_fwd(a, wgu, want_gu=True):
-    """(h, gu): gu[M,2F] = a·wguᵀ (None unless want_gu) and h[M,F] = silu(gate)·up, one launch."""
+def gemm_swiglu_fwd(a, wgu, want_gu=True, tiled=False):
+    """(h, gu): gu = a·wguᵀ (None unless want_gu) and h[M,F] = silu(gate)·up, one launch.
+    tiled: gu is the flat tile-major buffer only gemm_swiglu_bwd(tiled=True) can read."""
     M, K = a.shape
     F2, Kb = wgu.shape
     F = F2 // 2
     assert K == Kb and F % 128 == 0
     h = torch.empty((M, F), dtype=BF16, device=a.device)
-    gu = torch.empty((M, F2), dtype=BF16, device=a.device) if want_gu else None
+    gu = None
+    if want_gu:
+        gu = (torch.empty((((M + 127) // 128) * 128 * F2,), dtype=BF16, device=a.device) if tiled
+              else torch.empty((M, F2), dtype=BF16, device=a.device))
     pa, lda = _rows(a)
     pw, ldw = _rows(wgu)
-    pg, ldg = _rows(gu) if gu is not None else (0, 0)
+    pg, ldg = (gu.data_ptr(), F2) if gu is not None else (0, 0)
     t = _timed(2.0 * M * F2 * K)
-    _chk(_L().vpb_gemm_swiglu_fwd(pa, lda, pw, ldw, pg, ldg, h.data_ptr(), F, M, F, K, _stream()),
-         "gemm_swiglu_fwd")
+    _chk(_L().vpb_gemm_swiglu_fwd(pa, lda, pw, ldw, pg, ldg, 1 if tiled else 0, h.data_ptr(), F, M, F, K,
+                                  _stream()), "gemm_swiglu_fwd")
     _timed_end(t)
     return h, gu
 
 
-def gemm_swiglu_bwd(dy, w, gu, b_layout=1):
+def gemm_swiglu_bwd(dy, w, gu, b_layout=1, tiled=False, F=None):
     """dgu[M,2F] = swiglu'(gu) ∘ (dy·W); w is down_proj [D,F] (b_layout 1) or its transpose [F,D]."""
     M, K = dy.shape
-    F = gu.shape[1] // 2
+    if F is None:
+        F = gu.shape[1] // 2
     assert (w.shape == (K, F)) if b_layout == 1 else (w.shape == (F, K)), (w.shape, K, F)
     dgu = torch.empty((M, 2 * F), dtype=BF16, device=dy.device)
     pd, ldd = _rows(dy)
     pw, ldw = _rows(w)
-    pg, ldg = _rows(gu)
     t = _timed(2.0 * M * F * K)
-    _chk(_L().vpb_gemm_swiglu_bwd(pd, ldd, pw, ldw, b_layout, pg, ldg, dgu.data_ptr(), 2 * F, M, F, K,
-                                  _stream()), "gemm_swiglu_bwd")
+    _chk(_L().vpb_gemm_swiglu_bwd(pd, ldd, pw, ldw, b_layout, gu.data_ptr(), 2 * F, 1 if tiled else 0,
+                                  dgu.data_ptr(), 2 * F, M, F, K, _stream()), "gemm_swiglu_bwd")
     _timed_end(t)
     return dgu
 
