@@ -417,10 +417,14 @@ def run_b200(args):
         "clocks": clk,
         "loss": {"device_leg": loss_dev, "e2e_leg": loss_e2e},
         "roofline": {
-            "bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of the timed steps)",
+            "bound": "tensor",
+            "kernel": "gemm_tcgen05_pair_kernel / gemm_tcgen05_kernel (all GEMM launches of the timed steps)",
             "achieved": gemm_stats["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
             "frac": gemm_stats["tflops"] / peak_tf if gemm_stats["tflops"] else None,
-            "traffic": None, "peak_source": peak_src, "launches": gemm_stats["launches"],
+            # dram read+write of the dominant launch shape (down_proj dgrad, M=16384 N=14336 K=4096) from
+            # the ncu --set full capture profiles/r01_ncu_gemm_pair_instep.csv; algorithmic 0.72 GB
+            "traffic": 1.55e9 if full_model else None,
+            "peak_source": peak_src, "launches": gemm_stats["launches"],
             "gemm_ms_per_step": gemm_stats["ms"] / args.steps,
             "gemm_share_of_step": gemm_stats["ms"] / ms_dev if ms_dev else None,
             "step_model_flops_frac": (value / world * FLOPS[flop_key] / (peak_tf * 1e12)) if full_model else None,

@@ -30,6 +30,7 @@ struct GemmArgs {
   int act;  // VPB_ACT_*
   int F;    // SwiGLU epilogues: width of one half of the packed gate|up buffer
   int aux_tiled;  // SwiGLU epilogues: g|u saved in the tile-major layout (see gu_tiled_ptr)
+  int group_m;    // row blocks per L2 panel of the tile order (host-chosen from K)
 };
 
 // Tile-major layout of the saved gate|up activations: [M/128 row blocks][F/32 chunks][128 rows]
@@ -51,7 +52,6 @@ constexpr int EPI_SWIGLU_BWD = 2;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GROUP_M = 16;
 
 __device__ __forceinline__ float act_apply(float x, int act) {
   switch (act) {
@@ -249,10 +249,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   // tile order: groups of GROUP_M row-blocks swept over all column-blocks, so one wave of
   // 148 CTAs shares a ~2048-row A panel and a ~2300-row B panel in L2.
   auto decode_tile = [&](int t, int& mb, int& nb) {
-    const int per_group = GROUP_M * num_n;
+    const int per_group = args.group_m * num_n;
     const int g = t / per_group;
-    const int first_m = g * GROUP_M;
-    const int gsize = min(GROUP_M, num_m - first_m);
+    const int first_m = g * args.group_m;
+    const int gsize = min(args.group_m, num_m - first_m);
     const int r = t - g * per_group;
     mb = first_m + r % gsize;
     nb = r / gsize;
@@ -365,7 +365,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 // ----------------------------------------------------------------------------------------------
 constexpr int PAIR_BN = 256;
 constexpr int PAIR_STAGES = 6;
-constexpr int PAIR_GROUP_M = 8;  // 8 x 256 rows per L2 panel
 
 template <bool A_MN, bool B_MN, int EPI = EPI_STD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
@@ -420,10 +419,10 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA,
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode_tile = [&](int t, int& mb, int& nb) {
-    const int per_group = PAIR_GROUP_M * num_n;
+    const int per_group = args.group_m * num_n;
     const int g = t / per_group;
-    const int first_m = g * PAIR_GROUP_M;
-    const int gsize = min(PAIR_GROUP_M, num_m - first_m);
+    const int first_m = g * args.group_m;
+    const int gsize = min(args.group_m, num_m - first_m);
     const int r = t - g * per_group;
     mb = first_m + r % gsize;
     nb = r / gsize;
@@ -572,6 +571,18 @@ int num_sms() {
   return g_num_sms;
 }
 
+// Tile order: groups of `panel rows` of A are swept over all column blocks, so the A panel stays
+// in L2 while B streams past it once per group.  A bigger panel means fewer passes over B (the
+// weights); it must still fit next to the streaming operand in the 126 MB L2: ~32 MB of A.
+static int g_panel_mb = 32;
+static int panel_rows_for(int K) {
+  int64_t rows = ((int64_t)g_panel_mb << 20) / ((int64_t)K * 2);
+  rows = (rows / 256) * 256;
+  if (rows < 512) rows = 512;
+  if (rows > 8192) rows = 8192;
+  return (int)rows;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI = EPI_STD>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
                        cudaStream_t stream) {
@@ -586,7 +597,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   constexpr int BNO = (EPI == EPI_SWIGLU_FWD) ? BN / 2 : BN;
   const int tiles = ((args.M + BM - 1) / BM) * ((args.N + BNO - 1) / BNO);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 192, SMEM, stream>>>(tmA, tmB, args);
+  GemmArgs a2 = args;
+  a2.group_m = panel_rows_for(args.K) / BM;
+  kern<<<grid, 192, SMEM, stream>>>(tmA, tmB, a2);
   VPB_LAUNCH_OK();
   return 0;
 }
@@ -606,7 +619,9 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   const int tiles = ((args.M + 2 * BM - 1) / (2 * BM)) * ((args.N + BNO - 1) / BNO);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, 192, SMEM, stream>>>(tmA, tmB, args);
+  GemmArgs a2 = args;
+  a2.group_m = panel_rows_for(args.K) / (2 * BM);
+  kern<<<grid, 192, SMEM, stream>>>(tmA, tmB, a2);
   VPB_LAUNCH_OK();
   return 0;
 }
@@ -615,6 +630,7 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 // coarser 256 x 256 tiles can quantise into more waves than the 1-CTA kernel, so compare the two
 // wave efficiencies (measured: CLIP QKV M=4616 N=3072 is 3.08 pair waves vs exactly 3 single waves).
 static bool use_pair(int M, int N) {
+  if (get_option(VPB_OPT_GEMM_PANEL_MB) > 0) g_panel_mb = get_option(VPB_OPT_GEMM_PANEL_MB);
   if (get_option(VPB_OPT_GEMM_1CTA)) return false;
   if (N < 256 || M < 256) return false;
   const int pairs = num_sms() / 2, sms = num_sms();

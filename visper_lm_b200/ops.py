@@ -35,7 +35,7 @@ def _rows(t: torch.Tensor):
     return t.data_ptr(), t.stride(0)
 
 
-OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD, OPT_ATTN_TC_BWD_V1, OPT_GEMM_1CTA = 0, 1, 2, 3
+OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD, OPT_ATTN_TC_BWD_V1, OPT_GEMM_1CTA, OPT_GEMM_PANEL_MB = 0, 1, 2, 3, 4
 
 
 def set_option(key, value):
@@ -503,3 +503,7 @@ def clip_coef(sumsq, max_norm, extra_scale=1.0):
     _chk(_L().vpb_clip_coef(sumsq.data_ptr(), max_norm, extra_scale, coef.data_ptr(), norm.data_ptr(),
                             _stream()), "clip_coef")
     return coef, norm
+
+
+if os.environ.get("VPB_GEMM_PANEL_MB"):
+    set_option(OPT_GEMM_PANEL_MB, int(os.environ["VPB_GEMM_PANEL_MB"]))
