@@ -140,17 +140,20 @@ int vpb_group_mean_bwd(const void* dout, int64_t ldo, void* din, int64_t ldi, in
 /* ---- attention ------------------------------------------------------------------------------
  * Flash attention on packed projections; optional second K/V segment (k2/v2, length sk2) is
  * appended after the first (PerceiverAttention keys = cat(x, latents), resampler.py:61-62).
- * lse: [B,H,sq] fp32. delta: [B,H,sq] fp32 workspace for the backward. */
+ * lse: [B,H,sq] fp32. delta: [B,H,sq] fp32 workspace for the backward.
+ * window > 0 (causal only): sliding-window attention as HF 4.41.1 Phi3FlashAttention2 passes it to
+ * flash_attn (window_size=(sliding_window, sliding_window)): key j is visible to query i iff
+ * 0 <= i - j <= window.  Phi-3-mini: sliding_window 2047. */
 int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                  const void* k2, int64_t ldk2, const void* v2, int64_t ldv2, void* o, int64_t ldo,
                  float* lse, int B, int H, int KVH, int sq, int sk, int sk2, int head_dim,
-                 float scale, int causal, void* stream);
+                 float scale, int causal, int window, void* stream);
 int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                  const void* k2, int64_t ldk2, const void* v2, int64_t ldv2, const void* o,
                  int64_t ldo, const void* dO, int64_t lddo, const float* lse, float* delta, void* dq,
                  int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dk2,
                  int64_t lddk2, void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk,
-                 int sk2, int head_dim, float scale, int causal, void* stream);
+                 int sk2, int head_dim, float scale, int causal, int window, void* stream);
 
 /* ---- next-token cross-entropy (ola_llama.py:121-136) -----------------------------------------
  * labels: int64 [B,T] UNSHIFTED when shift=1 (row (b,t) is scored against labels[b,t+1]).

@@ -11,6 +11,9 @@ TINY_LLAMA = dict(
     tokenizer_model_max_length=1024)
 
 TINY_PHI3 = dict(TINY_LLAMA, family="phi3", kv_heads=4, rope_theta=10000.0, num_sys_tokens=13)
+# Phi-3's sliding-window attention (config 5: T=4096 > sliding_window 2047) at test size: the
+# embedded sequence is ~650 tokens, so a 200-token window cuts into image, task and text tokens.
+TINY_PHI3_SW = dict(TINY_PHI3, sliding_window=200)
 
 # real layer WIDTHS (Llama-3-8B / Phi-3-mini / CLIP-ViT-L dims, all three head widths) at reduced depth
 # and vocabulary: exercises the production kernel shapes (hd 128 GQA 32/8, hd 96, K=14336, dim-4096

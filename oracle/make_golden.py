@@ -25,6 +25,7 @@ CASES = [
     ("tiny_llama_dsg", "TINY_LLAMA", "llama", True, 2, 40, 0),
     ("tiny_llama_dsg_padded", "TINY_LLAMA", "llama", True, 3, 48, 1),
     ("tiny_phi3_dsg", "TINY_PHI3", "phi3", True, 2, 40, 0),
+    ("tiny_phi3_sw_dsg", "TINY_PHI3_SW", "phi3", True, 2, 40, 0),
     ("tiny_llama_ntp", "TINY_LLAMA", "llama", False, 2, 40, 0),
     ("wide_llama_dsg", "WIDE_LLAMA", "llama", True, 2, 40, 0),
     ("wide_phi3_dsg", "WIDE_PHI3", "phi3", True, 2, 40, 0),

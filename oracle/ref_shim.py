@@ -160,7 +160,11 @@ def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True
         Cfg = mod.OlaLlavaPhi3Config if distill else mod.LlavaPhi3Config
         Cls = mod.OlaLlavaPhi3ForCausalLM if distill else mod.LlavaPhi3ForCausalLM
         lm_kwargs = dict(rope_theta=cfg["rope_theta"], num_key_value_heads=cfg["kv_heads"],
-                         sliding_window=None, resid_pdrop=0.0, embd_pdrop=0.0, attention_dropout=0.0,
+                         # transformers 5.5 (this image) shows a query W keys including itself
+                         # (i-j < W); the reference's pin 4.41.1 / flash_attn shows W+1 (i-j <= W).
+                         # The shim therefore asks 5.5 for W+1 to reproduce the pinned behaviour.
+                         sliding_window=(cfg["sliding_window"] + 1) if cfg.get("sliding_window") else None,
+                         resid_pdrop=0.0, embd_pdrop=0.0, attention_dropout=0.0,
                          pad_token_id=0, bos_token_id=1, eos_token_id=2,
                          original_max_position_embeddings=cfg["max_pos"])
     config = Cfg(

@@ -298,6 +298,38 @@ def test_attention_fwd_bwd(B, H, KVH, sq, sk, sk2, hd, causal):
         close(dkv2, g[:, sk:].reshape(B * sk2, 2 * kw), rtol=3e-2, name="attn dkv2")
 
 
+@pytest.mark.parametrize("B,H,KVH,S,hd,window", [(2, 4, 4, 700, 96, 200), (1, 4, 2, 1000, 128, 255),
+                                                  (1, 2, 2, 300, 64, 17), (2, 4, 4, 4096, 96, 2047)])
+def test_attention_sliding_window(B, H, KVH, S, hd, window):
+    """Causal sliding-window attention (Phi-3): key j visible iff 0 <= i-j <= window."""
+    from visper_lm_b200 import ops
+    qw, kw = H * hd, KVH * hd
+    q = rnd(B * S, qw, seed=81)
+    kv = rnd(B * S, 2 * kw, seed=82)
+    do = rnd(B * S, qw, seed=83)
+    k, v = kv[:, :kw], kv[:, kw:]
+    scale = hd ** -0.5
+    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, True, window=window)
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    ops.attn_bwd(q, k, v, o, do, lse, dq, dkv[:, :kw], dkv[:, kw:], B, H, KVH, S, S, hd, scale, True,
+                 window=window)
+    torch.cuda.synchronize()
+    qf = q.float().view(B, S, H, hd).transpose(1, 2).detach().requires_grad_(True)
+    kvf = kv.float().view(B, S, 2, KVH, hd).detach().requires_grad_(True)
+    kf = kvf[:, :, 0].transpose(1, 2).repeat_interleave(H // KVH, 1)
+    vf = kvf[:, :, 1].transpose(1, 2).repeat_interleave(H // KVH, 1)
+    s_ = (qf @ kf.transpose(-1, -2)) * scale
+    i = torch.arange(S, device=s_.device)[:, None]
+    j = torch.arange(S, device=s_.device)[None, :]
+    vis = (j <= i) & (i - j <= window)
+    ref = (torch.softmax(s_.masked_fill(~vis, float("-inf")), -1) @ vf).transpose(1, 2).reshape(B * S, qw)
+    close(o, ref, name="window fwd")
+    ref.backward(do.float())
+    close(dq, qf.grad.transpose(1, 2).reshape(B * S, qw), rtol=3e-2, name="window dq")
+    close(dkv, kvf.grad.reshape(B * S, 2 * kw), rtol=3e-2, name="window dkv")
+
+
 @pytest.mark.parametrize("B,H,KVH,sq,sk,causal", [(2, 8, 2, 2048, 2048, True), (1, 4, 4, 333, 333, True),
                                                    (2, 4, 2, 200, 520, False), (1, 4, 1, 128, 128, True)])
 def test_attention_tcgen05_matches_legacy(B, H, KVH, sq, sk, causal):

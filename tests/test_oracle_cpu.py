@@ -7,7 +7,8 @@ from parity_utils import configs, restate
 
 GOLDEN = __import__("pathlib").Path(__file__).parent / "golden"
 CASES = [("tiny_llama_dsg", "TINY_LLAMA", True), ("tiny_llama_dsg_padded", "TINY_LLAMA", True),
-         ("tiny_phi3_dsg", "TINY_PHI3", True), ("tiny_llama_ntp", "TINY_LLAMA", False),
+         ("tiny_phi3_dsg", "TINY_PHI3", True), ("tiny_phi3_sw_dsg", "TINY_PHI3_SW", True),
+         ("tiny_llama_ntp", "TINY_LLAMA", False),
          ("wide_llama_dsg", "WIDE_LLAMA", True), ("wide_phi3_dsg", "WIDE_PHI3", True)]
 
 

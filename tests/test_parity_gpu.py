@@ -20,6 +20,8 @@ DEV = "cuda:0"
 CASES = [("tiny_llama_dsg", "TINY_LLAMA", True, 2, 40, 0),
          ("tiny_llama_dsg_padded", "TINY_LLAMA", True, 3, 48, 1),
          ("tiny_phi3_dsg", "TINY_PHI3", True, 2, 40, 0),
+         # Phi-3 sliding-window attention (window 200 < T ≈ 650): mma.sync kernels with the window mask
+         ("tiny_phi3_sw_dsg", "TINY_PHI3_SW", True, 2, 40, 0),
          ("tiny_llama_ntp", "TINY_LLAMA", False, 2, 40, 0),
          # production layer widths (hd 128 GQA → tcgen05 attention, hd 96, K=14336, 4096-dim depth head)
          ("wide_llama_dsg", "WIDE_LLAMA", True, 2, 40, 0),

@@ -90,7 +90,7 @@ class DecoderLayerFn(torch.autograd.Function):
         del h1
         ops.rope_(qkv, T, meta.cos, meta.sin, H + KVH, hd, pos_ids=meta.pos_ids)
         o, lse = ops.attn_fwd(qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:], B, H, KVH, T, T, hd,
-                              hd ** -0.5, True)
+                              hd ** -0.5, True, window=getattr(meta, "window", 0))
         x2 = ops.gemm(o, wo, residual=x)
         h2, rstd2 = ops.rmsnorm_fwd(x2, n2, eps)
         # g|u is saved tile-major when only the fused backward will read it (down_proj frozen)
@@ -160,7 +160,8 @@ class DecoderLayerFn(torch.autograd.Function):
             g[5] = ops.gemm(dx2, o, a_layout=1, b_layout=1)
         dqkv = torch.empty_like(qkv)
         ops.attn_bwd(qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:], o, do, lse, dqkv[:, :qw],
-                     dqkv[:, qw:qw + kw], dqkv[:, qw + kw:], B, H, KVH, T, T, hd, hd ** -0.5, True)
+                     dqkv[:, qw:qw + kw], dqkv[:, qw + kw:], B, H, KVH, T, T, hd, hd ** -0.5, True,
+                     window=getattr(meta, "window", 0))
         del do
         ops.rope_(dqkv, T, meta.cos, meta.sin, H + KVH, hd, inverse=True, pos_ids=meta.pos_ids)
         dn1 = dgrad(dqkv, wqkv, meta.wqkvT)

@@ -22,6 +22,7 @@ struct AttnParams {
   int64_t ldq, ldk, ldv, ldk2, ldv2, ldo;
   int B, H, KVH, sq, sk, sk2;
   float scale;
+  int window;  // causal sliding window: key j visible to query i iff 0 <= i + off - j <= window (0: off)
   // backward only
   const bf16* dO;
   int64_t lddo;
@@ -104,12 +105,18 @@ attn_fwd_kernel(const AttnParams p) {
 
   int n1 = (p.sk + BN - 1) / BN;
   int n2 = (p.sk2 + BN - 1) / BN;
+  int jt0 = 0;  // first key tile any row of this query tile can see (sliding window)
   if (CAUSAL) {
     int kv_end = q0 + BMQ + off;
     if (kv_end > p.sk) kv_end = p.sk;
     if (kv_end < 0) kv_end = 0;
     n1 = (kv_end + BN - 1) / BN;
     n2 = 0;
+    if (p.window > 0) {
+      const int lo = q0 + off - p.window;
+      jt0 = lo > 0 ? lo / BN : 0;
+      if (jt0 > n1) jt0 = n1;
+    }
   }
   const int ntiles = n1 + n2;
 
@@ -130,7 +137,7 @@ attn_fwd_kernel(const AttnParams p) {
     load_tile<BN, HD, NT>(sK0 + buf * BN * HDP * 2, kg, ldk, rv);
     load_tile<BN, HD, NT>(sV0 + buf * BN * HDP * 2, vg, ldv, rv);
   };
-  if (ntiles > 0) issue_kv(0, 0);
+  if (ntiles > jt0) issue_kv(jt0, jt0 & 1);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
@@ -145,7 +152,7 @@ attn_fwd_kernel(const AttnParams p) {
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
   const float sl2 = p.scale * LOG2E;
 
-  for (int jt = 0; jt < ntiles; ++jt) {
+  for (int jt = jt0; jt < ntiles; ++jt) {
     const int buf = jt & 1;
     if (jt + 1 < ntiles) {
       issue_kv(jt + 1, buf ^ 1);
@@ -174,7 +181,9 @@ attn_fwd_kernel(const AttnParams p) {
     const bool seg2 = jt >= n1;
     const int j0 = (seg2 ? jt - n1 : jt) * BN;
     const int len = seg2 ? p.sk2 : p.sk;
-    const bool need_mask = (j0 + BN > len) || (CAUSAL && (j0 + BN - 1 > q0 + off));
+    const bool win = CAUSAL && p.window > 0;
+    const bool need_mask = (j0 + BN > len) || (CAUSAL && (j0 + BN - 1 > q0 + off)) ||
+                           (win && j0 < q0 + BMQ - 1 + off - p.window);
     if (need_mask) {
 #pragma unroll
       for (int nb = 0; nb < BN / 8; ++nb) {
@@ -182,7 +191,7 @@ attn_fwd_kernel(const AttnParams p) {
         for (int e = 0; e < 4; ++e) {
           const int j = j0 + nb * 8 + 2 * t + (e & 1);
           const int i = q0 + warp * 16 + g + (e >> 1) * 8;
-          const bool ok = (j < len) && (!CAUSAL || j <= i + off);
+          const bool ok = (j < len) && (!CAUSAL || j <= i + off) && (!win || j >= i + off - p.window);
           if (!ok) s[nb][e] = -INFINITY;
         }
       }
@@ -365,15 +374,21 @@ attn_bwd_dkdv_kernel(const AttnParams p) {
   }
   const float sl2 = p.scale * LOG2E;
   const int nq_tiles = (p.sq + BQ - 1) / BQ;
-  int qt_begin = 0;
+  int qt_begin = 0, qt_end = nq_tiles;
+  const bool win = CAUSAL && p.window > 0;
   if (CAUSAL) {
     int first = kv0 - off;  // first query row that can see key kv0
     if (first < 0) first = 0;
     qt_begin = first / BQ;
+    if (win) {  // last query row that can see the tile's last key
+      const int last = kv0 + BKV - 1 - off + p.window;
+      if (last < 0) qt_end = 0;
+      else if (last / BQ + 1 < qt_end) qt_end = last / BQ + 1;
+    }
   }
 
   for (int hq = kvh * G; hq < (kvh + 1) * G; ++hq) {
-    for (int qt = qt_begin; qt < nq_tiles; ++qt) {
+    for (int qt = qt_begin; qt < qt_end; ++qt) {
       const int q0 = qt * BQ;
       __syncthreads();  // previous tile fully consumed
       int q_valid = p.sq - q0;
@@ -420,7 +435,8 @@ attn_bwd_dkdv_kernel(const AttnParams p) {
         for (int e = 0; e < 4; ++e) {
           const int qc = nb * 8 + 2 * t + (e & 1);
           const int kr = warp * 16 + g + (e >> 1) * 8;
-          const bool ok = (qc < q_valid) && (kr < kv_valid) && (!CAUSAL || kv0 + kr <= q0 + qc + off);
+          const bool ok = (qc < q_valid) && (kr < kv_valid) && (!CAUSAL || kv0 + kr <= q0 + qc + off) &&
+                          (!win || kv0 + kr >= q0 + qc + off - p.window);
           const float pv = ok ? exp2f(st[nb][e] * sl2 - sLse[qc]) : 0.f;
           st[nb][e] = pv;
           dpt[nb][e] = pv * (dpt[nb][e] - sDelta[qc]);
@@ -525,19 +541,26 @@ attn_bwd_dq_kernel(const AttnParams p) {
 
   int n1 = (p.sk + BKV - 1) / BKV;
   int n2 = (p.sk2 + BKV - 1) / BKV;
+  int jt0 = 0;
+  const bool win = CAUSAL && p.window > 0;
   if (CAUSAL) {
     int kv_end = q0 + BQ + off;
     if (kv_end > p.sk) kv_end = p.sk;
     if (kv_end < 0) kv_end = 0;
     n1 = (kv_end + BKV - 1) / BKV;
     n2 = 0;
+    if (win) {
+      const int lo = q0 + off - p.window;
+      jt0 = lo > 0 ? lo / BKV : 0;
+      if (jt0 > n1) jt0 = n1;
+    }
   }
   float dq[ND][4];
 #pragma unroll
   for (int i = 0; i < ND; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
   const float sl2 = p.scale * LOG2E;
 
-  for (int jt = 0; jt < n1 + n2; ++jt) {
+  for (int jt = jt0; jt < n1 + n2; ++jt) {
     const bool seg2 = jt >= n1;
     const int j0 = (seg2 ? jt - n1 : jt) * BKV;
     const int len = seg2 ? p.sk2 : p.sk;
@@ -580,7 +603,8 @@ attn_bwd_dq_kernel(const AttnParams p) {
         const int jc = nb * 8 + 2 * t + (e & 1);
         const int r = e >> 1;
         const int i = warp * 16 + g + r * 8;
-        const bool ok = (i < q_valid) && (jc < kv_valid) && (!CAUSAL || j0 + jc <= q0 + i + off);
+        const bool ok = (i < q_valid) && (jc < kv_valid) && (!CAUSAL || j0 + jc <= q0 + i + off) &&
+                        (!win || j0 + jc >= q0 + i + off - p.window);
         const float pv = ok ? exp2f(s[nb][e] * sl2 - lse2[r]) : 0.f;
         s[nb][e] = pv * (dp[nb][e] - dl[r]);  // dS
       }
@@ -716,17 +740,20 @@ using namespace vpb;
 extern "C" int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, const void* k2, int64_t ldk2, const void* v2, int64_t ldv2,
                             void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk,
-                            int sk2, int head_dim, float scale, int causal, void* stream) {
+                            int sk2, int head_dim, float scale, int causal, int window,
+                            void* stream) {
   AttnParams p = {};
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
   p.k2 = (const bf16*)k2; p.v2 = (const bf16*)v2;
   p.o = (bf16*)o; p.lse = lse;
+  p.window = (causal && window > 0 && window < sk) ? window : 0;
+  VPB_CHECK(window >= 0 && (window == 0 || causal), "attention: a sliding window needs causal=1");
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldk2 = ldk2; p.ldv2 = ldv2; p.ldo = ldo;
   p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk; p.sk2 = k2 ? sk2 : 0;
   p.scale = scale;
   if (check_attn(p, head_dim)) return -1;
   VPB_CHECK(!(causal && p.sk2 > 0), "attention: causal with a second key segment is not supported");
-  if (head_dim == 128 && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_FWD) &&
+  if (head_dim == 128 && p.sk2 == 0 && p.window == 0 && !get_option(VPB_OPT_ATTN_LEGACY_FWD) &&
       (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(v) & 15) == 0)
     return attn_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, KVH, sq, sk, scale, causal,
@@ -740,11 +767,13 @@ extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t l
                             const float* lse, float* delta, void* dq, int64_t lddq, void* dk,
                             int64_t lddk, void* dv, int64_t lddv, void* dk2, int64_t lddk2,
                             void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk, int sk2,
-                            int head_dim, float scale, int causal, void* stream) {
+                            int head_dim, float scale, int causal, int window, void* stream) {
   AttnParams p = {};
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
   p.k2 = (const bf16*)k2; p.v2 = (const bf16*)v2;
   p.lse = const_cast<float*>(lse);
+  p.window = (causal && window > 0 && window < sk) ? window : 0;
+  VPB_CHECK(window >= 0 && (window == 0 || causal), "attention: a sliding window needs causal=1");
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldk2 = ldk2; p.ldv2 = ldv2; p.ldo = ldo;
   p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk; p.sk2 = k2 ? sk2 : 0;
   p.scale = scale;
@@ -758,7 +787,8 @@ extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t l
   launch_delta((const bf16*)o, ldo, (const bf16*)dO, lddo, delta, B, H, sq, head_dim, (cudaStream_t)stream);
   VPB_LAUNCH_OK();
   auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
-  if (head_dim == 128 && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_BWD) && al16(q) && al16(k) &&
+  if (head_dim == 128 && p.sk2 == 0 && p.window == 0 && !get_option(VPB_OPT_ATTN_LEGACY_BWD) && al16(q) &&
+      al16(k) &&
       al16(v) && al16(dO))
     return attn_bwd_tc(q, ldq, k, ldk, v, ldv, dO, lddo, lse, delta, dq, lddq, dk, lddk, dv, lddv, B,
                        H, KVH, sq, sk, scale, causal, (cudaStream_t)stream);

@@ -13,6 +13,8 @@ def from_dict(c: dict, cls=VisperConfig, distill=True):
               num_key_value_heads=c["kv_heads"], max_position_embeddings=c["max_pos"],
               rope_theta=c["rope_theta"], vision=vision,
               tokenizer_model_max_length=c.get("tokenizer_model_max_length", c["max_pos"]))
+    if "sliding_window" in c:
+        cfg.sliding_window = c["sliding_window"]
     if distill:
         li = f"d{c['depth_layers']}_s{c['seg_layers']}_g{c['gen_layers']}"
         cfg.inject_aux(mode=c.get("aux_mode", "gen-depth-seg"), layer_indices=li,

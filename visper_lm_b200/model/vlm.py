@@ -70,6 +70,9 @@ class VisperConfig:
         self.tokenizer_padding_side = tokenizer_padding_side
         self.use_return_dict = True
         self.output_hidden_states = False
+        # Phi-3-mini-4k ships sliding_window=2047 (HF Phi3Config); HF 4.41.1 hands it to flash_attn as
+        # window_size=(2047, 2047): key j visible to query i iff 0 <= i - j <= 2047.  None = full causal.
+        self.sliding_window = 2047 if family == "phi3" else None
         self.zero_masks_like_reference = False  # off for training value
         self.materialize_logits = False         # .logits only on request while training
         self.num_task_tokens = 0
@@ -539,8 +542,9 @@ class VisperForCausalLM(nn.Module):
         H, KVH = cfg.num_attention_heads, cfg.num_key_value_heads
         hd = D // H
         cos, sin = ops.rope_tables(max(cfg.max_position_embeddings, T), hd, cfg.rope_theta, inputs_embeds.device)
+        sw = getattr(cfg, "sliding_window", None)
         meta = SimpleNamespace(B=B, T=T, H=H, KVH=KVH, hd=hd, eps=cfg.rms_norm_eps, cos=cos, sin=sin,
-                               pos_ids=None)
+                               pos_ids=None, window=int(sw) if (sw and T > sw + 1) else 0)
         x = inputs_embeds.reshape(B * T, D)
         if x.dtype != BF16:
             x = x.to(BF16)

@@ -391,7 +391,8 @@ def group_mean_bwd(dout, groups, gsize):
 
 
 # --------------------------------------------------------------------------------------------- attention
-def attn_fwd(q, k, v, B, H, KVH, sq, sk, head_dim, scale, causal, k2=None, v2=None, sk2=0, out=None):
+def attn_fwd(q, k, v, B, H, KVH, sq, sk, head_dim, scale, causal, k2=None, v2=None, sk2=0, out=None,
+             window=0):
     """q:[B*sq, >=H*hd] k,v:[B*sk, >=KVH*hd] row views (may alias one packed buffer)."""
     dev = q.device
     o = out if out is not None else torch.empty((B * sq, H * head_dim), dtype=BF16, device=dev)
@@ -403,13 +404,13 @@ def attn_fwd(q, k, v, B, H, KVH, sq, sk, head_dim, scale, causal, k2=None, v2=No
     pv2, ldv2 = _rows(v2) if v2 is not None else (0, 0)
     po, ldo = _rows(o)
     _chk(_L().vpb_attn_fwd(pq, ldq, pk, ldk, pv, ldv, pk2, ldk2, pv2, ldv2, po, ldo, lse.data_ptr(),
-                           B, H, KVH, sq, sk, sk2, head_dim, scale, 1 if causal else 0, _stream()),
-         "attn_fwd")
+                           B, H, KVH, sq, sk, sk2, head_dim, scale, 1 if causal else 0, int(window),
+                           _stream()), "attn_fwd")
     return o, lse
 
 
 def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, sq, sk, head_dim, scale, causal,
-             k2=None, v2=None, sk2=0, dk2=None, dv2=None):
+             k2=None, v2=None, sk2=0, dk2=None, dv2=None, window=0):
     """Writes dq/dk/dv (and dk2/dv2) row views in place."""
     delta = torch.empty((B, H, sq), dtype=torch.float32, device=q.device)
     pq, ldq = _rows(q)
@@ -427,7 +428,7 @@ def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, sq, sk, head_dim, scale
     _chk(_L().vpb_attn_bwd(pq, ldq, pk, ldk, pv, ldv, pk2, ldk2, pv2, ldv2, po, ldo, pdo, lddo,
                            lse.data_ptr(), delta.data_ptr(), pdq, lddq, pdk, lddk, pdv, lddv, pdk2,
                            lddk2, pdv2, lddv2, B, H, KVH, sq, sk, sk2, head_dim, scale,
-                           1 if causal else 0, _stream()), "attn_bwd")
+                           1 if causal else 0, int(window), _stream()), "attn_bwd")
 
 
 # --------------------------------------------------------------------------------------------- losses
