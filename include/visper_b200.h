@@ -119,6 +119,22 @@ int vpb_im2col_patches(const void* images, void* out, int B, int H, int W, int p
 int vpb_clip_embed(const void* patch, const void* cls, const void* pos, void* out, int B,
                    int npatch, int D, void* stream);
 
+/* ---- frozen DPT depth decoder (aux_heads/da_v2_head.py:181-321 → `depth_preds`) --------------
+ * NHWC bf16 activations; every conv is im2col + vpb_gemm_bf16 (K order ky,kx,c). */
+int vpb_im2col3x3_nhwc(const void* in, void* out, int B, int H, int W, int C, int stride, int relu_in,
+                       void* stream);
+/* F.interpolate(mode="bilinear", align_corners=True) */
+int vpb_bilinear_nhwc(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                      void* stream);
+/* ConvTranspose2d(kernel = stride = k) epilogue: [B*H*W, k*k*C] → [B, H*k, W*k, C] (+bias) */
+int vpb_pixel_shuffle_nhwc(const void* in, const void* bias, void* out, int B, int H, int W, int C,
+                           int k, void* stream);
+/* 1x1 conv to a single channel (+ReLU), fp32 output */
+int vpb_conv1x1_to1(const void* in, const void* w, const void* bias, float* out, int64_t P, int C,
+                    int relu, void* stream);
+/* per-image (x - min) / (max - min), base_ola_vlm.py:466-469 */
+int vpb_minmax_normalize(const float* in, float* out, int B, int64_t n, void* stream);
+
 /* ---- multimodal splice (ola_arch.py:256-444 prepare_inputs_labels_for_multimodal) -----------
  * One gather from a host-built index plan replaces the per-sample Python cat loop. */
 int vpb_gather_rows(void* out, int64_t ldo, int nrows, int D, const int* kind, const int* index,

@@ -60,8 +60,24 @@ def test_state_dict_abi(name, cfg_name, distill):
 
     fx = torch.load(GOLDEN / f"{name}.pt")
     model = build_product(getattr(configs, cfg_name), distill, None)
-    mine = {n: tuple(p.shape) for n, p in model.named_parameters()}
+    mine = {n: tuple(p.shape) for n, p in model.named_parameters() if "da_v2_head" not in n}
     assert mine == fx["state_spec"]
+
+
+def test_dpt_head_state_dict_abi_and_oracle():
+    """Frozen DPT decoder: parameter names/shapes equal the reference DAv2_Head's,
+    and the oracle restatement reproduces the reference's depth map (golden from make_golden_dpt)."""
+    from oracle.make_golden_dpt import dpt_inputs
+    from visper_lm_b200.model.dpt import DAv2_Head
+
+    fx = torch.load(GOLDEN / "dpt_head.pt")
+    mine = {"da_v2_head." + n: tuple(p.shape) for n, p in DAv2_Head().named_parameters()}
+    assert mine == fx["state_spec"]
+    sd = {n: restate.seeded_param(n, s) for n, s in fx["state_spec"].items()}
+    with torch.no_grad():
+        depth = restate.dav2_head(sd, dpt_inputs(fx["B"], fx["seed"]))
+    assert torch.allclose(depth[:, ::7, ::7], fx["depth_sub"], atol=1e-5)
+    assert torch.allclose(restate.depth_pred_normalized(depth)[:, ::7, ::7], fx["depth_norm_sub"], atol=1e-5)
 
 
 def test_oracle_matches_live_reference():

@@ -10,7 +10,7 @@ Tolerances (bf16 storage, fp32 accumulate; north_star asks 1e-3 rel on losses):
 import pytest
 import torch
 
-from parity_utils import (build_product, configs, cos_sim, oracle_state, pt_freeze, rel_err, restate,
+from parity_utils import (bf16_seeded, build_product, configs, cos_sim, oracle_state, pt_freeze, rel_err, restate,
                           round_batch, run_product)
 
 pytestmark = pytest.mark.gpu
@@ -169,3 +169,29 @@ def test_full_finetune_gradients(cfg_name):
         assert c >= 0.99 and abs(ratio - 1) <= 4e-2, f"{n}: cos {c:.5f} norm ratio {ratio:.4f}"
         checked += 1
     assert checked >= 30
+
+
+def test_dpt_decoder_depth_preds():
+    """Frozen DPT decoder → `depth_preds`: CUDA path (im2col + tcgen05 GEMM, NHWC)
+    against the fp32 oracle on bf16-rounded weights and against the reference's golden depth map.
+    ~25 bf16 conv layers deep: 3e-2 relative Frobenius on the depth map, 2e-2 abs on the normalised one."""
+    from oracle.make_golden_dpt import dpt_inputs
+    from visper_lm_b200.model.dpt import DAv2_Head
+
+    fx = torch.load(GOLDEN / "dpt_head.pt")
+    head = DAv2_Head(DEV)
+    with torch.no_grad():
+        for n, p in head.named_parameters():
+            p.copy_(bf16_seeded("da_v2_head." + n, tuple(p.shape)))
+    feats = [f.to(torch.bfloat16) for f in dpt_inputs(fx["B"], fx["seed"])]
+    depth = head([f.reshape(-1, 1024).to(DEV) for f in feats])
+    norm = head.normalized([f.reshape(-1, 1024).to(DEV) for f in feats])
+    torch.cuda.synchronize()
+    sd = {"da_v2_head." + n: p.detach().float().cpu() for n, p in head.named_parameters()}
+    with torch.no_grad():
+        ref = restate.dav2_head(sd, [f.float() for f in feats])
+    assert depth.shape == ref.shape == (fx["B"], 336, 336)
+    assert rel_err(depth, ref) <= 3e-2, rel_err(depth, ref)
+    assert (norm.cpu() - restate.depth_pred_normalized(ref)).abs().max().item() <= 3e-2
+    assert rel_err(depth[:, ::7, ::7], fx["depth_sub"]) <= 4e-2   # reference itself (fp32 weights)
+    assert float(norm.min()) == 0.0 and abs(float(norm.max()) - 1.0) < 1e-6

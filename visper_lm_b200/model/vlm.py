@@ -455,6 +455,11 @@ class VisperForCausalLM(nn.Module):
             self.image_depth_heads = nn.ModuleList([
                 M.TaskTokenDepthHead(config.image_depth, D, self.use_intermediate_depth, dev)
                 for _ in self.depth_layer_indices])
+            # frozen DPT decoder behind `depth_preds` (base_ola_vlm.py:141-148 loads it from
+            # config.depth_estimator); hard-wired to 1024-channel features like the reference's
+            if config.image_depth.get("output_dim") == 1024 and getattr(config, "depth_preds", True):
+                from .dpt import DAv2_Head
+                self.da_v2_head = DAv2_Head(dev)
         if "seg" in self.mode:
             self.seg_layer_indices, self.img_seg_loss_weight = self._layer_loss_weight(config.image_seg, "seg")
             self.seg_logit_scale = nn.Parameter(torch.tensor(2.0, device=dev)) if use_con else None
@@ -632,6 +637,11 @@ class VisperForCausalLM(nn.Module):
                     feats.append((e.view(B, plan.nq, -1), None))
                     out[out_name].append(feats)
                     pred = feats[0][0]  # base_ola_vlm.py:369 supervises features[0] only
+                    if getattr(self, "da_v2_head", None) is not None and getattr(cfg, "depth_preds", True):
+                        # base_ola_vlm.py:462-470 (no_grad): DPT decoder + per-image min-max
+                        lv = [f[0] for f in feats] if head.use_intermediate_depth else [feats[0][0]] * 4
+                        out["depth_preds"].append(self.da_v2_head.normalized(
+                            [f.detach().reshape(B * plan.nq, -1) for f in lv]))
                 elif task == "seg":
                     ev = e.view(B, plan.nq, -1)
                     side = int(math.sqrt(plan.nq))

@@ -327,6 +327,49 @@ def clip_embed(patch, cls, pos, B, npatch):
     return out
 
 
+# --------------------------------------------------------------------------------------------- DPT decoder
+def im2col3x3(x, B, H, W, C, stride=1, relu_in=False):
+    """NHWC rows [B*H*W, C] → [B*Ho*Wo, 9*C] (3x3, pad 1), K order (ky, kx, c)."""
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    assert x.is_contiguous() and x.shape == (B * H * W, C)
+    out = torch.empty((B * Ho * Wo, 9 * C), dtype=BF16, device=x.device)
+    _chk(_L().vpb_im2col3x3_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, C, stride, 1 if relu_in else 0,
+                                 _stream()), "im2col3x3")
+    return out, Ho, Wo
+
+
+def bilinear(x, B, Hi, Wi, Ho, Wo, C):
+    assert x.is_contiguous() and x.shape == (B * Hi * Wi, C)
+    out = torch.empty((B * Ho * Wo, C), dtype=BF16, device=x.device)
+    _chk(_L().vpb_bilinear_nhwc(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C, _stream()), "bilinear")
+    return out
+
+
+def pixel_shuffle(y, bias, B, H, W, C, k):
+    assert y.is_contiguous() and y.shape == (B * H * W, k * k * C)
+    out = torch.empty((B * H * k * W * k, C), dtype=BF16, device=y.device)
+    _chk(_L().vpb_pixel_shuffle_nhwc(y.data_ptr(), _p(bias), out.data_ptr(), B, H, W, C, k, _stream()),
+         "pixel_shuffle")
+    return out
+
+
+def conv1x1_to1(x, w, bias, relu=True):
+    P, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((P,), dtype=torch.float32, device=x.device)
+    _chk(_L().vpb_conv1x1_to1(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), P, C, 1 if relu else 0,
+                              _stream()), "conv1x1_to1")
+    return out
+
+
+def minmax_normalize(x):
+    B, n = x.shape[0], x[0].numel()
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _chk(_L().vpb_minmax_normalize(x.data_ptr(), out.data_ptr(), B, n, _stream()), "minmax_normalize")
+    return out
+
+
 # --------------------------------------------------------------------------------------------- gathers
 def gather_rows(index, srcs, D, kind=None, out=None):
     """out[r] = srcs[kind[r]][index[r]] (negative → zero row). index/kind: int32 CUDA tensors."""
