@@ -1,0 +1,4 @@
+"""Drop-in path of the pieces of ola_vlm/train/ola_vlm_train.py that sit on the training-step path:
+the supervised collator (:881-925) and the end-of-run save (:228-263)."""
+from visper_lm_b200.train.checkpoint import safe_save_model_for_hf_trainer  # noqa: F401
+from visper_lm_b200.train.data import DataCollatorForSupervisedDataset  # noqa: F401

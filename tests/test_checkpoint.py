@@ -1,0 +1,152 @@
+"""Checkpoint / resume on CPU: the trainer's save → resume round trip is
+bit-identical to an uninterrupted run (world 1 and world-2 gloo), the adapter-only files follow
+the reference layout (llava_trainer.py:997-1016, ola_vlm_train.py:228-249) and load back through
+the --pretrain_mm_mlp_adapter path (ola_arch.py:139-144).  The optimizer kernels are torch TEST
+DOUBLES here (tests/test_dist_gloo.py); what is under test is the host-side state handling."""
+import os
+import types
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from test_dist_gloo import _install_test_doubles
+from visper_lm_b200.train import checkpoint as C
+from visper_lm_b200.train.data import DataCollatorForSupervisedDataset, SyntheticSupervisedDataset
+
+
+class ToyVLM(torch.nn.Module):
+    """Parameter names of the real model's trainable PT-stage set; a differentiable toy forward."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(3)
+        mk = lambda *s: torch.nn.Parameter((0.1 * torch.randn(*s, generator=g)).to(torch.bfloat16))
+        self.model = torch.nn.Module()
+        self.model.mm_projector = torch.nn.Module()
+        l0, l2 = torch.nn.Module(), torch.nn.Module()
+        l0.weight, l0.bias = mk(16, 12), mk(16)
+        l2.weight, l2.bias = mk(16, 16), mk(16)
+        self.model.mm_projector.add_module("0", l0)
+        self.model.mm_projector.add_module("2", l2)
+        self.model.embed_tokens = torch.nn.Module()
+        self.model.embed_tokens.weight = torch.nn.Parameter(mk(300, 16).data, requires_grad=False)
+        self.depth_logit_scale = torch.nn.Parameter(torch.tensor(2.0))
+        self.config = types.SimpleNamespace(model_type="ola_llama", hidden_size=16, mm_hidden_size=12)
+
+    @property
+    def device(self):
+        return torch.device("cpu")
+
+    def forward(self, input_ids=None, labels=None, attention_mask=None, images=None, **kw):
+        pj = self.model.mm_projector
+        x = images.float().mean((2, 3))[:, :, None].expand(-1, -1, 4).reshape(images.shape[0], 12)
+        l0, l2 = getattr(pj, "0"), getattr(pj, "2")
+        h = torch.nn.functional.gelu(x @ l0.weight.float().t() + l0.bias.float())
+        h = h @ l2.weight.float().t() + l2.bias.float()
+        e = self.model.embed_tokens.weight.float()[input_ids.clamp_min(0)]
+        loss = ((e.mean(1) - h) ** 2).mean() * self.depth_logit_scale.float().exp()
+        return types.SimpleNamespace(loss=loss)
+
+
+def _make_trainer(out_dir, max_steps, save_steps, **kw):
+    from visper_lm_b200.train.trainer import LLaVATrainer, TrainingArguments
+
+    torch.manual_seed(0)
+    ds = SyntheticSupervisedDataset(64, vocab=300, n_sys=13, min_text=20, max_text=40, image_size=8,
+                                    distill=False, text_only_every=4, seed=5)
+    tok = types.SimpleNamespace(pad_token_id=0, model_max_length=64)
+    args = TrainingArguments(output_dir=str(out_dir), per_device_train_batch_size=4, learning_rate=1e-2,
+                             max_steps=max_steps, save_steps=save_steps, tune_mm_mlp_adapter=True,
+                             group_by_modality_length=True, logging_steps=1, **kw)
+    return LLaVATrainer(model=ToyVLM(), args=args, train_dataset=ds, data_collator=DataCollatorForSupervisedDataset(tok))
+
+
+class _Interrupted(Exception):
+    pass
+
+
+def _train_until(tr, n_steps):
+    """Run `tr.train()` and kill it when step n_steps+1 starts (a crash after checkpoint-n)."""
+    real = tr.step
+
+    def step(batch):
+        if tr.state["global_step"] >= n_steps:
+            raise _Interrupted()
+        return real(batch)
+
+    tr.step = step
+    with pytest.raises(_Interrupted):
+        tr.train()
+
+
+def _params(tr):
+    return {n: p.detach().float().clone() for n, p in tr.model.named_parameters()}
+
+
+def test_resume_is_bit_identical_and_layout(tmp_path):
+    _install_test_doubles()
+    full = _make_trainer(tmp_path / "a", 6, 3, save_total_limit=1)
+    full.train()
+    # rotation kept only the newest checkpoint
+    assert [os.path.basename(p) for p in C.list_checkpoints(str(tmp_path / "a"))] == ["checkpoint-6"]
+    part = _make_trainer(tmp_path / "b", 6, 3)
+    _train_until(part, 3)
+    ck = C.get_last_checkpoint(str(tmp_path / "b"))
+    assert os.path.basename(ck) == "checkpoint-3"
+    assert sorted(os.listdir(ck)) == ["config.json", "mm_projector.bin", "rng_state.pth", "trainable.bin",
+                                      "trainer_state.json", "zero2_rank0_of1.pt"]
+    adapter = torch.load(os.path.join(ck, "mm_projector.bin"))
+    assert sorted(adapter) == ["model.mm_projector.0.bias", "model.mm_projector.0.weight",
+                               "model.mm_projector.2.bias", "model.mm_projector.2.weight"]
+    resumed = _make_trainer(tmp_path / "b", 6, 3)
+    resumed.train(resume_from_checkpoint=True)  # ola_vlm_train.py:1306-1309
+    assert resumed.state["global_step"] == 6
+    a, b = _params(full), _params(resumed)
+    for n in a:
+        assert torch.equal(a[n], b[n]), n
+    assert [h["loss"] for h in full.state["log_history"]] == [h["loss"] for h in resumed.state["log_history"]]
+
+
+def test_final_adapter_save_and_pretrain_load(tmp_path):
+    _install_test_doubles()
+    tr = _make_trainer(tmp_path / "run", 2, 0)
+    tr.train()
+    C.safe_save_model_for_hf_trainer(tr, str(tmp_path / "run"))
+    assert os.path.exists(tmp_path / "run" / "mm_projector.bin") and os.path.exists(tmp_path / "run" / "config.json")
+    C.safe_save_model_for_hf_trainer(tr, str(tmp_path / "run" / "checkpoint-2"))
+    assert os.path.exists(tmp_path / "run" / "mm_projector" / "checkpoint-2.bin")
+    fresh = ToyVLM()
+    C.load_mm_projector(fresh, str(tmp_path / "run" / "mm_projector.bin"))
+    for (n, p), (_, q) in zip(fresh.model.mm_projector.named_parameters(), tr.model.model.mm_projector.named_parameters()):
+        assert torch.equal(p, q), n
+    # full (non-adapter) branch goes through trainer._save
+    tr.args.tune_mm_mlp_adapter = False
+    C.safe_save_model_for_hf_trainer(tr, str(tmp_path / "full"))
+    sd = torch.load(tmp_path / "full" / "pytorch_model.bin")
+    assert "model.embed_tokens.weight" in sd and "depth_logit_scale" in sd
+
+
+def _worker(rank, world, port, root, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _install_test_doubles()
+    full = _make_trainer(os.path.join(root, "a"), 4, 2)
+    full.train()
+    part = _make_trainer(os.path.join(root, "b"), 4, 2)
+    _train_until(part, 2)
+    dist.barrier()
+    resumed = _make_trainer(os.path.join(root, "b"), 4, 2)
+    resumed.train(resume_from_checkpoint=True)
+    a, b = _params(full), _params(resumed)
+    ret[rank] = all(torch.equal(a[n], b[n]) for n in a) and os.path.exists(
+        os.path.join(root, "b", "checkpoint-2", f"zero2_rank{rank}_of{world}.pt"))
+    dist.destroy_process_group()
+
+
+def test_resume_world2_gloo(tmp_path):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, 29547, str(tmp_path), ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

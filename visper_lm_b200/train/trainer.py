@@ -43,6 +43,9 @@ class TrainingArguments:
     max_steps: int = -1
     logging_steps: int = 1
     save_steps: int = 200
+    save_total_limit: Optional[int] = None
+    tune_mm_mlp_adapter: bool = False
+    use_im_start_end: bool = False
     bf16: bool = True
     mm_projector_lr: Optional[float] = None
     mm_vision_lr: Optional[float] = None
@@ -217,6 +220,8 @@ class LLaVATrainer:
                     out[k] = v  # consumed on the host by the splice planner
                 elif v.is_cuda:
                     out[k] = v
+                elif dev.type != "cuda":
+                    out[k] = v  # host-only unit tests of the trainer logic
                 else:
                     if not v.is_pinned():
                         buf = self._pinned.get(k)
@@ -255,44 +260,102 @@ class LLaVATrainer:
         self.state["global_step"] += 1
         return loss, out
 
-    def _batches(self):
+    def _index_order(self, epoch):
+        """Global sample order of one epoch.  --group_by_modality_length → the reference's
+        LengthGroupedSampler (llava_trainer.py:219-232) with batch = per-device batch and world =
+        world_size × grad-accum; otherwise HF's seeded RandomSampler (randperm of seed + epoch)."""
         a = self.args
         n = len(self.train_dataset)
-        per_rank = n // self.world
-        idx = list(range(self.rank * per_rank, (self.rank + 1) * per_rank))  # contiguous split by rank
+        g = torch.Generator().manual_seed(a.seed + epoch)
+        if a.group_by_modality_length and hasattr(self.train_dataset, "modality_lengths"):
+            from .data import LengthGroupedSampler
+            # the per-modality grouping draws from the GLOBAL torch RNG (as in the reference, where
+            # set_seed(args.seed) precedes it): pin it to (seed, epoch) so a resumed run sees the
+            # same order, and leave the caller's RNG stream untouched
+            keep = torch.get_rng_state()
+            torch.manual_seed(a.seed + epoch)
+            try:
+                return list(LengthGroupedSampler(a.per_device_train_batch_size,
+                                                 self.world * a.gradient_accumulation_steps,
+                                                 lengths=self.train_dataset.modality_lengths, generator=g,
+                                                 group_by_modality=True))
+            finally:
+                torch.set_rng_state(keep)
+        return torch.randperm(n, generator=g).tolist()
+
+    def _batches(self, epoch=0, skip=0):
+        """Per-rank batches: consecutive per-device batches of the global order are dealt to the
+        ranks round-robin (what accelerate's BatchSamplerShard does under HF Trainer), so one
+        length-grouped mega-batch spreads its balanced chunks over all ranks."""
+        a = self.args
         B = a.per_device_train_batch_size
-        for i in range(0, len(idx) - B + 1, B):
-            yield self.data_collator([self.train_dataset[j] for j in idx[i:i + B]])
+        order = self._index_order(epoch)
+        nb = len(order) // (B * self.world)  # drop the ragged tail (dataloader_drop_last semantics)
+        for k in range(skip, nb):
+            s = (k * self.world + self.rank) * B
+            yield self.data_collator([self.train_dataset[j] for j in order[s:s + B]])
+
+    def steps_per_epoch(self):
+        return len(self.train_dataset) // (self.args.per_device_train_batch_size * self.world)
 
     def train(self, resume_from_checkpoint=None):
+        from . import checkpoint as ckpt
+
         a = self.args
-        n = len(self.train_dataset) // self.world // a.per_device_train_batch_size
-        self.total_steps = a.max_steps if a.max_steps > 0 else int(n * a.num_train_epochs)
+        per_epoch = max(1, self.steps_per_epoch())
+        self.total_steps = a.max_steps if a.max_steps > 0 else int(per_epoch * a.num_train_epochs)
         self.create_optimizer()
+        if resume_from_checkpoint:
+            path = (ckpt.get_last_checkpoint(a.output_dir) if resume_from_checkpoint is True
+                    else resume_from_checkpoint)
+            if path is None:
+                raise ValueError(f"no checkpoint-* directory under {a.output_dir}")
+            ckpt.load_checkpoint(self, path)
         t0 = time.time()
         last = None
-        done = 0
+        done = self.state["global_step"]
         while done < self.total_steps:
-            for batch in self._batches():
+            epoch, skip = divmod(done, per_epoch)
+            for batch in self._batches(epoch, skip):  # a resumed run skips the batches already consumed
                 loss, _ = self.step(batch)
                 done += 1
                 if done % a.logging_steps == 0:
                     last = float(loss)  # the only host sync, outside forward (cf. ola_llama.py:146-168)
                     self.state["log_history"].append({"step": done, "loss": last})
+                if a.save_steps and a.save_steps > 0 and done % a.save_steps == 0:
+                    self._save_checkpoint()
                 if done >= self.total_steps:
                     break
         return {"global_step": done, "training_loss": last, "train_runtime": time.time() - t0}
 
-    # -- checkpoint surface (minimal; adapter-only save as in llava_trainer.py:997-1016)
+    # -- checkpoint surface (SURVEY.md §8f N3; llava_trainer.py:997-1021, ola_vlm_train.py:228-263) -----
+    def _save_checkpoint(self, model=None, trial=None, metrics=None):
+        from . import checkpoint as ckpt
+
+        out = os.path.join(self.args.output_dir, f"{ckpt.PREFIX_CHECKPOINT_DIR}-{self.state['global_step']}")
+        ckpt.save_checkpoint(self, out)
+        if self.is_dist:
+            dist.barrier()
+        if self.rank == 0:
+            ckpt.rotate_checkpoints(self.args.output_dir, self.args.save_total_limit)
+        return out
+
     def save_state(self):
         os.makedirs(self.args.output_dir, exist_ok=True)
         if self.rank == 0:
             with open(os.path.join(self.args.output_dir, "trainer_state.json"), "w") as f:
                 json.dump(self.state, f)
 
+    def save_model(self, output_dir=None):
+        self._save(output_dir)
+
     def _save(self, output_dir=None, state_dict=None):
+        """Full-model save used by safe_save_model_for_hf_trainer's non-adapter branch."""
         output_dir = output_dir or self.args.output_dir
         os.makedirs(output_dir, exist_ok=True)
         if self.rank == 0:
-            sd = state_dict or {k: v.detach().cpu() for k, v in self.model.named_parameters() if v.requires_grad}
-            torch.save(sd, os.path.join(output_dir, "mm_projector.bin"))
+            from . import checkpoint as ckpt
+
+            sd = state_dict if state_dict is not None else {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+            ckpt.save_config(self.model.config, output_dir)
+            torch.save(sd, os.path.join(output_dir, "pytorch_model.bin"))
