@@ -36,6 +36,7 @@ import torch.distributed as dist  # noqa: E402
 FLOPS = {  # algorithmic FLOP per sample, Llama-3-8B, T=2048 (no recompute counted)
     "ntp_adapter": 2 * 2.859e13 + 3.5 * 1.100e12 + 2 * 2.152e12 + 3.65e11 + 3 * 2.42e10,
     "dsg_adapter": 6.70e13,
+    "ntp_full": 3 * 2.859e13 + 3.5 * 1.100e12 + 3 * 2.152e12 + 3.65e11 + 3 * 2.42e10,  # IFT, SURVEY §8d
 }
 
 
@@ -47,6 +48,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ntp", choices=["ntp", "dsg"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (samples per step per GPU)")
+    ap.add_argument("--train", default="adapter", choices=["adapter", "full"],
+                    help="adapter: PT-stage freeze policy (default, BASELINE configs[1]); full: IFT-style "
+                         "full fine-tune of LLM + projector (finetune.sh) — weight gradients for every layer")
     ap.add_argument("--seq", type=int, default=2048, help="embedded sequence length T")
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "phi3-mini", "tiny"])
     ap.add_argument("--layers", type=int, default=None, help="override decoder depth (debug only; reported)")
@@ -267,7 +271,8 @@ def workload_config(args, c, distill):
     return {"workload": ("BASELINE configs[1]: " if not distill else "BASELINE configs[2] per-GPU slice: ")
             + f"{args.model} + CLIP-ViT-L/14-336, 336px, T={args.seq}, "
             + ("NTP only" if not distill else "NTP + dsg distill heads (d18-20_s10-18_g12-20)")
-            + ", PT freeze policy (mm_projector" + ("+heads+task tokens" if distill else "") + " trainable; LLM fwd+dgrad)",
+            + (", full fine-tune (LLM + mm_projector trainable: fwd + dgrad + wgrad)" if getattr(args, "train", "adapter") == "full"
+               else ", PT freeze policy (mm_projector" + ("+heads+task tokens" if distill else "") + " trainable; LLM fwd+dgrad)"),
             "per_gpu_batch": args.batch, "global_batch": args.batch * args.gpus, "seq_len": args.seq,
             "decoder_layers": c["layers"], "parallelism": f"dp{args.gpus} zero2",
             "l2_policy": "working set (16 GB weights + activations) exceeds the 126 MB L2; no explicit flush",
@@ -297,8 +302,11 @@ def run_b200(args):
     torch.manual_seed(0)
     model = cls(cfg, device=dev)
     model.init_weights(std=0.02, seed=0)
-    for n, p in model.named_parameters():  # PT freeze policy
-        p.requires_grad_(("mm_projector" in n) or ("_heads." in n) or ("special_" in n) or n.endswith("logit_scale"))
+    for n, p in model.named_parameters():
+        if args.train == "full":  # finetune.sh: everything but the frozen tower (and the frozen DPT head)
+            p.requires_grad_(("vision_tower" not in n) and ("da_v2_head" not in n))
+        else:  # PT freeze policy
+            p.requires_grad_(("mm_projector" in n) or ("_heads." in n) or ("special_" in n) or n.endswith("logit_scale"))
     targs = TrainingArguments(per_device_train_batch_size=args.batch, learning_rate=1e-3, max_steps=10_000)
     trainer = LLaVATrainer(model=model, args=targs)
     trainer.total_steps = 10_000
@@ -404,7 +412,7 @@ def run_b200(args):
         peaks = json.loads(pf.read_text())
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-    flop_key = "dsg_adapter" if distill else "ntp_adapter"
+    flop_key = "dsg_adapter" if distill else ("ntp_full" if args.train == "full" else "ntp_adapter")
     full_model = args.model == "llama3-8b" and args.layers is None and T == 2048
     line = {
         "metric": "train-step samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
