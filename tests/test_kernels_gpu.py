@@ -298,10 +298,59 @@ def test_attention_fwd_bwd(B, H, KVH, sq, sk, sk2, hd, causal):
         close(dkv2, g[:, sk:].reshape(B * sk2, 2 * kw), rtol=3e-2, name="attn dkv2")
 
 
+@pytest.mark.parametrize("B,H,KVH,sq,sk,causal", [(2, 8, 8, 1024, 1024, True), (1, 4, 4, 333, 333, True),
+                                                   (2, 4, 2, 200, 520, False), (1, 32, 32, 2048, 2048, True),
+                                                   (1, 3, 3, 577, 577, False)])
+def test_attention_tcgen05_head_dim_96(B, H, KVH, sq, sk, causal):
+    """Phi-3 head_dim 96 on the tcgen05 kernels (64 + 32-column TMA chunks, N=96 accumulators):
+    against the mma.sync kernels and torch, forward and backward."""
+    from visper_lm_b200 import ops
+    hd = 96
+    qw, kw = H * hd, KVH * hd
+    q = rnd(B * sq, qw, seed=91)
+    kv = rnd(B * sk, 2 * kw, seed=92)
+    do = rnd(B * sq, qw, seed=93)
+    k, v = kv[:, :kw], kv[:, kw:]
+    scale = hd ** -0.5
+
+    def run():
+        o, lse = ops.attn_fwd(q, k, v, B, H, KVH, sq, sk, hd, scale, causal)
+        dq = torch.zeros_like(q)
+        dkv = torch.zeros_like(kv)
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dkv[:, :kw], dkv[:, kw:], B, H, KVH, sq, sk, hd, scale, causal)
+        torch.cuda.synchronize()
+        return o, lse, dq, dkv
+
+    ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 1)
+    ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 1)
+    try:
+        o1, lse1, dq1, dkv1 = run()
+    finally:
+        ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
+        ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
+    o2, lse2, dq2, dkv2 = run()
+    close(o2, o1, name="hd96 tc fwd vs mma.sync")
+    assert (lse2 - lse1).abs().max().item() < 2e-2
+    close(dq2, dq1, rtol=2e-2, name="hd96 dq vs mma.sync")
+    close(dkv2, dkv1, rtol=2e-2, name="hd96 dkv vs mma.sync")
+    qf = q.float().view(B, sq, H, hd).transpose(1, 2).detach().requires_grad_(True)
+    kvf = kv.float().view(B, sk, 2, KVH, hd).detach().requires_grad_(True)
+    kf = kvf[:, :, 0].transpose(1, 2).repeat_interleave(H // KVH, 1)
+    vf = kvf[:, :, 1].transpose(1, 2).repeat_interleave(H // KVH, 1)
+    ref = _attn_ref(qf, kf, vf, scale, causal).transpose(1, 2).reshape(B * sq, qw)
+    close(o2, ref, name="hd96 fwd vs torch")
+    ref.backward(do.float())
+    close(dq2, qf.grad.transpose(1, 2).reshape(B * sq, qw), rtol=3e-2, name="hd96 dq vs torch")
+    close(dkv2, kvf.grad.reshape(B * sk, 2 * kw), rtol=3e-2, name="hd96 dkv vs torch")
+
+
 @pytest.mark.parametrize("B,H,KVH,S,hd,window", [(2, 4, 4, 700, 96, 200), (1, 4, 2, 1000, 128, 255),
-                                                  (1, 2, 2, 300, 64, 17), (2, 4, 4, 4096, 96, 2047)])
-def test_attention_sliding_window(B, H, KVH, S, hd, window):
-    """Causal sliding-window attention (Phi-3): key j visible iff 0 <= i-j <= window."""
+                                                  (1, 2, 2, 300, 64, 17), (2, 4, 4, 4096, 96, 2047),
+                                                  (1, 4, 4, 1500, 96, 100), (1, 2, 1, 777, 128, 64)])
+@pytest.mark.parametrize("legacy", [False, True])
+def test_attention_sliding_window(B, H, KVH, S, hd, window, legacy):
+    """Causal sliding-window attention (Phi-3): key j visible iff 0 <= i-j <= window — on the tcgen05
+    kernels (hd 96 / 128) and on the mma.sync kernels (legacy=True, and always for hd 64)."""
     from visper_lm_b200 import ops
     qw, kw = H * hd, KVH * hd
     q = rnd(B * S, qw, seed=81)
@@ -309,12 +358,18 @@ def test_attention_sliding_window(B, H, KVH, S, hd, window):
     do = rnd(B * S, qw, seed=83)
     k, v = kv[:, :kw], kv[:, kw:]
     scale = hd ** -0.5
-    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, True, window=window)
-    dq = torch.empty_like(q)
-    dkv = torch.empty_like(kv)
-    ops.attn_bwd(q, k, v, o, do, lse, dq, dkv[:, :kw], dkv[:, kw:], B, H, KVH, S, S, hd, scale, True,
-                 window=window)
-    torch.cuda.synchronize()
+    ops.set_option(ops.OPT_ATTN_LEGACY_FWD, int(legacy))
+    ops.set_option(ops.OPT_ATTN_LEGACY_BWD, int(legacy))
+    try:
+        o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, True, window=window)
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dkv[:, :kw], dkv[:, kw:], B, H, KVH, S, S, hd, scale, True,
+                     window=window)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
+        ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
     qf = q.float().view(B, S, H, hd).transpose(1, 2).detach().requires_grad_(True)
     kvf = kv.float().view(B, S, 2, KVH, hd).detach().requires_grad_(True)
     kf = kvf[:, :, 0].transpose(1, 2).repeat_interleave(H // KVH, 1)

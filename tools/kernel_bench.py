@@ -140,6 +140,11 @@ if __name__ == "__main__":
         ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
         attn_case(8, 16, 16, 577, 64, False)
         attn_case(4, 32, 32, 2048, 96, True)
+        ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 1)
+        ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 1)
+        attn_case(4, 32, 32, 2048, 96, True)
+        ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
+        ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
     if which == "attnprof":
         print(json.dumps({"variant": "tc backward v2 (ping-pong)"}), flush=True)
         attn_profile()

@@ -709,12 +709,12 @@ static int check_attn(const AttnParams& p, int HD) {
 
 namespace vpb {
 int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk, float scale,
-                int causal, cudaStream_t st);
+                void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk, int head_dim,
+                float scale, int causal, int window, cudaStream_t st);
 int attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 const void* dO, int64_t lddo, const float* lse, const float* delta, void* dq,
                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int KVH,
-                int sq, int sk, float scale, int causal, cudaStream_t st);
+                int sq, int sk, int head_dim, float scale, int causal, int window, cudaStream_t st);
 }
 using namespace vpb;
 
@@ -753,11 +753,13 @@ extern "C" int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   p.scale = scale;
   if (check_attn(p, head_dim)) return -1;
   VPB_CHECK(!(causal && p.sk2 > 0), "attention: causal with a second key segment is not supported");
-  if (head_dim == 128 && p.sk2 == 0 && p.window == 0 && !get_option(VPB_OPT_ATTN_LEGACY_FWD) &&
+  // tcgen05 path: head_dim 128 (Llama-3) and 96 (Phi-3); the 96 kernels need full 128-row tiles to exist
+  const bool tc_hd = (head_dim == 128 || head_dim == 96) && !(causal && sk < sq && (head_dim == 96 || p.window > 0));
+  if (tc_hd && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_FWD) &&
       (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(v) & 15) == 0)
-    return attn_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, KVH, sq, sk, scale, causal,
-                       (cudaStream_t)stream);
+    return attn_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, KVH, sq, sk, head_dim, scale, causal,
+                       p.window, (cudaStream_t)stream);
   DISPATCH_HD(head_dim, causal, launch_fwd, p, (cudaStream_t)stream);
 }
 
@@ -787,10 +789,10 @@ extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t l
   launch_delta((const bf16*)o, ldo, (const bf16*)dO, lddo, delta, B, H, sq, head_dim, (cudaStream_t)stream);
   VPB_LAUNCH_OK();
   auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
-  if (head_dim == 128 && p.sk2 == 0 && p.window == 0 && !get_option(VPB_OPT_ATTN_LEGACY_BWD) && al16(q) &&
-      al16(k) &&
-      al16(v) && al16(dO))
+  const bool tc_hd = (head_dim == 128 || head_dim == 96) && !(causal && sk < sq && (head_dim == 96 || p.window > 0));
+  if (tc_hd && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_BWD) && al16(q) &&
+      al16(k) && al16(v) && al16(dO))
     return attn_bwd_tc(q, ldq, k, ldk, v, ldv, dO, lddo, lse, delta, dq, lddq, dk, lddk, dv, lddv, B,
-                       H, KVH, sq, sk, scale, causal, (cudaStream_t)stream);
+                       H, KVH, sq, sk, head_dim, scale, causal, p.window, (cudaStream_t)stream);
   DISPATCH_HD(head_dim, causal, launch_bwd, p, (cudaStream_t)stream);
 }

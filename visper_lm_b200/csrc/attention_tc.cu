@@ -24,10 +24,11 @@ struct AttnTcParams {
   int64_t ldo;
   int B, H, KVH, sq, sk;
   float scale;
+  int window;  // causal sliding window: key j visible to query i iff 0 <= i + off - j <= window (0: off)
 };
 
 namespace tc {
-constexpr int BM = 128, BN = 128, HD = 128;
+constexpr int BM = 128, BN = 128;  // head_dim (128 or 96) is a template parameter of the kernel
 constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 64-column chunks of [128 rows x 128 B]
 constexpr int CHUNK_BYTES = 16384;
 constexpr int OFF_Q = 0;
@@ -45,7 +46,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, int HD>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -76,7 +77,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (kv_end > p.sk) kv_end = p.sk;
     if (kv_end < 0) kv_end = 0;
   }
-  const int ntiles = (kv_end + BN - 1) / BN;
+  // sliding window: the first key tile any row of this query tile can see; the loops below run
+  // over ntiles tiles starting there (ring indices stay 0-based)
+  int jb = 0;
+  if (CAUSAL && p.window > 0) {
+    const int lo = q0 + off - p.window;
+    jb = lo > 0 ? lo / BN : 0;
+    if (jb * BN > kv_end) jb = kv_end / BN;
+  }
+  const int ntiles = (kv_end + BN - 1) / BN - jb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -114,7 +123,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&k_empty[s], ((j / KST) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
         uint8_t* sk = smem + OFF_K + s * TILE_BYTES;
-        const int row = b * p.sk + j * BN;
+        const int row = b * p.sk + (j + jb) * BN;
         tma_load_2d(sk, &tmK, &k_full[s], kvh * HD, row);
         tma_load_2d(sk + CHUNK_BYTES, &tmK, &k_full[s], kvh * HD + 64, row);
       };
@@ -125,7 +134,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&v_empty[s], ((j / VST) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
         uint8_t* sv = smem + OFF_V + s * TILE_BYTES;
-        const int row = b * p.sk + j * BN;
+        const int row = b * p.sk + (j + jb) * BN;
         tma_load_2d(sv, &tmV, &v_full[s], kvh * HD, row);
         tma_load_2d(sv + CHUNK_BYTES, &tmV, &v_full[s], kvh * HD + 64, row);
       }
@@ -191,13 +200,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld32(TM_S + lane_addr + sb * BN + half * 64, r);
       tmem_ld32(TM_S + lane_addr + sb * BN + half * 64 + 32, r + 32);
       tmem_ld_wait();
-      const int j0 = j * BN + half * 64;
-      const bool need_mask = (j * BN + BN > p.sk) || (CAUSAL && (j * BN + BN - 1 > q0 + off));
+      const int jt0 = (j + jb) * BN;  // first key of this tile
+      const int j0 = jt0 + half * 64;
+      const bool win = CAUSAL && p.window > 0;
+      const bool need_mask = (jt0 + BN > p.sk) || (CAUSAL && (jt0 + BN - 1 > q0 + off)) ||
+                             (win && jt0 < q0 + BM - 1 + off - p.window);
       if (need_mask) {
         const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;  // last visible key
+        const int lo = win ? q0 + row + off - p.window : 0;                 // first visible key
 #pragma unroll
         for (int c = 0; c < 64; ++c)
-          if (j0 + c > lim) r[c] = 0xff800000u;  // -inf
+          if (j0 + c > lim || j0 + c < lo) r[c] = 0xff800000u;  // -inf
       }
       // max of the RAW scores (scaled once, scale > 0); four independent chains for ILP
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -236,6 +249,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
+          if (half * 64 + c * 32 >= HD) break;  // head_dim 96: the second half owns one chunk
           uint32_t o[32];
           tmem_ld32(TM_O + lane_addr + half * 64 + c * 32, o);
           tmem_ld_wait();
@@ -271,6 +285,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bf16* orow = p.o + ((int64_t)b * p.sq + q0 + row) * p.ldo + h * HD + half * 64;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
+      if (half * 64 + c * 32 >= HD) break;
       uint32_t o[32];
       if (ntiles > 0) {
         tmem_ld32(TM_O + lane_addr + half * 64 + c * 32, o);
@@ -298,14 +313,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, int HD>
 static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, const AttnTcParams& p, cudaStream_t st) {
   CUtensorMap tmQ, tmK, tmV;
-  if (make_tmap_2d(&tmQ, q, (uint64_t)p.H * tc::HD, (uint64_t)p.B * p.sq, (uint64_t)ldq, 64, 128)) return -1;
-  if (make_tmap_2d(&tmK, k, (uint64_t)p.KVH * tc::HD, (uint64_t)p.B * p.sk, (uint64_t)ldk, 64, 128)) return -1;
-  if (make_tmap_2d(&tmV, v, (uint64_t)p.KVH * tc::HD, (uint64_t)p.B * p.sk, (uint64_t)ldv, 64, 128)) return -1;
-  auto kern = attn_fwd_tc_kernel<CAUSAL>;
+  if (make_tmap_2d(&tmQ, q, (uint64_t)p.H * HD, (uint64_t)p.B * p.sq, (uint64_t)ldq, 64, 128)) return -1;
+  if (make_tmap_2d(&tmK, k, (uint64_t)p.KVH * HD, (uint64_t)p.B * p.sk, (uint64_t)ldk, 64, 128)) return -1;
+  if (make_tmap_2d(&tmV, v, (uint64_t)p.KVH * HD, (uint64_t)p.B * p.sk, (uint64_t)ldv, 64, 128)) return -1;
+  auto kern = attn_fwd_tc_kernel<CAUSAL, HD>;
   static bool cfg = false;
   if (!cfg) {
     VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -327,6 +342,7 @@ struct AttnTcBwdParams {
   int64_t lddq, lddk, lddv;
   int B, H, KVH, sq, sk;
   float scale;
+  int window;  // see AttnTcParams
 };
 
 namespace tcb {
@@ -814,8 +830,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // query tile are prefetched one iteration ahead.  The dQ kernel additionally pairs a heavy and a
 // light causal query tile in one CTA (balanced work, half the prologues) with dQ double-buffered
 // in TMEM.
-namespace tcb2 {
-constexpr int HD = 128;
+namespace tcb2 {  // head_dim (128 or 96) is a template parameter of the kernels
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int A_BKV = 128, A_BQ = 64, A_ST = 3;
 constexpr int A_OFF_K = 0, A_OFF_V = 32768;
@@ -841,7 +856,7 @@ __device__ __forceinline__ void poll_guard(uint32_t& spins, bool did) {
   }
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, int HD>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -878,7 +893,14 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     qt_begin = first / A_BQ;
     if (qt_begin > nq_tiles) qt_begin = nq_tiles;
   }
-  const int nper = nq_tiles - qt_begin;
+  int qt_end = nq_tiles;
+  const bool win = CAUSAL && p.window > 0;
+  if (win) {  // last query row that still sees this tile's last key
+    const int last = kv0 + A_BKV - 1 - off + p.window;
+    if (last / A_BQ + 1 < qt_end) qt_end = last / A_BQ + 1;
+    if (qt_end < qt_begin) qt_end = qt_begin;
+  }
+  const int nper = qt_end - qt_begin;
   const int nit = G * nper;
 
   if (warp == 0 && lane == 0) {
@@ -1036,7 +1058,8 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       named_bar_sync(1 + g, 128);
       const int q0 = (qt_begin + it % nper) * A_BQ;
       const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
-                             (CAUSAL && (kv0 + A_BKV - 1 > q0 + off));
+                             (CAUSAL && (kv0 + A_BKV - 1 > q0 + off)) ||
+                             (win && (q0 + A_BQ - 1 + off - p.window > kv0));
       mbar_wait(&sd_full[g], k & 1);
       tc_fence_after();
       // all 64 S^T / dP^T columns go to registers first, so the buffer is handed back to the MMA
@@ -1068,10 +1091,11 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
         if (need_mask) {  // one warp-uniform branch per chunk, never one per score
           const int first_q = key_ok ? (CAUSAL ? kv0 + row - off : 0) : 0x7fffffff;
+          const int last_q = win ? min(p.sq - 1, kv0 + row - off + p.window) : p.sq - 1;
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             const int qc = q0 + hc * 32 + c;
-            if (qc < first_q || qc >= p.sq) s[c] = 0u;
+            if (qc < first_q || qc > last_q) s[c] = 0u;
           }
         }
 #pragma unroll
@@ -1104,6 +1128,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c = g * 2 + cc;
+      if (c * 32 >= HD) break;  // head_dim 96: three 32-column chunks
       uint32_t a[32], gg[32];
       if (nit > 0) {
         tmem_ld32(TM_DK + lane_addr + c * 32, a);
@@ -1134,7 +1159,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 // dQ_i = scale * sum_j dS_ij K_j — two query tiles (heavy + light) per CTA, ping-pong groups
-template <bool CAUSAL>
+template <bool CAUSAL, int HD>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1162,13 +1187,19 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   int qt[2] = {nqt - 1 - (int)blockIdx.x, (int)blockIdx.x};
   const int ntl = (qt[0] != qt[1]) ? 2 : 1;
   int nit[2] = {0, 0};
+  int jb[2] = {0, 0};  // first key tile a query tile can see (sliding window)
+  const bool win = CAUSAL && p.window > 0;
   for (int t = 0; t < ntl; ++t) {
     int kv_end = p.sk;
     if (CAUSAL) {
       kv_end = qt[t] * B_BQ + B_BQ + off;
       if (kv_end > p.sk) kv_end = p.sk;
     }
-    nit[t] = (kv_end + B_BKV - 1) / B_BKV;  // >= 1: the launcher guarantees sk >= sq for causal
+    if (win) {
+      const int lo = qt[t] * B_BQ + off - p.window;
+      jb[t] = lo > 0 ? lo / B_BKV : 0;
+    }
+    nit[t] = (kv_end + B_BKV - 1) / B_BKV - jb[t];  // >= 1: the launcher guarantees sk >= sq for causal
   }
   const int total = nit[0] + nit[1];
 
@@ -1218,7 +1249,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tma_load_2d(smem + B_OFF_DO + 16384, &tmDO, q_full, h * HD + 64, qrow);
         for (int it = 0; it < nit[t]; ++it, ++n) {
           const int st = n % B_ST;
-          const int krow = b * p.sk + it * B_BKV;
+          const int krow = b * p.sk + (it + jb[t]) * B_BKV;
           mbar_wait(&kv_empty[st], ((n / B_ST) & 1) ^ 1);
           mbar_arrive_expect_tx(&kv_full[st], 32768);
           uint8_t* sk_ = smem + B_OFF_KV + st * 32768;
@@ -1284,7 +1315,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const uint64_t ds_desc = desc_adv(ds_desc0, (n_dq & 1) * 16384);
 #pragma unroll
             for (int k = 0; k < B_BKV / 16; ++k) {  // contraction over the 64 keys
-              umma_bf16(TM_DQ + t * HD, desc_adv(ds_desc, k * 32), desc_adv(k_mn, k * 2048), idesc_dq,
+              umma_bf16(TM_DQ + t * 128, desc_adv(ds_desc, k * 32), desc_adv(k_mn, k * 2048), idesc_dq,
                         (i | k) != 0);
             }
             umma_commit(&ds_empty[n_dq & 1]);
@@ -1319,12 +1350,14 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int t = n < nit[0] ? 0 : 1;
       const int it = n - (t ? nit[0] : 0);
       const int q0 = qt[t] * B_BQ;
-      const int j0 = it * B_BKV;
+      const int j0 = (it + (t ? jb[1] : jb[0])) * B_BKV;
       const bool rok = t ? row_ok[1] : row_ok[0];
       const float l2 = t ? lse2[1] : lse2[0];
       const float dlt = t ? dl[1] : dl[0];
-      const bool need_mask = !rok || (j0 + B_BKV > p.sk) || (CAUSAL && (j0 + B_BKV - 1 > q0 + off));
+      const bool need_mask = !rok || (j0 + B_BKV > p.sk) || (CAUSAL && (j0 + B_BKV - 1 > q0 + off)) ||
+                             (win && j0 < q0 + B_BQ - 1 + off - p.window);
       const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
+      const int lov = win ? q0 + row + off - p.window - j0 : 0;  // first visible column of this tile
       mbar_wait(&sd_full[g], k & 1);
       tc_fence_after();
       // all 64 S / dP columns go to registers first, so the buffer is handed back to the MMA
@@ -1344,7 +1377,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int vis = rok ? lim - j0 : -1;  // last visible column of this tile
 #pragma unroll
         for (int c = 0; c < 64; ++c)
-          if (c > vis) s[c] = 0u;
+          if (c > vis || c < lov) s[c] = 0u;
       }
 #pragma unroll
       for (int c = 0; c < 64; ++c)
@@ -1371,8 +1404,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int c = g * 2 + cc;
+        if (c * 32 >= HD) break;
         uint32_t a[32];
-        tmem_ld32(TM_DQ + t * HD + lane_addr + c * 32, a);
+        tmem_ld32(TM_DQ + t * 128 + lane_addr + c * 32, a);
         tmem_ld_wait();
         if (rok) {
 #pragma unroll
@@ -1433,7 +1467,7 @@ static int launch_bwd_tc_v1(const void* q, int64_t ldq, const void* k, int64_t l
   return 0;
 }
 
-template <bool CAUSAL>
+template <bool CAUSAL, int HD>
 static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
                             cudaStream_t st) {
@@ -1446,7 +1480,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, A_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, A_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, A_BKV)) return -1;
-    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL>;
+    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
@@ -1462,7 +1496,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, B_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, B_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, B_BKV)) return -1;
-    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL>;
+    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
@@ -1479,40 +1513,47 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
 template <bool CAUSAL>
 static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
-                         cudaStream_t st) {
-  // v2 assumes every query tile sees at least one key tile (sk >= sq when causal)
-  if (get_option(VPB_OPT_ATTN_TC_BWD_V1) || (CAUSAL && p.sk < p.sq))
+                         int head_dim, cudaStream_t st) {
+  // v2 assumes every query tile sees at least one key tile (attention.cu only routes sk >= sq here
+  // for head_dim 96; head_dim 128 can still fall back to the v1 kernels)
+  if (head_dim == 96) return launch_bwd_tc_v2<CAUSAL, 96>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+  if (p.window == 0 && (get_option(VPB_OPT_ATTN_TC_BWD_V1) || (CAUSAL && p.sk < p.sq)))
     return launch_bwd_tc_v1<CAUSAL>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
-  return launch_bwd_tc_v2<CAUSAL>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+  return launch_bwd_tc_v2<CAUSAL, 128>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
 }
 
-// entry used by vpb_attn_bwd (attention.cu) after the delta kernel, head_dim 128, one K/V segment
+// entry used by vpb_attn_bwd (attention.cu) after the delta kernel: head_dim 128 / 96, one K/V segment
 int attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 const void* dO, int64_t lddo, const float* lse, const float* delta, void* dq,
                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int KVH,
-                int sq, int sk, float scale, int causal, cudaStream_t st) {
+                int sq, int sk, int head_dim, float scale, int causal, int window, cudaStream_t st) {
   AttnTcBwdParams p;
+  p.window = causal ? window : 0;
   p.lse = lse; p.delta = delta;
   p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk;
   p.scale = scale;
-  return causal ? launch_bwd_tc<true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)
-                : launch_bwd_tc<false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+  return causal ? launch_bwd_tc<true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, head_dim, st)
+                : launch_bwd_tc<false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, head_dim, st);
 }
 
-// entry used by vpb_attn_fwd (attention.cu) for head_dim 128, single K/V segment
+// entry used by vpb_attn_fwd (attention.cu) for head_dim 128 / 96, single K/V segment
 int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk, float scale,
-                int causal, cudaStream_t st) {
+                void* o, int64_t ldo, float* lse, int B, int H, int KVH, int sq, int sk, int head_dim,
+                float scale, int causal, int window, cudaStream_t st) {
   AttnTcParams p;
+  p.window = causal ? window : 0;
   p.o = (bf16*)o;
   p.lse = lse;
   p.ldo = ldo;
   p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk;
   p.scale = scale;
-  return causal ? launch_fwd_tc<true>(q, ldq, k, ldk, v, ldv, p, st)
-                : launch_fwd_tc<false>(q, ldq, k, ldk, v, ldv, p, st);
+  if (head_dim == 96)
+    return causal ? launch_fwd_tc<true, 96>(q, ldq, k, ldk, v, ldv, p, st)
+                  : launch_fwd_tc<false, 96>(q, ldq, k, ldk, v, ldv, p, st);
+  return causal ? launch_fwd_tc<true, 128>(q, ldq, k, ldk, v, ldv, p, st)
+                : launch_fwd_tc<false, 128>(q, ldq, k, ldk, v, ldv, p, st);
 }
 
 }  // namespace vpb
