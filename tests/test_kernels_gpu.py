@@ -434,6 +434,13 @@ def test_attention_tc_backward_v2_matches_v1_and_torch(B, H, KVH, sq, sk, causal
     dq2, dkv2 = bwd()
     dq2b, dkv2b = bwd()
     assert torch.equal(dq2, dq2b) and torch.equal(dkv2, dkv2b), "v2 backward is not deterministic"
+    # P/dS through shared memory (SS) instead of TMEM (TS, default): same bf16 operands → same bits
+    ops.set_option(ops.OPT_ATTN_BWD_SS, 1)
+    try:
+        dq3, dkv3 = bwd()
+    finally:
+        ops.set_option(ops.OPT_ATTN_BWD_SS, 0)
+    assert torch.equal(dq2, dq3) and torch.equal(dkv2, dkv3), "TS and SS backward variants differ"
     close(dq2, dq1, rtol=2e-2, name="dq v2 vs v1")
     close(dkv2, dkv1, rtol=2e-2, name="dkv v2 vs v1")
     qf = q.float().view(B, sq, H, hd).transpose(1, 2).detach().requires_grad_(True)

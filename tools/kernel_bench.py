@@ -146,8 +146,12 @@ if __name__ == "__main__":
         ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
         ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
     if which == "attnprof":
-        print(json.dumps({"variant": "tc backward v2 (ping-pong)"}), flush=True)
+        print(json.dumps({"variant": "tc backward v2 (ping-pong), P/dS in TMEM (TS)"}), flush=True)
         attn_profile()
+        ops.set_option(ops.OPT_ATTN_BWD_SS, 1)
+        print(json.dumps({"variant": "tc backward v2, P/dS through shared memory (SS)"}), flush=True)
+        attn_profile()
+        ops.set_option(ops.OPT_ATTN_BWD_SS, 0)
         ops.set_option(ops.OPT_ATTN_TC_BWD_V1, 1)
         print(json.dumps({"variant": "tc backward v1"}), flush=True)
         attn_profile()

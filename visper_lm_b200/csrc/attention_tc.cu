@@ -832,17 +832,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // in TMEM.
 namespace tcb2 {  // head_dim (128 or 96) is a template parameter of the kernels
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr int A_BKV = 128, A_BQ = 64, A_ST = 3;
+// TS mode (default): P^T / dS^T are written back over their own scores in TMEM and feed the
+// accumulate MMAs as TMEM A operands (tcgen05.mma with [tmem] A) — no P/dS shared-memory tiles, no
+// generic→async proxy fence, and the 64 KB they occupied become two more TMA stages (5 instead of 3).
+// SS mode (VPB_OPT_ATTN_BWD_SS): P^T / dS^T staged through shared memory as K-major A tiles.
+constexpr int A_BKV = 128, A_BQ = 64, A_ST_SS = 3, A_ST_TS = 5;
 constexpr int A_OFF_K = 0, A_OFF_V = 32768;
 constexpr int A_OFF_QD = 65536;                      // stage s: Q (16 KB) then dO (16 KB)
-constexpr int A_OFF_PDS = A_OFF_QD + A_ST * 32768;   // group g: P^T (16 KB) then dS^T (16 KB)
+constexpr int A_OFF_PDS = A_OFF_QD + A_ST_SS * 32768;  // SS mode, group g: P^T (16 KB) then dS^T (16 KB)
 constexpr int A_OFF_LD = A_OFF_PDS + 2 * 32768;      // [2 groups][2 parity][64 lse | 64 delta] floats
 constexpr int A_OFF_BAR = A_OFF_LD + 2048;
 constexpr int A_SMEM = A_OFF_BAR + 256;              // 231 680 B: needs the 1024-aligned base
-constexpr int B_BQ = 128, B_BKV = 64, B_ST = 4;
+constexpr int B_BQ = 128, B_BKV = 64, B_ST_SS = 4, B_ST_TS = 5;
 constexpr int B_OFF_Q = 0, B_OFF_DO = 32768;
 constexpr int B_OFF_KV = 65536;                      // stage s: K (16 KB) then V (16 KB)
-constexpr int B_OFF_DS = B_OFF_KV + B_ST * 32768;    // group g: dS [128 queries x 64 keys] 16 KB
+constexpr int B_OFF_DS = B_OFF_KV + B_ST_SS * 32768; // SS mode, group g: dS [128 queries x 64 keys] 16 KB
 constexpr int B_OFF_BAR = B_OFF_DS + 2 * 16384;
 constexpr int B_SMEM = B_OFF_BAR + 256;
 }  // namespace tcb2
@@ -856,7 +860,7 @@ __device__ __forceinline__ void poll_guard(uint32_t& spins, bool did) {
   }
 }
 
-template <bool CAUSAL, int HD>
+template <bool CAUSAL, int HD, bool TS>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -864,15 +868,16 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   using namespace tcb2;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_OFF_BAR);
+  constexpr int A_ST = TS ? A_ST_TS : A_ST_SS;
   uint64_t* kv_full = bars + 0;
-  uint64_t* qd_full = bars + 1;     // [3]
-  uint64_t* qd_empty = bars + 4;    // [3]
-  uint64_t* sd_full = bars + 7;     // [2] S^T/dP^T of buffer b complete
-  uint64_t* s_free = bars + 9;      // [2] group b has its S^T/dP^T in registers
-  uint64_t* pds_full = bars + 11;   // [2] group b wrote P^T/dS^T
-  uint64_t* pds_empty = bars + 13;  // [2] dV/dK MMAs reading buffer b retired
-  uint64_t* all_done = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* qd_full = bars + 1;     // [A_ST <= 5]
+  uint64_t* qd_empty = bars + 6;    // [A_ST <= 5]
+  uint64_t* sd_full = bars + 11;    // [2] S^T/dP^T of buffer b complete
+  uint64_t* s_free = bars + 13;     // [2] SS mode: group b has its S^T/dP^T in registers
+  uint64_t* pds_full = bars + 15;   // [2] group b wrote P^T/dS^T
+  uint64_t* pds_empty = bars + 17;  // [2] SS mode: dV/dK MMAs reading smem buffer b retired
+  uint64_t* all_done = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   float* ld_buf = reinterpret_cast<float*>(smem + A_OFF_LD);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -977,7 +982,10 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         bool did = false;
         if (n_sd < nit) {
           const int sb = n_sd & 1, st = n_sd % A_ST;
-          bool ok = (n_sd < 2) || mbar_test(&s_free[sb], ((n_sd >> 1) - 1) & 1);
+          // buffer sb is free once iteration n_sd-2 is done with it: SS — its scores are in the
+          // group's registers (s_free); TS — its P^T/dS^T were consumed, i.e. the dV/dK MMAs of
+          // n_sd-2 were ISSUED (tcgen05.mma of one thread execute in order)
+          bool ok = (n_sd < 2) || (TS ? (n_acc >= n_sd - 1) : mbar_test(&s_free[sb], ((n_sd >> 1) - 1) & 1));
           ok = ok && mbar_test(&qd_full[st], (n_sd / A_ST) & 1);
           if (ok) {
             tc_fence_after();
@@ -1010,15 +1018,25 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             const uint64_t do_mn = desc_adv(q_mn, 16384);
             const uint64_t p_desc = desc_adv(p_desc0, (n_acc & 1) * 32768);
             const uint64_t ds_desc = desc_adv(p_desc, 16384);
+            if constexpr (TS) {
+              const uint32_t gcol = (n_acc & 1) * A_BQ;  // P^T over S^T[g], dS^T over dP^T[g]: 32 packed columns
 #pragma unroll
-            for (int k = 0; k < A_BQ / 16; ++k) {  // contraction over the 64 queries
-              umma_bf16(TM_DV, desc_adv(p_desc, k * 32), desc_adv(do_mn, k * 2048), idesc_acc,
-                        (n_acc | k) != 0);
-            }
+              for (int k = 0; k < A_BQ / 16; ++k)  // contraction over the 64 queries
+                umma_bf16_ts(TM_DV, TM_S + gcol + k * 8, desc_adv(do_mn, k * 2048), idesc_acc, (n_acc | k) != 0);
 #pragma unroll
-            for (int k = 0; k < A_BQ / 16; ++k) {
-              umma_bf16(TM_DK, desc_adv(ds_desc, k * 32), desc_adv(q_mn, k * 2048), idesc_acc,
-                        (n_acc | k) != 0);
+              for (int k = 0; k < A_BQ / 16; ++k)
+                umma_bf16_ts(TM_DK, TM_DP + gcol + k * 8, desc_adv(q_mn, k * 2048), idesc_acc, (n_acc | k) != 0);
+            } else {
+#pragma unroll
+              for (int k = 0; k < A_BQ / 16; ++k) {  // contraction over the 64 queries
+                umma_bf16(TM_DV, desc_adv(p_desc, k * 32), desc_adv(do_mn, k * 2048), idesc_acc,
+                          (n_acc | k) != 0);
+              }
+#pragma unroll
+              for (int k = 0; k < A_BQ / 16; ++k) {
+                umma_bf16(TM_DK, desc_adv(ds_desc, k * 32), desc_adv(q_mn, k * 2048), idesc_acc,
+                          (n_acc | k) != 0);
+              }
             }
             umma_commit(&pds_empty[n_acc & 1]);
             umma_commit(&qd_empty[st]);
@@ -1070,9 +1088,11 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_ld32(TM_DP + lane_addr + g * A_BQ, dall);
       tmem_ld32(TM_DP + lane_addr + g * A_BQ + 32, dall + 32);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[g]);
+      if constexpr (!TS) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);
+      }
 #pragma unroll
       for (int hc = 0; hc < 2; ++hc) {  // two chunks of 32 query columns
         uint32_t* s = sall + hc * 32;
@@ -1100,21 +1120,34 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c) d[c] = __float_as_uint(__uint_as_float(s[c]) * __uint_as_float(d[c]));
-        if (hc == 0 && k > 0) mbar_wait(&pds_empty[g], (k - 1) & 1);  // dV/dK of it-2 read this buffer
+        if constexpr (TS) {
+          // bf16 pairs back into TMEM over this thread's own scores: columns [16*hc, 16*hc+16)
+          uint32_t wp[16], wd[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float a[8], gg[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            a[i] = __uint_as_float(s[u * 8 + i]);
-            gg[i] = __uint_as_float(d[u * 8 + i]);
+          for (int i = 0; i < 16; ++i) {
+            wp[i] = pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+            wd[i] = pack2(__uint_as_float(d[2 * i]), __uint_as_float(d[2 * i + 1]));
           }
-          const int so = ((hc * 4 + u) ^ (row & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + so) = pack8(a);
-          *reinterpret_cast<uint4*>(dsrow + so) = pack8(gg);
+          tmem_st16(TM_S + lane_addr + g * A_BQ + hc * 16, wp);
+          tmem_st16(TM_DP + lane_addr + g * A_BQ + hc * 16, wd);
+        } else {
+          if (hc == 0 && k > 0) mbar_wait(&pds_empty[g], (k - 1) & 1);  // dV/dK of it-2 read this buffer
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float a[8], gg[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              a[i] = __uint_as_float(s[u * 8 + i]);
+              gg[i] = __uint_as_float(d[u * 8 + i]);
+            }
+            const int so = ((hc * 4 + u) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + so) = pack8(a);
+            *reinterpret_cast<uint4*>(dsrow + so) = pack8(gg);
+          }
         }
       }
-      fence_proxy_async();
+      if constexpr (TS) tmem_st_wait();
+      else fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[g]);
@@ -1159,7 +1192,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 // dQ_i = scale * sum_j dS_ij K_j — two query tiles (heavy + light) per CTA, ping-pong groups
-template <bool CAUSAL, int HD>
+template <bool CAUSAL, int HD, bool TS>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1167,16 +1200,17 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   using namespace tcb2;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
+  constexpr int B_ST = TS ? B_ST_TS : B_ST_SS;
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;    // [4]
-  uint64_t* kv_empty = bars + 6;   // [4]
-  uint64_t* sd_full = bars + 10;   // [2]
-  uint64_t* s_free = bars + 12;    // [2]
-  uint64_t* ds_full = bars + 14;   // [2]
-  uint64_t* ds_empty = bars + 16;  // [2]
-  uint64_t* tile_done = bars + 18; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* kv_full = bars + 2;    // [B_ST <= 5]
+  uint64_t* kv_empty = bars + 7;   // [B_ST <= 5]
+  uint64_t* sd_full = bars + 12;   // [2]
+  uint64_t* s_free = bars + 14;    // [2] SS mode
+  uint64_t* ds_full = bars + 16;   // [2]
+  uint64_t* ds_empty = bars + 18;  // [2] SS mode
+  uint64_t* tile_done = bars + 20; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -1278,7 +1312,8 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           const int t = n_sd < nit[0] ? 0 : 1;
           const int i = n_sd - (t ? nit[0] : 0);
           const int sb = n_sd & 1, st = n_sd % B_ST;
-          bool ok = (n_sd < 2) || mbar_test(&s_free[sb], ((n_sd >> 1) - 1) & 1);
+          // see the dK/dV kernel: TS frees a score buffer when the dQ MMAs of n_sd-2 are issued
+          bool ok = (n_sd < 2) || (TS ? (n_dq >= n_sd - 1) : mbar_test(&s_free[sb], ((n_sd >> 1) - 1) & 1));
           ok = ok && mbar_test(&kv_full[st], (n_sd / B_ST) & 1);
           if (ok && i == 0) ok = mbar_test(q_full, t);
           if (ok) {
@@ -1315,8 +1350,12 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const uint64_t ds_desc = desc_adv(ds_desc0, (n_dq & 1) * 16384);
 #pragma unroll
             for (int k = 0; k < B_BKV / 16; ++k) {  // contraction over the 64 keys
-              umma_bf16(TM_DQ + t * 128, desc_adv(ds_desc, k * 32), desc_adv(k_mn, k * 2048), idesc_dq,
-                        (i | k) != 0);
+              if constexpr (TS)
+                umma_bf16_ts(TM_DQ + t * 128, TM_DP + (n_dq & 1) * B_BKV + k * 8, desc_adv(k_mn, k * 2048),
+                             idesc_dq, (i | k) != 0);
+              else
+                umma_bf16(TM_DQ + t * 128, desc_adv(ds_desc, k * 32), desc_adv(k_mn, k * 2048), idesc_dq,
+                          (i | k) != 0);
             }
             umma_commit(&ds_empty[n_dq & 1]);
             umma_commit(&kv_empty[st]);
@@ -1368,9 +1407,11 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tmem_ld32(TM_DP + lane_addr + g * B_BKV, d);
       tmem_ld32(TM_DP + lane_addr + g * B_BKV + 32, d + 32);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[g]);
+      if constexpr (!TS) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);
+      }
 #pragma unroll
       for (int c = 0; c < 64; ++c) s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
       if (need_mask) {  // one warp-uniform branch per tile, never one per score
@@ -1382,15 +1423,23 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
       for (int c = 0; c < 64; ++c)
         d[c] = __float_as_uint(__uint_as_float(s[c]) * (__uint_as_float(d[c]) - dlt));
-      if (k > 0) mbar_wait(&ds_empty[g], (k - 1) & 1);
+      if constexpr (TS) {
+        uint32_t wd[32];  // dS as bf16 pairs over this thread's own dP scores in TMEM
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float gg[8];
+        for (int i = 0; i < 32; ++i) wd[i] = pack2(__uint_as_float(d[2 * i]), __uint_as_float(d[2 * i + 1]));
+        tmem_st32(TM_DP + lane_addr + g * B_BKV, wd);
+        tmem_st_wait();
+      } else {
+        if (k > 0) mbar_wait(&ds_empty[g], (k - 1) & 1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gg[i] = __uint_as_float(d[u * 8 + i]);
-        *reinterpret_cast<uint4*>(dsrow + ((u ^ (row & 7)) << 4)) = pack8(gg);
+        for (int u = 0; u < 8; ++u) {
+          float gg[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gg[i] = __uint_as_float(d[u * 8 + i]);
+          *reinterpret_cast<uint4*>(dsrow + ((u ^ (row & 7)) << 4)) = pack8(gg);
+        }
+        fence_proxy_async();
       }
-      fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[g]);
@@ -1467,7 +1516,7 @@ static int launch_bwd_tc_v1(const void* q, int64_t ldq, const void* k, int64_t l
   return 0;
 }
 
-template <bool CAUSAL, int HD>
+template <bool CAUSAL, int HD, bool TS>
 static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
                             cudaStream_t st) {
@@ -1480,7 +1529,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, A_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, A_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, A_BKV)) return -1;
-    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD>;
+    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD, TS>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
@@ -1496,7 +1545,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, B_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, B_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, B_BKV)) return -1;
-    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD>;
+    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
@@ -1516,10 +1565,14 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
                          int head_dim, cudaStream_t st) {
   // v2 assumes every query tile sees at least one key tile (attention.cu only routes sk >= sq here
   // for head_dim 96; head_dim 128 can still fall back to the v1 kernels)
-  if (head_dim == 96) return launch_bwd_tc_v2<CAUSAL, 96>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+  const bool ss = get_option(VPB_OPT_ATTN_BWD_SS) != 0;
+  if (head_dim == 96)
+    return ss ? launch_bwd_tc_v2<CAUSAL, 96, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)
+              : launch_bwd_tc_v2<CAUSAL, 96, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
   if (p.window == 0 && (get_option(VPB_OPT_ATTN_TC_BWD_V1) || (CAUSAL && p.sk < p.sq)))
     return launch_bwd_tc_v1<CAUSAL>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
-  return launch_bwd_tc_v2<CAUSAL, 128>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+  return ss ? launch_bwd_tc_v2<CAUSAL, 128, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)
+            : launch_bwd_tc_v2<CAUSAL, 128, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
 }
 
 // entry used by vpb_attn_bwd (attention.cu) after the delta kernel: head_dim 128 / 96, one K/V segment
