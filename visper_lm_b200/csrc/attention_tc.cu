@@ -1073,12 +1073,11 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       float* lbuf = lbase + (k & 1) * 128;
       lbuf[gtid] = pre;
       if (it + 2 < nit) pre = fetch(it + 2);  // in flight during this iteration
-      named_bar_sync(1 + g, 128);
       const int q0 = (qt_begin + it % nper) * A_BQ;
       const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
                              (CAUSAL && (kv0 + A_BKV - 1 > q0 + off)) ||
                              (win && (q0 + A_BQ - 1 + off - p.window > kv0));
-      mbar_wait(&sd_full[g], k & 1);
+      mbar_wait_spin(&sd_full[g], k & 1);
       tc_fence_after();
       // all 64 S^T / dP^T columns go to registers first, so the buffer is handed back to the MMA
       // issuer (S/dP of iteration it+2) before any of the exp / dS work starts
@@ -1087,6 +1086,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_ld32(TM_S + lane_addr + g * A_BQ + 32, sall + 32);
       tmem_ld32(TM_DP + lane_addr + g * A_BQ, dall);
       tmem_ld32(TM_DP + lane_addr + g * A_BQ + 32, dall + 32);
+      named_bar_sync(1 + g, 128);  // lse/delta staged — under the TMEM load latency
       tmem_ld_wait();
       if constexpr (!TS) {
         tc_fence_before();
@@ -1397,7 +1397,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                              (win && j0 < q0 + B_BQ - 1 + off - p.window);
       const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
       const int lov = win ? q0 + row + off - p.window - j0 : 0;  // first visible column of this tile
-      mbar_wait(&sd_full[g], k & 1);
+      mbar_wait_spin(&sd_full[g], k & 1);
       tc_fence_after();
       // all 64 S / dP columns go to registers first, so the buffer is handed back to the MMA
       // issuer (S/dP of iteration n+2) before any of the exp / dS work starts

@@ -187,6 +187,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Spin on test_wait (no hardware suspend): lower wake-up latency than try_wait for waits that sit
+// on a kernel's critical chain, at the price of issue slots the waiting warp has to spare.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test(bar, parity)) {
+    if (++spins > (1u << 30)) {
+      printf("[vpb] mbarrier spin-wait timed out (block %d thread %d parity %u)\n", blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
