@@ -386,7 +386,9 @@ def test_attention_sliding_window(B, H, KVH, S, hd, window, legacy):
 
 
 @pytest.mark.parametrize("B,H,KVH,sq,sk,causal", [(2, 8, 2, 2048, 2048, True), (1, 4, 4, 333, 333, True),
-                                                   (2, 4, 2, 200, 520, False), (1, 4, 1, 128, 128, True)])
+                                                   (2, 4, 2, 200, 520, False), (1, 4, 1, 128, 128, True),
+                                                   (1, 4, 2, 900, 900, True), (1, 2, 2, 257, 1000, True),
+                                                   (2, 2, 1, 640, 640, False)])
 def test_attention_tcgen05_matches_legacy(B, H, KVH, sq, sk, causal):
     """hd=128 forward: the tcgen05/TMEM kernel against the mma.sync kernel (both vs torch above)."""
     from visper_lm_b200 import ops
@@ -401,6 +403,15 @@ def test_attention_tcgen05_matches_legacy(B, H, KVH, sq, sk, causal):
     torch.cuda.synchronize()
     close(o, o_ref, name="tc fwd vs legacy")
     assert (lse - lse_ref).abs().max().item() < 2e-2
+    ops.set_option(ops.OPT_ATTN_FWD_V2, 1)  # experimental two-query-tile kernel: same results
+    try:
+        o2, lse2 = ops.attn_fwd(q, k, v, B, H, KVH, sq, sk, hd, hd ** -0.5, causal)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_ATTN_FWD_V2, 0)
+    close(o2, o_ref, name="tc fwd v2 vs legacy")
+    close(o2, o, rtol=8e-3, name="tc fwd v2 vs v1")
+    assert (lse2 - lse).abs().max().item() < 2e-2
 
 
 @pytest.mark.parametrize("B,H,KVH,sq,sk,causal", [

@@ -313,6 +313,338 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// bounded polling for the MMA issuers that watch several barriers (a broken invariant traps)
+__device__ __forceinline__ void poll_guard(uint32_t& spins, bool did) {
+  if (did) {
+    spins = 0;
+  } else if (++spins > (1u << 28)) {
+    printf("[vpb] attention MMA issuer starved (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+    __trap();
+  }
+}
+
+// =============================================================================================
+// forward v2: TWO 128-query tiles per CTA, one softmax group (4 warps) per tile
+// =============================================================================================
+// v1 (above) runs one query tile per CTA: its softmax is MUFU-bound at about the same 1024 cycles
+// per key tile as the two MMAs, the two phases of ONE tile depend on each other, and a causal CTA
+// lives for only ~8 key tiles, so the tensor pipe was 37 % active (profiles/r01_ncu_attn_tc_v2.csv).
+// v2 pairs two adjacent query tiles: while one tile's rows are in exp2, the tensor pipe works on
+// the other tile's S / PV; every K/V tile is fetched once for 256 query rows; each softmax thread
+// owns a whole 128-column score row (no cross-warp max exchange); the MMA warp polls for whichever
+// of {S_A, S_B, PV_A, PV_B} is ready.  TMEM: S_A | S_B | O_A | O_B (4 x 128 columns), P over S.
+namespace tc2 {
+constexpr int BM = 128, BN = 128;
+constexpr int TILE_BYTES = 128 * 128 * 2, CHUNK_BYTES = 16384;
+constexpr int KST = 3, VST = 2;
+constexpr int OFF_Q = 0;                             // Q_A, Q_B
+constexpr int OFF_K = 2 * TILE_BYTES;
+constexpr int OFF_V = OFF_K + KST * TILE_BYTES;
+constexpr int OFF_BAR = OFF_V + VST * TILE_BYTES;    // 7 x 32 KB = 224 KB of tiles
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+constexpr float LOG2E = 1.4426950408889634f;
+}  // namespace tc2
+
+template <bool CAUSAL, int HD>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  using namespace tc2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;    // [2] per query tile
+  uint64_t* k_full = bars + 2;    // [3]
+  uint64_t* k_empty = bars + 5;   // [3]
+  uint64_t* v_full = bars + 8;    // [2]
+  uint64_t* v_empty = bars + 10;  // [2]
+  uint64_t* s_full = bars + 12;   // [2] per query tile: S_t complete
+  uint64_t* p_full = bars + 14;   // [2] per query tile: P_t written (4 warps)
+  uint64_t* pv_done = bars + 16;  // [2] per query tile: PV_t retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pr = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy pairs first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (p.H / p.KVH);
+  const int off = p.sk - p.sq;
+  const int nqt = (p.sq + BM - 1) / BM;
+  const bool win = CAUSAL && p.window > 0;
+  // per query tile: first query row, first / one-past-last visible key tile
+  int q0[2], jb[2], je[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int qt = 2 * pr + t;
+    q0[t] = qt * BM;
+    jb[t] = je[t] = 0;
+    if (qt < nqt) {
+      int kv_end = p.sk;
+      if (CAUSAL) {
+        kv_end = q0[t] + BM + off;
+        if (kv_end > p.sk) kv_end = p.sk;
+        if (kv_end < 0) kv_end = 0;
+      }
+      je[t] = (kv_end + BN - 1) / BN;
+      if (win) {
+        const int lo = q0[t] + off - p.window;
+        jb[t] = lo > 0 ? lo / BN : 0;
+        if (jb[t] > je[t]) jb[t] = je[t];
+      }
+    }
+  }
+  const int cnt0 = je[0] - jb[0], cnt1 = je[1] - jb[1];
+  int jmin = jb[0], jmax = je[0];
+  if (cnt1 > 0) {
+    if (cnt0 == 0 || jb[1] < jmin) jmin = jb[1];
+    if (cnt0 == 0 || je[1] > jmax) jmax = je[1];
+  }
+  const int nkv = (cnt0 > 0 || cnt1 > 0) ? jmax - jmin : 0;  // key tiles this CTA streams
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("[vpb] dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < KST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t TM_S = tmem_base;        // S_t at + t*128 (P_t over its first 64 columns)
+  const uint32_t TM_O = tmem_base + 256;  // O_t at + t*128
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int t = 0; t < 2; ++t) {
+        if ((t ? cnt1 : cnt0) == 0) continue;
+        mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
+        tma_load_2d(smem + OFF_Q + t * TILE_BYTES, &tmQ, &q_full[t], h * HD, b * p.sq + q0[t]);
+        tma_load_2d(smem + OFF_Q + t * TILE_BYTES + CHUNK_BYTES, &tmQ, &q_full[t], h * HD + 64, b * p.sq + q0[t]);
+      }
+      auto load_k = [&](int i) {
+        const int s = i % KST;
+        mbar_wait(&k_empty[s], ((i / KST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+        uint8_t* sk = smem + OFF_K + s * TILE_BYTES;
+        const int row = b * p.sk + (jmin + i) * BN;
+        tma_load_2d(sk, &tmK, &k_full[s], kvh * HD, row);
+        tma_load_2d(sk + CHUNK_BYTES, &tmK, &k_full[s], kvh * HD + 64, row);
+      };
+      if (nkv > 0) load_k(0);
+      for (int i = 0; i < nkv; ++i) {
+        if (i + 1 < nkv) load_k(i + 1);  // K runs one tile ahead of V
+        const int s = i % VST;
+        mbar_wait(&v_empty[s], ((i / VST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+        uint8_t* sv = smem + OFF_V + s * TILE_BYTES;
+        const int row = b * p.sk + (jmin + i) * BN;
+        tma_load_2d(sv, &tmV, &v_full[s], kvh * HD, row);
+        tma_load_2d(sv + CHUNK_BYTES, &tmV, &v_full[s], kvh * HD + 64, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (nkv > 0) {  // warp-uniform polling loop, one elected lane issues
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BM, HD, 0, 1);
+      const uint64_t q_desc0 = make_smem_desc(smem_u32(smem + OFF_Q), 16, 1024);
+      const uint64_t k_desc0 = make_smem_desc(smem_u32(smem + OFF_K), 16, 1024);
+      const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + OFF_V), CHUNK_BYTES, 1024);  // MN-major
+      int ns[2] = {0, 0}, npv[2] = {0, 0};  // next S / PV iteration of each query tile
+      const int cnt[2] = {cnt0, cnt1};
+      const int kb[2] = {jb[0] - jmin, jb[1] - jmin};  // tile-local iteration i uses K/V ring entry kb+i
+      int k_rel = 0, v_rel = 0;
+      bool q_ready[2] = {false, false};
+      uint32_t spins = 0;
+      while (npv[0] < cnt[0] || npv[1] < cnt[1]) {
+        bool did = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          // S_t(i): the score buffer doubles as P_t(i-1), so PV_t(i-1) must have been issued
+          if (ns[t] < cnt[t] && npv[t] >= ns[t]) {
+            const int e = kb[t] + ns[t];
+            bool ok = mbar_test(&k_full[e % KST], (e / KST) & 1);
+            if (ok && !q_ready[t]) ok = q_ready[t] = mbar_test(&q_full[t], 0);
+            if (ok) {
+              tc_fence_after();
+              if (leader) {
+                const uint64_t q_desc = desc_adv(q_desc0, t * TILE_BYTES);
+                const uint64_t k_desc = desc_adv(k_desc0, (e % KST) * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                  const uint32_t o = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
+                  umma_bf16(TM_S + t * BN, desc_adv(q_desc, o), desc_adv(k_desc, o), idesc_s, k != 0);
+                }
+                umma_commit(&s_full[t]);
+              }
+              ++ns[t];
+              did = true;
+              // K ring entries no tile still needs
+              int lim = nkv;
+              if (ns[0] < cnt[0]) lim = kb[0] + ns[0];
+              if (ns[1] < cnt[1] && kb[1] + ns[1] < lim) lim = kb[1] + ns[1];
+              for (; k_rel < lim; ++k_rel)
+                if (leader) umma_commit(&k_empty[k_rel % KST]);
+            }
+          }
+          if (npv[t] < ns[t]) {
+            const int e = kb[t] + npv[t];
+            if (mbar_test(&p_full[t], npv[t] & 1) && mbar_test(&v_full[e % VST], (e / VST) & 1)) {
+              tc_fence_after();
+              if (leader) {
+                const uint64_t v_desc = desc_adv(v_desc0, (e % VST) * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BN / 16; ++k)
+                  umma_bf16_ts(TM_O + t * 128, TM_S + t * BN + k * 8, desc_adv(v_desc, k * 2048), idesc_pv,
+                               (npv[t] | k) != 0);
+                umma_commit(&pv_done[t]);
+              }
+              ++npv[t];
+              did = true;
+              int lim = nkv;
+              if (npv[0] < cnt[0]) lim = kb[0] + npv[0];
+              if (npv[1] < cnt[1] && kb[1] + npv[1] < lim) lim = kb[1] + npv[1];
+              for (; v_rel < lim; ++v_rel)
+                if (leader) umma_commit(&v_empty[v_rel % VST]);
+            }
+          }
+        }
+        poll_guard(spins, did);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int t = (warp - 2) >> 2;        // query tile of this softmax group
+    const int row = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    const int cnt = t ? cnt1 : cnt0;
+    const int q0t = t ? q0[1] : q0[0], jbt = t ? jb[1] : jb[0];
+    const uint32_t tS = TM_S + lane_addr + t * BN, tO = TM_O + lane_addr + t * 128;
+    float m_used = -INFINITY, l = 0.f;
+    for (int i = 0; i < cnt; ++i) {
+      mbar_wait_spin(&s_full[t], i & 1);
+      tc_fence_after();
+      uint32_t r[128];
+      tmem_ld32(tS, r);
+      tmem_ld32(tS + 32, r + 32);
+      tmem_ld32(tS + 64, r + 64);
+      tmem_ld32(tS + 96, r + 96);
+      tmem_ld_wait();
+      const int j0 = (jbt + i) * BN;  // first key of this tile
+      const bool need_mask = (j0 + BN > p.sk) || (CAUSAL && (j0 + BN - 1 > q0t + off)) ||
+                             (win && j0 < q0t + BM - 1 + off - p.window);
+      if (need_mask) {
+        const int lim = CAUSAL ? min(p.sk - 1, q0t + row + off) : p.sk - 1;  // last visible key
+        const int lo = win ? q0t + row + off - p.window : 0;                 // first visible key
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (j0 + c > lim || j0 + c < lo) r[c] = 0xff800000u;  // -inf
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(r[c + e]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+      // lazy rescale: keep the old reference max unless the new one is > 2^8 larger
+      const bool upd = mx > m_used + 8.f;
+      float alpha = 1.f;
+      if (upd) {
+        alpha = exp2f(m_used - mx);  // m_used = -inf → 0
+        m_used = mx;
+        l *= alpha;
+      }
+      const float mb = (m_used == -INFINITY) ? 0.f : m_used;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
+          sum4[e] += pv;
+          r[c + e] = __float_as_uint(pv);
+        }
+      }
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (i > 0 && __any_sync(0xffffffffu, upd)) {
+        mbar_wait(&pv_done[t], (i - 1) & 1);  // PV_{i-1} finished: O may be rescaled
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+          tmem_st32(tO + c * 32, o);
+        }
+      }
+      // P (bf16 pairs) overwrites this thread's own scores: columns [0,64) of S_t
+#pragma unroll
+      for (int c = 0; c < 64; ++c) r[c] = pack2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1]));
+      tmem_st32(tS, r);
+      tmem_st32(tS + 32, r + 32);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    if (2 * pr + t < nqt) {
+      const bool row_ok = q0t + row < p.sq;
+      if (cnt > 0) {
+        mbar_wait(&pv_done[t], (cnt - 1) & 1);
+        tc_fence_after();
+      }
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* orow = p.o + ((int64_t)b * p.sq + q0t + row) * p.ldo + h * HD;
+#pragma unroll 1
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        if (cnt > 0) {
+          tmem_ld32(tO + c * 32, o);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] = 0;
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(o[g * 8 + k]) * inv;
+            stg16(orow + c * 32 + g * 8, pack8(v));
+          }
+        }
+      }
+      if (p.lse && row_ok)
+        p.lse[((int64_t)b * p.H + h) * p.sq + q0t + row] =
+            l > 0.f ? m_used * 0.6931471805599453f + logf(l) : -INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 template <bool CAUSAL, int HD>
 static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, const AttnTcParams& p, cudaStream_t st) {
@@ -320,6 +652,23 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   if (make_tmap_2d(&tmQ, q, (uint64_t)p.H * HD, (uint64_t)p.B * p.sq, (uint64_t)ldq, 64, 128)) return -1;
   if (make_tmap_2d(&tmK, k, (uint64_t)p.KVH * HD, (uint64_t)p.B * p.sk, (uint64_t)ldk, 64, 128)) return -1;
   if (make_tmap_2d(&tmV, v, (uint64_t)p.KVH * HD, (uint64_t)p.B * p.sk, (uint64_t)ldv, 64, 128)) return -1;
+  const int nqt = (p.sq + 127) / 128;
+  // EXPERIMENTAL (off by default): two query tiles per CTA.  Correct (tests run it), but each softmax
+  // thread then holds a 128-score row and the register file is split per SM sub-partition (three of
+  // this CTA's ten warps share 16 K registers → 168 per thread), so the hot loop spills and it measures
+  // 0.47 ms against 0.42 ms for the one-tile kernel at B=8,H=32,S=2048.
+  if (get_option(VPB_OPT_ATTN_FWD_V2) && nqt >= 2) {
+    auto kern = attn_fwd_tc2_kernel<CAUSAL, HD>;
+    static bool cfg2 = false;
+    if (!cfg2) {
+      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      cfg2 = true;
+    }
+    dim3 grid((nqt + 1) / 2, p.H, p.B);
+    kern<<<grid, 320, tc2::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    VPB_LAUNCH_OK();
+    return 0;
+  }
   auto kern = attn_fwd_tc_kernel<CAUSAL, HD>;
   static bool cfg = false;
   if (!cfg) {
@@ -850,15 +1199,6 @@ constexpr int B_OFF_DS = B_OFF_KV + B_ST_SS * 32768; // SS mode, group g: dS [12
 constexpr int B_OFF_BAR = B_OFF_DS + 2 * 16384;
 constexpr int B_SMEM = B_OFF_BAR + 256;
 }  // namespace tcb2
-
-__device__ __forceinline__ void poll_guard(uint32_t& spins, bool did) {
-  if (did) {
-    spins = 0;
-  } else if (++spins > (1u << 28)) {
-    printf("[vpb] attention MMA issuer starved (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
-    __trap();
-  }
-}
 
 template <bool CAUSAL, int HD, bool TS>
 __global__ void __launch_bounds__(320, 1)

@@ -303,6 +303,16 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// Register re-balancing between warpgroups (4 consecutive warps, all must execute it): the
+// data-movement warpgroup gives registers back, the softmax warpgroups take them.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 // One lane of a converged warp (elect.sync): the MMA warps run their loops warp-uniformly so
 // that descriptor arithmetic stays on the uniform datapath, and only this lane issues.
 __device__ __forceinline__ bool elect_one() {

@@ -36,7 +36,7 @@ def _rows(t: torch.Tensor):
 
 
 OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD, OPT_ATTN_TC_BWD_V1, OPT_GEMM_1CTA, OPT_GEMM_PANEL_MB = 0, 1, 2, 3, 4
-OPT_ATTN_BWD_SS = 5
+OPT_ATTN_BWD_SS, OPT_ATTN_FWD_V2 = 5, 6
 
 
 def set_option(key, value):
