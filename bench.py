@@ -155,7 +155,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference(c, T, distill, layers_sampled, repeats=1, warmup=0):
+def cpu_reference(c, T, distill, layers_sampled, repeats=1, warmup=0, budget_s=None):
     """Times the oracle restatement (CPU fp32, all host threads) on a BOUNDED sample of the same
     workload: B=1, full CLIP tower + projector, `layers_sampled` of the decoder layers (fwd + bwd wrt
     activations, extrapolated linearly to all layers), final norm + full-vocab lm_head/CE fwd+bwd.
@@ -214,7 +214,10 @@ def cpu_reference(c, T, distill, layers_sampled, repeats=1, warmup=0):
     cfg = dict(c, num_sys_tokens=n_sys(c), num_task_tokens=0)
     b = host_batch(c, 1, T, False, 1234)
     times = []
+    t_begin = time.perf_counter()
     for r in range(warmup + repeats):
+        if budget_s is not None and times and time.perf_counter() - t_begin > budget_s:
+            break  # keep the whole run within a few minutes whatever --steps asks for
         t0 = time.perf_counter()
         with torch.no_grad():
             feats = restate.clip_tower(sd, b["images"], cfg)
@@ -252,11 +255,14 @@ def run_reference(args):
     c = model_cfg(args.model, args.layers)
     distill = args.workload == "dsg"
     sps, desc, times, cores = cpu_reference(c, args.seq, distill, args.cpu_baseline_layers,
-                                            repeats=max(1, args.steps), warmup=min(args.warmup, 1))
+                                            repeats=max(1, args.steps), warmup=min(args.warmup, 1),
+                                            budget_s=150.0)
+    desc += f"; {len(times)} timed repeat(s) of the sample (150 s budget)"
     ms = 1000.0 / sps
     line = {
         "impl": "reference", "metric": "train-step samples/sec", "value": sps, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "n_gpus": args.gpus, "steps": args.steps, "steps_timed": len(times), "warmup": args.warmup,
+        "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": workload_config(args, c, distill),

@@ -43,6 +43,30 @@ PHI3_MINI = dict(
     num_sys_tokens=13, tokenizer_model_max_length=4096)
 
 
+def synthetic_batch_mixed(cfg, n_text, seed=1234):
+    """Modality edge cases of the splice (ola_arch.py:345-391) for the NTP-only classes: row 0 has
+    one image, row 1 is TEXT-ONLY (still consumes an image slot, :348-355) and is right-padded, row 2
+    has TWO images.  `images` therefore carries 4 images for 3 rows."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    S, V = cfg["num_sys_tokens"], cfg["vocab"]
+    B = 3
+    ids = torch.randint(0, V - 1, (B, n_text), generator=g)
+    ids[0, S] = -200
+    ids[2, S] = -200
+    ids[2, S + 5] = -200
+    labels = ids.clone()
+    labels[:, :S + 8] = -100
+    am = torch.ones(B, n_text, dtype=torch.bool)
+    keep = (2 * n_text) // 3
+    ids[1, keep:] = V - 1
+    labels[1, keep:] = -100
+    am[1, keep:] = False
+    images = torch.randn(4, 3, cfg["image_size"], cfg["image_size"], generator=g)
+    return dict(input_ids=ids, labels=labels, attention_mask=am, images=images)
+
+
 def synthetic_batch(cfg, B, n_text, seed=1234, distill=True, pad_rows=0, dtype=None):
     """SURVEY.md §8(d) synthetic batch: one IMAGE_TOKEN_INDEX at position S, labels = ids with the
     first S+8 positions ignored, N(0,1) images/targets, ones masks (int64 as the collator makes them).

@@ -27,6 +27,8 @@ CASES = [
     ("tiny_phi3_dsg", "TINY_PHI3", "phi3", True, 2, 40, 0),
     ("tiny_phi3_sw_dsg", "TINY_PHI3_SW", "phi3", True, 2, 40, 0),
     ("tiny_llama_ntp", "TINY_LLAMA", "llama", False, 2, 40, 0),
+    # pad_rows = -1 selects configs.synthetic_batch_mixed: text-only row + two-image row + one-image row
+    ("tiny_llama_ntp_mixed", "TINY_LLAMA", "llama", False, 3, 48, -1),
     ("wide_llama_dsg", "WIDE_LLAMA", "llama", True, 2, 40, 0),
     ("wide_phi3_dsg", "WIDE_PHI3", "phi3", True, 2, 40, 0),
 ]
@@ -48,7 +50,8 @@ def run_case(name, cfg_name, family, distill, B, n_text, pad_rows):
     model = ref_shim.build_reference_model(cfg, family, distill, seed_fn=restate.seeded_param)
     for n, p in model.named_parameters():
         p.requires_grad_(trainable_pt(n))
-    batch = configs.synthetic_batch(cfg, B, n_text, seed=1234, distill=distill, pad_rows=pad_rows)
+    batch = (configs.synthetic_batch_mixed(cfg, n_text, seed=1234) if pad_rows < 0 else
+             configs.synthetic_batch(cfg, B, n_text, seed=1234, distill=distill, pad_rows=pad_rows))
     kwargs = dict(input_ids=batch["input_ids"], labels=batch["labels"],
                   attention_mask=batch["attention_mask"], images=batch["images"])
     fx = {"name": name, "cfg_name": cfg_name, "family": family, "distill": distill, "B": B,

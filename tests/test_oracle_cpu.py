@@ -8,7 +8,7 @@ from parity_utils import configs, restate
 GOLDEN = __import__("pathlib").Path(__file__).parent / "golden"
 CASES = [("tiny_llama_dsg", "TINY_LLAMA", True), ("tiny_llama_dsg_padded", "TINY_LLAMA", True),
          ("tiny_phi3_dsg", "TINY_PHI3", True), ("tiny_phi3_sw_dsg", "TINY_PHI3_SW", True),
-         ("tiny_llama_ntp", "TINY_LLAMA", False),
+         ("tiny_llama_ntp", "TINY_LLAMA", False), ("tiny_llama_ntp_mixed", "TINY_LLAMA", False),
          ("wide_llama_dsg", "WIDE_LLAMA", True), ("wide_phi3_dsg", "WIDE_PHI3", True)]
 
 
@@ -21,8 +21,9 @@ def test_oracle_matches_golden(name, cfg_name, distill):
     fx = torch.load(GOLDEN / f"{name}.pt")
     cfg = getattr(configs, cfg_name)
     sd = {k: v.requires_grad_(k in fx["grads"]) for k, v in _state(fx).items()}
-    batch = configs.synthetic_batch(cfg, fx["B"], fx["n_text"], seed=fx["seed"], distill=distill,
-                                    pad_rows=fx["pad_rows"])
+    batch = (configs.synthetic_batch_mixed(cfg, fx["n_text"], seed=fx["seed"]) if fx["pad_rows"] < 0 else
+             configs.synthetic_batch(cfg, fx["B"], fx["n_text"], seed=fx["seed"], distill=distill,
+                                     pad_rows=fx["pad_rows"]))
     pub = restate.forward_step(sd, cfg, batch, distill=distill, zero_masks_like_reference=True)
     assert abs(pub["loss"].item() - fx["loss_as_published"]) < 1e-5
     out = restate.forward_step(sd, cfg, batch, distill=distill, zero_masks_like_reference=False)
@@ -54,7 +55,7 @@ def test_depth_heads_linear_2_3_get_no_gradient():
     assert any("linear_2" in n for n in fx["state_spec"])
 
 
-@pytest.mark.parametrize("name,cfg_name,distill", [c for c in CASES if c[0].startswith("tiny") and c[0] != "tiny_llama_dsg_padded"])
+@pytest.mark.parametrize("name,cfg_name,distill", [c for c in CASES if c[0].startswith("tiny") and c[0] not in ("tiny_llama_dsg_padded", "tiny_llama_ntp_mixed")])
 def test_state_dict_abi(name, cfg_name, distill):
     from parity_utils import build_product
 
