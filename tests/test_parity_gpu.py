@@ -47,9 +47,14 @@ def test_forward_backward_vs_oracle_and_golden(name, cfg_name, distill, B, n_tex
     ref = restate.forward_step(sd, ocfg, batch, distill=distill, zero_masks_like_reference=False)
     ref["loss"].backward()
 
-    assert abs(out.text_loss.item() - ref["text_loss"].item()) <= 2e-3 * abs(ref["text_loss"].item()), \
+    # north_star tolerance: losses within 1e-3 relative of the reference arithmetic (fp32 oracle on the
+    # same bf16-rounded weights and inputs)
+    print(f"[parity] {name}: text_loss {out.text_loss.item():.6f} vs {ref['text_loss'].item():.6f} "
+          f"(rel {abs(out.text_loss.item() / ref['text_loss'].item() - 1):.2e}); loss {out.loss.item():.6f} vs "
+          f"{ref['loss'].item():.6f} (rel {abs(out.loss.item() / ref['loss'].item() - 1):.2e})")
+    assert abs(out.text_loss.item() - ref["text_loss"].item()) <= 1e-3 * abs(ref["text_loss"].item()), \
         (out.text_loss.item(), ref["text_loss"].item())
-    assert abs(out.loss.item() - ref["loss"].item()) <= 2e-3 * abs(ref["loss"].item()), \
+    assert abs(out.loss.item() - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item()), \
         (out.loss.item(), ref["loss"].item())
     assert len(out.hidden_states) == len(ref["hidden_states"])
     # hidden states are compared on REAL positions only: rows of the right-padded tail are undefined —
