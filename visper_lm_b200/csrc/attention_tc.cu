@@ -346,7 +346,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 }  // namespace tc2
 
 template <bool CAUSAL, int HD>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using namespace tc2;
@@ -429,6 +429,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t TM_S = tmem_base;        // S_t at + t*128 (P_t over its first 64 columns)
   const uint32_t TM_O = tmem_base + 256;  // O_t at + t*128
 
+  // 384 threads = three warpgroups: {TMA warp, MMA warp, two idle warps} and one softmax warpgroup per
+  // query tile.  Registers are partitioned per SM sub-partition (16 K each, three warps of this CTA
+  // on each), so 168 is what every thread gets at launch; the data-movement warpgroup then hands
+  // registers to the softmax warpgroups, whose threads each keep a 128-score row in registers.
+  // (the setmaxnreg sits INSIDE each role's branch: ptxas budgets registers per region only when no
+  // control-flow merge separates the instruction from the code it governs)
+  if (warp < 4) {
+  setmaxnreg_dec<80>();
   if (warp == 0) {
     if (lane == 0) {
       for (int t = 0; t < 2; ++t) {
@@ -528,9 +536,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         poll_guard(spins, did);
       }
     }
+  }
   } else {
+    setmaxnreg_inc<208>();
     const int quarter = warp & 3;
-    const int t = (warp - 2) >> 2;        // query tile of this softmax group
+    const int t = (warp - 4) >> 2;        // query tile of this softmax warpgroup
     const int row = quarter * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
@@ -665,7 +675,7 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
       cfg2 = true;
     }
     dim3 grid((nqt + 1) / 2, p.H, p.B);
-    kern<<<grid, 320, tc2::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    kern<<<grid, 384, tc2::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
     VPB_LAUNCH_OK();
     return 0;
   }
