@@ -46,6 +46,9 @@ void vpb_reset_launch_count(void);
 #define VPB_OPT_ATTN_BWD_SS 5      /* 1: attention backward stages P/dS through shared memory (not TMEM) */
 #define VPB_OPT_ATTN_FWD_V2 6      /* 1: experimental tcgen05 attention forward with two query tiles per CTA */
 int vpb_set_option(int key, int value);
+/* profiling aid: device buffer of 16*512 int64 that CTA 0 of the attention dK/dV kernel fills with
+ * clock64 stamps of its pipeline events (NULL = off, the default) */
+void vpb_set_trace_buffer(void* device_ptr);
 
 /* ---- GEMM: tcgen05 + TMEM + TMA ----------------------------------------------------------
  * C[M,N] = act(A·Bᵀ + bias) + residual ; optional aux = A·Bᵀ + bias (pre-activation copy).

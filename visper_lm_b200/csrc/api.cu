@@ -24,6 +24,8 @@ extern "C" int vpb_abi_version(void) { return VPB_ABI_VERSION; }
 extern "C" const char* vpb_last_error(void) { return vpb::g_err; }
 extern "C" int64_t vpb_launch_count(void) { return vpb::g_launches.load(); }
 extern "C" void vpb_reset_launch_count(void) { vpb::g_launches.store(0); }
+namespace vpb { void set_trace_buffer(void* p); }
+extern "C" void vpb_set_trace_buffer(void* device_ptr) { vpb::set_trace_buffer(device_ptr); }
 extern "C" int vpb_set_option(int key, int value) {
   if (key < 0 || key >= 16) return -1;
   vpb::g_options[key].store(value);

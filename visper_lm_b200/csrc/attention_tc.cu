@@ -694,6 +694,9 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
 // =============================================================================================
 // backward (head_dim 128)
 // =============================================================================================
+static long long* g_trace_buffer = nullptr;  // device buffer of >= 16*512 int64, or null
+void set_trace_buffer(void* p) { g_trace_buffer = static_cast<long long*>(p); }
+
 struct AttnTcBwdParams {
   const float* lse;    // [B,H,sq] natural log
   const float* delta;  // [B,H,sq] rowsum(dO*O)
@@ -702,7 +705,14 @@ struct AttnTcBwdParams {
   int B, H, KVH, sq, sk;
   float scale;
   int window;  // see AttnTcParams
+  long long* trace;  // optional timeline buffer (vpb_set_trace_buffer): clock64 stamps of CTA 0
 };
+
+// timeline instrumentation of the v2 backward kernels: row `slot`, column `it` (512 columns per row)
+#define VPB_TRACE(slot, it)                                                        \
+  do {                                                                             \
+    if (p.trace && lin_cta == 0 && (it) < 512) p.trace[(slot) * 512 + (it)] = clock64(); \
+  } while (0)
 
 namespace tcb {
 constexpr int HD = 128;
@@ -1235,6 +1245,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   // most work, so the linear id is re-read as (key tile major, (kv head, batch) minor): every SM
   // starts on heavy tiles and the tail of the grid is made of the lightest ones.
   const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int lin_cta = lin;
   const int nhb = gridDim.y * gridDim.z;
   const int kv0 = (lin / nhb) * A_BKV;
   const int kvh = (lin % nhb) % gridDim.y, b = (lin % nhb) / gridDim.y;
@@ -1304,6 +1315,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int hq = kvh * G + it / nper;
         const int qrow = b * p.sq + (qt_begin + it % nper) * A_BQ;
         mbar_wait(&qd_empty[st], ((it / A_ST) & 1) ^ 1);
+        VPB_TRACE(0, it);  // producer: stage free, loads issued
         mbar_arrive_expect_tx(&qd_full[st], 32768);
         uint8_t* sq_ = smem + A_OFF_QD + st * 32768;
         tma_load_2d(sq_, &tmQ, &qd_full[st], hq * HD, qrow);
@@ -1339,6 +1351,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           ok = ok && mbar_test(&qd_full[st], (n_sd / A_ST) & 1);
           if (ok) {
             tc_fence_after();
+            if (leader) VPB_TRACE(1, n_sd);  // MMA: S/dP issue
             if (leader) {
               const uint64_t q_desc = desc_adv(q_desc0, st * 32768);
               const uint64_t do_desc = desc_adv(q_desc, 16384);
@@ -1363,6 +1376,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         if (n_acc < n_sd && mbar_test(&pds_full[n_acc & 1], (n_acc >> 1) & 1)) {
           tc_fence_after();
           const int st = n_acc % A_ST;
+          if (leader) VPB_TRACE(2, n_acc);  // MMA: dV/dK issue
           if (leader) {
             const uint64_t q_mn = desc_adv(q_mn0, st * 32768);
             const uint64_t do_mn = desc_adv(q_mn, 16384);
@@ -1427,7 +1441,9 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
                              (CAUSAL && (kv0 + A_BKV - 1 > q0 + off)) ||
                              (win && (q0 + A_BQ - 1 + off - p.window > kv0));
+      if (quarter == 0 && lane == 0) VPB_TRACE(3, it);  // softmax: ready to wait for S/dP
       mbar_wait_spin(&sd_full[g], k & 1);
+      if (quarter == 0 && lane == 0) VPB_TRACE(4, it);  // softmax: S/dP complete seen
       tc_fence_after();
       // all 64 S^T / dP^T columns go to registers first, so the buffer is handed back to the MMA
       // issuer (S/dP of iteration it+2) before any of the exp / dS work starts
@@ -1438,6 +1454,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_ld32(TM_DP + lane_addr + g * A_BQ + 32, dall + 32);
       named_bar_sync(1 + g, 128);  // lse/delta staged — under the TMEM load latency
       tmem_ld_wait();
+      if (quarter == 0 && lane == 0) VPB_TRACE(5, it);  // softmax: scores in registers
       if constexpr (!TS) {
         tc_fence_before();
         __syncwarp();
@@ -1496,11 +1513,13 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           }
         }
       }
+      if (quarter == 0 && lane == 0) VPB_TRACE(6, it);  // softmax: P/dS computed and stored (issued)
       if constexpr (TS) tmem_st_wait();
       else fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[g]);
+      if (quarter == 0 && lane == 0) VPB_TRACE(7, it);  // softmax: arrived
     }
     if (nit > 0) {
       mbar_wait(all_done, 0);
@@ -1932,6 +1951,7 @@ int attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
                 int sq, int sk, int head_dim, float scale, int causal, int window, cudaStream_t st) {
   AttnTcBwdParams p;
   p.window = causal ? window : 0;
+  p.trace = g_trace_buffer;
   p.lse = lse; p.delta = delta;
   p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
