@@ -44,6 +44,7 @@ void vpb_reset_launch_count(void);
 #define VPB_OPT_GEMM_1CTA 3        /* 1: never use the CTA-pair (cta_group::2) GEMM kernel */
 #define VPB_OPT_GEMM_PANEL_MB 4    /* >0: MB of the A operand kept L2-resident per tile-order group (default 32) */
 #define VPB_OPT_ATTN_BWD_SS 5      /* 1: attention backward stages P/dS through shared memory (not TMEM) */
+#define VPB_OPT_ATTN_BWD_PINGPONG 7 /* 1: attention backward with two softmax groups on alternate iterations (default: column split) */
 #define VPB_OPT_ATTN_FWD_V2 6      /* 1: experimental tcgen05 attention forward with two query tiles per CTA */
 int vpb_set_option(int key, int value);
 /* profiling aid: device buffer of 16*512 int64 that CTA 0 of the attention dK/dV kernel fills with

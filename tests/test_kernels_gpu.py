@@ -452,6 +452,13 @@ def test_attention_tc_backward_v2_matches_v1_and_torch(B, H, KVH, sq, sk, causal
     finally:
         ops.set_option(ops.OPT_ATTN_BWD_SS, 0)
     assert torch.equal(dq2, dq3) and torch.equal(dkv2, dkv3), "TS and SS backward variants differ"
+    # two softmax groups on alternate iterations instead of the default column split: same bits
+    ops.set_option(ops.OPT_ATTN_BWD_PINGPONG, 1)
+    try:
+        dq4, dkv4 = bwd()
+    finally:
+        ops.set_option(ops.OPT_ATTN_BWD_PINGPONG, 0)
+    assert torch.equal(dq2, dq4) and torch.equal(dkv2, dkv4), "column-split and ping-pong variants differ"
     close(dq2, dq1, rtol=2e-2, name="dq v2 vs v1")
     close(dkv2, dkv1, rtol=2e-2, name="dkv v2 vs v1")
     qf = q.float().view(B, sq, H, hd).transpose(1, 2).detach().requires_grad_(True)

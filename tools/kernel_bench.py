@@ -146,8 +146,12 @@ if __name__ == "__main__":
         ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
         ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
     if which == "attnprof":
-        print(json.dumps({"variant": "tc backward v2 (ping-pong), P/dS in TMEM (TS)"}), flush=True)
+        print(json.dumps({"variant": "tc backward v2, column split, P/dS in TMEM (default)"}), flush=True)
         attn_profile()
+        ops.set_option(ops.OPT_ATTN_BWD_PINGPONG, 1)
+        print(json.dumps({"variant": "tc backward v2, ping-pong groups, P/dS in TMEM"}), flush=True)
+        attn_profile()
+        ops.set_option(ops.OPT_ATTN_BWD_PINGPONG, 0)
         ops.set_option(ops.OPT_ATTN_FWD_V2, 1)
         ops.set_option(ops.OPT_ATTN_BWD_SS, 1)
         print(json.dumps({"variant": "fwd v2 (experimental, two query tiles per CTA); tc backward v2, P/dS through shared memory (SS)"}), flush=True)

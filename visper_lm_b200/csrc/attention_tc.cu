@@ -1220,7 +1220,11 @@ constexpr int B_OFF_BAR = B_OFF_DS + 2 * 16384;
 constexpr int B_SMEM = B_OFF_BAR + 256;
 }  // namespace tcb2
 
-template <bool CAUSAL, int HD, bool TS>
+// SPLIT (TS only): instead of two groups on alternate iterations, all 8 softmax warps work on EVERY
+// iteration, two per TMEM lane quarter splitting the 64 query columns — the exp / dS phase of one
+// group turned out to be the serial bottleneck (one warp per sub-partition issues ~0.26 IPC; the
+// timeline in profiles/r01_attn_dkdv_timeline_cta0.txt shows the two groups' phases do not overlap).
+template <bool CAUSAL, int HD, bool TS, bool SPLIT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1286,7 +1290,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sd_full[i], 1);
       mbar_init(&s_free[i], 4);
-      mbar_init(&pds_full[i], 4);
+      mbar_init(&pds_full[i], SPLIT ? 8 : 4);
       mbar_init(&pds_empty[i], 1);
     }
     mbar_init(all_done, 1);
@@ -1310,11 +1314,10 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tma_load_2d(smem + A_OFF_K + 16384, &tmK, kv_full, kvh * HD + 64, krow);
       tma_load_2d(smem + A_OFF_V, &tmV, kv_full, kvh * HD, krow);
       tma_load_2d(smem + A_OFF_V + 16384, &tmV, kv_full, kvh * HD + 64, krow);
+      int hq = kvh * G, qi = 0, st = 0, ph = 1;
       for (int it = 0; it < nit; ++it) {
-        const int st = it % A_ST;
-        const int hq = kvh * G + it / nper;
-        const int qrow = b * p.sq + (qt_begin + it % nper) * A_BQ;
-        mbar_wait(&qd_empty[st], ((it / A_ST) & 1) ^ 1);
+        const int qrow = b * p.sq + (qt_begin + qi) * A_BQ;
+        mbar_wait(&qd_empty[st], ph);
         VPB_TRACE(0, it);  // producer: stage free, loads issued
         mbar_arrive_expect_tx(&qd_full[st], 32768);
         uint8_t* sq_ = smem + A_OFF_QD + st * 32768;
@@ -1322,6 +1325,14 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tma_load_2d(sq_ + 8192, &tmQ, &qd_full[st], hq * HD + 64, qrow);
         tma_load_2d(sq_ + 16384, &tmDO, &qd_full[st], hq * HD, qrow);
         tma_load_2d(sq_ + 24576, &tmDO, &qd_full[st], hq * HD + 64, qrow);
+        if (++qi == nper) {
+          qi = 0;
+          ++hq;
+        }
+        if (++st == A_ST) {
+          st = 0;
+          ph ^= 1;
+        }
       }
     }
   } else if (warp == 1) {
@@ -1385,11 +1396,16 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             if constexpr (TS) {
               const uint32_t gcol = (n_acc & 1) * A_BQ;  // P^T over S^T[g], dS^T over dP^T[g]: 32 packed columns
 #pragma unroll
-              for (int k = 0; k < A_BQ / 16; ++k)  // contraction over the 64 queries
-                umma_bf16_ts(TM_DV, TM_S + gcol + k * 8, desc_adv(do_mn, k * 2048), idesc_acc, (n_acc | k) != 0);
+              for (int k = 0; k < A_BQ / 16; ++k) {  // contraction over the 64 queries
+                // packed columns of k-step k: contiguous (k*8), or per column-half in SPLIT mode
+                const uint32_t ac = SPLIT ? (k >> 1) * 32 + (k & 1) * 8 : k * 8;
+                umma_bf16_ts(TM_DV, TM_S + gcol + ac, desc_adv(do_mn, k * 2048), idesc_acc, (n_acc | k) != 0);
+              }
 #pragma unroll
-              for (int k = 0; k < A_BQ / 16; ++k)
-                umma_bf16_ts(TM_DK, TM_DP + gcol + k * 8, desc_adv(q_mn, k * 2048), idesc_acc, (n_acc | k) != 0);
+              for (int k = 0; k < A_BQ / 16; ++k) {
+                const uint32_t ac = SPLIT ? (k >> 1) * 32 + (k & 1) * 8 : k * 8;
+                umma_bf16_ts(TM_DK, TM_DP + gcol + ac, desc_adv(q_mn, k * 2048), idesc_acc, (n_acc | k) != 0);
+              }
             } else {
 #pragma unroll
               for (int k = 0; k < A_BQ / 16; ++k) {  // contraction over the 64 queries
@@ -1423,21 +1439,124 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     uint8_t* prow = smem + A_OFF_PDS + g * 32768 + row * 128;
     uint8_t* dsrow = prow + 16384;
     float* lbase = ld_buf + g * 256;
-    auto fetch = [&](int it) -> float {  // this thread's share of the tile's lse*log2e | delta
-      const int hq = kvh * G + it / nper;
+    auto fetch = [&](int hq, int qi) -> float {  // this thread's share of the tile's lse*log2e | delta
       const int c = gtid & 63;
-      const int q = (qt_begin + it % nper) * A_BQ + c;
+      const int q = (qt_begin + qi) * A_BQ + c;
       if (q >= p.sq) return 0.f;
       const int64_t li = ((int64_t)b * p.H + hq) * p.sq + q;
       return gtid < 64 ? p.lse[li] * LOG2E : p.delta[li];
     };
-    float pre = (g < nit) ? fetch(g) : 0.f;
+    auto advance = [&](int& hq, int& qi, int steps) {  // (head, query tile) `steps` iterations later
+      for (int s_ = 0; s_ < steps; ++s_)
+        if (++qi == nper) {
+          qi = 0;
+          ++hq;
+        }
+    };
+    if constexpr (SPLIT) {
+      static_assert(!SPLIT || TS, "SPLIT needs P/dS in TMEM");
+      const int half = g;                   // which 32 of the 64 query columns this warp handles
+      const int tid = threadIdx.x - 64;     // 0..255 among the softmax warps
+      // (head, query tile) of an iteration are tracked incrementally: the div/mod by the runtime
+      // tile count cost ~600 dependent cycles at the top of every iteration (timeline trace)
+      auto fetch8 = [&](int hq, int qi) -> float {  // threads 0..127 stage lse*log2e | delta of the tile
+        const int q = (qt_begin + qi) * A_BQ + (tid & 63);
+        if (tid >= 128 || q >= p.sq) return 0.f;
+        const int64_t li = ((int64_t)b * p.H + hq) * p.sq + q;
+        return tid < 64 ? p.lse[li] * LOG2E : p.delta[li];
+      };
+      // lse/delta of iteration it+1 are staged at the END of iteration it (store + barrier sit in the
+      // shadow of the wait for the next S/dP), those of it+2 are in flight in a register meanwhile
+      int hq_n = kvh * G, qi_n = 0;  // (head, query tile) of the iteration whose values are fetched next
+      auto step = [&]() {
+        if (++qi_n == nper) {
+          qi_n = 0;
+          ++hq_n;
+        }
+      };
+      int qi_c = 0;  // query tile of the current iteration
+      if (nit > 0) {
+        if (tid < 128) ld_buf[tid] = fetch8(hq_n, qi_n);
+        step();
+      }
+      float pre8 = nit > 1 ? fetch8(hq_n, qi_n) : 0.f;  // iteration 1
+      step();
+      named_bar_sync(1, 256);
+      for (int it = 0; it < nit; ++it) {
+        const int sb = it & 1;
+        float* lbuf = ld_buf + sb * 128;
+        const int q0 = (qt_begin + qi_c) * A_BQ;
+        if (++qi_c == nper) qi_c = 0;
+        const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
+                               (CAUSAL && (kv0 + A_BKV - 1 > q0 + off)) ||
+                               (win && (q0 + A_BQ - 1 + off - p.window > kv0));
+        if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(3, it);
+        mbar_wait_spin(&sd_full[sb], (it >> 1) & 1);
+        if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(4, it);
+        tc_fence_after();
+        uint32_t s[32], d[32];
+        tmem_ld32(TM_S + lane_addr + sb * A_BQ + half * 32, s);
+        tmem_ld32(TM_DP + lane_addr + sb * A_BQ + half * 32, d);
+        tmem_ld_wait();
+        if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(5, it);
+        const float4* l4 = reinterpret_cast<const float4*>(lbuf) + half * 8;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 ls = l4[c4], dl4 = l4[16 + c4];
+          const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e])));
+            d[c] = __float_as_uint(__uint_as_float(d[c]) - dlv[e]);
+          }
+        }
+        if (need_mask) {  // one warp-uniform branch per tile, never one per score
+          const int first_q = key_ok ? (CAUSAL ? kv0 + row - off : 0) : 0x7fffffff;
+          const int last_q = win ? min(p.sq - 1, kv0 + row - off + p.window) : p.sq - 1;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int qc = q0 + half * 32 + c;
+            if (qc < first_q || qc > last_q) s[c] = 0u;
+          }
+        }
+        uint32_t wp[16], wd[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float d0 = __uint_as_float(s[2 * i]) * __uint_as_float(d[2 * i]);
+          const float d1 = __uint_as_float(s[2 * i + 1]) * __uint_as_float(d[2 * i + 1]);
+          wp[i] = pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+          wd[i] = pack2(d0, d1);
+        }
+        // bf16 pairs back over this warp's OWN score columns: packed columns [32*half, 32*half+16)
+        tmem_st16(TM_S + lane_addr + sb * A_BQ + half * 32, wp);
+        tmem_st16(TM_DP + lane_addr + sb * A_BQ + half * 32, wd);
+        if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(6, it);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pds_full[sb]);
+        if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(7, it);
+        // stage iteration it+1 (buffer sb^1: its last readers finished iteration it-1 before the
+        // previous barrier), fetch it+2
+        if (it + 1 < nit) {
+          if (tid < 128) ld_buf[(sb ^ 1) * 128 + tid] = pre8;
+          if (it + 2 < nit) pre8 = fetch8(hq_n, qi_n);
+          step();
+          named_bar_sync(1, 256);
+        }
+      }
+    } else {
+    int hq_c = kvh * G, qi_c = 0;
+    if (nper > 0) advance(hq_c, qi_c, g);
+    float pre = (g < nit) ? fetch(hq_c, qi_c) : 0.f;
     int k = 0;
     for (int it = g; it < nit; it += 2, ++k) {
       float* lbuf = lbase + (k & 1) * 128;
       lbuf[gtid] = pre;
-      if (it + 2 < nit) pre = fetch(it + 2);  // in flight during this iteration
-      const int q0 = (qt_begin + it % nper) * A_BQ;
+      const int q0 = (qt_begin + qi_c) * A_BQ;
+      advance(hq_c, qi_c, 2);
+      if (it + 2 < nit) pre = fetch(hq_c, qi_c);  // in flight during this iteration
       const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
                              (CAUSAL && (kv0 + A_BKV - 1 > q0 + off)) ||
                              (win && (q0 + A_BQ - 1 + off - p.window > kv0));
@@ -1521,6 +1640,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (lane == 0) mbar_arrive(&pds_full[g]);
       if (quarter == 0 && lane == 0) VPB_TRACE(7, it);  // softmax: arrived
     }
+    }
     if (nit > 0) {
       mbar_wait(all_done, 0);
       tc_fence_after();
@@ -1561,7 +1681,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 // dQ_i = scale * sum_j dS_ij K_j — two query tiles (heavy + light) per CTA, ping-pong groups
-template <bool CAUSAL, int HD, bool TS>
+template <bool CAUSAL, int HD, bool TS, bool SPLIT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1624,7 +1744,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sd_full[i], 1);
       mbar_init(&s_free[i], 4);
-      mbar_init(&ds_full[i], 4);
+      mbar_init(&ds_full[i], SPLIT ? 8 : 4);
       mbar_init(&ds_empty[i], 1);
       mbar_init(&tile_done[i], 1);
     }
@@ -1720,8 +1840,9 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
             for (int k = 0; k < B_BKV / 16; ++k) {  // contraction over the 64 keys
               if constexpr (TS)
-                umma_bf16_ts(TM_DQ + t * 128, TM_DP + (n_dq & 1) * B_BKV + k * 8, desc_adv(k_mn, k * 2048),
-                             idesc_dq, (i | k) != 0);
+                umma_bf16_ts(TM_DQ + t * 128,
+                             TM_DP + (n_dq & 1) * B_BKV + (SPLIT ? (k >> 1) * 32 + (k & 1) * 8 : k * 8),
+                             desc_adv(k_mn, k * 2048), idesc_dq, (i | k) != 0);
               else
                 umma_bf16(TM_DQ + t * 128, desc_adv(ds_desc, k * 32), desc_adv(k_mn, k * 2048), idesc_dq,
                           (i | k) != 0);
@@ -1753,6 +1874,48 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     }
     uint8_t* dsrow = smem + B_OFF_DS + g * 16384 + row * 128;
+    if constexpr (SPLIT) {
+      static_assert(!SPLIT || TS, "SPLIT needs dS in TMEM");
+      const int half = g;  // which 32 of the 64 key columns this warp handles
+      for (int n = 0; n < total; ++n) {
+        const int sb = n & 1;
+        const int t = n < nit[0] ? 0 : 1;
+        const int it = n - (t ? nit[0] : 0);
+        const int q0 = qt[t] * B_BQ;
+        const int j0 = (it + (t ? jb[1] : jb[0])) * B_BKV;
+        const bool rok = t ? row_ok[1] : row_ok[0];
+        const float l2 = t ? lse2[1] : lse2[0];
+        const float dlt = t ? dl[1] : dl[0];
+        const bool need_mask = !rok || (j0 + B_BKV > p.sk) || (CAUSAL && (j0 + B_BKV - 1 > q0 + off)) ||
+                               (win && j0 < q0 + B_BQ - 1 + off - p.window);
+        mbar_wait_spin(&sd_full[sb], (n >> 1) & 1);
+        tc_fence_after();
+        uint32_t s[32], d[32];
+        tmem_ld32(TM_S + lane_addr + sb * B_BKV + half * 32, s);
+        tmem_ld32(TM_DP + lane_addr + sb * B_BKV + half * 32, d);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
+        if (need_mask) {  // one warp-uniform branch per tile, never one per score
+          const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
+          const int vis = rok ? lim - (j0 + half * 32) : -1;                      // last visible column
+          const int lov = win ? q0 + row + off - p.window - (j0 + half * 32) : 0;  // first visible column
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c > vis || c < lov) s[c] = 0u;
+        }
+        uint32_t wd[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          wd[i] = pack2(__uint_as_float(s[2 * i]) * (__uint_as_float(d[2 * i]) - dlt),
+                        __uint_as_float(s[2 * i + 1]) * (__uint_as_float(d[2 * i + 1]) - dlt));
+        tmem_st16(TM_DP + lane_addr + sb * B_BKV + half * 32, wd);  // over this warp's own dP columns
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ds_full[sb]);
+      }
+    } else {
     int k = 0;
     for (int n = g; n < total; n += 2, ++k) {
       const int t = n < nit[0] ? 0 : 1;
@@ -1812,6 +1975,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[g]);
+    }
     }
     // epilogue: both query tiles' dQ sit in TMEM; the 8 warps split the 128 head-dim columns
     for (int t = 0; t < ntl; ++t) {
@@ -1885,7 +2049,7 @@ static int launch_bwd_tc_v1(const void* q, int64_t ldq, const void* k, int64_t l
   return 0;
 }
 
-template <bool CAUSAL, int HD, bool TS>
+template <bool CAUSAL, int HD, bool TS, bool SPLIT>
 static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
                             cudaStream_t st) {
@@ -1898,7 +2062,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, A_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, A_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, A_BKV)) return -1;
-    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD, TS>;
+    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD, TS, SPLIT>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
@@ -1914,7 +2078,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, B_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, B_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, B_BKV)) return -1;
-    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS>;
+    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS, SPLIT>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
@@ -1935,13 +2099,16 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   // v2 assumes every query tile sees at least one key tile (attention.cu only routes sk >= sq here
   // for head_dim 96; head_dim 128 can still fall back to the v1 kernels)
   const bool ss = get_option(VPB_OPT_ATTN_BWD_SS) != 0;
-  if (head_dim == 96)
-    return ss ? launch_bwd_tc_v2<CAUSAL, 96, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)
-              : launch_bwd_tc_v2<CAUSAL, 96, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+  const bool pingpong = get_option(VPB_OPT_ATTN_BWD_PINGPONG) != 0;
+#define VPB_BWD_V2(HDv)                                                                              \
+  (ss ? launch_bwd_tc_v2<CAUSAL, HDv, false, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)          \
+      : pingpong ? launch_bwd_tc_v2<CAUSAL, HDv, true, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st) \
+                 : launch_bwd_tc_v2<CAUSAL, HDv, true, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st))
+  if (head_dim == 96) return VPB_BWD_V2(96);
   if (p.window == 0 && (get_option(VPB_OPT_ATTN_TC_BWD_V1) || (CAUSAL && p.sk < p.sq)))
     return launch_bwd_tc_v1<CAUSAL>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
-  return ss ? launch_bwd_tc_v2<CAUSAL, 128, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)
-            : launch_bwd_tc_v2<CAUSAL, 128, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
+  return VPB_BWD_V2(128);
+#undef VPB_BWD_V2
 }
 
 // entry used by vpb_attn_bwd (attention.cu) after the delta kernel: head_dim 128 / 96, one K/V segment
