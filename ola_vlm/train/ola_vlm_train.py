@@ -2,3 +2,5 @@
 the supervised collator (:881-925) and the end-of-run save (:228-263)."""
 from visper_lm_b200.train.checkpoint import safe_save_model_for_hf_trainer  # noqa: F401
 from visper_lm_b200.train.data import DataCollatorForSupervisedDataset  # noqa: F401
+from visper_lm_b200.train.prompts import (preprocess_llama_3, preprocess_multimodal,  # noqa: F401,E402
+                                          preprocess_phi_3)

@@ -112,3 +112,84 @@ def test_modality_lengths_sign_convention():
     order = list(D.LengthGroupedSampler(2, 2, lengths=ds.modality_lengths, group_by_modality=True,
                                         generator=torch.Generator().manual_seed(0)))
     assert sorted(order) == list(range(6))
+
+
+# ------------------------------------------------------------------------------------------------ prompts
+import copy  # noqa: E402
+import re  # noqa: E402
+import types  # noqa: E402
+
+from visper_lm_b200.train import prompts as P  # noqa: E402
+
+
+class MarkerTokenizer:
+    """Context-free toy tokenizer: chat markers (<|...|>), words and punctuation are single tokens,
+    whitespace is dropped — so tokenising a conversation piecewise or whole gives the same tokens."""
+    bos_token_id, pad_token_id, model_max_length = 1, 0, 512
+    _re = re.compile(r"<\|[^|]+\|>|<image>|\w+|[^\w\s]")
+
+    def _ids(self, text):
+        return [self.bos_token_id] + [2 + (sum(map(ord, t)) * 31 + len(t)) % 9973 for t in self._re.findall(text)]
+
+    def __call__(self, text, return_tensors=None, padding=None, max_length=None, truncation=None):
+        if isinstance(text, str):
+            return types.SimpleNamespace(input_ids=self._ids(text))
+        rows = [self._ids(t)[:max_length] for t in text]
+        n = max(map(len, rows))
+        return types.SimpleNamespace(input_ids=torch.tensor([r + [self.pad_token_id] * (n - len(r)) for r in rows]))
+
+
+def _sources(multi_round):
+    one = [{"from": "human", "value": "What is in the <image> picture ?"},
+           {"from": "gpt", "value": "A cat sitting on a mat."}]
+    two = one + [{"from": "human", "value": "Which colour ?"}, {"from": "gpt", "value": "It is black , with white paws."}]
+    lead = [{"from": "gpt", "value": "ignored leading turn"}] + one
+    return [copy.deepcopy(two if multi_round else one), copy.deepcopy(lead)]
+
+
+@pytest.mark.parametrize("version", ["llama3", "phi3"])
+@pytest.mark.parametrize("multi_round", [False, True])
+@pytest.mark.parametrize("has_image", [True, False])
+def test_preprocess_label_masking(version, multi_round, has_image):
+    tok = MarkerTokenizer()
+    mine_fn = P.preprocess_llama_3 if version == "llama3" else P.preprocess_phi_3
+    src = P.preprocess_multimodal(_sources(multi_round))
+    assert src[0][0]["value"].startswith("<image>\n")
+    if multi_round or not has_image:
+        src = [src[0]] if has_image is False else src   # stacked tensors need equal lengths with images
+    if has_image and len(src) == 2 and len(tok(P.render([src[0]], P.conv_templates["llava_" + ("llama_3" if version == "llama3" else "phi_3")])[0]).input_ids) != \
+            len(tok(P.render([src[1]], P.conv_templates["llava_" + ("llama_3" if version == "llama3" else "phi_3")])[0]).input_ids):
+        src = [src[0]]
+    out = mine_fn(copy.deepcopy(src), tok, has_image=has_image)
+    ids, lab = out["input_ids"], out["labels"]
+    assert ids.shape == lab.shape
+    if has_image:
+        assert (ids == D.IMAGE_TOKEN_INDEX).sum().item() == len(src)
+    scored = lab != D.IGNORE_INDEX
+    assert torch.equal(lab[scored], ids[scored])
+    if version == "llama3" or not multi_round:
+        assert out["mismatches"] == 0 and scored.any(), "assistant answers must be scored"
+        assert not scored[:, 0].any()  # BOS never scored
+    if ref_shim.available():
+        ref = ref_functions.preprocess_fns(version)
+        ref_src = ref["preprocess_multimodal"](copy.deepcopy(_sources(multi_round))[: len(src)],
+                                               types.SimpleNamespace(is_multimodal=True, mm_use_im_start_end=False))
+        assert ref_src == src
+        want = ref["preprocess_llama_3" if version == "llama3" else "preprocess_phi_3"](copy.deepcopy(src), tok,
+                                                                                       has_image=has_image)
+        assert torch.equal(want["input_ids"], ids)
+        assert torch.equal(want["labels"], lab)
+
+
+def test_templates_equal_reference():
+    if not ref_shim.available():
+        pytest.skip("/root/reference not mounted")
+    for version, mine in (("llama3", P.LLAMA3), ("phi3", P.PHI3)):
+        lib = ref_functions.conversation_lib(version)
+        ref = lib.default_conversation
+        assert (ref.system, tuple(ref.roles), ref.sep, ref.version) == (mine.system, mine.roles, mine.sep, mine.version)
+        c, m = ref.copy(), mine.copy()
+        for role_i, text in ((0, "hello <image>"), (1, "hi"), (0, "and ?"), (1, None)):
+            c.append_message(ref.roles[role_i], text)
+            m.append_message(mine.roles[role_i], text)
+        assert c.get_prompt() == m.get_prompt()

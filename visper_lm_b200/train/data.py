@@ -7,8 +7,7 @@
     boundary consumes (SURVEY.md §8b);
   * a synthetic dataset in `LazySupervisedDataset.__getitem__`'s item schema (:811-878) for runs
     without the LLaVA json / image folders.
-Prompt templating and per-template label masking (conversation.py, preprocess_llama_3 / phi3) need
-the real tokenizers and stay out of scope; the collator takes their output as is.
+Prompt templating and label masking live in train/prompts.py.
 """
 from __future__ import annotations
 
