@@ -82,6 +82,13 @@ int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, int64_t ldw
                         const void* gu, int64_t ldgu, int gu_tiled, void* dgu, int64_t lddgu, int M,
                         int F, int K, void* stream);
 
+/* Fused QKV projection + rotary embedding (HF LlamaAttention q/k/v_proj + apply_rotary_pos_emb):
+ * C = A·Bᵀ with the first rope_heads 128-wide heads of every row rotated by the row's position
+ * (pos_ids[row], or row % seq_len when NULL) in the GEMM epilogue.  head_dim 128, N % 256 == 0. */
+int vpb_gemm_rope_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                       int M, int N, int K, const float* cos_t, const float* sin_t, int seq_len,
+                       const int* pos_ids, int rope_heads, void* stream);
+
 /* ---- normalisation -------------------------------------------------------------------------
  * HF LlamaRMSNorm / Phi3RMSNorm (eps 1e-5) and nn.LayerNorm (CLIP, resampler.py). */
 int vpb_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd,

@@ -149,6 +149,30 @@ def test_gemm_swiglu_fused(M, F, K):
     assert torch.equal(h3, h_ref) and torch.equal(dgu3, dgu_ref), "tile-major g|u path differs"
 
 
+@pytest.mark.parametrize("M,H,KVH,K,T", [(300, 2, 2, 128, 100), (2048, 32, 8, 512, 512), (1000, 4, 2, 264, 1000)])
+def test_gemm_rope_fused(M, H, KVH, K, T):
+    """RoPE in the QKV GEMM epilogue: bit-identical to GEMM + in-place rope kernel."""
+    from visper_lm_b200 import ops
+    hd = 128
+    N = (H + 2 * KVH) * hd
+    if N % 256:
+        pytest.skip("needs N % 256 == 0")
+    x = rnd(M, K, seed=35, scale=0.5)
+    w = rnd(N, K, seed=36, scale=0.2)
+    cos, sin = ops.rope_tables(max(T, 64), hd, 500000.0, dev())
+    ref = ops.gemm(x, w)
+    ops.rope_(ref, T, cos, sin, H + KVH, hd)
+    out = ops.gemm_rope(x, w, T, cos, sin, H + KVH)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref), f"fused rope differs: {(out.float() - ref.float()).abs().max().item()}"
+    pos = torch.randint(0, max(T, 64), (M,), device=dev(), dtype=torch.int32)
+    ref2 = ops.gemm(x, w)
+    ops.rope_(ref2, T, cos, sin, H + KVH, hd, pos_ids=pos)
+    out2 = ops.gemm_rope(x, w, T, cos, sin, H + KVH, pos_ids=pos)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, ref2), "fused rope with explicit position ids differs"
+
+
 # ------------------------------------------------------------------------------------------- norms
 @pytest.mark.parametrize("M,D", [(37, 128), (512, 4096), (100, 3072), (64, 1024)])
 def test_rmsnorm(M, D):

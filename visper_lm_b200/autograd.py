@@ -86,9 +86,12 @@ class DecoderLayerFn(torch.autograd.Function):
         wqkv, wgu = meta.wqkv, meta.wgu
         qw, kw = H * hd, KVH * hd
         h1, rstd1 = ops.rmsnorm_fwd(x, n1, eps)
-        qkv = ops.gemm(h1, wqkv)
+        if ops.FUSE_ROPE and hd == 128 and wqkv.shape[0] % 256 == 0:
+            qkv = ops.gemm_rope(h1, wqkv, T, meta.cos, meta.sin, H + KVH, pos_ids=meta.pos_ids)  # RoPE in the epilogue
+        else:
+            qkv = ops.gemm(h1, wqkv)
+            ops.rope_(qkv, T, meta.cos, meta.sin, H + KVH, hd, pos_ids=meta.pos_ids)
         del h1
-        ops.rope_(qkv, T, meta.cos, meta.sin, H + KVH, hd, pos_ids=meta.pos_ids)
         o, lse = ops.attn_fwd(qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:], B, H, KVH, T, T, hd,
                               hd ** -0.5, True, window=getattr(meta, "window", 0))
         x2 = ops.gemm(o, wo, residual=x)

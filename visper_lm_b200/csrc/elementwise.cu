@@ -49,9 +49,11 @@ rope_kernel(bf16* __restrict__ x, int64_t ld, const int* __restrict__ pos_ids, i
     unpack8(*reinterpret_cast<const uint4*>(p2), b);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      // explicit rounding points: the fused QKV-GEMM epilogue (gemm_tcgen05.cu, EPI_ROPE) uses the
+      // same expressions and must give the same bits
       const float cc = c[v * 8 + j], ss = sign * s[v * 8 + j];
-      o1[j] = a[j] * cc - b[j] * ss;
-      o2[j] = b[j] * cc + a[j] * ss;
+      o1[j] = __fmaf_rn(a[j], cc, -__fmul_rn(b[j], ss));
+      o2[j] = __fmaf_rn(b[j], cc, __fmul_rn(a[j], ss));
     }
     stg16(p1, pack8(o1));
     stg16(p2, pack8(o2));

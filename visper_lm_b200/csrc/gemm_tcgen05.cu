@@ -31,6 +31,11 @@ struct GemmArgs {
   int F;    // SwiGLU epilogues: width of one half of the packed gate|up buffer
   int aux_tiled;  // SwiGLU epilogues: g|u saved in the tile-major layout (see gu_tiled_ptr)
   int group_m;    // row blocks per L2 panel of the tile order (host-chosen from K)
+  // EPI_ROPE: rotary embedding of the first rope_heads 128-wide heads of the output row
+  const float* rope_cos;  // [max_pos, 64]
+  const float* rope_sin;
+  const int* rope_pos;    // [M] or null (position = row % rope_T)
+  int rope_T, rope_heads;
 };
 
 // Tile-major layout of the saved gate|up activations: [M/128 row blocks][F/32 chunks][128 rows]
@@ -49,6 +54,10 @@ __device__ __forceinline__ bf16* gu_tiled_ptr(bf16* base, int F, int row, int ch
 constexpr int EPI_STD = 0;
 constexpr int EPI_SWIGLU_FWD = 1;
 constexpr int EPI_SWIGLU_BWD = 2;
+// EPI_ROPE: the fused QKV projection; a 256-column tile is two 128-wide heads, the thread that owns a
+// row rotates (x[j], x[j+64]) by its position's angle before the store (HF apply_rotary_pos_emb,
+// rotate_half convention) — V heads pass through.
+constexpr int EPI_ROPE = 3;
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -110,6 +119,59 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = gv[j] / (1.f + __expf(-gv[j])) * uv[j];
           stg16(crow + n, pack8(o));
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_ROPE) {
+    static_assert(EPI != EPI_ROPE || BN == 256, "rope epilogue: two 128-wide heads per tile");
+    const int pos = args.rope_pos ? (row_ok ? args.rope_pos[row] : 0) : (row % args.rope_T);
+    const float* cs = args.rope_cos + (int64_t)pos * 64;
+    const float* sn = args.rope_sin + (int64_t)pos * 64;
+#pragma unroll 1
+    for (int hh = 0; hh < 2; ++hh) {
+      const int head = nb * 2 + hh;
+      if (head * 128 >= args.N) break;  // warp-uniform
+      const bool rot = head < args.rope_heads;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {  // columns [32c, 32c+32) pair with [64+32c, 64+32c+32)
+        uint32_t ra[32], rb[32];
+        tmem_ld32(taddr + hh * 128 + c * 32, ra);
+        tmem_ld32(taddr + hh * 128 + 64 + c * 32, rb);
+        tmem_ld_wait();
+        if (row_ok) {
+          bf16* o1p = crow + head * 128 + c * 32;
+          bf16* o2p = o1p + 64;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float a[8], b[8], o1[8], o2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              a[j] = __uint_as_float(ra[g * 8 + j]);
+              b[j] = __uint_as_float(rb[g * 8 + j]);
+            }
+            // the unfused path stores the projection in bf16 and rotates that: same rounding here
+            const uint4 pa = pack8(a), pb = pack8(b);
+            if (rot) {
+              unpack8(pa, a);
+              unpack8(pb, b);
+              const float4 c0 = __ldg(reinterpret_cast<const float4*>(cs + c * 32 + g * 8));
+              const float4 c1 = __ldg(reinterpret_cast<const float4*>(cs + c * 32 + g * 8 + 4));
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(sn + c * 32 + g * 8));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(sn + c * 32 + g * 8 + 4));
+              const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                o1[j] = __fmaf_rn(a[j], cc[j], -__fmul_rn(b[j], ss[j]));
+                o2[j] = __fmaf_rn(b[j], cc[j], __fmul_rn(a[j], ss[j]));
+              }
+              stg16(o1p + g * 8, pack8(o1));
+              stg16(o2p + g * 8, pack8(o2));
+            } else {
+              stg16(o1p + g * 8, pa);
+              stg16(o2p + g * 8, pb);
+            }
+          }
         }
       }
     }
@@ -692,6 +754,10 @@ extern "C" int vpb_gemm_bf16(const void* A, int64_t lda, int a_layout, const voi
   args.act = act;
   args.F = 0;
   args.aux_tiled = 0;
+  args.rope_cos = args.rope_sin = nullptr;
+  args.rope_pos = nullptr;
+  args.rope_T = 1;
+  args.rope_heads = 0;
 
   if (pair) {
     switch ((a_layout ? 2 : 0) | (b_layout ? 1 : 0)) {
@@ -741,6 +807,10 @@ extern "C" int vpb_gemm_swiglu_fwd(const void* A, int64_t lda, const void* Wgu, 
   args.act = VPB_ACT_NONE;
   args.F = F;
   args.aux_tiled = gu_tiled;
+  args.rope_cos = args.rope_sin = nullptr;
+  args.rope_pos = nullptr;
+  args.rope_T = 1;
+  args.rope_heads = 0;
   if (use_pair(M, 2 * F)) return launch_gemm_pair<false, false, EPI_SWIGLU_FWD>(tmA, tmB, args, stream);
   return launch_gemm<256, false, false, EPI_SWIGLU_FWD>(tmA, tmB, args, stream);
 }
@@ -779,10 +849,51 @@ extern "C" int vpb_gemm_swiglu_bwd(const void* dY, int64_t lddy, const void* W, 
   args.act = VPB_ACT_NONE;
   args.F = F;
   args.aux_tiled = gu_tiled;
+  args.rope_cos = args.rope_sin = nullptr;
+  args.rope_pos = nullptr;
+  args.rope_T = 1;
+  args.rope_heads = 0;
   if (pair) {
     if (b_layout == 0) return launch_gemm_pair<false, false, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
     return launch_gemm_pair<false, true, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
   }
   if (b_layout == 0) return launch_gemm<256, false, false, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
   return launch_gemm<256, false, true, EPI_SWIGLU_BWD>(tmA, tmB, args, stream);
+}
+
+// C[M,N] = rope(A·Bᵀ): the fused QKV projection of a decoder layer with rotary embedding applied to
+// the first `rope_heads` 128-wide heads in the epilogue (head_dim 128, N % 256 == 0).
+extern "C" int vpb_gemm_rope_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                                  int64_t ldc, int M, int N, int K, const float* cos_t,
+                                  const float* sin_t, int seq_len, const int* pos_ids, int rope_heads,
+                                  void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VPB_CHECK(M > 0 && N > 0 && K > 0 && N % 256 == 0, "gemm_rope: N=%d must be a positive multiple of 256", N);
+  VPB_CHECK(ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_rope: C alignment");
+  VPB_CHECK(cos_t && sin_t && seq_len > 0 && rope_heads >= 0 && rope_heads * 128 <= N, "gemm_rope: bad rope arguments");
+  const bool pair = use_pair(M, N);
+  CUtensorMap tmA, tmB;
+  if (make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)) return -1;
+  if (make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, pair ? 128 : 256)) return -1;
+  GemmArgs args;
+  args.C = static_cast<bf16*>(C);
+  args.ldc = ldc;
+  args.bias = nullptr;
+  args.res = nullptr;
+  args.ldr = 0;
+  args.aux = nullptr;
+  args.ldaux = 0;
+  args.M = M;
+  args.N = N;
+  args.K = K;
+  args.act = VPB_ACT_NONE;
+  args.F = 0;
+  args.aux_tiled = 0;
+  args.rope_cos = cos_t;
+  args.rope_sin = sin_t;
+  args.rope_pos = pos_ids;
+  args.rope_T = seq_len;
+  args.rope_heads = rope_heads;
+  if (pair) return launch_gemm_pair<false, false, EPI_ROPE>(tmA, tmB, args, stream);
+  return launch_gemm<256, false, false, EPI_ROPE>(tmA, tmB, args, stream);
 }

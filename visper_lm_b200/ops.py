@@ -161,6 +161,24 @@ def gemm_swiglu_bwd(dy, w, gu, b_layout=1, tiled=False, F=None):
     return dgu
 
 
+FUSE_ROPE = os.environ.get("VPB_FUSE_ROPE", "1") != "0"
+
+
+def gemm_rope(a, w, seq_len, cos, sin, rope_heads, pos_ids=None):
+    """qkv[M,N] = a·wᵀ with RoPE applied in the epilogue to the first rope_heads 128-wide heads."""
+    M, K = a.shape
+    N, Kb = w.shape
+    assert K == Kb and N % 256 == 0
+    out = torch.empty((M, N), dtype=BF16, device=a.device)
+    pa, lda = _rows(a)
+    pw, ldw = _rows(w)
+    t = _timed(2.0 * M * N * K)
+    _chk(_L().vpb_gemm_rope_bf16(pa, lda, pw, ldw, out.data_ptr(), N, M, N, K, cos.data_ptr(), sin.data_ptr(),
+                                 seq_len, _p(pos_ids), rope_heads, _stream()), "gemm_rope")
+    _timed_end(t)
+    return out
+
+
 def transpose(x, out=None):
     R, C = x.shape
     if out is None:
