@@ -436,8 +436,9 @@ def run_b200(args):
             "achieved": gemm_stats["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
             "frac": gemm_stats["tflops"] / peak_tf if gemm_stats["tflops"] else None,
             # dram read+write of the dominant launch shape (down_proj dgrad, M=16384 N=14336 K=4096) from
-            # the ncu --set full capture profiles/r01_ncu_gemm_pair_instep.csv; algorithmic 0.72 GB
-            "traffic": 1.55e9 if full_model else None,
+            # the ncu --set full capture profiles/r01_ncu_gemm_pair_shapes.csv (1.06 GB read + 0.45 GB
+            # written); algorithmic: 0.25 GB of operands + 0.47 GB of output
+            "traffic": 1.51e9 if full_model else None,
             "peak_source": peak_src, "launches": gemm_stats["launches"],
             "gemm_ms_per_step": gemm_stats["ms"] / args.steps,
             "gemm_share_of_step": gemm_stats["ms"] / ms_dev if ms_dev else None,

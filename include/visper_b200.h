@@ -42,6 +42,7 @@ void vpb_reset_launch_count(void);
 #define VPB_OPT_ATTN_LEGACY_BWD 1 /* 1: force the mma.sync attention backward */
 #define VPB_OPT_ATTN_TC_BWD_V1 2   /* 1: tcgen05 attention backward without the ping-pong groups */
 #define VPB_OPT_GEMM_1CTA 3        /* 1: never use the CTA-pair (cta_group::2) GEMM kernel */
+#define VPB_OPT_GEMM_L2_HINTS 8    /* 1: CTA-pair GEMM loads carry L2 eviction hints (A panel evict_last, B evict_first) */
 #define VPB_OPT_GEMM_PANEL_MB 4    /* >0: MB of the A operand kept L2-resident per tile-order group (default 32) */
 #define VPB_OPT_ATTN_BWD_SS 5      /* 1: attention backward stages P/dS through shared memory (not TMEM) */
 #define VPB_OPT_ATTN_BWD_PINGPONG 7 /* 1: attention backward with two softmax groups on alternate iterations (default: column split) */

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+VPB_GEMM_L2_HINTS=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x --timeout=120 -k "gemm" -p no:cacheprovider 2>&1 | tail -2
+for rep in 1 2; do
+for v in 0 1; do
+VPB_GEMM_L2_HINTS=$v timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_l2h${v}_${rep}.json 2> gpurun_out/bench.err; python - <<PY
+import json
+d=json.loads([l for l in open("gpurun_out/bench_l2h${v}_${rep}.json") if l.startswith("{")][-1])
+print("l2_hints=$v rep=$rep", round(d["value"],3), round(d["ms_per_step"],1), d["clocks"]["sm_mhz"], round(d["roofline"]["achieved"]), round(d["roofline"]["gemm_ms_per_step"],1))
+PY
+done
+done
