@@ -149,7 +149,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + OFF_V), CHUNK_BYTES, 1024);  // MN-major
       auto issue_s = [&](int j) {
         const int s = j % KST, sb = j & 1;
-        mbar_wait(&k_full[s], (j / KST) & 1);
+        mbar_wait_spin(&k_full[s], (j / KST) & 1);
         tc_fence_after();
         if (leader) {
           const uint64_t k_desc = desc_adv(k_desc0, s * TILE_BYTES);
@@ -166,8 +166,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       issue_s(0);
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) issue_s(j + 1);
-        mbar_wait(&v_full[j % VST], (j / VST) & 1);
-        mbar_wait(p_full, j & 1);
+        mbar_wait_spin(&v_full[j % VST], (j / VST) & 1);
+        mbar_wait_spin(p_full, j & 1);
         tc_fence_after();
         if (leader) {
           const uint64_t v_desc = desc_adv(v_desc0, (j % VST) * TILE_BYTES);
@@ -194,7 +194,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float* xchg = reinterpret_cast<float*>(smem + OFF_X);  // [2 parity][2 half][128 rows] + [2][128]
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j & 1;
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      mbar_wait_spin(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
       uint32_t r[64];
       tmem_ld32(TM_S + lane_addr + sb * BN + half * 64, r);
