@@ -184,6 +184,18 @@ int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
                  int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dk2,
                  int64_t lddk2, void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk,
                  int sk2, int head_dim, float scale, int causal, int window, void* stream);
+/* Self-attention backward (sq == sk == seq_len, one K/V segment) that also undoes the rotary
+ * embedding: dq / dk come back as gradients w.r.t. the PRE-rotation projections, i.e. what
+ * vpb_attn_bwd followed by vpb_rope_inplace(inverse=1) on dq (H heads) and dk (KVH heads) returns,
+ * bit for bit (the backward of HF apply_rotary_pos_emb, modeling_llama.py).  head_dim 128 runs the
+ * rotation in the tcgen05 backward epilogues; other shapes fall back to the separate rope kernel.
+ * cos_t / sin_t: vpb_rope_table output; pos_ids: int32 [B*seq_len] or NULL (position = t). */
+int vpb_attn_bwd_rope(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                      int64_t ldv, const void* o, int64_t ldo, const void* dO, int64_t lddo,
+                      const float* lse, float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                      void* dv, int64_t lddv, int B, int H, int KVH, int seq_len, int head_dim,
+                      float scale, int causal, int window, const float* cos_t, const float* sin_t,
+                      const int* pos_ids, void* stream);
 
 /* ---- next-token cross-entropy (ola_llama.py:121-136) -----------------------------------------
  * labels: int64 [B,T] UNSHIFTED when shift=1 (row (b,t) is scored against labels[b,t+1]).

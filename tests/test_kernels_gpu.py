@@ -610,3 +610,46 @@ def test_adamw_and_clip():
         ops.adamw_step_(master, m, v, g, param, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, grad_scale=coef)
     assert (master - ref_p.data).abs().max().item() < 1e-5
     assert torch.equal(param, master.to(BF))
+
+
+@pytest.mark.parametrize("B,H,KVH,S,hd,window,use_pos,mode", [
+    (2, 8, 2, 1024, 128, 0, False, "v2"), (1, 4, 4, 333, 128, 0, True, "v2"),
+    (2, 4, 1, 777, 128, 0, True, "v2"), (1, 4, 2, 1300, 128, 500, False, "v2"),
+    (1, 4, 2, 640, 128, 0, False, "pingpong"), (1, 4, 2, 640, 128, 0, True, "ss"),
+    (1, 4, 2, 500, 128, 0, True, "v1"), (1, 4, 2, 500, 128, 0, False, "legacy"),
+    (1, 4, 4, 450, 96, 0, True, "v2"), (1, 4, 2, 300, 64, 0, False, "v2")])
+def test_attention_backward_fused_inverse_rope(B, H, KVH, S, hd, window, use_pos, mode):
+    """vpb_attn_bwd_rope == vpb_attn_bwd followed by the inverse rope kernel on dQ and dK, bit for bit:
+    in the tcgen05 v2 epilogues (hd 128) and through the fallback (v1 / legacy / hd 96 / hd 64)."""
+    from visper_lm_b200 import ops
+    qw, kw = H * hd, KVH * hd
+    qkv = rnd(B * S, qw + 2 * kw, seed=91)
+    do = rnd(B * S, qw, seed=92)
+    q, k, v = qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:]
+    scale = hd ** -0.5
+    cos, sin = ops.rope_tables(4096, hd, 10000.0, qkv.device)
+    pos = None
+    if use_pos:
+        g = torch.Generator().manual_seed(5)
+        pos = torch.randint(0, 4096, (B * S,), generator=g).to(torch.int32).cuda()
+    opt = {"pingpong": ops.OPT_ATTN_BWD_PINGPONG, "ss": ops.OPT_ATTN_BWD_SS, "v1": ops.OPT_ATTN_TC_BWD_V1,
+           "legacy": ops.OPT_ATTN_LEGACY_BWD}.get(mode)
+    if opt is not None:
+        ops.set_option(opt, 1)
+    try:
+        o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, True, window=window)
+        ref = torch.empty_like(qkv)
+        ops.attn_bwd(q, k, v, o, do, lse, ref[:, :qw], ref[:, qw:qw + kw], ref[:, qw + kw:], B, H, KVH, S, S,
+                     hd, scale, True, window=window)
+        ops.rope_(ref, S, cos, sin, H + KVH, hd, inverse=True, pos_ids=pos)
+        got = torch.empty_like(qkv)
+        ops.attn_bwd_rope(q, k, v, o, do, lse, got[:, :qw], got[:, qw:qw + kw], got[:, qw + kw:], B, H, KVH,
+                          S, hd, scale, True, cos, sin, pos_ids=pos, window=window)
+        torch.cuda.synchronize()
+    finally:
+        if opt is not None:
+            ops.set_option(opt, 0)
+    assert torch.equal(got[:, :qw], ref[:, :qw]), "dq"
+    assert torch.equal(got[:, qw:qw + kw], ref[:, qw:qw + kw]), "dk"
+    assert torch.equal(got[:, qw + kw:], ref[:, qw + kw:]), "dv"
+    assert ref[:, :qw + kw].float().abs().max() > 0

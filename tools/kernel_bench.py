@@ -117,6 +117,39 @@ def attn_profile(B=8, H=32, KVH=8, S=2048, hd=128):
                               "avg_us": round(e.device_time_total / e.count, 1)}), flush=True)
 
 
+def rope_bwd_case(B=8, H=32, KVH=8, S=2048, hd=128, rounds=4):
+    """attention backward + inverse-RoPE kernel vs the backward with the rotation in its epilogues
+    (alternating, medians over `rounds`, same box)."""
+    qkv = torch.randn(B * S, (H + 2 * KVH) * hd, device=dev).to(BF)
+    qw, kw = H * hd, KVH * hd
+    q, k, v = qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:]
+    scale = hd ** -0.5
+    cos, sin = ops.rope_tables(S, hd, 500000.0, dev)
+    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, scale, True)
+    do = torch.randn_like(o)
+    dqkv = torch.empty_like(qkv)
+    dq, dk, dv = dqkv[:, :qw], dqkv[:, qw:qw + kw], dqkv[:, qw + kw:]
+
+    def unfused():
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, S, S, hd, scale, True)
+        ops.rope_(dqkv, S, cos, sin, H + KVH, hd, inverse=True)
+
+    def plain():
+        ops.attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, S, S, hd, scale, True)
+
+    def fused():
+        ops.attn_bwd_rope(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, S, hd, scale, True, cos, sin)
+
+    res = {"unfused": [], "fused": [], "bwd_only": []}
+    for _ in range(rounds):
+        res["unfused"].append(timeit(unfused))
+        res["fused"].append(timeit(fused))
+        res["bwd_only"].append(timeit(plain))
+    print(json.dumps({"kernel": "attn_bwd + inverse rope", "B": B, "H": H, "KVH": KVH, "S": S, "hd": hd,
+                      **{n: round(sorted(v)[len(v) // 2], 4) for n, v in res.items()},
+                      "all": {n: [round(x, 4) for x in v] for n, v in res.items()}}), flush=True)
+
+
 if __name__ == "__main__":
     M = 16384
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -145,6 +178,8 @@ if __name__ == "__main__":
         attn_case(4, 32, 32, 2048, 96, True)
         ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
         ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
+    if which == "ropebwd":
+        rope_bwd_case()
     if which == "attnprof":
         print(json.dumps({"variant": "tc backward v2, column split, P/dS in TMEM (default)"}), flush=True)
         attn_profile()

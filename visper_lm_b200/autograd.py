@@ -162,11 +162,17 @@ class DecoderLayerFn(torch.autograd.Function):
         if nig[5]:
             g[5] = ops.gemm(dx2, o, a_layout=1, b_layout=1)
         dqkv = torch.empty_like(qkv)
-        ops.attn_bwd(qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:], o, do, lse, dqkv[:, :qw],
-                     dqkv[:, qw:qw + kw], dqkv[:, qw + kw:], B, H, KVH, T, T, hd, hd ** -0.5, True,
-                     window=getattr(meta, "window", 0))
+        if ops.FUSE_ROPE_BWD:  # inverse RoPE of dQ/dK in the backward epilogues (hd 128), else after
+            ops.attn_bwd_rope(qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:], o, do, lse,
+                              dqkv[:, :qw], dqkv[:, qw:qw + kw], dqkv[:, qw + kw:], B, H, KVH, T, hd,
+                              hd ** -0.5, True, meta.cos, meta.sin, pos_ids=meta.pos_ids,
+                              window=getattr(meta, "window", 0))
+        else:
+            ops.attn_bwd(qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:], o, do, lse, dqkv[:, :qw],
+                         dqkv[:, qw:qw + kw], dqkv[:, qw + kw:], B, H, KVH, T, T, hd, hd ** -0.5, True,
+                         window=getattr(meta, "window", 0))
+            ops.rope_(dqkv, T, meta.cos, meta.sin, H + KVH, hd, inverse=True, pos_ids=meta.pos_ids)
         del do
-        ops.rope_(dqkv, T, meta.cos, meta.sin, H + KVH, hd, inverse=True, pos_ids=meta.pos_ids)
         dn1 = dgrad(dqkv, wqkv, meta.wqkvT)
         if nig[2] or nig[3] or nig[4]:
             h1, _ = ops.rmsnorm_fwd(x, n1, eps)

@@ -714,7 +714,9 @@ int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
 int attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 const void* dO, int64_t lddo, const float* lse, const float* delta, void* dq,
                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int KVH,
-                int sq, int sk, int head_dim, float scale, int causal, int window, cudaStream_t st);
+                int sq, int sk, int head_dim, float scale, int causal, int window,
+                const float* rope_cos, const float* rope_sin, const int* rope_pos, int* rope_fused,
+                cudaStream_t st);
 }
 using namespace vpb;
 
@@ -763,13 +765,21 @@ extern "C" int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   DISPATCH_HD(head_dim, causal, launch_fwd, p, (cudaStream_t)stream);
 }
 
-extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
-                            int64_t ldv, const void* k2, int64_t ldk2, const void* v2, int64_t ldv2,
-                            const void* o, int64_t ldo, const void* dO, int64_t lddo,
-                            const float* lse, float* delta, void* dq, int64_t lddq, void* dk,
-                            int64_t lddk, void* dv, int64_t lddv, void* dk2, int64_t lddk2,
-                            void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk, int sk2,
-                            int head_dim, float scale, int causal, int window, void* stream) {
+extern "C" int vpb_rope_inplace(void* x, int64_t ld, int M, int seq_len, const int* pos_ids,
+                                const float* cos_t, const float* sin_t, int nheads, int head_dim,
+                                int inverse, void* stream);
+
+// rope_cos != null: dQ and dK come back rotated by the inverse RoPE (the gradient w.r.t. the
+// pre-rotation projections) — in the tcgen05 v2 epilogues when they run, by the rope kernel otherwise
+static int attn_bwd_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                         int64_t ldv, const void* k2, int64_t ldk2, const void* v2, int64_t ldv2,
+                         const void* o, int64_t ldo, const void* dO, int64_t lddo,
+                         const float* lse, float* delta, void* dq, int64_t lddq, void* dk,
+                         int64_t lddk, void* dv, int64_t lddv, void* dk2, int64_t lddk2,
+                         void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk, int sk2,
+                         int head_dim, float scale, int causal, int window, const float* rope_cos,
+                         const float* rope_sin, const int* rope_pos, int* rope_fused, void* stream) {
+  if (rope_fused) *rope_fused = 0;
   AttnParams p = {};
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
   p.k2 = (const bf16*)k2; p.v2 = (const bf16*)v2;
@@ -793,6 +803,39 @@ extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t l
   if (tc_hd && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_BWD) && al16(q) &&
       al16(k) && al16(v) && al16(dO))
     return attn_bwd_tc(q, ldq, k, ldk, v, ldv, dO, lddo, lse, delta, dq, lddq, dk, lddk, dv, lddv, B,
-                       H, KVH, sq, sk, head_dim, scale, causal, p.window, (cudaStream_t)stream);
+                       H, KVH, sq, sk, head_dim, scale, causal, p.window, rope_cos, rope_sin, rope_pos,
+                       rope_fused, (cudaStream_t)stream);
   DISPATCH_HD(head_dim, causal, launch_bwd, p, (cudaStream_t)stream);
+}
+
+extern "C" int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                            int64_t ldv, const void* k2, int64_t ldk2, const void* v2, int64_t ldv2,
+                            const void* o, int64_t ldo, const void* dO, int64_t lddo,
+                            const float* lse, float* delta, void* dq, int64_t lddq, void* dk,
+                            int64_t lddk, void* dv, int64_t lddv, void* dk2, int64_t lddk2,
+                            void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk, int sk2,
+                            int head_dim, float scale, int causal, int window, void* stream) {
+  return attn_bwd_impl(q, ldq, k, ldk, v, ldv, k2, ldk2, v2, ldv2, o, ldo, dO, lddo, lse, delta, dq,
+                       lddq, dk, lddk, dv, lddv, dk2, lddk2, dv2, lddv2, B, H, KVH, sq, sk, sk2,
+                       head_dim, scale, causal, window, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int vpb_attn_bwd_rope(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                 int64_t ldv, const void* o, int64_t ldo, const void* dO,
+                                 int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq,
+                                 void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int KVH,
+                                 int seq_len, int head_dim, float scale, int causal, int window,
+                                 const float* cos_t, const float* sin_t, const int* pos_ids,
+                                 void* stream) {
+  VPB_CHECK(cos_t && sin_t, "attn_bwd_rope: rotary tables missing");
+  int fused = 0;
+  if (attn_bwd_impl(q, ldq, k, ldk, v, ldv, nullptr, 0, nullptr, 0, o, ldo, dO, lddo, lse, delta, dq,
+                    lddq, dk, lddk, dv, lddv, nullptr, 0, nullptr, 0, B, H, KVH, seq_len, seq_len, 0,
+                    head_dim, scale, causal, window, cos_t, sin_t, pos_ids, &fused, stream))
+    return -1;
+  if (fused) return 0;
+  // kernels without the fused epilogue (legacy / v1 / head_dim != 128): rotate dQ and dK afterwards
+  if (vpb_rope_inplace(dq, lddq, B * seq_len, seq_len, pos_ids, cos_t, sin_t, H, head_dim, 1, stream))
+    return -1;
+  return vpb_rope_inplace(dk, lddk, B * seq_len, seq_len, pos_ids, cos_t, sin_t, KVH, head_dim, 1, stream);
 }

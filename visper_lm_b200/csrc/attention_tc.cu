@@ -706,7 +706,63 @@ struct AttnTcBwdParams {
   float scale;
   int window;  // see AttnTcParams
   long long* trace;  // optional timeline buffer (vpb_set_trace_buffer): clock64 stamps of CTA 0
+  // optional fused INVERSE rotary embedding of dQ / dK in the epilogues (head_dim 128, sq == sk):
+  // cos/sin tables [max_pos, 64], positions per row or null (position = row index in the sequence)
+  const float* rope_cos;
+  const float* rope_sin;
+  const int* rope_pos;
 };
+
+// cos / sin of one row's 32 rotary angles (fp32, as vpb_rope_table wrote them).  Loaded BEFORE the
+// wait on the last MMA so the L2 latency of the table rows (one row per lane: nothing coalesces)
+// hides behind the tail of the tensor work.
+struct RopeRow {
+  float4 c[8], s[8];
+};
+__device__ __forceinline__ void load_rope_row(RopeRow& r, const float* cs, const float* sn) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    r.c[i] = __ldg(reinterpret_cast<const float4*>(cs) + i);
+    r.s[i] = __ldg(reinterpret_cast<const float4*>(sn) + i);
+  }
+}
+
+// One 32-column chunk pair (x = columns [32g, 32g+32), y = the same + 64) of a gradient row:
+// scale, bf16-round like the unfused store, rotate by the INVERSE angle (the backward of HF
+// apply_rotary_pos_emb), store.  Same expressions as rope_kernel (elementwise.cu) → same bits.
+template <bool ROPE>
+__device__ __forceinline__ void store_pair_inverse_rope(bf16* o1p, bf16* o2p, const uint32_t* xa,
+                                                        const uint32_t* xb, float scale,
+                                                        const RopeRow& r) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float a[8], b[8], o1[8], o2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a[i] = __uint_as_float(xa[q * 8 + i]) * scale;
+      b[i] = __uint_as_float(xb[q * 8 + i]) * scale;
+    }
+    const uint4 pa = pack8(a), pb = pack8(b);
+    if constexpr (ROPE) {
+      unpack8(pa, a);
+      unpack8(pb, b);
+      const float4 c0 = r.c[2 * q], c1 = r.c[2 * q + 1], s0 = r.s[2 * q], s1 = r.s[2 * q + 1];
+      const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ss = -1.f * sv[i];
+        o1[i] = __fmaf_rn(a[i], cc[i], -__fmul_rn(b[i], ss));
+        o2[i] = __fmaf_rn(b[i], cc[i], __fmul_rn(a[i], ss));
+      }
+      stg16(o1p + q * 8, pack8(o1));
+      stg16(o2p + q * 8, pack8(o2));
+    } else {
+      stg16(o1p + q * 8, pa);
+      stg16(o2p + q * 8, pb);
+    }
+  }
+}
 
 // timeline instrumentation of the v2 backward kernels: row `slot`, column `it` (512 columns per row)
 #define VPB_TRACE(slot, it)                                                        \
@@ -1641,12 +1697,43 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (quarter == 0 && lane == 0) VPB_TRACE(7, it);  // softmax: arrived
     }
     }
+    [[maybe_unused]] RopeRow rr;
+    if constexpr (HD == 128) {
+      if (p.rope_cos && key_ok) {
+        const int m = b * p.sk + kv0 + row;
+        const int pos = p.rope_pos ? p.rope_pos[m] : kv0 + row;
+        load_rope_row(rr, p.rope_cos + (int64_t)pos * 64 + g * 32, p.rope_sin + (int64_t)pos * 64 + g * 32);
+      }
+    }
     if (nit > 0) {
       mbar_wait(all_done, 0);
       tc_fence_after();
     }
     bf16* dkrow = p.dk + ((int64_t)b * p.sk + kv0 + row) * p.lddk + kvh * HD;
     bf16* dvrow = p.dv + ((int64_t)b * p.sk + kv0 + row) * p.lddv + kvh * HD;
+    if constexpr (HD == 128) {
+      // warp half g owns the column pair [32g, 32g+32) | [64+32g, ...): inverse RoPE of dK in place
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {  // 0: dK (scaled, rotated back), 1: dV
+        uint32_t a[32], a2[32];
+        if (nit > 0) {
+          const uint32_t tm = (which ? TM_DV : TM_DK) + lane_addr + g * 32;
+          tmem_ld32(tm, a);
+          tmem_ld32(tm + 64, a2);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] = a2[i] = 0;
+        }
+        if (key_ok) {
+          bf16* orow = which ? dvrow : dkrow;
+          if (which == 0 && p.rope_cos)
+            store_pair_inverse_rope<true>(orow + g * 32, orow + 64 + g * 32, a, a2, p.scale, rr);
+          else
+            store_pair_inverse_rope<false>(orow + g * 32, orow + 64 + g * 32, a, a2, which ? 1.f : p.scale, rr);
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c = g * 2 + cc;
@@ -1673,6 +1760,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           stg16(dvrow + c * 32 + q * 8, pack8(y));
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -1979,24 +2067,45 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     // epilogue: both query tiles' dQ sit in TMEM; the 8 warps split the 128 head-dim columns
     for (int t = 0; t < ntl; ++t) {
+      const bool rok = t ? row_ok[1] : row_ok[0];
+      [[maybe_unused]] RopeRow rr;
+      if constexpr (HD == 128) {
+        if (p.rope_cos && rok) {
+          const int m = b * p.sq + qt[t] * B_BQ + row;
+          const int pos = p.rope_pos ? p.rope_pos[m] : qt[t] * B_BQ + row;
+          load_rope_row(rr, p.rope_cos + (int64_t)pos * 64 + g * 32, p.rope_sin + (int64_t)pos * 64 + g * 32);
+        }
+      }
       mbar_wait(&tile_done[t], 0);
       tc_fence_after();
       bf16* dqrow = p.dq + ((int64_t)b * p.sq + qt[t] * B_BQ + row) * p.lddq + h * HD;
-      const bool rok = t ? row_ok[1] : row_ok[0];
-#pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = g * 2 + cc;
-        if (c * 32 >= HD) break;
-        uint32_t a[32];
-        tmem_ld32(TM_DQ + t * 128 + lane_addr + c * 32, a);
+      if constexpr (HD == 128) {
+        // warp half g owns the column pair [32g, 32g+32) | [64+32g, 64+32g+32): the two halves of a
+        // rotary pair sit in one thread, so the inverse RoPE of dQ can happen here
+        uint32_t a[32], bb[32];
+        tmem_ld32(TM_DQ + t * 128 + lane_addr + g * 32, a);
+        tmem_ld32(TM_DQ + t * 128 + lane_addr + 64 + g * 32, bb);
         tmem_ld_wait();
         if (rok) {
+          if (p.rope_cos) store_pair_inverse_rope<true>(dqrow + g * 32, dqrow + 64 + g * 32, a, bb, p.scale, rr);
+          else store_pair_inverse_rope<false>(dqrow + g * 32, dqrow + 64 + g * 32, a, bb, p.scale, rr);
+        }
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = g * 2 + cc;
+          if (c * 32 >= HD) break;
+          uint32_t a[32];
+          tmem_ld32(TM_DQ + t * 128 + lane_addr + c * 32, a);
+          tmem_ld_wait();
+          if (rok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float x[8];
+            for (int q = 0; q < 4; ++q) {
+              float x[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(a[q * 8 + i]) * p.scale;
-            stg16(dqrow + c * 32 + q * 8, pack8(x));
+              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(a[q * 8 + i]) * p.scale;
+              stg16(dqrow + c * 32 + q * 8, pack8(x));
+            }
           }
         }
       }
@@ -2092,6 +2201,10 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
   return 0;
 }
 
+static bool bwd_tc_takes_v1(int window, bool causal, int sq, int sk) {
+  return window == 0 && (get_option(VPB_OPT_ATTN_TC_BWD_V1) || (causal && sk < sq));
+}
+
 template <bool CAUSAL>
 static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
@@ -2104,8 +2217,10 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   (ss ? launch_bwd_tc_v2<CAUSAL, HDv, false, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)          \
       : pingpong ? launch_bwd_tc_v2<CAUSAL, HDv, true, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st) \
                  : launch_bwd_tc_v2<CAUSAL, HDv, true, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st))
+  // (a caller asking for the fused inverse RoPE only gets here with head_dim 128 on the v2 kernels:
+  // attn_bwd_tc clears the request otherwise)
   if (head_dim == 96) return VPB_BWD_V2(96);
-  if (p.window == 0 && (get_option(VPB_OPT_ATTN_TC_BWD_V1) || (CAUSAL && p.sk < p.sq)))
+  if (bwd_tc_takes_v1(p.window, CAUSAL, p.sq, p.sk))
     return launch_bwd_tc_v1<CAUSAL>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st);
   return VPB_BWD_V2(128);
 #undef VPB_BWD_V2
@@ -2115,9 +2230,18 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
 int attn_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                 const void* dO, int64_t lddo, const float* lse, const float* delta, void* dq,
                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, int B, int H, int KVH,
-                int sq, int sk, int head_dim, float scale, int causal, int window, cudaStream_t st) {
+                int sq, int sk, int head_dim, float scale, int causal, int window,
+                const float* rope_cos, const float* rope_sin, const int* rope_pos, int* rope_fused,
+                cudaStream_t st) {
   AttnTcBwdParams p;
   p.window = causal ? window : 0;
+  // inverse RoPE of dQ / dK in the epilogues: v2 kernels, head_dim 128, self-attention shapes
+  const bool fuse = rope_cos && head_dim == 128 && sq == sk &&
+                    !bwd_tc_takes_v1(p.window, causal != 0, sq, sk);
+  p.rope_cos = fuse ? rope_cos : nullptr;
+  p.rope_sin = fuse ? rope_sin : nullptr;
+  p.rope_pos = fuse ? rope_pos : nullptr;
+  if (rope_fused) *rope_fused = fuse ? 1 : 0;
   p.trace = g_trace_buffer;
   p.lse = lse; p.delta = delta;
   p.dq = (bf16*)dq; p.dk = (bf16*)dk; p.dv = (bf16*)dv;

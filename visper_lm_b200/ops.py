@@ -162,6 +162,11 @@ def gemm_swiglu_bwd(dy, w, gu, b_layout=1, tiled=False, F=None):
 
 
 FUSE_ROPE = os.environ.get("VPB_FUSE_ROPE", "1") != "0"
+# inverse RoPE of dQ/dK inside the attention-backward epilogues (head_dim 128).  Bit-identical to the
+# separate kernel but not faster: the backward CTAs own the whole SM (512 TMEM columns), so their
+# epilogue is exposed, while the stand-alone rope kernel runs at L2 speed on the still-resident dqkv
+# (profiles/r01_rope_bwd_fusion_ab.txt) — off by default.
+FUSE_ROPE_BWD = os.environ.get("VPB_FUSE_ROPE_BWD", "0") == "1"
 
 
 def gemm_rope(a, w, seq_len, cos, sin, rope_heads, pos_ids=None):
@@ -491,6 +496,25 @@ def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, sq, sk, head_dim, scale
                            lse.data_ptr(), delta.data_ptr(), pdq, lddq, pdk, lddk, pdv, lddv, pdk2,
                            lddk2, pdv2, lddv2, B, H, KVH, sq, sk, sk2, head_dim, scale,
                            1 if causal else 0, int(window), _stream()), "attn_bwd")
+
+
+def attn_bwd_rope(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, T, head_dim, scale, causal, cos, sin,
+                  pos_ids=None, window=0):
+    """Self-attention backward whose dq/dk come back with the inverse RoPE already applied
+    (== attn_bwd followed by rope_(inverse=True) on the q and k heads, bit for bit)."""
+    delta = torch.empty((B, H, T), dtype=torch.float32, device=q.device)
+    pq, ldq = _rows(q)
+    pk, ldk = _rows(k)
+    pv, ldv = _rows(v)
+    po, ldo = _rows(o)
+    pdo, lddo = _rows(do)
+    pdq, lddq = _rows(dq)
+    pdk, lddk = _rows(dk)
+    pdv, lddv = _rows(dv)
+    _chk(_L().vpb_attn_bwd_rope(pq, ldq, pk, ldk, pv, ldv, po, ldo, pdo, lddo, lse.data_ptr(),
+                                delta.data_ptr(), pdq, lddq, pdk, lddk, pdv, lddv, B, H, KVH, T,
+                                head_dim, scale, 1 if causal else 0, int(window), cos.data_ptr(),
+                                sin.data_ptr(), _p(pos_ids), _stream()), "attn_bwd_rope")
 
 
 # --------------------------------------------------------------------------------------------- losses
