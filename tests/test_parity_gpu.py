@@ -209,3 +209,63 @@ def test_dpt_decoder_depth_preds():
     assert (norm.cpu() - restate.depth_pred_normalized(ref)).abs().max().item() <= 3e-2
     assert rel_err(depth[:, ::7, ::7], fx["depth_sub"]) <= 4e-2   # reference itself (fp32 weights)
     assert float(norm.min()) == 0.0 and abs(float(norm.max()) - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["dinov2_vits_224", "dav2_teacher_vitl_336"])
+def test_depth_teacher_targets(name):
+    """Frozen depth teacher, batched on the GPU: DINOv2 taps → mean target features
+    (and, for ViT-L, the DPT-decoded normalised depth map) against the fp32 oracle on the same
+    bf16-rounded weights and against the golden vectors of the unmodified reference (fp32 weights,
+    batch-1 loop).  24 bf16 transformer blocks: CPU emulation of the rounding points gives 0.9e-2."""
+    from types import SimpleNamespace
+
+    from oracle.make_golden_dinov2 import teacher_images, teacher_param
+    from visper_lm_b200.model.dinov2 import DepthAnythingV2
+    from visper_lm_b200.model.dpt import DAv2_Head
+    from visper_lm_b200.model.vlm import OlaLlavaLlamaForCausalLM
+
+    fx = torch.load(GOLDEN / f"{name}.pt")
+    enc, size, B = fx["encoder"], fx["size"], fx["B"]
+    teacher = DepthAnythingV2(enc, device=DEV, with_depth_head=False)
+    with torch.no_grad():
+        for n, p in teacher.named_parameters():
+            p.copy_(teacher_param("dav2_backbone." + n, tuple(p.shape)).to(torch.bfloat16))
+    raw = teacher_images(B, size, fx["seed"])
+    ft = teacher.dsg_targets(raw.to(DEV), size)
+    torch.cuda.synchronize()
+    sd = {n: p.detach().float().cpu() for n, p in teacher.named_parameters()}
+    hsd = None
+    head = None
+    if fx["head_spec"] is not None:
+        head = DAv2_Head(DEV)
+        with torch.no_grad():
+            for n, p in head.named_parameters():
+                p.copy_(bf16_seeded("da_v2_head." + n, tuple(p.shape)))
+        hsd = {"da_v2_head." + n: p.detach().float().cpu() for n, p in head.named_parameters()}
+    with torch.no_grad():
+        ref_ft, ref_gts = restate.dav2_depth_teacher(sd, hsd, raw, enc)
+        ref_taps = restate.dinov2_intermediate(sd, restate.dav2_image_tensor(raw), enc)
+    N, D = ref_ft.shape[1], ref_ft.shape[2]
+    assert ft.shape == (B * N, D)
+    e = rel_err(ft.view(B, N, D), ref_ft)
+    assert e <= 2e-2, f"target features rel err {e:.4f}"
+    assert rel_err(ft.view(B, N, D)[:, ::7, ::16], fx["ft_sub"]) <= 4e-2       # the reference itself
+    # the reference-shaped API: forward(normalised tensor) → ((patch tokens, cls) x 4); infer_image(one array)
+    feats = teacher(restate.dav2_image_tensor(raw).to(DEV))
+    assert len(feats) == 4 and feats[0][0].shape == (B, N, D) and feats[0][1].shape == (B, D)
+    for (pt, cls), (rpt, rcls) in zip(feats, ref_taps):
+        assert rel_err(pt, rpt) <= 2e-2 and rel_err(cls, rcls) <= 2e-2, (rel_err(pt, rpt), rel_err(cls, rcls))
+    one = teacher.infer_image(raw[1].numpy(), input_size=size, is_dsg=True)
+    assert rel_err(one[3][0][0], ref_taps[3][0][1]) <= 2e-2
+    if head is not None:
+        # _get_dav2_feats (base_ola_vlm.py:348-366) through the model hook, uint8 batch in
+        host = SimpleNamespace(dav2_backbone=teacher, da_v2_head=head)
+        targets, gts = OlaLlavaLlamaForCausalLM._get_dav2_feats(host, raw, DEV)
+        torch.cuda.synchronize()
+        assert targets[0][1] is None and torch.equal(targets[0][0].reshape(B * N, D), ft)
+        assert gts.shape == ref_gts.shape == (B, size, size)
+        # min-max normalised map in [0,1] after ~50 bf16 layers (24 blocks + the DPT decoder)
+        d = (gts.cpu() - ref_gts).abs()
+        assert d.mean().item() <= 1e-2 and d.max().item() <= 8e-2, (d.mean().item(), d.max().item())
+        assert (gts.cpu()[:, ::7, ::7] - fx["depth_gts_sub"]).abs().mean().item() <= 1.5e-2
+        assert float(gts.min()) == 0.0 and abs(float(gts.max()) - 1.0) < 1e-6

@@ -150,6 +150,31 @@ def rope_bwd_case(B=8, H=32, KVH=8, S=2048, hd=128, rounds=4):
                       "all": {n: [round(x, 4) for x in v] for n, v in res.items()}}), flush=True)
 
 
+def teacher_case(B=8, size=336):
+    """Batched depth teacher (DINOv2-L taps -> mean target features, + DPT decode of the targets) for
+    one training batch; the reference runs the same work as a batch-1 Python loop per image."""
+    from visper_lm_b200.model.dinov2 import DepthAnythingV2
+    from visper_lm_b200.model.dpt import DAv2_Head
+    teacher = DepthAnythingV2("vitl", device=dev, with_depth_head=False)
+    head = DAv2_Head(dev)
+    with torch.no_grad():
+        for m in (teacher, head):
+            for p_ in m.parameters():
+                p_.normal_(0.0, 0.02)
+    raw = torch.randint(0, 256, (B, size, size, 3), dtype=torch.uint8, device=dev)
+    from visper_lm_b200 import lib
+    ms_t = timeit(lambda: teacher.dsg_targets(raw, size))
+    lib.reset_launch_count()
+    ft = teacher.dsg_targets(raw, size)
+    launches = lib.launch_count()
+    ms_d = timeit(lambda: head.normalized([ft] * 4))
+    S = (size // 14) ** 2 + 1
+    fl = B * 24 * (2.0 * S * 12 * 1024 * 1024 + 4.0 * S * S * 1024)
+    print(json.dumps({"kernel": "depth teacher DINOv2-L (4 taps, mean)", "B": B, "size": size,
+                      "ms": round(ms_t, 3), "tflops": round(fl / ms_t / 1e9, 1), "launches": launches,
+                      "images_per_s": round(B / ms_t * 1e3, 1), "dpt_decode_ms": round(ms_d, 3)}), flush=True)
+
+
 if __name__ == "__main__":
     M = 16384
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -178,6 +203,8 @@ if __name__ == "__main__":
         attn_case(4, 32, 32, 2048, 96, True)
         ops.set_option(ops.OPT_ATTN_LEGACY_FWD, 0)
         ops.set_option(ops.OPT_ATTN_LEGACY_BWD, 0)
+    if which == "teacher":
+        teacher_case()
     if which == "ropebwd":
         rope_bwd_case()
     if which == "attnprof":

@@ -10,10 +10,11 @@ forward(...) takes the collator's batch and returns an object w
 (ola_arch.py:256-259) but is sync-free on the device: the splice is planned on the host from the
 token ids and executed as one gather kernel.
 
-Out of scope here (SURVEY.md §8f "next" rows): the frozen teachers (targets are supplied by the
-caller or by overriding _get_dav2_feats/_get_seg_targets/_get_gen_feats, the same hooks the
-reference has at base_ola_vlm.py:323,347,382), the frozen DPT decoder behind `depth_preds`,
-generation, wandb logging.
+Teachers: the depth teacher (Depth-Anything-V2's DINOv2-L, model/dinov2.py) and the frozen DPT decoder
+behind `depth_preds` (model/dpt.py) run on the GPU, batched.  The OneFormer and unCLIP teachers are
+third-party models outside the reference tree: their targets are supplied by the caller
+(`distill_targets=`) or by overriding _get_seg_targets/_get_gen_feats, the same hooks the reference
+has at base_ola_vlm.py:323,382.  Out of scope: generation, wandb logging.
 """
 from __future__ import annotations
 
@@ -427,8 +428,34 @@ class VisperForCausalLM(nn.Module):
         return self.lm_head.weight.device
 
     def init_target_models(self, config):
-        """Frozen teachers are OUT OF SCOPE (SURVEY.md §2.1 #13): targets come from the caller."""
-        return
+        """base_ola_vlm.py:61-95.  The depth teacher (`dav2_backbone`, Depth-Anything-V2 DINOv2-L) is
+        built here and runs batched on the GPU (model/dinov2.py); the OneFormer and unCLIP teachers are
+        third-party models outside the reference tree — their targets come from the caller
+        (`distill_targets=`) or from overriding `_get_seg_targets` / `_get_gen_feats`.
+        Weights: `config.depth_estimator` (depth_anything_v2_vitl.pth, loaded strict like :81); there
+        is no network here, so a missing file raises unless `config.random_init_teachers` is set
+        (benchmarks / tests: seeded or random weights)."""
+        import os
+
+        if not (hasattr(config, "image_depth") and "depth" in getattr(config, "aux_mode", "gen-depth-seg")):
+            return
+        from .dinov2 import DepthAnythingV2
+        self.dav2_backbone = DepthAnythingV2(encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024),
+                                             device=self._device)
+        path = getattr(config, "depth_estimator", None)
+        if path and os.path.exists(path):
+            self.dav2_backbone.load_state_dict(torch.load(path, map_location="cpu"))
+        elif getattr(config, "random_init_teachers", False):
+            with torch.no_grad():
+                for p_ in self.dav2_backbone.parameters():
+                    p_.normal_(0.0, 0.02)
+                for blk in self.dav2_backbone.pretrained.blocks:
+                    blk.norm1.weight.fill_(1.0), blk.norm2.weight.fill_(1.0)
+                self.dav2_backbone.pretrained.norm.weight.fill_(1.0)
+        else:
+            raise FileNotFoundError(f"depth teacher weights not found: {path!r} (the reference downloads "
+                                    "depth_anything_v2_vitl.pth; no network here)")
+        self.dav2_backbone.requires_grad_(False)
 
     def _layer_loss_weight(self, cfgd, prefix):
         idx = [int(i) - 1 for i in cfgd[f"{prefix}_layer_indices"].split("-")]  # base_ola_vlm.py:97-102
@@ -562,7 +589,24 @@ class VisperForCausalLM(nn.Module):
 
     # ---- teachers (hooks kept for drop-in monkeypatching; OUT OF SCOPE by default) --------------
     def _get_dav2_feats(self, pil_images, device):
-        raise NotImplementedError("frozen depth teacher is out of scope: pass distill_targets=")
+        """base_ola_vlm.py:348-366, batched: one DINOv2 pass over all images instead of a batch-1
+        Python loop.  pil_images: PIL images (resized to 336x336 like :351) or uint8 [B,336,336,3].
+        Returns ([(targets [B,576,1024], None)], depth_gts [B,336,336] min-max normalised or None
+        when the DPT decoder is not loaded)."""
+        teacher = getattr(self, "dav2_backbone", None)
+        if teacher is None:
+            raise NotImplementedError("depth teacher not initialised: call init_target_models(config) or "
+                                      "pass distill_targets=")
+        if torch.is_tensor(pil_images):
+            raw = pil_images
+        else:
+            import numpy as np
+            raw = torch.from_numpy(np.stack([np.array(im.resize((336, 336))) for im in pil_images]))
+        B = raw.shape[0]
+        ft = teacher.dsg_targets(raw, 336)
+        head = getattr(self, "da_v2_head", None)
+        gts = head.normalized([ft] * 4) if head is not None else None
+        return [(ft.view(B, -1, ft.shape[-1]), None)], gts
 
     def _get_seg_targets(self, pil_images, seg_preds):
         raise NotImplementedError("frozen seg teacher is out of scope: pass distill_targets=")
@@ -571,9 +615,15 @@ class VisperForCausalLM(nn.Module):
         raise NotImplementedError("frozen gen teacher is out of scope: pass distill_targets=")
 
     def _targets(self, task, pil_images, distill_targets, device):
-        if distill_targets is not None:
-            return distill_targets.get(task)
-        if pil_images is None:
+        """Caller-supplied targets win; the depth task falls back to the on-GPU teacher when it is
+        loaded and real images came with the batch; otherwise the reference's hooks."""
+        if distill_targets is not None and task in distill_targets:
+            return distill_targets[task]
+        have_images = torch.is_tensor(pil_images) or (pil_images is not None and len(pil_images) > 0
+                                                      and pil_images[0] is not None)
+        if task == "depth" and have_images and getattr(self, "dav2_backbone", None) is not None:
+            return self._get_dav2_feats(pil_images, device)[0][0][0]
+        if distill_targets is not None or pil_images is None:
             return None
         if task == "depth":
             return self._get_dav2_feats(pil_images, device)[0][0][0]
