@@ -269,3 +269,34 @@ def test_depth_teacher_targets(name):
         assert d.mean().item() <= 1e-2 and d.max().item() <= 8e-2, (d.mean().item(), d.max().item())
         assert (gts.cpu()[:, ::7, ::7] - fx["depth_gts_sub"]).abs().mean().item() <= 1.5e-2
         assert float(gts.min()) == 0.0 and abs(float(gts.max()) - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["gen_teacher_mini", "gen_teacher_vith_224"])
+def test_gen_teacher_targets(name):
+    """Frozen generation teacher, batched on the GPU: unCLIP ViT-H/14 image_embeds
+    (head_dim 80 zero-padded onto the head_dim-96 tcgen05 attention) against the fp32 oracle on the
+    same bf16-rounded weights and against golden vectors of transformers' own model (fp32 weights)."""
+    from types import SimpleNamespace
+
+    from oracle.make_golden_gen_teacher import gen_pixels
+    from visper_lm_b200.model.gen_teacher import CLIPVisionModelWithProjection
+    from visper_lm_b200.model.vlm import OlaLlavaLlamaForCausalLM
+
+    fx = torch.load(GOLDEN / f"{name}.pt")
+    cfg, B = fx["config"], fx["B"]
+    enc = CLIPVisionModelWithProjection(cfg, DEV)
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            p.copy_(bf16_seeded("image_encoder." + n, tuple(p.shape)))
+    px = gen_pixels(B, cfg["image_size"], fx["seed"]).to(torch.bfloat16)
+    host = SimpleNamespace(pipe=SimpleNamespace(image_encoder=enc, feature_extractor=None))
+    emb = OlaLlavaLlamaForCausalLM._get_gen_feats(host, px.to(DEV), DEV)   # base_ola_vlm.py:323-333
+    torch.cuda.synchronize()
+    sd = {n: p.detach().float().cpu() for n, p in enc.named_parameters()}
+    with torch.no_grad():
+        ref = restate.gen_teacher_targets(sd, px.float(), cfg["num_attention_heads"], cfg["hidden_act"])
+    assert emb.shape == ref.shape == (B, 1, cfg["projection_dim"])
+    e = rel_err(emb, ref)   # CPU emulation of the bf16 rounding points: 0.6e-2 (mini), 1.1e-2 (ViT-H, 32 layers)
+    assert e <= 3e-2, f"image_embeds rel err {e:.4f}"
+    assert rel_err(emb, fx["image_embeds"]) <= 5e-2                       # the library model itself
+    assert enc(px.to(DEV)).image_embeds.shape == (B, cfg["projection_dim"])

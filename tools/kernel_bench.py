@@ -168,6 +168,16 @@ def teacher_case(B=8, size=336):
     ft = teacher.dsg_targets(raw, size)
     launches = lib.launch_count()
     ms_d = timeit(lambda: head.normalized([ft] * 4))
+    from visper_lm_b200.model.gen_teacher import UNCLIP_VIT_H, CLIPVisionModelWithProjection
+    enc = CLIPVisionModelWithProjection(UNCLIP_VIT_H, dev)
+    with torch.no_grad():
+        for p_ in enc.parameters():
+            p_.normal_(0.0, 0.02)
+    px = torch.randn(B, 3, 224, 224, device=dev).to(BF)
+    ms_g = timeit(lambda: enc.image_embeds(px))
+    flg = B * 32 * (2.0 * 257 * 12 * 1280 * 1280 + 4.0 * 257 * 257 * 1280)
+    print(json.dumps({"kernel": "gen teacher unCLIP ViT-H/14 image_embeds", "B": B, "ms": round(ms_g, 3),
+                      "tflops": round(flg / ms_g / 1e9, 1), "images_per_s": round(B / ms_g * 1e3, 1)}), flush=True)
     S = (size // 14) ** 2 + 1
     fl = B * 24 * (2.0 * S * 12 * 1024 * 1024 + 4.0 * S * S * 1024)
     print(json.dumps({"kernel": "depth teacher DINOv2-L (4 taps, mean)", "B": B, "size": size,

@@ -437,7 +437,10 @@ class VisperForCausalLM(nn.Module):
         (benchmarks / tests: seeded or random weights)."""
         import os
 
-        if not (hasattr(config, "image_depth") and "depth" in getattr(config, "aux_mode", "gen-depth-seg")):
+        mode = getattr(config, "aux_mode", "gen-depth-seg")
+        if hasattr(config, "image_gen") and "gen" in mode:
+            self._init_gen_teacher(config)
+        if not (hasattr(config, "image_depth") and "depth" in mode):
             return
         from .dinov2 import DepthAnythingV2
         self.dav2_backbone = DepthAnythingV2(encoder="vitl", features=256, out_channels=(256, 512, 1024, 1024),
@@ -456,6 +459,36 @@ class VisperForCausalLM(nn.Module):
             raise FileNotFoundError(f"depth teacher weights not found: {path!r} (the reference downloads "
                                     "depth_anything_v2_vitl.pth; no network here)")
         self.dav2_backbone.requires_grad_(False)
+
+    def _init_gen_teacher(self, config):
+        """base_ola_vlm.py:61-67: `self.pipe` = the unCLIP pipeline, of which only feature_extractor
+        and image_encoder are used in training (:323-333).  Here `pipe` holds exactly those two: HF's
+        CLIPImageProcessor (host-side PIL preprocessing) and the on-GPU encoder (model/gen_teacher.py).
+        Weights: <config.image_generator>/image_encoder/{model.safetensors | pytorch_model.bin}."""
+        import os
+        from .gen_teacher import UNCLIP_VIT_H, CLIPVisionModelWithProjection
+
+        enc = CLIPVisionModelWithProjection(UNCLIP_VIT_H, self._device)
+        root = os.path.join(str(getattr(config, "image_generator", "")), "image_encoder")
+        st, pt = os.path.join(root, "model.safetensors"), os.path.join(root, "pytorch_model.bin")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            enc.load_state_dict(load_file(st), strict=False)
+        elif os.path.exists(pt):
+            enc.load_state_dict(torch.load(pt, map_location="cpu"), strict=False)
+        elif getattr(config, "random_init_teachers", False):
+            with torch.no_grad():
+                for n_, p_ in enc.named_parameters():
+                    p_.fill_(1.0) if ("norm" in n_ and n_.endswith("weight")) else p_.normal_(0.0, 0.02)
+        else:
+            raise FileNotFoundError(f"gen teacher weights not found under {root!r} (the reference downloads "
+                                    "stabilityai/stable-diffusion-2-1-unclip; no network here)")
+        try:
+            from transformers import CLIPImageProcessor
+            fe = CLIPImageProcessor()  # the unCLIP feature_extractor's settings are the class defaults
+        except Exception:  # pragma: no cover
+            fe = None
+        self.pipe = SimpleNamespace(image_encoder=enc, feature_extractor=fe)
 
     def _layer_loss_weight(self, cfgd, prefix):
         idx = [int(i) - 1 for i in cfgd[f"{prefix}_layer_indices"].split("-")]  # base_ola_vlm.py:97-102
@@ -612,24 +645,37 @@ class VisperForCausalLM(nn.Module):
         raise NotImplementedError("frozen seg teacher is out of scope: pass distill_targets=")
 
     def _get_gen_feats(self, pil_images, device):
-        raise NotImplementedError("frozen gen teacher is out of scope: pass distill_targets=")
+        """base_ola_vlm.py:323-333, batched: image_embeds of the unCLIP image encoder → [B,1,1024].
+        pil_images: PIL images (through pipe.feature_extractor, as the reference) or an already
+        preprocessed pixel_values tensor [B,3,224,224]."""
+        pipe = getattr(self, "pipe", None)
+        if pipe is None:
+            raise NotImplementedError("gen teacher not initialised: call init_target_models(config) or "
+                                      "pass distill_targets=")
+        if torch.is_tensor(pil_images):
+            px = pil_images
+        else:
+            px = pipe.feature_extractor(images=list(pil_images), return_tensors="pt").pixel_values
+        return pipe.image_encoder.image_embeds(px)[:, None]
 
     def _targets(self, task, pil_images, distill_targets, device):
-        """Caller-supplied targets win; the depth task falls back to the on-GPU teacher when it is
-        loaded and real images came with the batch; otherwise the reference's hooks."""
+        """Caller-supplied targets win; otherwise the task's on-GPU teacher when it is loaded and the
+        batch carries images for it (PIL images, or a dict {task: preprocessed tensor}); otherwise the
+        reference's hooks."""
         if distill_targets is not None and task in distill_targets:
             return distill_targets[task]
-        have_images = torch.is_tensor(pil_images) or (pil_images is not None and len(pil_images) > 0
-                                                      and pil_images[0] is not None)
-        if task == "depth" and have_images and getattr(self, "dav2_backbone", None) is not None:
-            return self._get_dav2_feats(pil_images, device)[0][0][0]
-        if distill_targets is not None or pil_images is None:
+        images = pil_images.get(task) if isinstance(pil_images, dict) else pil_images
+        have_images = torch.is_tensor(images) or (images is not None and len(images) > 0
+                                                  and images[0] is not None)
+        loaded = {"depth": getattr(self, "dav2_backbone", None) is not None,
+                  "gen": getattr(self, "pipe", None) is not None, "seg": False}[task]
+        if not (have_images and loaded) and (distill_targets is not None or images is None):
             return None
         if task == "depth":
-            return self._get_dav2_feats(pil_images, device)[0][0][0]
+            return self._get_dav2_feats(images, device)[0][0][0]
         if task == "seg":
-            return self._get_seg_targets(pil_images, None)
-        return self._get_gen_feats(pil_images, device)
+            return self._get_seg_targets(images, None)
+        return self._get_gen_feats(images, device)
 
     def _gather_targets(self, tgt_flat):
         """dist_collect (ola_utils.py:96-106): targets carry no grad → plain NCCL all-gather, once
