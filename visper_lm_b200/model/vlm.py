@@ -621,7 +621,7 @@ class VisperForCausalLM(nn.Module):
         return states
 
     # ---- teachers (hooks kept for drop-in monkeypatching; OUT OF SCOPE by default) --------------
-    def _get_dav2_feats(self, pil_images, device):
+    def _get_dav2_feats(self, pil_images, device, decode=True):
         """base_ola_vlm.py:348-366, batched: one DINOv2 pass over all images instead of a batch-1
         Python loop.  pil_images: PIL images (resized to 336x336 like :351) or uint8 [B,336,336,3].
         Returns ([(targets [B,576,1024], None)], depth_gts [B,336,336] min-max normalised or None
@@ -638,7 +638,8 @@ class VisperForCausalLM(nn.Module):
         B = raw.shape[0]
         ft = teacher.dsg_targets(raw, 336)
         head = getattr(self, "da_v2_head", None)
-        gts = head.normalized([ft] * 4) if head is not None else None
+        # depth_gts only feed the reference's wandb depth logging; the training step skips the decode
+        gts = head.normalized([ft] * 4) if (decode and head is not None) else None
         return [(ft.view(B, -1, ft.shape[-1]), None)], gts
 
     def _get_seg_targets(self, pil_images, seg_preds):
@@ -672,7 +673,7 @@ class VisperForCausalLM(nn.Module):
         if not (have_images and loaded) and (distill_targets is not None or images is None):
             return None
         if task == "depth":
-            return self._get_dav2_feats(images, device)[0][0][0]
+            return self._get_dav2_feats(images, device, decode=False)[0][0][0]
         if task == "seg":
             return self._get_seg_targets(images, None)
         return self._get_gen_feats(images, device)
