@@ -57,8 +57,8 @@ def parse():
     ap.add_argument("--torch-profile", action="store_true",
                     help="diagnostic: torch.profiler over 2 device-leg steps, prints kernel totals and busy time")
     ap.add_argument("--teachers", action="store_true",
-                    help="dsg only: compute the depth and gen targets with the on-GPU frozen teachers from "
-                         "synthetic images every step (seg targets stay synthetic tensors)")
+                    help="dsg only: compute the depth / seg / gen targets with the on-GPU frozen teachers "
+                         "(DINOv2-L, Swin-L, unCLIP ViT-H) from synthetic images every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-input leg")
     ap.add_argument("--profile", action="store_true",
@@ -109,10 +109,11 @@ def host_batch(c, B, T, distill, seed, teachers=False):
         for k in ("depth_mask", "seg_mask", "gen_mask"):
             batch[k] = torch.ones(B, dtype=torch.long)
         if teachers:  # what the image pipeline hands the teachers: 336² uint8 RGB and CLIP-preprocessed 224²
-            del batch["distill_targets"]["depth"], batch["distill_targets"]["gen"]
+            del batch["distill_targets"]
             batch["pil_images"] = dict(
                 depth=torch.randint(0, 256, (B, 336, 336, 3), generator=g, dtype=torch.uint8),
-                gen=torch.randn(B, 3, 224, 224, generator=g))
+                gen=torch.randn(B, 3, 224, 224, generator=g),
+                seg=torch.randn(B, 3, 800, 800, generator=g).to(torch.bfloat16))  # OneFormerProcessor: 800²
     return batch
 
 
@@ -285,7 +286,7 @@ def workload_config(args, c, distill):
     return {"workload": ("BASELINE configs[1]: " if not distill else "BASELINE configs[2] per-GPU slice: ")
             + f"{args.model} + CLIP-ViT-L/14-336, 336px, T={args.seq}, "
             + ("NTP only" if not distill else "NTP + dsg distill heads (d18-20_s10-18_g12-20)")
-            + (", depth (DINOv2-L) and gen (unCLIP ViT-H) targets from the on-GPU frozen teachers each step"
+            + (", depth (DINOv2-L) / seg (Swin-L @800) / gen (unCLIP ViT-H) targets from the on-GPU frozen teachers each step"
                if distill and getattr(args, "teachers", False) else "")
             + (", full fine-tune (LLM + mm_projector trainable: fwd + dgrad + wgrad)" if getattr(args, "train", "adapter") == "full"
                else ", PT freeze policy (mm_projector" + ("+heads+task tokens" if distill else "") + " trainable; LLM fwd+dgrad)"),
@@ -320,11 +321,11 @@ def run_b200(args):
     model.init_weights(std=0.02, seed=0)
     teachers = bool(args.teachers and distill)
     if teachers:
-        cfg.random_init_teachers = True  # no network: DINOv2-L / unCLIP ViT-H geometry, random weights
+        cfg.random_init_teachers = True  # no network: DINOv2-L / Swin-L / unCLIP ViT-H geometry, random weights
         model.init_target_models(cfg)
     for n, p in model.named_parameters():
         if args.train == "full":  # finetune.sh: everything but the frozen tower (and the frozen DPT head / teacher)
-            p.requires_grad_(("vision_tower" not in n) and ("da_v2_head" not in n) and ("dav2_backbone" not in n))
+            p.requires_grad_(("vision_tower" not in n) and ("da_v2_head" not in n) and ("dav2_backbone" not in n) and ("oneformer" not in n))
         else:  # PT freeze policy
             p.requires_grad_(("mm_projector" in n) or ("_heads." in n) or ("special_" in n) or n.endswith("logit_scale"))
     targs = TrainingArguments(per_device_train_batch_size=args.batch, learning_rate=1e-3, max_steps=10_000)

@@ -140,6 +140,10 @@ int vpb_im2col3x3_nhwc(const void* in, void* out, int B, int H, int W, int C, in
 /* F.interpolate(mode="bilinear", align_corners=True) */
 int vpb_bilinear_nhwc(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
                       void* stream);
+/* F.interpolate(mode="bilinear", align_corners=False) — the 25x25 → 24x24 resize of the seg teacher's
+ * last feature map (aux_heads/oneformer_head.py:31) */
+int vpb_bilinear_nhwc_half_pixel(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                 void* stream);
 /* ConvTranspose2d(kernel = stride = k) epilogue: [B*H*W, k*k*C] → [B, H*k, W*k, C] (+bias) */
 int vpb_pixel_shuffle_nhwc(const void* in, const void* bias, void* out, int B, int H, int W, int C,
                            int k, void* stream);
@@ -184,6 +188,13 @@ int vpb_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
                  int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, void* dk2,
                  int64_t lddk2, void* dv2, int64_t lddv2, int B, int H, int KVH, int sq, int sk,
                  int sk2, int head_dim, float scale, int causal, int window, void* stream);
+/* Forward-only window attention with an additive score bias (frozen Swin teacher: HF
+ * SwinSelfAttention.forward — scores = q.k/sqrt(hd) + relative_position_bias[h] + attn_mask[window]):
+ * bias fp32 [H, sq, sk]; bias_mask fp32 [mask_mod, sq, sk] or NULL, batch entry b uses mask b % mask_mod
+ * (windows are batch-major: b = image * n_windows + window).  head_dim 32, non-causal, KVH == H. */
+int vpb_attn_fwd_bias(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                      void* o, int64_t ldo, float* lse, int B, int H, int sq, int sk, int head_dim,
+                      float scale, const float* bias, const float* bias_mask, int mask_mod, void* stream);
 /* Self-attention backward (sq == sk == seq_len, one K/V segment) that also undoes the rotary
  * embedding: dq / dk come back as gradients w.r.t. the PRE-rotation projections, i.e. what
  * vpb_attn_bwd followed by vpb_rope_inplace(inverse=1) on dq (H heads) and dk (KVH heads) returns,

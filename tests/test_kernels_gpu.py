@@ -653,3 +653,40 @@ def test_attention_backward_fused_inverse_rope(B, H, KVH, S, hd, window, use_pos
     assert torch.equal(got[:, qw:qw + kw], ref[:, qw:qw + kw]), "dk"
     assert torch.equal(got[:, qw + kw:], ref[:, qw + kw:]), "dv"
     assert ref[:, :qw + kw].float().abs().max() > 0
+
+
+@pytest.mark.parametrize("B,H,S,nmask", [(8, 6, 144, 4), (3, 2, 144, 0), (18, 4, 16, 9), (5, 1, 16, 0), (4, 3, 100, 2)])
+def test_window_attention_with_score_bias(B, H, S, nmask):
+    """vpb_attn_fwd_bias (frozen Swin teacher): softmax(q.k/sqrt(32) + bias[h] + mask[b % nmask]) v, head_dim
+    32, window sizes 144 (12x12), 16 (4x4) and a ragged 100, against torch fp32."""
+    from visper_lm_b200 import ops
+    hd = 32
+    qkv = rnd(B * S, 3 * H * hd, seed=95)
+    g = torch.Generator().manual_seed(96)
+    bias = (2.0 * torch.randn(H, S, S, generator=g)).cuda()
+    mask = None
+    if nmask:
+        mask = torch.where(torch.rand(nmask, S, S, generator=g) < 0.3, torch.tensor(-100.0), torch.tensor(0.0))
+        mask[:, torch.arange(S), torch.arange(S)] = 0.0   # never a fully masked row (Swin masks keep the diagonal)
+        mask = mask.contiguous().cuda()
+    W = H * hd
+    o = ops.attn_fwd_bias(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, S, hd, hd ** -0.5, bias, mask)
+    torch.cuda.synchronize()
+    q, k, v = (qkv.float()[:, i * W:(i + 1) * W].view(B, S, H, hd).transpose(1, 2) for i in range(3))
+    sc = q @ k.transpose(-1, -2) * hd ** -0.5 + bias[None]
+    if mask is not None:
+        sc = sc + mask[torch.arange(B) % nmask][:, None]
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, W)
+    close(o, ref, name="window attention + bias")
+
+
+@pytest.mark.parametrize("B,Hi,Wi,Ho,Wo,C", [(2, 25, 25, 24, 24, 1536), (1, 4, 4, 24, 24, 256), (3, 7, 5, 3, 9, 64)])
+def test_bilinear_half_pixel(B, Hi, Wi, Ho, Wo, C):
+    """F.interpolate(mode='bilinear', align_corners=False) on NHWC rows (seg teacher: 25x25 → 24x24)."""
+    from visper_lm_b200 import ops
+    x = rnd(B * Hi * Wi, C, seed=97)
+    y = ops.bilinear(x, B, Hi, Wi, Ho, Wo, C, align_corners=False)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.interpolate(x.float().view(B, Hi, Wi, C).permute(0, 3, 1, 2), size=(Ho, Wo),
+                                          mode="bilinear", align_corners=False)
+    close(y, ref.permute(0, 2, 3, 1).reshape(B * Ho * Wo, C), name="bilinear half-pixel")

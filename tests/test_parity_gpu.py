@@ -300,3 +300,38 @@ def test_gen_teacher_targets(name):
     assert e <= 3e-2, f"image_embeds rel err {e:.4f}"
     assert rel_err(emb, fx["image_embeds"]) <= 5e-2                       # the library model itself
     assert enc(px.to(DEV)).image_embeds.shape == (B, cfg["projection_dim"])
+
+
+@pytest.mark.parametrize("name", ["seg_teacher_mini_120", "seg_teacher_swinl_800"])
+def test_seg_teacher_targets(name):
+    """Frozen segmentation teacher, batched on the GPU: OneFormer's Swin backbone
+    (window gathers with padding / cyclic shift, relative-position bias + shift mask inside the attention
+    kernel, patch merging, half-pixel resize to 24x24) against the fp32 oracle on the same bf16-rounded
+    weights and against golden vectors of transformers' own SwinBackbone (fp32 weights)."""
+    from types import SimpleNamespace
+
+    from oracle.make_golden_seg_teacher import seg_param, seg_pixels
+    from visper_lm_b200.model.seg_teacher import OneFormerHead
+    from visper_lm_b200.model.vlm import OlaLlavaLlamaForCausalLM
+
+    fx = torch.load(GOLDEN / f"{name}.pt")
+    cfg, B = fx["config"], fx["B"]
+    net = OneFormerHead(cfg, DEV)
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            p.copy_(seg_param("oneformer." + n, tuple(p.shape)).to(torch.bfloat16))
+    px = seg_pixels(B, fx["size"], fx["seed"]).to(torch.bfloat16)
+    host = SimpleNamespace(oneformer=net, oneformer_processor=None)
+    host._seg_pixel_values = lambda im: im
+    tgt = OlaLlavaLlamaForCausalLM._get_seg_targets(host, px.to(DEV), None)   # base_ola_vlm.py:382-397
+    rows = net.seg_target_rows(px.to(DEV))
+    torch.cuda.synchronize()
+    sd = {n: p.detach().float().cpu() for n, p in net.named_parameters()}
+    with torch.no_grad():
+        ref = restate.seg_teacher_targets(sd, px.float(), cfg)
+    C = ref.shape[1]
+    assert tgt.shape == ref.shape == (B, C, 24, 24) and rows.shape == (B * 576, C)
+    assert torch.equal(rows.view(B, 576, C).transpose(1, 2).reshape(B, C, 24, 24), tgt)
+    e = rel_err(tgt, ref)
+    assert e <= 3e-2, f"seg targets rel err {e:.4f}"
+    assert rel_err(tgt[:, ::8, ::2, ::2], fx["targets_sub"]) <= 5e-2          # the library model itself

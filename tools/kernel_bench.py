@@ -178,6 +178,17 @@ def teacher_case(B=8, size=336):
     flg = B * 32 * (2.0 * 257 * 12 * 1280 * 1280 + 4.0 * 257 * 257 * 1280)
     print(json.dumps({"kernel": "gen teacher unCLIP ViT-H/14 image_embeds", "B": B, "ms": round(ms_g, 3),
                       "tflops": round(flg / ms_g / 1e9, 1), "images_per_s": round(B / ms_g * 1e3, 1)}), flush=True)
+    from visper_lm_b200.model.seg_teacher import OneFormerHead
+    seg = OneFormerHead(None, dev)
+    with torch.no_grad():
+        for n_, p_ in seg.named_parameters():
+            p_.fill_(1.0) if ("norm" in n_ and n_.endswith("weight")) else p_.normal_(0.0, 0.02)
+    spx = torch.randn(B, 3, 800, 800, device=dev).to(BF)
+    ms_s = timeit(lambda: seg.seg_target_rows(spx), iters=5, warmup=2)
+    lib.reset_launch_count()
+    seg.seg_target_rows(spx)
+    print(json.dumps({"kernel": "seg teacher OneFormer Swin-L backbone @800 -> 24x24", "B": B, "ms": round(ms_s, 3),
+                      "launches": lib.launch_count(), "images_per_s": round(B / ms_s * 1e3, 1)}), flush=True)
     S = (size // 14) ** 2 + 1
     fl = B * 24 * (2.0 * S * 12 * 1024 * 1024 + 4.0 * S * S * 1024)
     print(json.dumps({"kernel": "depth teacher DINOv2-L (4 taps, mean)", "B": B, "size": size,

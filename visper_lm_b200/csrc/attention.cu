@@ -29,6 +29,10 @@ struct AttnParams {
   const float* delta;  // [B,H,sq]
   bf16 *dq, *dk, *dv, *dk2, *dv2;
   int64_t lddq, lddk, lddv, lddk2, lddv2;
+  // additive score bias (forward only, vpb_attn_fwd_bias): scores = scale*q.k + bias[h] + bias_mask[b % mask_mod]
+  const float* bias;       // [H, sq, sk] fp32
+  const float* bias_mask;  // [mask_mod, sq, sk] fp32 or null
+  int mask_mod;
 };
 
 template <int HD>
@@ -84,7 +88,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 // =============================================================================================
 // forward
 // =============================================================================================
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, bool BIAS = false>
 __global__ void __launch_bounds__(256)
 attn_fwd_kernel(const AttnParams p) {
   using C = Cfg<HD>;
@@ -177,10 +181,35 @@ attn_fwd_kernel(const AttnParams p) {
         mma16816(s[nb + 1], qf[ks], bf + 2);
       }
     }
-    // masking (boundary tiles only)
     const bool seg2 = jt >= n1;
     const int j0 = (seg2 ? jt - n1 : jt) * BN;
     const int len = seg2 ? p.sk2 : p.sk;
+    if constexpr (BIAS) {
+      // s holds the unscaled q.k; the softmax below scales by p.scale, so the additive terms go in
+      // divided by it.  Fragment element e of n-block nb: row g + 8*(e>>1), column 2t + (e&1).
+      const float inv = 1.f / p.scale;
+      const float* bh = p.bias + (int64_t)h * p.sq * p.sk;
+      const float* mw = p.bias_mask ? p.bias_mask + (int64_t)(b % p.mask_mod) * p.sq * p.sk : nullptr;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int i = q0 + warp * 16 + g + r * 8;
+        if (i < p.sq) {
+#pragma unroll
+          for (int nb = 0; nb < BN / 8; ++nb) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int j = j0 + nb * 8 + 2 * t + c;
+              if (j < p.sk) {
+                float a = __ldg(bh + (int64_t)i * p.sk + j);
+                if (mw) a += __ldg(mw + (int64_t)i * p.sk + j);
+                s[nb][2 * r + c] = fmaf(a, inv, s[nb][2 * r + c]);
+              }
+            }
+          }
+        }
+      }
+    }
+    // masking (boundary tiles only)
     const bool win = CAUSAL && p.window > 0;
     const bool need_mask = (j0 + BN > len) || (CAUSAL && (j0 + BN - 1 > q0 + off)) ||
                            (win && j0 < q0 + BMQ - 1 + off - p.window);
@@ -650,11 +679,11 @@ attn_bwd_dq_kernel(const AttnParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int HD, bool CAUSAL>
+template <int HD, bool CAUSAL, bool BIAS = false>
 static int launch_fwd(const AttnParams& p, cudaStream_t st) {
   constexpr int HDP = Cfg<HD>::HDP;
   constexpr int SMEM = (128 + 4 * 64) * HDP * 2;
-  auto kern = attn_fwd_kernel<HD, CAUSAL>;
+  auto kern = attn_fwd_kernel<HD, CAUSAL, BIAS>;
   static bool cfg = false;
   if (!cfg) {
     VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -763,6 +792,27 @@ extern "C" int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
     return attn_fwd_tc(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, KVH, sq, sk, head_dim, scale, causal,
                        p.window, (cudaStream_t)stream);
   DISPATCH_HD(head_dim, causal, launch_fwd, p, (cudaStream_t)stream);
+}
+
+// Window attention with an additive score bias (Swin: relative-position bias per head + the
+// shifted-window mask per window), forward only, head_dim 32, non-causal, one K/V segment.
+extern "C" int vpb_attn_fwd_bias(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                 int64_t ldv, void* o, int64_t ldo, float* lse, int B, int H, int sq,
+                                 int sk, int head_dim, float scale, const float* bias,
+                                 const float* bias_mask, int mask_mod, void* stream) {
+  AttnParams p = {};
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v;
+  p.o = (bf16*)o; p.lse = lse;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+  p.B = B; p.H = H; p.KVH = H; p.sq = sq; p.sk = sk; p.sk2 = 0;
+  p.scale = scale;
+  p.bias = bias; p.bias_mask = bias_mask; p.mask_mod = bias_mask ? mask_mod : 1;
+  if (check_attn(p, head_dim)) return -1;
+  VPB_CHECK(head_dim == 32, "attn_fwd_bias: head_dim %d (only 32 is built)", head_dim);
+  VPB_CHECK(bias != nullptr && scale > 0.f, "attn_fwd_bias: bias table missing or scale <= 0");
+  VPB_CHECK(!bias_mask || (mask_mod > 0 && B % mask_mod == 0), "attn_fwd_bias: B=%d is not a multiple of mask_mod=%d", B, mask_mod);
+  VPB_CHECK(B <= 65535, "attn_fwd_bias: B=%d windows exceed gridDim.z; split the batch", B);
+  return launch_fwd<32, false, true>(p, (cudaStream_t)stream);
 }
 
 extern "C" int vpb_rope_inplace(void* x, int64_t ld, int M, int seq_len, const int* pos_ids,

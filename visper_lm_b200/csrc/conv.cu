@@ -48,14 +48,16 @@ im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int
   }
 }
 
-// F.interpolate(mode="bilinear", align_corners=True) on NHWC
+// F.interpolate(mode="bilinear") on NHWC; AC = align_corners.  align_corners=False uses torch's
+// half-pixel rule: src = max((dst + 0.5) * in/out - 0.5, 0).
+template <bool AC>
 __global__ void __launch_bounds__(256)
 bilinear_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int Hi, int Wi, int Ho,
                 int Wo, int C) {
   const int cv = C >> 3;
   const int64_t total = (int64_t)B * Ho * Wo * cv;
-  const float sy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
-  const float sx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  const float sy = AC ? (Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f) : (float)Hi / (float)Ho;
+  const float sx = AC ? (Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f) : (float)Wi / (float)Wo;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(i % cv);
@@ -64,7 +66,8 @@ bilinear_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int 
     r /= Wo;
     const int oy = (int)(r % Ho);
     const int b = (int)(r / Ho);
-    const float fy = sy * oy, fx = sx * ox;
+    const float fy = AC ? sy * oy : fmaxf(sy * (oy + 0.5f) - 0.5f, 0.f);
+    const float fx = AC ? sx * ox : fmaxf(sx * (ox + 0.5f) - 0.5f, 0.f);
     int y0 = (int)fy, x0 = (int)fx;
     if (y0 > Hi - 1) y0 = Hi - 1;
     if (x0 > Wi - 1) x0 = Wi - 1;
@@ -170,8 +173,18 @@ extern "C" int vpb_bilinear_nhwc(const void* in, void* out, int B, int Hi, int W
                                  void* stream) {
   VPB_CHECK(B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, "bilinear: bad shape");
   const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
-  bilinear_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)in, (bf16*)out, B, Hi, Wi, Ho,
-                                                                Wo, C);
+  bilinear_kernel<true><<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)in, (bf16*)out, B, Hi, Wi,
+                                                                      Ho, Wo, C);
+  VPB_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int vpb_bilinear_nhwc_half_pixel(const void* in, void* out, int B, int Hi, int Wi, int Ho, int Wo,
+                                            int C, void* stream) {
+  VPB_CHECK(B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, "bilinear: bad shape");
+  const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
+  bilinear_kernel<false><<<grid_for(total, 256), 256, 0, ST(stream)>>>((const bf16*)in, (bf16*)out, B, Hi, Wi,
+                                                                       Ho, Wo, C);
   VPB_LAUNCH_OK();
   return 0;
 }

@@ -11,10 +11,10 @@ forward(...) takes the collator's batch and returns an object w
 token ids and executed as one gather kernel.
 
 Teachers: the depth teacher (Depth-Anything-V2's DINOv2-L, model/dinov2.py) and the frozen DPT decoder
-behind `depth_preds` (model/dpt.py) run on the GPU, batched.  The OneFormer and unCLIP teachers are
-third-party models outside the reference tree: their targets are supplied by the caller
-(`distill_targets=`) or by overriding _get_seg_targets/_get_gen_feats, the same hooks the reference
-has at base_ola_vlm.py:323,382.  Out of scope: generation, wandb logging.
+behind `depth_preds` (model/dpt.py), the unCLIP image encoder (model/gen_teacher.py) and OneFormer's
+Swin-L backbone (model/seg_teacher.py) run on the GPU, batched, behind the reference's hooks
+_get_dav2_feats / _get_gen_feats / _get_seg_targets (base_ola_vlm.py:323,347,382); targets can also be
+supplied by the caller (`distill_targets=`).  Out of scope: generation, wandb logging.
 """
 from __future__ import annotations
 
@@ -428,18 +428,19 @@ class VisperForCausalLM(nn.Module):
         return self.lm_head.weight.device
 
     def init_target_models(self, config):
-        """base_ola_vlm.py:61-95.  The depth teacher (`dav2_backbone`, Depth-Anything-V2 DINOv2-L) is
-        built here and runs batched on the GPU (model/dinov2.py); the OneFormer and unCLIP teachers are
-        third-party models outside the reference tree — their targets come from the caller
-        (`distill_targets=`) or from overriding `_get_seg_targets` / `_get_gen_feats`.
-        Weights: `config.depth_estimator` (depth_anything_v2_vitl.pth, loaded strict like :81); there
-        is no network here, so a missing file raises unless `config.random_init_teachers` is set
-        (benchmarks / tests: seeded or random weights)."""
+        """base_ola_vlm.py:61-95: builds the frozen teachers, all of which run batched on the GPU —
+        `dav2_backbone` (Depth-Anything-V2 DINOv2-L, model/dinov2.py), `pipe.image_encoder` (unCLIP
+        ViT-H/14, model/gen_teacher.py) and `oneformer` (Swin-L backbone, model/seg_teacher.py).
+        Weights come from the reference's paths (`config.depth_estimator`, `config.image_generator`,
+        `config.image_segmentor`); there is no network here, so a missing file raises unless
+        `config.random_init_teachers` is set (benchmarks / tests)."""
         import os
 
         mode = getattr(config, "aux_mode", "gen-depth-seg")
         if hasattr(config, "image_gen") and "gen" in mode:
             self._init_gen_teacher(config)
+        if hasattr(config, "image_seg") and "seg" in mode:
+            self._init_seg_teacher(config)
         if not (hasattr(config, "image_depth") and "depth" in mode):
             return
         from .dinov2 import DepthAnythingV2
@@ -489,6 +490,40 @@ class VisperForCausalLM(nn.Module):
         except Exception:  # pragma: no cover
             fe = None
         self.pipe = SimpleNamespace(image_encoder=enc, feature_extractor=fe)
+
+    def _init_seg_teacher(self, config):
+        """base_ola_vlm.py:84-94: `self.oneformer` (OneFormerHead — only its Swin-L backbone runs in
+        training, model/seg_teacher.py) and `self.oneformer_processor` (HF OneFormerProcessor, host-side
+        PIL preprocessing; needs the checkpoint directory's preprocessor_config.json).
+        Weights: <config.image_segmentor>/{model.safetensors | pytorch_model.bin}, backbone keys only."""
+        import os
+        from .seg_teacher import OneFormerHead
+
+        net = OneFormerHead(None, self._device)
+        root = str(getattr(config, "image_segmentor", ""))
+        st, pt = os.path.join(root, "model.safetensors"), os.path.join(root, "pytorch_model.bin")
+        sd = None
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        elif os.path.exists(pt):
+            sd = torch.load(pt, map_location="cpu")
+        if sd is not None:
+            sd = {(k[6:] if k.startswith("model.") else k): v for k, v in sd.items()}
+            want = set(net.state_dict().keys())
+            net.load_state_dict({k: v for k, v in sd.items() if k in want}, strict=True)
+        elif getattr(config, "random_init_teachers", False):
+            with torch.no_grad():
+                for n_, p_ in net.named_parameters():
+                    p_.fill_(1.0) if ("norm" in n_ and n_.endswith("weight")) else p_.normal_(0.0, 0.02)
+        else:
+            raise FileNotFoundError(f"seg teacher weights not found under {root!r} (the reference downloads "
+                                    "oneformer/oneformer_coco_swin_large; no network here)")
+        self.oneformer = net
+        self.oneformer_processor = None
+        if os.path.exists(os.path.join(root, "preprocessor_config.json")):
+            from transformers import OneFormerProcessor
+            self.oneformer_processor = OneFormerProcessor.from_pretrained(root)
 
     def _layer_loss_weight(self, cfgd, prefix):
         idx = [int(i) - 1 for i in cfgd[f"{prefix}_layer_indices"].split("-")]  # base_ola_vlm.py:97-102
@@ -642,8 +677,24 @@ class VisperForCausalLM(nn.Module):
         gts = head.normalized([ft] * 4) if (decode and head is not None) else None
         return [(ft.view(B, -1, ft.shape[-1]), None)], gts
 
+    def _seg_pixel_values(self, pil_images):
+        if torch.is_tensor(pil_images):
+            return pil_images
+        proc = getattr(self, "oneformer_processor", None)
+        if proc is None:
+            raise NotImplementedError("no OneFormerProcessor loaded: pass preprocessed pixel_values")
+        return torch.cat([proc(im.resize((768, 768)), ["panoptic"], return_tensors="pt")["pixel_values"]
+                          for im in pil_images], 0)            # base_ola_vlm.py:383-386
+
     def _get_seg_targets(self, pil_images, seg_preds):
-        raise NotImplementedError("frozen seg teacher is out of scope: pass distill_targets=")
+        """base_ola_vlm.py:382-397, batched: the Swin-L backbone's last feature map resized to 24x24 →
+        [B,1536,24,24].  pil_images: PIL images (through oneformer_processor, as the reference) or an
+        already preprocessed pixel_values tensor [B,3,H,W]."""
+        net = getattr(self, "oneformer", None)
+        if net is None:
+            raise NotImplementedError("seg teacher not initialised: call init_target_models(config) or "
+                                      "pass distill_targets=")
+        return net.forward_features(self._seg_pixel_values(pil_images))
 
     def _get_gen_feats(self, pil_images, device):
         """base_ola_vlm.py:323-333, batched: image_embeds of the unCLIP image encoder → [B,1,1024].
@@ -669,13 +720,18 @@ class VisperForCausalLM(nn.Module):
         have_images = torch.is_tensor(images) or (images is not None and len(images) > 0
                                                   and images[0] is not None)
         loaded = {"depth": getattr(self, "dav2_backbone", None) is not None,
-                  "gen": getattr(self, "pipe", None) is not None, "seg": False}[task]
+                  "gen": getattr(self, "pipe", None) is not None,
+                  "seg": getattr(self, "oneformer", None) is not None}[task]
         if not (have_images and loaded) and (distill_targets is not None or images is None):
             return None
         if task == "depth":
             return self._get_dav2_feats(images, device, decode=False)[0][0][0]
         if task == "seg":
-            return self._get_seg_targets(images, None)
+            net = getattr(self, "oneformer", None)
+            if net is None:
+                return self._get_seg_targets(images, None)
+            rows = net.seg_target_rows(self._seg_pixel_values(images))   # token-major: no NCHW round trip
+            return rows.view(-1, 576, rows.shape[-1])
         return self._get_gen_feats(images, device)
 
     def _gather_targets(self, tgt_flat):
@@ -711,7 +767,7 @@ class VisperForCausalLM(nn.Module):
             tgt_all = off = None
             if tgt is not None:
                 tgt = tgt.to(dev, BF16)
-                if task == "seg":  # [B,C,24,24] → token-major [B,576,C] to match the head's layout
+                if task == "seg" and tgt.dim() == 4:  # [B,C,24,24] → token-major [B,576,C] (head layout)
                     Bc, C = tgt.shape[0], tgt.shape[1]
                     tflat = torch.empty((Bc, 576 * C), dtype=BF16, device=dev)
                     tgt = tgt.contiguous()

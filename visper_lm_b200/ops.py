@@ -362,10 +362,11 @@ def im2col3x3(x, B, H, W, C, stride=1, relu_in=False):
     return out, Ho, Wo
 
 
-def bilinear(x, B, Hi, Wi, Ho, Wo, C):
+def bilinear(x, B, Hi, Wi, Ho, Wo, C, align_corners=True):
     assert x.is_contiguous() and x.shape == (B * Hi * Wi, C)
     out = torch.empty((B * Ho * Wo, C), dtype=BF16, device=x.device)
-    _chk(_L().vpb_bilinear_nhwc(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C, _stream()), "bilinear")
+    fn = _L().vpb_bilinear_nhwc if align_corners else _L().vpb_bilinear_nhwc_half_pixel
+    _chk(fn(x.data_ptr(), out.data_ptr(), B, Hi, Wi, Ho, Wo, C, _stream()), "bilinear")
     return out
 
 
@@ -474,6 +475,22 @@ def attn_fwd(q, k, v, B, H, KVH, sq, sk, head_dim, scale, causal, k2=None, v2=No
                            B, H, KVH, sq, sk, sk2, head_dim, scale, 1 if causal else 0, int(window),
                            _stream()), "attn_fwd")
     return o, lse
+
+
+def attn_fwd_bias(q, k, v, B, H, S, head_dim, scale, bias, mask=None):
+    """Window attention with additive bias: softmax(scale*q.k + bias[h] + mask[b % len(mask)]) v.
+    q/k/v: row views [B*S, H*head_dim]; bias fp32 [H,S,S]; mask fp32 [nW,S,S] or None."""
+    assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape == (H, S, S)
+    assert mask is None or (mask.dtype == torch.float32 and mask.is_contiguous() and mask.shape[1:] == (S, S))
+    o = torch.empty((B * S, H * head_dim), dtype=BF16, device=q.device)
+    lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+    pq, ldq = _rows(q)
+    pk, ldk = _rows(k)
+    pv, ldv = _rows(v)
+    _chk(_L().vpb_attn_fwd_bias(pq, ldq, pk, ldk, pv, ldv, o.data_ptr(), H * head_dim, lse.data_ptr(), B, H,
+                                S, S, head_dim, scale, bias.data_ptr(), _p(mask),
+                                0 if mask is None else mask.shape[0], _stream()), "attn_fwd_bias")
+    return o
 
 
 def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, sq, sk, head_dim, scale, causal,
