@@ -690,3 +690,19 @@ def test_bilinear_half_pixel(B, Hi, Wi, Ho, Wo, C):
     ref = torch.nn.functional.interpolate(x.float().view(B, Hi, Wi, C).permute(0, 3, 1, 2), size=(Ho, Wo),
                                           mode="bilinear", align_corners=False)
     close(y, ref.permute(0, 2, 3, 1).reshape(B * Ho * Wo, C), name="bilinear half-pixel")
+
+
+@pytest.mark.parametrize("M,D", [(20000, 192), (16384, 384), (33333, 768), (16390, 64), (16384, 776)])
+def test_layernorm_many_short_rows(M, D):
+    """LayerNorm forward on the warp-per-row kernel (M >= 16384 rows of D <= 768: the Swin teacher's
+    shapes; D = 776 stays on the CTA-per-row kernel) against torch fp32, statistics included."""
+    from visper_lm_b200 import ops
+    x = rnd(M, D, seed=31, scale=2.0)
+    w = (1 + 0.1 * rnd(D, seed=32).float()).to(BF)
+    b = rnd(D, seed=33, scale=0.1)
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-5)
+    torch.cuda.synchronize()
+    xf = x.float()
+    close(y, torch.nn.functional.layer_norm(xf, (D,), w.float(), b.float(), 1e-5), name="ln fwd (warp rows)")
+    assert torch.allclose(mean, xf.mean(1), atol=1e-5)
+    assert torch.allclose(rstd, (xf.var(1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-4)

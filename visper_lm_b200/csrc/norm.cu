@@ -87,6 +87,65 @@ norm_fwd_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict_
   }
 }
 
+// LayerNorm forward for MANY SHORT rows (the Swin teacher: up to 330k rows of 192 / 384 / 768): one warp
+// per row, eight rows per CTA, shuffle-only reductions — the CTA-per-row kernel above leaves 7/8 of its
+// threads idle and pays three block reductions per 384-byte row there.  Same two-pass arithmetic.
+constexpr int WNORM_MAXV = 3;      // 32 lanes x 3 vectors of 8 → D <= 768
+constexpr int WNORM_MIN_ROWS = 16384;
+__global__ void __launch_bounds__(256)
+layernorm_fwd_warp_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w,
+                          const bf16* __restrict__ b, bf16* __restrict__ y, int64_t ldy,
+                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
+                          float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = D >> 3;
+  const bf16* xr = x + (int64_t)row * ldx;
+  float v[WNORM_MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < WNORM_MAXV; ++k) {
+    const int i = lane + k * 32;
+    if (i < nvec) {
+      unpack8(ldg16_stream(xr + i * 8), v[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[k][j];
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float vs = 0.f;
+#pragma unroll
+  for (int k = 0; k < WNORM_MAXV; ++k) {
+    const int i = lane + k * 32;
+    if (i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[k][j] - mean;
+        vs += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(vs) / D + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  bf16* yr = y + (int64_t)row * ldy;
+#pragma unroll
+  for (int k = 0; k < WNORM_MAXV; ++k) {
+    const int i = lane + k * 32;
+    if (i < nvec) {
+      float wv[8], bv[8], o[8];
+      unpack8(ldg16(w + i * 8), wv);
+      unpack8(ldg16(b + i * 8), bv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean) * rstd * wv[j] + bv[j];
+      stg16(yr + i * 8, pack8(o));
+    }
+  }
+}
+
 // dx = rstd * (g - [mean(g)] - xhat * mean(g*xhat)),  g = dy * w ;  dx (+)= dres if given
 template <bool RMS>
 __global__ void __launch_bounds__(NORM_THREADS)
@@ -218,6 +277,12 @@ extern "C" int vpb_layernorm_fwd(const void* x, int64_t ldx, const void* w, cons
                                  int64_t ldy, float* mean, float* rstd, int M, int D, float eps,
                                  void* stream) {
   if (check_norm(M, D)) return -1;
+  if (D <= 8 * 32 * WNORM_MAXV && M >= WNORM_MIN_ROWS) {
+    layernorm_fwd_warp_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy, mean, rstd, M, D, eps);
+    VPB_LAUNCH_OK();
+    return 0;
+  }
   norm_fwd_kernel<false><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, ldx, (const bf16*)w, (const bf16*)b, (bf16*)y, ldy, mean, rstd, D, eps);
   VPB_LAUNCH_OK();
