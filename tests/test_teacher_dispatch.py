@@ -1,0 +1,84 @@
+"""Host logic of the distillation-target plumbing (no GPU): which source feeds each task's targets —
+caller-supplied tensors, the on-GPU teachers behind the reference's hooks (base_ola_vlm.py:323,347,382),
+or nothing — and init_target_models' failure mode when the (un-downloadable) weights are absent."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from visper_lm_b200.model.vlm import OlaLlavaLlamaForCausalLM as M
+
+
+class _Stub(SimpleNamespace):
+    def _get_dav2_feats(self, images, device, decode=True):
+        self.calls.append(("depth", decode))
+        return [(torch.full((len(images), 576, 4), 1.0), None)], None
+
+    def _get_gen_feats(self, images, device):
+        self.calls.append(("gen",))
+        return torch.full((len(images), 1, 4), 2.0)
+
+    def _get_seg_targets(self, images, seg_preds):
+        self.calls.append(("seg",))
+        return torch.full((len(images), 4, 24, 24), 3.0)
+
+    def _seg_pixel_values(self, images):
+        return images
+
+
+def _host(**kw):
+    return _Stub(calls=[], **kw)
+
+
+def test_caller_targets_win():
+    h = _host(dav2_backbone=object(), pipe=object())
+    t = {"depth": torch.zeros(2, 576, 4)}
+    assert M._targets(h, "depth", [object(), object()], t, "cpu") is t["depth"] and h.calls == []
+
+
+def test_teacher_fills_missing_task_when_images_present():
+    h = _host(dav2_backbone=object(), pipe=object())
+    out = M._targets(h, "depth", torch.zeros(2, 336, 336, 3, dtype=torch.uint8), {"seg": torch.zeros(1)}, "cpu")
+    assert out.shape == (2, 576, 4) and h.calls == [("depth", False)]       # the logging-only decode is skipped
+    out = M._targets(h, "gen", {"gen": torch.zeros(2, 3, 224, 224)}, {}, "cpu")  # per-task preprocessed tensors
+    assert out.shape == (2, 1, 4) and h.calls[-1] == ("gen",)
+
+
+def test_no_teacher_no_targets():
+    h = _host()
+    assert M._targets(h, "seg", [None, None], {"depth": torch.zeros(1)}, "cpu") is None   # caller gave others only
+    assert M._targets(h, "gen", None, None, "cpu") is None
+    assert M._targets(h, "depth", {"gen": torch.zeros(1)}, {}, "cpu") is None              # no depth images in the dict
+    assert h.calls == []
+
+
+def test_reference_hooks_without_caller_targets():
+    h = _host()
+    out = M._targets(h, "seg", [object()], None, "cpu")      # reference behaviour: hook is called
+    assert out.shape == (1, 4, 24, 24) and h.calls == [("seg",)]
+
+
+def test_seg_teacher_rows_skip_the_nchw_round_trip():
+    net = SimpleNamespace(seg_target_rows=lambda px: torch.arange(2 * 576 * 8, dtype=torch.float32).view(2 * 576, 8))
+    h = _host(oneformer=net)
+    out = M._targets(h, "seg", torch.zeros(2, 3, 8, 8), {}, "cpu")
+    assert out.shape == (2, 576, 8) and h.calls == []
+
+
+def test_hooks_raise_before_init():
+    h = SimpleNamespace()
+    for fn, args in ((M._get_dav2_feats, ([None], "cpu")), (M._get_gen_feats, ([None], "cpu")),
+                     (M._get_seg_targets, ([None], None))):
+        with pytest.raises(NotImplementedError):
+            fn(h, *args)
+
+
+def test_init_target_models_needs_weights_or_opt_in():
+    cfg = SimpleNamespace(aux_mode="depth", image_depth={"x": 1}, depth_estimator="/nonexistent/depth_anything_v2_vitl.pth")
+    h = SimpleNamespace(_device=None)
+    with pytest.raises(FileNotFoundError):
+        M.init_target_models(h, cfg)
+    cfg.random_init_teachers = True
+    M.init_target_models(h, cfg)
+    assert sum(p.numel() for p in h.dav2_backbone.pretrained.parameters()) == 304_368_640   # DINOv2-L
+    assert not any(p.requires_grad for p in h.dav2_backbone.parameters())
