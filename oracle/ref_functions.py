@@ -62,3 +62,18 @@ def preprocess_fns(default_version: str):
          "DEFAULT_IM_START_TOKEN": "<im_start>", "DEFAULT_IM_END_TOKEN": "<im_end>",
          "DataArguments": object}
     return extract("ola_vlm/train/ola_vlm_train.py", ["preprocess_multimodal", "preprocess_llama_3", "preprocess_phi_3"], g)
+
+
+def extract_method(rel_path: str, cls: str, method: str, extra_globals: Optional[dict] = None):
+    """One method of a reference class as a plain function (first argument = self)."""
+    path = os.path.join(ref_shim.REF_ROOT, rel_path)
+    tree = ast.parse(open(path).read(), filename=path)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == method:
+                    ns = {"torch": torch}
+                    ns.update(extra_globals or {})
+                    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+                    return ns[method]
+    raise KeyError(f"{cls}.{method} not found in {rel_path}")

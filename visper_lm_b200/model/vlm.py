@@ -403,6 +403,75 @@ class VisperForCausalLM(nn.Module):
     def get_vision_tower(self):
         return self.model.get_vision_tower()
 
+    # ---- tokenizer / embedding surface (ola_arch.py:446-488; HF PreTrainedModel names) ------------
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    @torch.no_grad()
+    def resize_token_embeddings(self, new_num_tokens, pad_to_multiple_of=None):
+        """HF PreTrainedModel.resize_token_embeddings for embed_tokens + lm_head (setup time, not step
+        work): old rows kept, new rows ~ N(0, 0.02).  The GEMM / CE kernels need a row count that is a
+        multiple of 8, so the size is rounded up to one (what HF's pad_to_multiple_of=8 does: the padding
+        rows are ordinary vocabulary entries that never occur as labels)."""
+        mult = max(8, int(pad_to_multiple_of or 1))
+        mult = mult if mult % 8 == 0 else mult * 8
+        n = (int(new_num_tokens) + mult - 1) // mult * mult
+        for holder in (self.model.embed_tokens, self.lm_head):
+            old = holder.weight
+            if old.shape[0] == n:
+                continue
+            w = torch.empty((n, old.shape[1]), dtype=old.dtype, device=old.device)
+            w.normal_(0.0, 0.02)
+            k = min(n, old.shape[0])
+            w[:k] = old[:k]
+            holder.weight = nn.Parameter(w, requires_grad=old.requires_grad)
+        self.config.vocab_size = self.vocab_size = n
+        self._lm_head_t = M.FrozenTranspose()
+        return self.model.embed_tokens
+
+    def initialize_vision_tokenizer(self, model_args, tokenizer):
+        """ola_arch.py:446-488, statement for statement: optional <im_patch> / <im_start>,<im_end>
+        tokens, new rows set to the mean of the old ones, the adapter-tuning freeze policy and the
+        pretrain_mm_mlp_adapter embedding hand-over.  (Both flags are False in every shipped script.)"""
+        from ola_vlm.constants import DEFAULT_IM_END_TOKEN, DEFAULT_IM_START_TOKEN, DEFAULT_IMAGE_PATCH_TOKEN
+
+        if model_args.mm_use_im_patch_token:
+            tokenizer.add_tokens([DEFAULT_IMAGE_PATCH_TOKEN], special_tokens=True)
+            self.resize_token_embeddings(len(tokenizer))
+        if model_args.mm_use_im_start_end:
+            num_new_tokens = tokenizer.add_tokens([DEFAULT_IM_START_TOKEN, DEFAULT_IM_END_TOKEN], special_tokens=True)
+            self.resize_token_embeddings(len(tokenizer))
+            n_tok = len(tokenizer)        # rows beyond len(tokenizer) are kernel padding, not new tokens
+            if num_new_tokens > 0:
+                input_embeddings = self.get_input_embeddings().weight.data
+                output_embeddings = self.get_output_embeddings().weight.data
+                lo = n_tok - num_new_tokens
+                input_embeddings[lo:n_tok] = input_embeddings[:lo].float().mean(dim=0, keepdim=True).to(input_embeddings.dtype)
+                output_embeddings[lo:n_tok] = output_embeddings[:lo].float().mean(dim=0, keepdim=True).to(output_embeddings.dtype)
+            if model_args.tune_mm_mlp_adapter:
+                self.get_input_embeddings().weight.requires_grad = True
+                self.get_output_embeddings().weight.requires_grad = False
+            if model_args.pretrain_mm_mlp_adapter:
+                mm_projector_weights = torch.load(model_args.pretrain_mm_mlp_adapter, map_location="cpu")
+                embed_tokens_weight = mm_projector_weights["model.embed_tokens.weight"]
+                assert num_new_tokens == 2
+                input_embeddings = self.get_input_embeddings().weight.data
+                lo = n_tok - num_new_tokens
+                if embed_tokens_weight.shape[0] == num_new_tokens:
+                    input_embeddings[lo:n_tok] = embed_tokens_weight.to(input_embeddings)
+                elif embed_tokens_weight.shape[1] == input_embeddings.shape[1] and embed_tokens_weight.shape[0] >= n_tok:
+                    input_embeddings[lo:n_tok] = embed_tokens_weight[lo:n_tok].to(input_embeddings)
+                else:
+                    raise ValueError(f"Unexpected embed_tokens_weight shape. Pretrained: {embed_tokens_weight.shape}. "
+                                     f"Current: {input_embeddings.shape}. Numer of new tokens: {num_new_tokens}.")
+        elif model_args.mm_use_im_patch_token:
+            if model_args.tune_mm_mlp_adapter:
+                self.get_input_embeddings().weight.requires_grad = False
+                self.get_output_embeddings().weight.requires_grad = False
+
     @property
     def depth_tokens(self):
         return self.model.get_special_tokens()[0]
