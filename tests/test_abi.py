@@ -49,5 +49,9 @@ def test_reference_module_paths_resolve():
     assert m.OlaLlavaLlamaConfig.model_type == "ola_llama" and m.LlavaConfig.model_type == "llava_llama"
     t = importlib.import_module("ola_vlm.train.llava_trainer")
     assert hasattr(t, "LLaVATrainer")
+    a = importlib.import_module("ola_vlm.model.aux_heads")       # base_ola_vlm.py:13-15 imports
+    for name in ("DAv2_Head", "TaskTokenGenHead", "TaskTokenDepthHead", "OneFormerTaskTokenSegHead", "OneFormerHead"):
+        assert hasattr(a, name)
+    assert hasattr(importlib.import_module("ola_vlm.model.aux_heads.depth_anything_v2.dpt"), "DepthAnythingV2")
     for k in [k for k in sys.modules if k == "ola_vlm" or k.startswith("ola_vlm.")]:
         del sys.modules[k]
