@@ -124,8 +124,39 @@ def test_final_adapter_save_and_pretrain_load(tmp_path):
     # full (non-adapter) branch goes through trainer._save
     tr.args.tune_mm_mlp_adapter = False
     C.safe_save_model_for_hf_trainer(tr, str(tmp_path / "full"))
-    sd = torch.load(tmp_path / "full" / "pytorch_model.bin")
+    assert os.path.exists(tmp_path / "full" / "model.safetensors")         # HF save_pretrained layout
+    sd = C.load_pretrained_weights(str(tmp_path / "full"))
     assert "model.embed_tokens.weight" in sd and "depth_logit_scale" in sd
+    for k, v in tr.model.state_dict().items():
+        assert torch.equal(sd[k], v.detach().cpu()), k
+
+
+def test_sharded_safetensors_layout_equals_hf_save_pretrained(tmp_path):
+    """save_pretrained_weights writes what transformers' own save_pretrained writes for the same state dict
+    and shard size (file names, index weight_map / total_size, tensors), and HF from_pretrained loads it."""
+    import json
+
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    torch.manual_seed(0)
+    hf = LlamaForCausalLM(LlamaConfig(vocab_size=160, hidden_size=32, intermediate_size=64, num_hidden_layers=3,
+                                      num_attention_heads=4, num_key_value_heads=2, tie_word_embeddings=False))
+    hf.save_pretrained(tmp_path / "hf", max_shard_size="20KB", safe_serialization=True)
+    files = C.save_pretrained_weights(hf.state_dict(), str(tmp_path / "mine"), max_shard_size="20KB")
+    ref_files = sorted(f for f in os.listdir(tmp_path / "hf") if f.endswith(".safetensors"))
+    assert files == ref_files and len(files) > 2
+    a = json.load(open(tmp_path / "hf" / C.SAFE_WEIGHTS_INDEX_NAME))
+    b = json.load(open(tmp_path / "mine" / C.SAFE_WEIGHTS_INDEX_NAME))
+    assert a["weight_map"] == b["weight_map"] and a["metadata"]["total_size"] == b["metadata"]["total_size"]
+    back = C.load_pretrained_weights(str(tmp_path / "mine"))
+    for k, v in hf.state_dict().items():
+        assert torch.equal(back[k], v), k
+    hf.config.save_pretrained(tmp_path / "mine")
+    again = LlamaForCausalLM.from_pretrained(tmp_path / "mine")
+    for (k, v), (_, w) in zip(hf.state_dict().items(), again.state_dict().items()):
+        assert torch.equal(v, w), k
+    one = C.save_pretrained_weights(hf.state_dict(), str(tmp_path / "one"))   # under the limit: single file, no index
+    assert one == ["model.safetensors"] and not os.path.exists(tmp_path / "one" / C.SAFE_WEIGHTS_INDEX_NAME)
 
 
 def _worker(rank, world, port, root, ret):
@@ -150,3 +181,29 @@ def test_resume_world2_gloo(tmp_path):
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, 29547, str(tmp_path), ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_full_save_round_trips_through_from_pretrained(tmp_path):
+    """config.json + sharded safetensors written the way trainer._save does → from_pretrained rebuilds the
+    same model (heads, task tokens, logit scales, DPT decoder included)."""
+    from parity_utils import build_product, configs
+    from visper_lm_b200.model import OlaLlavaLlamaForCausalLM
+
+    torch.manual_seed(3)
+    model = build_product(configs.TINY_LLAMA, True, None)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn(p.shape))
+    C.save_config(model.config, str(tmp_path))
+    files = C.save_pretrained_weights(model.state_dict(), str(tmp_path), max_shard_size="300KB")
+    assert len(files) > 1
+    again = OlaLlavaLlamaForCausalLM.from_pretrained(str(tmp_path))
+    a, b = model.state_dict(), again.state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert again.config.aux_mode == model.config.aux_mode and again.depth_layer_indices == model.depth_layer_indices
+    os.remove(tmp_path / files[0])
+    import pytest
+    with pytest.raises(Exception):
+        OlaLlavaLlamaForCausalLM.from_pretrained(str(tmp_path))

@@ -396,6 +396,31 @@ class VisperForCausalLM(nn.Module):
         if self.distill and hasattr(config, "image_gen"):
             self.init_heads(config)
 
+    @classmethod
+    def from_pretrained(cls, model_dir, device=None, **config_overrides):
+        """Load what `trainer._save` / `save_pretrained` wrote (config.json + model.safetensors or its
+        5 GB shards + index; builder.py:58-138 loads the reference's models the same way).  Teacher
+        submodules are not part of the architecture: call init_target_models afterwards if needed."""
+        import json
+        import os
+
+        from ..train.checkpoint import load_pretrained_weights
+
+        with open(os.path.join(model_dir, "config.json")) as fh:
+            d = json.load(fh)
+        d.pop("model_type", None)
+        d.pop("family", None)
+        d.update(config_overrides)
+        model = cls(cls.config_class(**d), device=device)
+        sd = load_pretrained_weights(model_dir)
+        own = model.state_dict()
+        missing = [k for k in own if k not in sd]
+        unexpected = [k for k in sd if k not in own and not k.startswith(("dav2_backbone.", "oneformer."))]
+        if missing or unexpected:
+            raise KeyError(f"checkpoint does not match {cls.__name__}: missing {missing[:5]}, unexpected {unexpected[:5]}")
+        model.load_state_dict({k: v for k, v in sd.items() if k in own})
+        return model
+
     # ---- reference accessors ---------------------------------------------------------------
     def get_model(self):
         return self.model

@@ -162,3 +162,82 @@ def load_mm_projector(model, path: str):
     with torch.no_grad():
         for k, v in sub.items():
             pj[k].copy_(v.to(pj[k].device, pj[k].dtype))
+
+
+# ---- HF-layout full-model weights (what `trainer._save` → `save_pretrained` writes in the reference) ----
+SAFE_WEIGHTS_NAME = "model.safetensors"
+SAFE_WEIGHTS_INDEX_NAME = "model.safetensors.index.json"
+
+
+def _parse_size(size) -> int:
+    if isinstance(size, int):
+        return size
+    s = str(size).upper().strip()
+    for unit, mul in (("GIB", 2 ** 30), ("MIB", 2 ** 20), ("KIB", 2 ** 10), ("GB", 10 ** 9), ("MB", 10 ** 6), ("KB", 10 ** 3)):
+        if s.endswith(unit):
+            return int(float(s[:-len(unit)]) * mul)
+    return int(s)
+
+
+def shard_state_dict(state_dict: Dict[str, torch.Tensor], max_shard_size="5GB"):
+    """Greedy split in key order with huggingface_hub's rules (split_state_dict_into_shards_factory, which
+    transformers' save_pretrained calls): a tensor larger than max_shard_size gets a shard of its own
+    WITHOUT closing the shard being filled; any other tensor that would push the current shard over the
+    limit closes it first.  → ({file: {name: tensor}}, index-or-None)."""
+    limit = _parse_size(max_shard_size)
+    shards, cur, cur_size, total = [], {}, 0, 0
+    for k, v in state_dict.items():
+        n = v.numel() * v.element_size()
+        total += n
+        if n > limit:
+            shards.append({k: v})
+            continue
+        if cur_size + n > limit:
+            shards.append(cur)
+            cur, cur_size = {}, 0
+        cur[k] = v
+        cur_size += n
+    if cur:
+        shards.append(cur)
+    if len(shards) <= 1:
+        return {SAFE_WEIGHTS_NAME: shards[0] if shards else {}}, None
+    files, weight_map = {}, {}
+    for i, sh in enumerate(shards):
+        name = f"model-{i + 1:05d}-of-{len(shards):05d}.safetensors"
+        files[name] = sh
+        for k in sh:
+            weight_map[k] = name
+    return files, {"metadata": {"total_size": total}, "weight_map": weight_map}
+
+
+def save_pretrained_weights(state_dict: Dict[str, torch.Tensor], output_dir: str, max_shard_size="5GB"):
+    """model.safetensors, or model-0000i-of-0000N.safetensors + model.safetensors.index.json — the
+    layout `from_pretrained` (builder.py:58-138) reads."""
+    from safetensors.torch import save_file
+
+    os.makedirs(output_dir, exist_ok=True)
+    files, index = shard_state_dict({k: v.detach().cpu().contiguous() for k, v in state_dict.items()}, max_shard_size)
+    for name, sh in files.items():
+        save_file(sh, os.path.join(output_dir, name), metadata={"format": "pt"})
+    if index is not None:
+        with open(os.path.join(output_dir, SAFE_WEIGHTS_INDEX_NAME), "w") as fh:
+            fh.write(json.dumps(index, indent=2, sort_keys=True) + "\n")
+    return sorted(files)
+
+
+def load_pretrained_weights(model_dir: str) -> Dict[str, torch.Tensor]:
+    """Reads either layout back (also a legacy pytorch_model.bin)."""
+    from safetensors.torch import load_file
+
+    idx = os.path.join(model_dir, SAFE_WEIGHTS_INDEX_NAME)
+    if os.path.exists(idx):
+        with open(idx) as fh:
+            wm = json.load(fh)["weight_map"]
+        out = {}
+        for name in sorted(set(wm.values())):
+            out.update(load_file(os.path.join(model_dir, name)))
+        return {k: out[k] for k in wm}
+    one = os.path.join(model_dir, SAFE_WEIGHTS_NAME)
+    if os.path.exists(one):
+        return load_file(one)
+    return torch.load(os.path.join(model_dir, "pytorch_model.bin"), map_location="cpu")

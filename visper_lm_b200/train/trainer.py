@@ -358,4 +358,5 @@ class LLaVATrainer:
 
             sd = state_dict if state_dict is not None else {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
             ckpt.save_config(self.model.config, output_dir)
-            torch.save(sd, os.path.join(output_dir, "pytorch_model.bin"))
+            # HF save_pretrained layout (safetensors, 5 GB shards + index) so builder.py / from_pretrained load it
+            ckpt.save_pretrained_weights(sd, output_dir, getattr(self.args, "max_shard_size", "5GB"))
