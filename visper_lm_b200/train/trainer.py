@@ -52,6 +52,7 @@ class TrainingArguments:
     group_by_modality_length: bool = False
     model_max_length: int = 4096
     dataloader_num_workers: int = 0
+    dataloader_prefetch_factor: int = 2
     zero_stage: int = 2
     seed: int = 42
 
@@ -291,9 +292,33 @@ class LLaVATrainer:
         B = a.per_device_train_batch_size
         order = self._index_order(epoch)
         nb = len(order) // (B * self.world)  # drop the ragged tail (dataloader_drop_last semantics)
-        for k in range(skip, nb):
+        def build(k):
             s = (k * self.world + self.rank) * B
-            yield self.data_collator([self.train_dataset[j] for j in order[s:s + B]])
+            return self.data_collator([self.train_dataset[j] for j in order[s:s + B]])
+
+        workers = int(getattr(a, "dataloader_num_workers", 0) or 0)
+        if workers <= 0:
+            for k in range(skip, nb):
+                yield build(k)
+            return
+        # dataloader_num_workers (pretrain.sh: 4): image decode / preprocessing / collation of the next
+        # batches runs on host threads while the GPU executes the current step; batches come back in order
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+
+        depth = workers * int(getattr(a, "dataloader_prefetch_factor", 2) or 2)
+        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="vpb-data") as pool:
+            pending = deque()
+            nxt = skip
+            try:
+                while nxt < nb or pending:
+                    while nxt < nb and len(pending) < depth:
+                        pending.append(pool.submit(build, nxt))
+                        nxt += 1
+                    yield pending.popleft().result()
+            finally:
+                for f in pending:
+                    f.cancel()
 
     def steps_per_epoch(self):
         return len(self.train_dataset) // (self.args.per_device_train_batch_size * self.world)
