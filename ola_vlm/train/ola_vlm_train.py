@@ -1,6 +1,8 @@
 """Drop-in path of the pieces of ola_vlm/train/ola_vlm_train.py that sit on the training-step path:
-the supervised collator (:881-925) and the end-of-run save (:228-263)."""
+the dataset / collator / data module (:774-937), the prompt preprocessing (:350-548) and the
+end-of-run save (:228-263)."""
 from visper_lm_b200.train.checkpoint import safe_save_model_for_hf_trainer  # noqa: F401
-from visper_lm_b200.train.data import DataCollatorForSupervisedDataset  # noqa: F401
+from visper_lm_b200.train.data import (DataArguments, DataCollatorForSupervisedDataset,  # noqa: F401
+                                       LazySupervisedDataset, make_supervised_data_module)
 from visper_lm_b200.train.prompts import (preprocess_llama_3, preprocess_multimodal,  # noqa: F401,E402
                                           preprocess_phi_3)

@@ -5,8 +5,9 @@
   * `tokenizer_image_token` (ola_vlm/mm_utils.py:336-355) — `<image>` → IMAGE_TOKEN_INDEX splice;
   * the supervised collator (ola_vlm/train/ola_vlm_train.py:881-925) — the batch schema the model
     boundary consumes (SURVEY.md §8b);
-  * a synthetic dataset in `LazySupervisedDataset.__getitem__`'s item schema (:811-878) for runs
-    without the LLaVA json / image folders.
+  * `LazySupervisedDataset` / `make_supervised_data_module` (:774-878, 928-937): LLaVA json / jsonl +
+    image folder → items, equal to the reference class on the same files (tests/test_lazy_dataset.py);
+  * a synthetic dataset in the same item schema for runs without the json / image folders.
 Prompt templating and label masking live in train/prompts.py.
 """
 from __future__ import annotations
@@ -149,6 +150,125 @@ class DataCollatorForSupervisedDataset:
 
 
 # ------------------------------------------------------------------------------------------------ dataset
+@dataclass
+class DataArguments:
+    """ola_vlm_train.py:111-118 (+ the fields train() attaches: image_processor, mm_use_im_start_end)."""
+    data_path: Optional[str] = None
+    lazy_preprocess: bool = False
+    is_multimodal: bool = False
+    image_folder: Optional[str] = None
+    image_aspect_ratio: str = "square"
+    image_processor: object = None
+    mm_use_im_start_end: bool = False
+    version: str = "llava_llama_3"   # --version: selects the chat template (conversation_lib.default_conversation)
+
+
+def read_jsonl(path):
+    import json
+
+    with open(path, "r") as fh:
+        return [json.loads(line) for line in fh]
+
+
+def expand2square(pil_img, background_color):
+    """Pad to a square on the mean colour (ola_vlm_train.py:826-838, image_aspect_ratio == 'pad')."""
+    from PIL import Image
+
+    w, h = pil_img.size
+    if w == h:
+        return pil_img
+    side = max(w, h)
+    out = Image.new(pil_img.mode, (side, side), background_color)
+    out.paste(pil_img, (0, (w - h) // 2) if w > h else ((h - w) // 2, 0))
+    return out
+
+
+class LazySupervisedDataset(torch.utils.data.Dataset):
+    """ola_vlm_train.py:774-878: JSON / JSONL conversations, images opened on access, preprocessed with
+    the tower's image processor, prompts rendered + label-masked by the llama3 / phi3 template; text-only
+    samples of a multimodal run get a black image and zero distillation masks."""
+
+    def __init__(self, data_path: str, tokenizer, data_args):
+        import json
+
+        super().__init__()
+        self.list_data_dict = read_jsonl(data_path) if "jsonl" in data_path else json.load(open(data_path, "r"))
+        self.tokenizer = tokenizer
+        self.data_args = data_args
+
+    def __len__(self):
+        return len(self.list_data_dict)
+
+    @property
+    def lengths(self):
+        return [sum(len(c["value"].split()) for c in s["conversations"]) + (128 if "image" in s else 0)
+                for s in self.list_data_dict]
+
+    @property
+    def modality_lengths(self):
+        out = []
+        for s in self.list_data_dict:
+            n = sum(len(c["value"].split()) for c in s["conversations"])
+            out.append(n if "image" in s else -n)
+        return out
+
+    def _crop_size(self):
+        proc = self.data_args.image_processor
+        size = getattr(proc, "crop_size", None) or proc.size
+        return size
+
+    def _preprocess(self, sources, has_image):
+        from . import prompts as P
+
+        version = getattr(self.data_args, "version", "llava_llama_3")
+        if "phi" in version:
+            return P.preprocess_phi_3(sources, self.tokenizer, has_image=has_image)
+        if "llama_3" in version or "llama3" in version:
+            return P.preprocess_llama_3(sources, self.tokenizer, has_image=has_image)
+        raise NotImplementedError(f"chat template {version!r}: only the llama3 / phi3 templates are on the shipped path")
+
+    def __getitem__(self, i) -> Dict[str, torch.Tensor]:
+        import copy
+        import os
+
+        from PIL import Image
+
+        from . import prompts as P
+
+        sample = self.list_data_dict[i]
+        has_image = "image" in sample
+        if has_image:
+            path = os.path.join(self.data_args.image_folder, sample["image"])
+            proc = self.data_args.image_processor
+            image = Image.open(path).convert("RGB")
+            pil_image = Image.open(path).convert("RGB")
+            if self.data_args.image_aspect_ratio == "pad":
+                image = expand2square(image, tuple(int(x * 255) for x in proc.image_mean))
+            image = proc.preprocess(image, return_tensors="pt")["pixel_values"][0]
+            sources = P.preprocess_multimodal(copy.deepcopy([sample["conversations"]]),
+                                              is_multimodal=self.data_args.is_multimodal,
+                                              mm_use_im_start_end=self.data_args.mm_use_im_start_end)
+        else:
+            sources = copy.deepcopy([sample["conversations"]])
+        d = self._preprocess(sources, has_image)
+        out = dict(input_ids=d["input_ids"][0], labels=d["labels"][0])
+        if has_image:
+            out.update(image=image, pil_image=pil_image, seg_mask=1, depth_mask=1, gen_mask=1)
+        elif self.data_args.is_multimodal:
+            cs = self._crop_size()
+            out.update(image=torch.zeros(3, cs["height"], cs["width"]),
+                       pil_image=Image.new("RGB", (cs["width"], cs["height"]), color="black"),
+                       seg_mask=0, depth_mask=0, gen_mask=0)
+        return out
+
+
+def make_supervised_data_module(tokenizer, data_args) -> Dict:
+    """ola_vlm_train.py:928-937."""
+    return dict(train_dataset=LazySupervisedDataset(tokenizer=tokenizer, data_path=data_args.data_path,
+                                                    data_args=data_args),
+                eval_dataset=None, data_collator=DataCollatorForSupervisedDataset(tokenizer=tokenizer))
+
+
 class SyntheticSupervisedDataset(torch.utils.data.Dataset):
     """Items in LazySupervisedDataset.__getitem__'s schema with seeded synthetic content
     (SURVEY.md §8d): one image token at `n_sys`, labels masked up to n_sys+8, N(0,1) image."""
