@@ -82,3 +82,30 @@ def test_init_target_models_needs_weights_or_opt_in():
     M.init_target_models(h, cfg)
     assert sum(p.numel() for p in h.dav2_backbone.pretrained.parameters()) == 304_368_640   # DINOv2-L
     assert not any(p.requires_grad for p in h.dav2_backbone.parameters())
+
+
+def test_target_tiling_matches_reference_emb_loss():
+    """Fewer target rows than predictions (base_ola_vlm.py:292-299): product helper and oracle tile the
+    way the reference's own _emb_loss does."""
+    from oracle import ref_shim, restate
+    from visper_lm_b200.model.vlm import tile_targets
+
+    g = torch.Generator().manual_seed(0)
+    preds = torch.randn(4, 6, 8, generator=g)
+    tgt = torch.randn(2, 6, 8, generator=g)
+    mask = torch.tensor([1, 0])
+    t2, m2 = tile_targets(tgt, mask, 4)
+    assert torch.equal(t2, torch.cat([tgt, tgt])) and m2.tolist() == [1, 0, 1, 0]
+    t3, m3 = tile_targets(tgt, torch.ones(4), 4)
+    assert m3.shape == (4,) and torch.equal(t3, t2)
+    same, msame = tile_targets(preds, mask, 4)
+    assert same is preds and msame is mask
+    scale = torch.tensor(2.0)
+    mine = restate.emb_loss(preds, mask, tgt, scale)
+    want = restate.emb_loss(preds, m2, t2, scale)
+    assert all(torch.equal(a, b) for a, b in zip(mine, want))
+    if ref_shim.available():
+        R = ref_shim.load()
+        ref = R.base.BaseOLA_VLM._emb_loss(SimpleNamespace(contrastive_loss_weight=0.3), preds, mask, tgt, scale)
+        for a, b in zip(mine, ref):
+            assert abs(float(a) - float(b)) < 1e-6

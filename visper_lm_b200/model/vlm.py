@@ -310,6 +310,17 @@ class HeadPlan:
             self.gen_index = None
 
 
+def tile_targets(tgt, mask, B):
+    """_emb_loss (base_ola_vlm.py:292-299): teacher targets (and their mask) with fewer rows than the
+    predictions — fewer images than samples — are tiled along the batch and cut to B rows."""
+    if tgt is not None and tgt.shape[0] != B:
+        rf = max(1, B // tgt.shape[0])
+        tgt = tgt.repeat(rf, *([1] * (tgt.dim() - 1)))[:B]
+        if mask is not None and mask.shape[0] != B:
+            mask = mask.reshape(-1).repeat(rf)[:B]
+    return tgt, mask
+
+
 def gather_targets(tgt_flat, group=None):
     """dist_collect (ola_utils.py:96-106) for the InfoNCE negatives: all-gather of the rank-local
     targets [B, n] → ([world·B, n], offset of the local rows = rank·B, cf. ola_utils.py:111).
@@ -860,6 +871,7 @@ class VisperForCausalLM(nn.Module):
             tgt = self._targets(task, pil_images, distill_targets, dev)
             tgt_all = off = None
             if tgt is not None:
+                tgt, masks[task] = tile_targets(tgt, masks.get(task), B)
                 tgt = tgt.to(dev, BF16)
                 if task == "seg" and tgt.dim() == 4:  # [B,C,24,24] → token-major [B,576,C] (head layout)
                     Bc, C = tgt.shape[0], tgt.shape[1]
@@ -872,6 +884,8 @@ class VisperForCausalLM(nn.Module):
                     tgt_flat = tgt.reshape(tgt.shape[0], -1).contiguous()
                 tgt_all, off = self._gather_targets(tgt_flat)
             mask = masks.get(task)
+            if tgt is not None and tgt.shape[0] != B:
+                raise ValueError(f"{task} targets: {tgt.shape[0]} rows cannot be tiled to a batch of {B}")
             for i, idx in enumerate(getattr(self, idx_name)):
                 head = heads[i]
                 n_lat = 1 if task == "gen" else special.shape[0]
