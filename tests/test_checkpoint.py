@@ -229,3 +229,34 @@ def test_prefetching_workers_keep_batch_order_and_results(tmp_path):
     it = pre._batches(0, 0)   # abandoning the iterator early must not hang or leak the pool
     next(it)
     it.close()
+
+
+def test_loads_plain_hf_llama_and_clip_checkpoints(tmp_path):
+    """A stock HF Llama checkpoint (sharded safetensors) loads into the product's decoder by name, the
+    multimodal modules keep their fresh init; a stock HF CLIP vision checkpoint loads into the tower."""
+    from transformers import CLIPVisionConfig, CLIPVisionModel, LlamaConfig, LlamaForCausalLM
+
+    from visper_lm_b200.model import LlavaLlamaForCausalLM
+
+    torch.manual_seed(1)
+    hf = LlamaForCausalLM(LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                                      num_attention_heads=4, num_key_value_heads=2, tie_word_embeddings=False,
+                                      max_position_embeddings=256, rope_theta=500000.0))
+    hf.save_pretrained(tmp_path / "llm", max_shard_size="60KB", safe_serialization=True)
+    vis = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2, image_size=28, patch_size=14)
+    model = LlavaLlamaForCausalLM.from_pretrained(str(tmp_path / "llm"), vision=vis)
+    own = model.state_dict()
+    for k, v in hf.state_dict().items():
+        assert torch.equal(own[k].float(), v.to(torch.bfloat16).float()), k
+    assert model.config.num_key_value_heads == 2 and model.config.rope_theta == 500000.0
+    clip = CLIPVisionModel(CLIPVisionConfig(**vis))
+    clip.save_pretrained(tmp_path / "clip", safe_serialization=True)
+    tower = model.get_vision_tower()
+    tower.load_model(path=str(tmp_path / "clip"))
+    for k, v in clip.state_dict().items():
+        if k in tower.vision_tower.state_dict():
+            assert torch.equal(tower.vision_tower.state_dict()[k].float(), v.to(torch.bfloat16).float()), k
+    assert tower.is_loaded and not any(p.requires_grad for p in tower.parameters())
+    import pytest
+    with pytest.raises(KeyError):
+        tower.load_model(path=str(tmp_path / "llm"))

@@ -248,8 +248,28 @@ class CLIPVisionTower(nn.Module):
         self._patch_w = None
         self._drop_cls = {}
 
-    def load_model(self, device_map=None):
-        return
+    def load_model(self, device_map=None, path=None):
+        """clip_encoder.py:27-35: load the frozen tower's weights.  `path` (or `vision_tower_name`) is a
+        local HF CLIPVisionModel / CLIPModel directory (model.safetensors, its shards or
+        pytorch_model.bin); only the `vision_model.*` tensors are read.  Without a path this is a no-op
+        (the modules already exist; tests and benchmarks initialise them directly)."""
+        import os
+
+        path = path or getattr(self, "vision_tower_name", None)
+        if not path or not os.path.isdir(str(path)):
+            return
+        from ..train.checkpoint import load_pretrained_weights
+
+        sd = load_pretrained_weights(str(path))
+        own = self.vision_tower.state_dict()
+        picked = {k: v for k, v in sd.items() if k in own}
+        missing = [k for k in own if k not in picked]
+        if missing:
+            raise KeyError(f"{path}: CLIP vision weights missing {missing[:4]} (+{max(0, len(missing) - 4)} more)")
+        self.vision_tower.load_state_dict(picked)
+        self.vision_tower.requires_grad_(False)
+        self._patch_w = None
+        self.is_loaded = True
 
     @property
     def config(self):

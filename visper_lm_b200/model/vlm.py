@@ -407,11 +407,18 @@ class VisperForCausalLM(nn.Module):
         if self.distill and hasattr(config, "image_gen"):
             self.init_heads(config)
 
+    # parameters a plain HF Llama-3 / Phi-3 checkpoint does not have: they keep their fresh init, as with
+    # the reference's `from_pretrained(base_llm)` (ola_vlm_train.py:1007-1021)
+    NEW_MODULE_KEYS = ("model.mm_projector.", "model.vision_tower.", "model.special_", "image_gen_heads.",
+                       "image_depth_heads.", "image_seg_heads.", "_logit_scale", "da_v2_head.")
+
     @classmethod
     def from_pretrained(cls, model_dir, device=None, **config_overrides):
         """Load what `trainer._save` / `save_pretrained` wrote (config.json + model.safetensors or its
-        5 GB shards + index; builder.py:58-138 loads the reference's models the same way).  Teacher
-        submodules are not part of the architecture: call init_target_models afterwards if needed."""
+        5 GB shards + index; builder.py:58-138 loads the reference's models the same way) — or a plain
+        HF Llama-3 / Phi-3 checkpoint, whose config keys and tensor names are the same; the multimodal
+        modules it lacks stay freshly initialised.  Teacher submodules are not part of the architecture:
+        call init_target_models afterwards if needed."""
         import json
         import os
 
@@ -421,15 +428,16 @@ class VisperForCausalLM(nn.Module):
             d = json.load(fh)
         d.pop("model_type", None)
         d.pop("family", None)
+        d.pop("architectures", None)
         d.update(config_overrides)
         model = cls(cls.config_class(**d), device=device)
         sd = load_pretrained_weights(model_dir)
         own = model.state_dict()
-        missing = [k for k in own if k not in sd]
+        missing = [k for k in own if k not in sd and not any(t in k for t in cls.NEW_MODULE_KEYS)]
         unexpected = [k for k in sd if k not in own and not k.startswith(("dav2_backbone.", "oneformer."))]
         if missing or unexpected:
             raise KeyError(f"checkpoint does not match {cls.__name__}: missing {missing[:5]}, unexpected {unexpected[:5]}")
-        model.load_state_dict({k: v for k, v in sd.items() if k in own})
+        model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
         return model
 
     # ---- reference accessors ---------------------------------------------------------------
