@@ -260,3 +260,33 @@ def test_loads_plain_hf_llama_and_clip_checkpoints(tmp_path):
     import pytest
     with pytest.raises(KeyError):
         tower.load_model(path=str(tmp_path / "llm"))
+
+
+def test_distill_model_on_top_of_a_plain_llm_checkpoint(tmp_path):
+    """The train() recipe (ola_vlm_train.py:1007-1021,1149-1266): base LLM from a stock checkpoint, aux
+    config injected, task tokens + heads created and initialised without touching the loaded weights."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from visper_lm_b200.model import OlaLlavaLlamaForCausalLM
+
+    hf = LlamaForCausalLM(LlamaConfig(vocab_size=160, hidden_size=64, intermediate_size=128, num_hidden_layers=4,
+                                      num_attention_heads=4, num_key_value_heads=2, tie_word_embeddings=False))
+    hf.save_pretrained(tmp_path, safe_serialization=True)
+    vis = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2, image_size=28, patch_size=14)
+    m = OlaLlavaLlamaForCausalLM.from_pretrained(str(tmp_path), vision=vis)
+    assert not hasattr(m, "image_depth_heads")
+    m.config.inject_aux(mode="gen-depth-seg", layer_indices="d2-3_s1-2_g2-3", num_task_tokens=8, gen_dim=32,
+                        seg_dim=48, depth_dim=32)
+    m.get_model().initialize_special_tokens(m.config)
+    m.init_heads(m.config)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if any(t in n for t in m.NEW_MODULE_KEYS):
+                p.fill_(float("nan"))
+    m.init_weights(seed=3, only=m.NEW_MODULE_KEYS)
+    sd = m.state_dict()
+    assert all(torch.isfinite(v.float()).all() for v in sd.values())
+    for k, v in hf.state_dict().items():
+        assert torch.equal(sd[k].float(), v.to(torch.bfloat16).float()), k       # loaded LLM untouched
+    assert m.depth_layer_indices == [1, 2] and float(m.depth_logit_scale) == 2.0
+    assert abs(float(m.model.special_depth_tokens.float().std()) - 1.0) < 0.1    # randn task tokens (ola_arch.py:77-93)

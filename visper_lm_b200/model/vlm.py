@@ -676,10 +676,14 @@ class VisperForCausalLM(nn.Module):
 
     # ---- weights -----------------------------------------------------------------------------
     @torch.no_grad()
-    def init_weights(self, seed_fn=None, std=0.02, seed=0):
-        """Random init (HF std=0.02 style) or deterministic by-name init (tests: seed_fn(name, shape))."""
+    def init_weights(self, seed_fn=None, std=0.02, seed=0, only=None):
+        """Random init (HF std=0.02 style) or deterministic by-name init (tests: seed_fn(name, shape)).
+        only: substrings selecting the parameters to touch — `only=self.NEW_MODULE_KEYS` initialises the
+        projector / task tokens / heads added on top of a loaded LLM and leaves the loaded weights alone."""
         g = torch.Generator(device="cpu").manual_seed(seed)
         for name, p in self.named_parameters():
+            if only is not None and not any(t in name for t in only):
+                continue
             if seed_fn is not None:
                 p.copy_(seed_fn(name, tuple(p.shape)).to(p.dtype))
                 continue
