@@ -121,3 +121,40 @@ def test_plans_small_cases():
     assert torch.equal(shift_mask(8, 8, 4, 2), restate.swin_shift_mask(8, 8, 4, 2))
     idx, H2, W2 = merge_plans(1, 5, 4)
     assert (H2, W2) == (3, 2) and idx[1].tolist() == [4, 6, 12, 14, -1, -1] and idx[3].tolist() == [5, 7, 13, 15, -1, -1]
+
+
+def test_plans_property_random_grids():
+    """hypothesis: for random grids / window sizes / shifts the gather plans equal F.pad → torch.roll →
+    window_partition (and its inverse), the shift mask equals HF's get_attn_mask, and the merge plans equal
+    SwinPatchMerging's strided slices."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from visper_lm_b200.model.seg_teacher import merge_plans, shift_mask, window_plans
+
+    @settings(max_examples=60, deadline=None)
+    @given(B=st.integers(1, 3), H=st.integers(1, 23), W=st.integers(1, 23), ws=st.sampled_from([2, 3, 4, 7, 12]),
+           shifted=st.booleans())
+    def check(B, H, W, ws, shifted):
+        shift = ws // 2 if shifted else 0
+        part, rev, Hp, Wp = window_plans(B, H, W, ws, shift)
+        x = torch.arange(B * H * W, dtype=torch.float32).view(B, H, W) + 1
+        ref = F.pad(x, (0, Wp - W, 0, Hp - H))
+        if shift:
+            ref = torch.roll(ref, (-shift, -shift), (1, 2))
+        win = ref.view(B, Hp // ws, ws, Wp // ws, ws).permute(0, 1, 3, 2, 4).reshape(-1)
+        got = torch.where(part >= 0, x.reshape(-1)[part.long().clamp_min(0)], torch.zeros(()))
+        assert torch.equal(got, win)
+        back = win.view(B, Hp // ws, Wp // ws, ws, ws).permute(0, 1, 3, 2, 4).reshape(B, Hp, Wp)   # window_reverse
+        if shift:
+            back = torch.roll(back, (shift, shift), (1, 2))
+        assert torch.equal(win[rev.long()], back[:, :H, :W].reshape(-1))
+        if shift:
+            assert torch.equal(shift_mask(Hp, Wp, ws, shift), restate.swin_shift_mask(Hp, Wp, ws, shift))
+        idx, H2, W2 = merge_plans(B, H, W)
+        xp = F.pad(x, (0, W % 2, 0, H % 2))
+        for ix, sl in zip(idx, (xp[:, 0::2, 0::2], xp[:, 1::2, 0::2], xp[:, 0::2, 1::2], xp[:, 1::2, 1::2])):
+            g = torch.where(ix >= 0, x.reshape(-1)[ix.long().clamp_min(0)], torch.zeros(()))
+            assert (H2, W2) == tuple(sl.shape[1:]) and torch.equal(g, sl.reshape(-1))
+
+    check()
