@@ -69,14 +69,19 @@ class _Interrupted(Exception):
 
 def _train_until(tr, n_steps):
     """Run `tr.train()` and kill it when step n_steps+1 starts (a crash after checkpoint-n)."""
-    real = tr.step
+    real, real_acc = tr.step, tr.accumulated_step
 
     def step(batch):
         if tr.state["global_step"] >= n_steps:
             raise _Interrupted()
         return real(batch)
 
-    tr.step = step
+    def acc_step(micro):
+        if tr.state["global_step"] >= n_steps:
+            raise _Interrupted()
+        return real_acc(micro)
+
+    tr.step, tr.accumulated_step = step, acc_step
     with pytest.raises(_Interrupted):
         tr.train()
 
@@ -290,3 +295,46 @@ def test_distill_model_on_top_of_a_plain_llm_checkpoint(tmp_path):
         assert torch.equal(sd[k].float(), v.to(torch.bfloat16).float()), k       # loaded LLM untouched
     assert m.depth_layer_indices == [1, 2] and float(m.depth_logit_scale) == 2.0
     assert abs(float(m.model.special_depth_tokens.float().std()) - 1.0) < 0.1    # randn task tokens (ola_arch.py:77-93)
+
+
+def test_gradient_accumulation_equals_the_big_batch(tmp_path):
+    """gradient_accumulation_steps=2 at per-device batch 2 takes the same optimizer steps as batch 4 without
+    accumulation: every step covers the same length-grouped mega-batch, the losses are averaged over the
+    micro-batches (HF Trainer semantics) — parameters agree to bf16 gradient rounding; resume works."""
+    from visper_lm_b200.train.trainer import LLaVATrainer, TrainingArguments
+
+    _install_test_doubles()
+
+    def make(out, B, ga, **kw):
+        torch.manual_seed(0)
+        # equal text lengths: the toy loss averages over the padded length, so padding must not differ
+        ds = SyntheticSupervisedDataset(64, vocab=300, n_sys=13, min_text=30, max_text=30, image_size=8,
+                                        distill=False, text_only_every=4, seed=5)
+        tok = types.SimpleNamespace(pad_token_id=0, model_max_length=64)
+        args = TrainingArguments(output_dir=str(out), per_device_train_batch_size=B, gradient_accumulation_steps=ga,
+                                 learning_rate=1e-2, max_steps=6, save_steps=3, tune_mm_mlp_adapter=True,
+                                 group_by_modality_length=True, logging_steps=1, **kw)
+        return LLaVATrainer(model=ToyVLM(), args=args, train_dataset=ds, data_collator=DataCollatorForSupervisedDataset(tok))
+
+    big = make(tmp_path / "big", 4, 1)
+    acc = make(tmp_path / "acc", 2, 2)
+    assert big.steps_per_epoch() == acc.steps_per_epoch() == 16
+    for k in range(3):   # each optimizer step sees the same 4 samples
+        a = sorted(big._index_order(0)[k * 4:(k + 1) * 4])
+        b = sorted(acc._index_order(0)[k * 4:(k + 1) * 4])
+        assert a == b
+    big.train()
+    acc.train()
+    assert acc.state["global_step"] == big.state["global_step"] == 6
+    pa, pb = _params(big), _params(acc)
+    for n in pa:
+        assert torch.allclose(pa[n].float(), pb[n].float(), atol=2e-2, rtol=5e-2), n
+    la, lb = [h["loss"] for h in big.state["log_history"]], [h["loss"] for h in acc.state["log_history"]]
+    assert all(abs(x - y) <= 0.05 * abs(x) + 1e-3 for x, y in zip(la, lb))
+    part = make(tmp_path / "acc2", 2, 2)
+    _train_until(part, 3)
+    resumed = make(tmp_path / "acc2", 2, 2)
+    resumed.train(resume_from_checkpoint=True)
+    pc = _params(resumed)
+    for n in pb:
+        assert torch.equal(pb[n], pc[n]), n

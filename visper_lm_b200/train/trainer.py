@@ -261,6 +261,27 @@ class LLaVATrainer:
         self.state["global_step"] += 1
         return loss, out
 
+    def accumulated_step(self, micro_batches):
+        """gradient_accumulation_steps > 1 (HF Trainer semantics): each micro-batch's loss is divided by
+        the number of micro-batches before backward, gradients add up in p.grad, one optimizer step."""
+        opt = self.create_optimizer()
+        opt.zero_grad()
+        k = len(micro_batches)
+        total = None
+        for mb in micro_batches:
+            out = self.model(**self._to_device(mb))
+            (out.loss / k).backward()
+            total = out.loss.detach() / k if total is None else total + out.loss.detach() / k
+        a = self.args
+        steps = self.total_steps or max(1, a.max_steps)
+        warm = math.ceil(steps * a.warmup_ratio)
+        mult = cosine_with_warmup(self.state["global_step"], steps, warm) if a.lr_scheduler_type == "cosine" else 1.0
+        if self.total_steps is None and a.max_steps <= 0:
+            mult = 1.0
+        opt.step(lr_mult=mult)
+        self.state["global_step"] += 1
+        return total, out
+
     def _index_order(self, epoch):
         """Global sample order of one epoch.  --group_by_modality_length → the reference's
         LengthGroupedSampler (llava_trainer.py:219-232) with batch = per-device batch and world =
@@ -292,6 +313,9 @@ class LLaVATrainer:
         B = a.per_device_train_batch_size
         order = self._index_order(epoch)
         nb = len(order) // (B * self.world)  # drop the ragged tail (dataloader_drop_last semantics)
+        ga = max(1, int(a.gradient_accumulation_steps))
+        nb -= nb % ga                        # whole optimizer steps only
+        skip *= ga                           # `skip` counts optimizer steps
         def build(k):
             s = (k * self.world + self.rank) * B
             return self.data_collator([self.train_dataset[j] for j in order[s:s + B]])
@@ -321,7 +345,8 @@ class LLaVATrainer:
                     f.cancel()
 
     def steps_per_epoch(self):
-        return len(self.train_dataset) // (self.args.per_device_train_batch_size * self.world)
+        return len(self.train_dataset) // (self.args.per_device_train_batch_size * self.world
+                                           * max(1, int(self.args.gradient_accumulation_steps)))
 
     def train(self, resume_from_checkpoint=None):
         from . import checkpoint as ckpt
@@ -341,8 +366,17 @@ class LLaVATrainer:
         done = self.state["global_step"]
         while done < self.total_steps:
             epoch, skip = divmod(done, per_epoch)
+            ga = max(1, int(a.gradient_accumulation_steps))
+            micro = []
             for batch in self._batches(epoch, skip):  # a resumed run skips the batches already consumed
-                loss, _ = self.step(batch)
+                if ga == 1:
+                    loss, _ = self.step(batch)
+                else:
+                    micro.append(batch)
+                    if len(micro) < ga:
+                        continue
+                    loss, _ = self.accumulated_step(micro)
+                    micro = []
                 done += 1
                 if done % a.logging_steps == 0:
                     last = float(loss)  # the only host sync, outside forward (cf. ola_llama.py:146-168)
