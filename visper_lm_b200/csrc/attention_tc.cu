@@ -46,7 +46,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <bool CAUSAL, int HD>
+// POLY (EXPERIMENTAL, VPB_OPT_ATTN_POLY_EXP2, off by default, not yet measured on hardware): every fourth
+// exponential of the softmax goes through ex2_poly on the FMA pipe instead of MUFU ex2.approx.
+template <bool CAUSAL, int HD, bool POLY = false>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -238,7 +240,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int c = 0; c < 64; c += 4) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
+          float pv;
+          if constexpr (POLY) {
+            const float xs = fmaf(__uint_as_float(r[c + e]), sl2, -mb);
+            pv = (e == 3) ? ex2_poly(xs) : ex2_approx(xs);
+          } else {
+            pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
+          }
           sum4[e] += pv;
           r[c + e] = __float_as_uint(pv);
         }
@@ -679,13 +687,24 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
     VPB_LAUNCH_OK();
     return 0;
   }
+  dim3 grid((p.sq + tc::BM - 1) / tc::BM, p.H, p.B);
+  if (get_option(VPB_OPT_ATTN_POLY_EXP2)) {
+    auto kernp = attn_fwd_tc_kernel<CAUSAL, HD, true>;
+    static bool cfgp = false;
+    if (!cfgp) {
+      VPB_CUDA(cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      cfgp = true;
+    }
+    kernp<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    VPB_LAUNCH_OK();
+    return 0;
+  }
   auto kern = attn_fwd_tc_kernel<CAUSAL, HD>;
   static bool cfg = false;
   if (!cfg) {
     VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     cfg = true;
   }
-  dim3 grid((p.sq + tc::BM - 1) / tc::BM, p.H, p.B);
   kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
   VPB_LAUNCH_OK();
   return 0;
