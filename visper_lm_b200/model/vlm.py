@@ -280,7 +280,7 @@ class HeadPlan:
         t0 = S + 576 + nt * k
         end = S + 576 + nt * len(order)
         if nt == 0 or T < 600:
-            cols = np.arange(T) if pass_text else np.arange(S + 576)
+            cols = np.arange(T) if pass_text else np.arange(min(S + 576, T))  # the slice clamps at T
         else:
             parts = [np.arange(S + 576), np.arange(t0, t0 + nt)]
             if pass_text:
@@ -297,7 +297,8 @@ class HeadPlan:
         if task == "gen":
             # latents = the 8 hidden states of this task's tokens INSIDE inp_tokens
             # (base_ola_vlm.py:439: inp_tokens[:, S+576 : S+576+nt]), mean-pooled to 1 query
-            lat_cols = cols[S + 576:S + 576 + nt]
+            # (:437 without text in the head input: the LAST nt tokens of inp_tokens)
+            lat_cols = cols[S + 576:S + 576 + nt] if pass_text else cols[-nt:]
             gi = (np.arange(B)[:, None] * T + lat_cols[None, :])
             self.gen_index = t(gi.reshape(-1))
             self.nq = 1
