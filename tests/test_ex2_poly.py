@@ -60,3 +60,15 @@ def test_attention_forward_poly_exp2_matches_default(B, H, KVH, S, hd, causal):
         ops.set_option(ops.OPT_ATTN_POLY_EXP2, 0)
     assert ((o1.float() - o0.float()).norm() / o0.float().norm()).item() < 4e-3
     assert (l1 - l0).abs().max().item() < 2e-3
+    # backward (column-split tcgen05 kernels): same switch
+    do = torch.randn(B * S, H * hd, generator=g).to(torch.bfloat16).cuda()
+    d0, d1 = torch.empty_like(qkv), torch.empty_like(qkv)
+    sl = (slice(None), slice(0, H * hd)), (slice(None), slice(H * hd, (H + KVH) * hd)), (slice(None), slice((H + KVH) * hd, None))
+    ops.attn_bwd(q, k, v, o0, do, l0, d0[sl[0]], d0[sl[1]], d0[sl[2]], B, H, KVH, S, S, hd, hd ** -0.5, causal)
+    ops.set_option(ops.OPT_ATTN_POLY_EXP2, 1)
+    try:
+        ops.attn_bwd(q, k, v, o0, do, l0, d1[sl[0]], d1[sl[1]], d1[sl[2]], B, H, KVH, S, S, hd, hd ** -0.5, causal)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_ATTN_POLY_EXP2, 0)
+    assert ((d1.float() - d0.float()).norm() / d0.float().norm()).item() < 6e-3

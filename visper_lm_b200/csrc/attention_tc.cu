@@ -1299,7 +1299,8 @@ constexpr int B_SMEM = B_OFF_BAR + 256;
 // iteration, two per TMEM lane quarter splitting the 64 query columns — the exp / dS phase of one
 // group turned out to be the serial bottleneck (one warp per sub-partition issues ~0.26 IPC; the
 // timeline in profiles/r01_attn_dkdv_timeline_cta0.txt shows the two groups' phases do not overlap).
-template <bool CAUSAL, int HD, bool TS, bool SPLIT>
+// POLY: see attn_fwd_tc_kernel — every fourth exponential on the FMA pipe (column-split variant only).
+template <bool CAUSAL, int HD, bool TS, bool SPLIT, bool POLY = false>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1582,7 +1583,12 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = c4 * 4 + e;
-            s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e])));
+            if constexpr (POLY) {
+              const float xs = fmaf(__uint_as_float(s[c]), sl2, -lsv[e]);
+              s[c] = __float_as_uint(e == 3 ? ex2_poly(xs) : ex2_approx(xs));
+            } else {
+              s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e])));
+            }
             d[c] = __float_as_uint(__uint_as_float(d[c]) - dlv[e]);
           }
         }
@@ -1788,7 +1794,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 // dQ_i = scale * sum_j dS_ij K_j — two query tiles (heavy + light) per CTA, ping-pong groups
-template <bool CAUSAL, int HD, bool TS, bool SPLIT>
+template <bool CAUSAL, int HD, bool TS, bool SPLIT, bool POLY = false>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -2002,7 +2008,14 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tmem_ld32(TM_DP + lane_addr + sb * B_BKV + half * 32, d);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
+        for (int c = 0; c < 32; ++c) {
+          if constexpr (POLY) {
+            const float xs = fmaf(__uint_as_float(s[c]), sl2, -l2);
+            s[c] = __float_as_uint((c & 3) == 3 ? ex2_poly(xs) : ex2_approx(xs));
+          } else {
+            s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
+          }
+        }
         if (need_mask) {  // one warp-uniform branch per tile, never one per score
           const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
           const int vis = rok ? lim - (j0 + half * 32) : -1;                      // last visible column
@@ -2177,7 +2190,7 @@ static int launch_bwd_tc_v1(const void* q, int64_t ldq, const void* k, int64_t l
   return 0;
 }
 
-template <bool CAUSAL, int HD, bool TS, bool SPLIT>
+template <bool CAUSAL, int HD, bool TS, bool SPLIT, bool POLY = false>
 static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
                             cudaStream_t st) {
@@ -2190,7 +2203,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, A_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, A_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, A_BKV)) return -1;
-    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD, TS, SPLIT>;
+    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD, TS, SPLIT, POLY>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
@@ -2206,7 +2219,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, B_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, B_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, B_BKV)) return -1;
-    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS, SPLIT>;
+    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS, SPLIT, POLY>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
@@ -2232,10 +2245,12 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   // for head_dim 96; head_dim 128 can still fall back to the v1 kernels)
   const bool ss = get_option(VPB_OPT_ATTN_BWD_SS) != 0;
   const bool pingpong = get_option(VPB_OPT_ATTN_BWD_PINGPONG) != 0;
+  const bool poly = get_option(VPB_OPT_ATTN_POLY_EXP2) != 0;  // experimental, see ex2_poly
 #define VPB_BWD_V2(HDv)                                                                              \
   (ss ? launch_bwd_tc_v2<CAUSAL, HDv, false, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)          \
       : pingpong ? launch_bwd_tc_v2<CAUSAL, HDv, true, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st) \
-                 : launch_bwd_tc_v2<CAUSAL, HDv, true, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st))
+      : poly ? launch_bwd_tc_v2<CAUSAL, HDv, true, true, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)   \
+             : launch_bwd_tc_v2<CAUSAL, HDv, true, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st))
   // (a caller asking for the fused inverse RoPE only gets here with head_dim 128 on the v2 kernels:
   // attn_bwd_tc clears the request otherwise)
   if (head_dim == 96) return VPB_BWD_V2(96);
