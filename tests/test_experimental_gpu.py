@@ -1,0 +1,44 @@
+"""Kernel variants that were written after the round's GPU budget was spent: compiled and shipped OFF by
+default, NOT yet run on hardware.  Skipped unless VPB_TEST_EXPERIMENTAL=1 — the first GPU call of the next
+round runs `VPB_TEST_EXPERIMENTAL=1 pytest tests/test_experimental_gpu.py tests/test_ex2_poly.py -m gpu`."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("VPB_TEST_EXPERIMENTAL") != "1",
+                                 reason="experimental kernel variant, not yet validated on hardware")]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,H,S,nmask", [(8, 6, 144, 4), (3, 2, 144, 0), (18, 4, 16, 9), (5, 1, 16, 0), (4, 3, 100, 2),
+                                         (2, 2, 99, 2)])
+def test_one_pass_window_attention(B, H, S, nmask, variant):
+    """VPB_OPT_WIN_ATTN_V2: vpb_attn_fwd_bias on the one-pass kernel == torch fp32 and == the default kernel."""
+    from visper_lm_b200 import ops
+
+    hd = 32
+    g = torch.Generator().manual_seed(95 + S)
+    qkv = torch.randn(B * S, 3 * H * hd, generator=g).to(torch.bfloat16).cuda()
+    bias = (2.0 * torch.randn(H, S, S, generator=g)).cuda()
+    mask = None
+    if nmask:
+        mask = torch.where(torch.rand(nmask, S, S, generator=g) < 0.3, torch.tensor(-100.0), torch.tensor(0.0))
+        mask[:, torch.arange(S), torch.arange(S)] = 0.0
+        mask = mask.contiguous().cuda()
+    W = H * hd
+    base = ops.attn_fwd_bias(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, S, hd, hd ** -0.5, bias, mask)
+    ops.set_option(ops.OPT_WIN_ATTN_V2, variant)
+    try:
+        o = ops.attn_fwd_bias(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, S, hd, hd ** -0.5, bias, mask)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_WIN_ATTN_V2, 0)
+    q, k, v = (qkv.float()[:, i * W:(i + 1) * W].view(B, S, H, hd).transpose(1, 2) for i in range(3))
+    sc = q @ k.transpose(-1, -2) * hd ** -0.5 + bias[None]
+    if mask is not None:
+        sc = sc + mask[torch.arange(B) % nmask][:, None]
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, W)
+    assert ((o.float() - ref).norm() / ref.norm()).item() < 1.6e-2
+    assert ((o.float() - base.float()).norm() / base.float().norm()).item() < 1e-2

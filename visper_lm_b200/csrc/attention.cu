@@ -678,6 +678,159 @@ attn_bwd_dq_kernel(const AttnParams p) {
   }
 }
 
+// =============================================================================================
+// EXPERIMENTAL (VPB_OPT_WIN_ATTN_V2, off by default, not yet run on hardware): window attention with score
+// bias for windows of up to 144 tokens, head_dim 32.  One CTA per (window, head); nine warps own 16 query
+// rows each and see ALL keys in one pass (18 n-blocks of scores in registers), so there is no online
+// softmax, no second 128-row query tile with 16 live rows, and the bias comes in as float2 loads.
+// =============================================================================================
+constexpr int WIN_MAX = 144;
+// MINB = resident CTAs per SM the register budget is cut for: 2 → 96 registers and ~260 B of spills,
+// 1 → no spills but nine warps per SM; which one wins has to be measured.
+template <int MINB>
+__global__ void __launch_bounds__(288, MINB)
+win_attn_fwd_kernel(const AttnParams p) {
+  constexpr int HD = 32, CPR = Cfg<HD>::CPR, KS = Cfg<HD>::KS, ND = Cfg<HD>::ND, NT = 288, NB = WIN_MAX / 8;
+  __shared__ __align__(128) uint8_t smem[3 * WIN_MAX * HD * 2];
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + WIN_MAX * HD * 2;
+  const uint32_t sV = sK + WIN_MAX * HD * 2;
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int S = p.sq;  // == p.sk <= WIN_MAX
+
+  load_tile<WIN_MAX, HD, NT>(sQ, p.q + (int64_t)b * S * p.ldq + h * HD, p.ldq, S);
+  load_tile<WIN_MAX, HD, NT>(sK, p.k + (int64_t)b * S * p.ldk + h * HD, p.ldk, S);
+  load_tile<WIN_MAX, HD, NT>(sV, p.v + (int64_t)b * S * p.ldv + h * HD, p.ldv, S);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  uint32_t qf[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) ld_a<CPR>(qf[ks], sQ, warp * 16, ks, lane);
+  float s[NB][4];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int nb = 0; nb < NB; nb += 2) {
+      uint32_t bf[4];
+      ld_b<CPR>(bf, sK, nb, ks, lane);
+      mma16816(s[nb], qf[ks], bf);
+      mma16816(s[nb + 1], qf[ks], bf + 2);
+    }
+  }
+  // scores = scale * q.k + bias[h] (+ mask[window]); -inf outside the window.  Element (2r+c) of n-block nb
+  // is row g + 8r, column 8 nb + 2t + c.
+  const float* bh = p.bias + (int64_t)h * S * S;
+  const float* mw = p.bias_mask ? p.bias_mask + (int64_t)(b % p.mask_mod) * S * S : nullptr;
+  const bool even = (S & 1) == 0;
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = warp * 16 + g + r * 8;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const int j = nb * 8 + 2 * t;
+      float a0 = -INFINITY, a1 = -INFINITY;
+      if (i < S && j < S) {
+        const int64_t off = (int64_t)i * S + j;
+        float b0, b1 = 0.f;
+        if (even) {  // j even, S even → 8-byte aligned pair, both columns inside the window
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(bh + off));
+          b0 = bb.x;
+          b1 = bb.y;
+          if (mw) {
+            const float2 mm = __ldg(reinterpret_cast<const float2*>(mw + off));
+            b0 += mm.x;
+            b1 += mm.y;
+          }
+        } else {
+          b0 = __ldg(bh + off) + (mw ? __ldg(mw + off) : 0.f);
+          if (j + 1 < S) b1 = __ldg(bh + off + 1) + (mw ? __ldg(mw + off + 1) : 0.f);
+        }
+        a0 = fmaf(s[nb][2 * r], p.scale, b0);
+        if (j + 1 < S) a1 = fmaf(s[nb][2 * r + 1], p.scale, b1);
+      }
+      s[nb][2 * r] = a0;
+      s[nb][2 * r + 1] = a1;
+      mx[r] = fmaxf(mx[r], fmaxf(a0, a1));
+    }
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+  float inv[2], lsum[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float base = (mx[r] == -INFINITY) ? 0.f : mx[r] * LOG2E;
+    float sum = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const float p0 = exp2f(fmaf(s[nb][2 * r], LOG2E, -base));
+      const float p1 = exp2f(fmaf(s[nb][2 * r + 1], LOG2E, -base));
+      s[nb][2 * r] = p0;
+      s[nb][2 * r + 1] = p1;
+      sum += p0 + p1;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    lsum[r] = sum;
+    inv[r] = sum > 0.f ? 1.f / sum : 0.f;
+  }
+  float o[ND][4];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < WIN_MAX / 16; ++kk) {
+    uint32_t pf[4];
+    pf[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+    pf[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+    pf[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    pf[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+    for (int nd = 0; nd < ND; nd += 2) {
+      uint32_t vf[4];
+      ld_bt<CPR>(vf, sV, kk, nd, lane);
+      mma16816(o[nd], pf, vf);
+      mma16816(o[nd + 1], pf, vf + 2);
+    }
+  }
+  // each warp stages its own 16 output rows over its own (already consumed) Q rows, then 16-byte stores
+  __syncwarp();
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) {
+    const int r0 = warp * 16 + g;
+    const uint32_t a0 = saddr<CPR>(sQ, r0, nd) + t * 4;
+    const uint32_t a1 = saddr<CPR>(sQ, r0 + 8, nd) + t * 4;
+    const uint32_t v0 = pack2(o[nd][0] * inv[0], o[nd][1] * inv[0]);
+    const uint32_t v1 = pack2(o[nd][2] * inv[1], o[nd][3] * inv[1]);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0), "r"(v0));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1), "r"(v1));
+  }
+  __syncwarp();
+  bf16* og = p.o + (int64_t)b * S * p.ldo + h * HD;
+  for (int idx = lane; idx < 16 * ND; idx += 32) {
+    const int r = warp * 16 + idx / ND, c = idx % ND;
+    if (r < S) {
+      uint4 val;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                   : "r"(saddr<CPR>(sQ, r, c)));
+      stg16(og + (int64_t)r * p.ldo + c * 8, val);
+    }
+  }
+  if (p.lse && t == 0) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = warp * 16 + g + r * 8;
+      if (i < S) p.lse[((int64_t)b * p.H + h) * S + i] = lsum[r] > 0.f ? mx[r] + logf(lsum[r]) : -INFINITY;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 template <int HD, bool CAUSAL, bool BIAS = false>
 static int launch_fwd(const AttnParams& p, cudaStream_t st) {
@@ -811,6 +964,14 @@ extern "C" int vpb_attn_fwd_bias(const void* q, int64_t ldq, const void* k, int6
   VPB_CHECK(head_dim == 32, "attn_fwd_bias: head_dim %d (only 32 is built)", head_dim);
   VPB_CHECK(bias != nullptr && scale > 0.f, "attn_fwd_bias: bias table missing or scale <= 0");
   VPB_CHECK(!bias_mask || (mask_mod > 0 && B % mask_mod == 0), "attn_fwd_bias: B=%d is not a multiple of mask_mod=%d", B, mask_mod);
+  if (get_option(VPB_OPT_WIN_ATTN_V2) && sq == sk && sq <= WIN_MAX) {  // experimental one-pass window kernel
+    if (get_option(VPB_OPT_WIN_ATTN_V2) == 2)
+      win_attn_fwd_kernel<1><<<dim3(B, H), 288, 0, (cudaStream_t)stream>>>(p);
+    else
+      win_attn_fwd_kernel<2><<<dim3(B, H), 288, 0, (cudaStream_t)stream>>>(p);
+    VPB_LAUNCH_OK();
+    return 0;
+  }
   VPB_CHECK(B <= 65535, "attn_fwd_bias: B=%d windows exceed gridDim.z; split the batch", B);
   return launch_fwd<32, false, true>(p, (cudaStream_t)stream);
 }
