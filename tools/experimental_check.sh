@@ -1,0 +1,22 @@
+#!/bin/bash
+# First GPU call of the next round: validate the kernel variants that were written after round 1's GPU
+# budget ran out (all OFF by default) and A/B them on one box.  Results land in gpurun_out/.
+#   gpurun --timeout 900 -- 'bash tools/experimental_check.sh'
+mkdir -p gpurun_out
+VPB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py tests/test_ex2_poly.py -m gpu -q \
+  -p no:cacheprovider > gpurun_out/experimental_tests.log 2>&1; echo "experimental tests exit $?"; tail -n 8 gpurun_out/experimental_tests.log
+# polynomial exp2 in the tcgen05 attention kernels: isolated forward / backward times, off vs on (alternating)
+for r in 1 2; do for v in 0 1; do
+  echo "{\"VPB_ATTN_POLY_EXP2\": $v}" >> gpurun_out/poly_exp2_ab.jsonl
+  VPB_ATTN_POLY_EXP2=$v timeout 120 python tools/kernel_bench.py attnprof 2>&1 | grep -v -i warn | grep "attn_" >> gpurun_out/poly_exp2_ab.jsonl
+done; done; tail -n 12 gpurun_out/poly_exp2_ab.jsonl
+# one-pass window attention in the seg teacher: per-kernel split, default vs the two occupancy variants
+for v in 0 1 2; do
+  echo "{\"VPB_WIN_ATTN_V2\": $v}" >> gpurun_out/win_attn_v2_ab.jsonl
+  VPB_WIN_ATTN_V2=$v timeout 120 python tools/teacher_profile.py seg 2>&1 | grep -v -i warn | head -4 >> gpurun_out/win_attn_v2_ab.jsonl
+done; cat gpurun_out/win_attn_v2_ab.jsonl
+# whole step, off vs on
+for v in 0 1; do
+  VPB_ATTN_POLY_EXP2=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_poly_$v.json
+  python -c "import json; d=json.load(open('gpurun_out/bench_poly_$v.json')); print('POLY=$v', d['ms_per_step'], d['value'], d['clocks'])"
+done
