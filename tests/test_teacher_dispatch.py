@@ -109,3 +109,26 @@ def test_target_tiling_matches_reference_emb_loss():
         ref = R.base.BaseOLA_VLM._emb_loss(SimpleNamespace(contrastive_loss_weight=0.3), preds, mask, tgt, scale)
         for a, b in zip(mine, ref):
             assert abs(float(a) - float(b)) < 1e-6
+
+
+def test_freeze_policy_sets():
+    """PT (tune_mm_mlp_adapter) trains projector + heads + task tokens + logit scales only — the set
+    bench.py selects by name and the golden gradients cover; fine-tuning trains everything but the tower,
+    the DPT decoder and the teachers."""
+    from parity_utils import build_product, configs
+    from visper_lm_b200.train.policy import apply_freeze_policy
+
+    model = build_product(configs.TINY_LLAMA, True, None)
+    pt = apply_freeze_policy(model, tune_mm_mlp_adapter=True)
+    fx = torch.load(__import__("pathlib").Path(__file__).parent / "golden" / "tiny_llama_dsg.pt")
+    # the reference's PT-stage tensors that received a gradient; linear_2 / linear_3 of the depth heads are
+    # trainable too but get none (SURVEY Appendix A), so the golden does not list them
+    extra = set(pt) - set(fx["grads"])
+    assert set(fx["grads"]) <= set(pt) and all(("linear_2" in n) or ("linear_3" in n) for n in extra)
+    assert all(("mm_projector" in n) or ("_heads." in n) or ("special_" in n) or n.endswith("logit_scale") for n in pt)
+    ft = apply_freeze_policy(model)
+    assert not any(("vision_tower" in n) or ("da_v2_head" in n) for n in ft)
+    assert {"lm_head.weight", "model.embed_tokens.weight", "model.layers.0.self_attn.q_proj.weight"} <= set(ft)
+    assert set(pt) <= set(ft)
+    frozen_tokens = apply_freeze_policy(model, tune_mm_mlp_adapter=True, freeze_task_token=True, freeze_mm_mlp_adapter=True)
+    assert not any(("special_" in n) or ("mm_projector" in n) for n in frozen_tokens) and frozen_tokens
