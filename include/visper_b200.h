@@ -155,6 +155,13 @@ int vpb_conv1x1_to1(const void* in, const void* w, const void* bias, float* out,
 /* per-image (x - min) / (max - min), base_ola_vlm.py:466-469 */
 int vpb_minmax_normalize(const float* in, float* out, int B, int64_t n, void* stream);
 
+/* ---- ConvNeXt tower (multimodal_encoder/clip_convnext_encoder.py:150-174 → timm ConvNeXt block) ----
+ * depthwise Conv2d(C, C, 7, padding=3, groups=C) on NHWC bf16: out[b,y,x,c] = bias[c] +
+ * sum_{ky,kx} in[b, y+ky-3, x+kx-3, c] * w49[ky*7+kx, c]  (zero outside), fp32 accumulate.
+ * w49 is the [C,1,7,7] filter repacked tap-major [49, C]; C % 64 == 0; out must not alias in. */
+int vpb_dwconv7x7_nhwc(const void* in, const void* w49, const void* bias, void* out, int B, int H, int W,
+                       int C, void* stream);
+
 /* ---- multimodal splice (ola_arch.py:256-444 prepare_inputs_labels_for_multimodal) -----------
  * One gather from a host-built index plan replaces the per-sample Python cat loop. */
 int vpb_gather_rows(void* out, int64_t ldo, int nrows, int D, const int* kind, const int* index,

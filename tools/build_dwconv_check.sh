@@ -1,0 +1,10 @@
+#!/bin/bash
+# Builds tools/_bin/dwconv_check (git-ignored, travels with gpurun) against the in-tree library.
+set -e
+cd "$(dirname "$0")/.."
+python -m visper_lm_b200.build > /dev/null
+mkdir -p tools/_bin oracle/_ref
+gcc -O2 -c oracle/c/dwconv_ref.c -o tools/_bin/dwconv_ref.o
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -Iinclude tools/dwconv_check.cu tools/_bin/dwconv_ref.o \
+  -o tools/_bin/dwconv_check -Lvisper_lm_b200 -l:libvisper_b200.so -Xlinker -rpath -Xlinker '$ORIGIN/../../visper_lm_b200'
+echo tools/_bin/dwconv_check
