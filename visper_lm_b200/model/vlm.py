@@ -62,8 +62,18 @@ class VisperConfig:
         self.rms_norm_eps = rms_norm_eps
         self.vision = vision or dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24,
                                      num_attention_heads=16, image_size=336, patch_size=14)
-        self.mm_vision_tower = "openai/clip-vit-large-patch14-336"
-        self.mm_hidden_size = self.vision["hidden_size"]
+        # multimodal_encoder/builder.py:6-13 picks the tower class from this name: "convnext" in it selects
+        # CLIPConvNextVisionTower (e.g. "CLIP-convnext_xxlarge-res768", BASELINE config 4), else the CLIP ViT
+        self.mm_vision_tower = extra.pop("mm_vision_tower", None) or "openai/clip-vit-large-patch14-336"
+        if "convnext" in self.mm_vision_tower.lower():
+            from .convnext import CONVNEXT_PRESETS, extract_res_interp
+
+            base, res, _ = extract_res_interp(self.mm_vision_tower)
+            if vision is None or "dims" not in vision:
+                self.vision = dict(CONVNEXT_PRESETS[base], image_size=res or 768)
+            self.mm_hidden_size = self.vision["dims"][-1]
+        else:
+            self.mm_hidden_size = self.vision["hidden_size"]
         self.mm_projector_type = mm_projector_type
         self.mm_vision_select_layer = mm_vision_select_layer
         self.mm_vision_select_feature = mm_vision_select_feature
@@ -346,8 +356,14 @@ class VisperModel(nn.Module):
         self.embed_tokens = M.Weight((config.vocab_size, D), None, device)
         self.layers = nn.ModuleList([M.DecoderLayer(config, device) for _ in range(config.num_hidden_layers)])
         self.norm = M.Norm(D, False, device)
-        self.vision_tower = M.CLIPVisionTower(config.vision, config.mm_vision_select_layer,
-                                              config.mm_vision_select_feature, device)
+        if "convnext" in config.mm_vision_tower.lower():
+            from .convnext import CLIPConvNextVisionTower
+
+            self.vision_tower = CLIPConvNextVisionTower(config.mm_vision_tower, args=config, device=device,
+                                                        cfg=config.vision)
+        else:
+            self.vision_tower = M.CLIPVisionTower(config.vision, config.mm_vision_select_layer,
+                                                  config.mm_vision_select_feature, device)
         self.mm_projector = M.Seq(_0=M.Linear(config.mm_hidden_size, D, True, device),
                                   _2=M.Linear(D, D, True, device))
         self.aux_tokens = "depth-seg-gen"

@@ -396,6 +396,18 @@ def minmax_normalize(x):
     return out
 
 
+# --------------------------------------------------------------------------------------------- ConvNeXt tower
+def dwconv7x7(x, w49, bias, B, H, W, C, out=None):
+    """Depthwise 7x7, pad 3, on NHWC rows [B*H*W, C]; w49 = the [C,1,7,7] filter repacked to [49, C]."""
+    assert x.is_contiguous() and x.shape == (B * H * W, C) and x.dtype == BF16
+    assert w49.is_contiguous() and w49.shape == (49, C) and w49.dtype == BF16
+    if out is None:
+        out = torch.empty_like(x)
+    _chk(_L().vpb_dwconv7x7_nhwc(x.data_ptr(), w49.data_ptr(), _p(bias), out.data_ptr(), B, H, W, C, _stream()),
+         "dwconv7x7")
+    return out
+
+
 # --------------------------------------------------------------------------------------------- gathers
 def gather_rows(index, srcs, D, kind=None, out=None):
     """out[r] = srcs[kind[r]][index[r]] (negative → zero row). index/kind: int32 CUDA tensors."""
