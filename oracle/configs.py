@@ -10,6 +10,11 @@ TINY_LLAMA = dict(
     gen_layers="2-4", aux_mode="gen-depth-seg", num_task_tokens=8, num_sys_tokens=26,
     tokenizer_model_max_length=1024)
 
+# BASELINE config 4 at test size: the CLIP-ConvNeXt tower (768 px → 24x24 = 576 image tokens, like the ViT)
+# in front of the tiny Llama; widths are multiples of 64 (one 128-byte line per pixel in the depthwise kernel)
+TINY_LLAMA_CONVNEXT = dict(TINY_LLAMA, tower="convnext", cnx_depths=(1, 1, 2, 1), cnx_dims=(64, 64, 128, 64),
+                           cnx_eps=1e-5, image_size=768)
+
 TINY_PHI3 = dict(TINY_LLAMA, family="phi3", kv_heads=4, rope_theta=10000.0, num_sys_tokens=13)
 # Phi-3's sliding-window attention (config 5: T=4096 > sliding_window 2047) at test size: the
 # embedded sequence is ~650 tokens, so a 200-token window cuts into image, task and text tokens.

@@ -98,3 +98,28 @@ def test_convnext_tower_vs_oracle(case):
             got = stages[i][0].float().cpu().view(B, stages[i][1], stages[i][2], -1).permute(0, 3, 1, 2)
             sub = got[:, ::4, ::2, ::2] if i < 3 else got
             assert ((sub - fx["stages_sub"][i]).norm() / fx["stages_sub"][i].norm()).item() < 3.5e-2
+
+
+def test_step_with_convnext_tower_vs_oracle():
+    """BASELINE config 4 at test size: tiny Llama + dsg heads behind the ConvNeXt tower — loss within the
+    north_star's 1e-3 rel of the CPU oracle on identical bf16-rounded weights / inputs, projector gradient
+    (which sees the tower's features) aligned with the oracle's."""
+    from parity_utils import (build_product, configs, cos_sim, oracle_state, pt_freeze, round_batch, run_product)
+
+    cfg = configs.TINY_LLAMA_CONVNEXT
+    model = build_product(cfg, True, "cuda:0")
+    pt_freeze(model)
+    batch = round_batch(configs.synthetic_batch(cfg, 2, 48, seed=4321))
+    out = run_product(model, batch, True, "cuda:0")
+    out.loss.backward()
+    torch.cuda.synchronize()
+    sd = oracle_state(model)
+    req = {n: sd[n].clone().requires_grad_(True) for n in ("model.mm_projector.0.weight", "model.mm_projector.2.weight")}
+    ref = restate.forward_step({**sd, **req}, cfg, batch, distill=True)
+    ref["loss"].backward()
+    got, want = out.loss.item(), ref["loss"].item()
+    print(f"convnext step: loss {got:.6f} oracle {want:.6f} rel {abs(got - want) / abs(want):.2e}")
+    assert abs(got - want) <= 1e-3 * abs(want), (got, want)
+    for n, r in req.items():
+        g = dict(model.named_parameters())[n].grad
+        assert g is not None and cos_sim(g, r.grad) > 0.99, (n, cos_sim(g, r.grad))

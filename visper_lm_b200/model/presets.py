@@ -8,11 +8,16 @@ def from_dict(c: dict, cls=VisperConfig, distill=True):
     vision = dict(hidden_size=c["vis_hidden"], intermediate_size=c["vis_inter"],
                   num_hidden_layers=c["vis_layers"], num_attention_heads=c["vis_heads"],
                   image_size=c["image_size"], patch_size=c["patch_size"])
+    extra = {}
+    if c.get("tower") == "convnext":
+        vision = dict(depths=tuple(c["cnx_depths"]), dims=tuple(c["cnx_dims"]), eps=c["cnx_eps"],
+                      image_size=c["image_size"])
+        extra["mm_vision_tower"] = c.get("mm_vision_tower", f"CLIP-convnext_xxlarge-res{c['image_size']}")
     cfg = cls(family=c["family"], vocab_size=c["vocab"], hidden_size=c["hidden"],
               intermediate_size=c["inter"], num_hidden_layers=c["layers"], num_attention_heads=c["heads"],
               num_key_value_heads=c["kv_heads"], max_position_embeddings=c["max_pos"],
               rope_theta=c["rope_theta"], vision=vision,
-              tokenizer_model_max_length=c.get("tokenizer_model_max_length", c["max_pos"]))
+              tokenizer_model_max_length=c.get("tokenizer_model_max_length", c["max_pos"]), **extra)
     if "sliding_window" in c:
         cfg.sliding_window = c["sliding_window"]
     if distill:
