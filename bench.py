@@ -53,6 +53,9 @@ def parse():
                          "full fine-tune of LLM + projector (finetune.sh) — weight gradients for every layer")
     ap.add_argument("--seq", type=int, default=2048, help="embedded sequence length T")
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "phi3-mini", "tiny"])
+    ap.add_argument("--tower", default="clip-vit-l", choices=["clip-vit-l", "convnext-xxl"],
+                    help="vision tower: CLIP-ViT-L/14-336 (default, the BASELINE metric's config) or the frozen "
+                         "CLIP-ConvNeXt-XXL at 768 px of BASELINE configs[3] (576 image tokens of width 3072)")
     ap.add_argument("--layers", type=int, default=None, help="override decoder depth (debug only; reported)")
     ap.add_argument("--torch-profile", action="store_true",
                     help="diagnostic: torch.profiler over 2 device-leg steps, prints kernel totals and busy time")
@@ -68,7 +71,18 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-def model_cfg(name, layers=None):
+CONVNEXT_XXL_FLOP = 3.563e12   # per 768 px image: stem + 3 downsamples + 40 blocks (fc1/fc2 GEMMs + 98 FLOP/elt depthwise)
+
+
+def model_cfg(name, layers=None, tower="clip-vit-l"):
+    c = _model_cfg(name, layers)
+    if tower == "convnext-xxl":  # clip_convnext_encoder.py:61-174, timm convnext_xxlarge (norm_eps 1e-5)
+        c.update(tower="convnext", cnx_depths=(3, 4, 30, 3), cnx_dims=(384, 768, 1536, 3072), cnx_eps=1e-5,
+                 image_size=768)
+    return c
+
+
+def _model_cfg(name, layers=None):
     from visper_lm_b200.model import presets
 
     if name == "tiny":
@@ -199,19 +213,29 @@ def cpu_reference(c, T, distill, layers_sampled, repeats=1, warmup=0, budget_s=N
     sd["model.norm.weight"] = torch.ones(D)
     sd["lm_head.weight"] = w(V, D)
     sd["model.embed_tokens.weight"] = sd["lm_head.weight"]
-    Dv, Fv = c["vis_hidden"], c["vis_inter"]
+    convnext = c.get("tower") == "convnext"
+    if convnext:  # one set of block weights per stage, aliased over its blocks
+        cnx = dict(depths=c["cnx_depths"], dims=c["cnx_dims"], eps=c["cnx_eps"])
+        stage_w = {}
+        for k, shp in restate.convnext_state_spec(cnx).items():
+            k0 = __import__("re").sub(r"blocks\.\d+\.", "blocks.0.", k)
+            if k0 not in stage_w:
+                stage_w[k0] = torch.ones(shp) if k.endswith(("norm.weight", "stem.1.weight", "downsample.0.weight")) \
+                    else (torch.zeros(shp) if k.endswith("bias") else w(*shp))
+            sd[k] = stage_w[k0]
+    Dv, Fv = (c["cnx_dims"][-1], 0) if convnext else (c["vis_hidden"], c["vis_inter"])
     pv = "model.vision_tower.vision_tower.vision_model."
     sd[pv + "embeddings.patch_embedding.weight"] = w(Dv, 3, c["patch_size"], c["patch_size"])
     sd[pv + "embeddings.class_embedding"] = w(Dv)
     sd[pv + "embeddings.position_embedding.weight"] = w((c["image_size"] // c["patch_size"]) ** 2 + 1, Dv)
     vl = {}
-    for nm, shp in (("self_attn.q_proj", (Dv, Dv)), ("self_attn.k_proj", (Dv, Dv)), ("self_attn.v_proj", (Dv, Dv)),
+    for nm, shp in () if convnext else (("self_attn.q_proj", (Dv, Dv)), ("self_attn.k_proj", (Dv, Dv)), ("self_attn.v_proj", (Dv, Dv)),
                     ("self_attn.out_proj", (Dv, Dv)), ("mlp.fc1", (Fv, Dv)), ("mlp.fc2", (Dv, Fv))):
         vl[nm + ".weight"] = w(*shp)
         vl[nm + ".bias"] = torch.zeros(shp[0])
     for nm in ("layer_norm1", "layer_norm2"):
         vl[nm + ".weight"], vl[nm + ".bias"] = torch.ones(Dv), torch.zeros(Dv)
-    for i in range(c["vis_layers"]):
+    for i in range(0 if convnext else c["vis_layers"]):
         for k, v in vl.items():
             sd[f"{pv}encoder.layers.{i}.{k}"] = v
     for nm in ("pre_layrnorm",):
@@ -229,7 +253,7 @@ def cpu_reference(c, T, distill, layers_sampled, repeats=1, warmup=0, budget_s=N
             break  # keep the whole run within a few minutes whatever --steps asks for
         t0 = time.perf_counter()
         with torch.no_grad():
-            feats = restate.clip_tower(sd, b["images"], cfg)
+            feats = restate.convnext_tower(sd, b["images"], cnx) if convnext else restate.clip_tower(sd, b["images"], cfg)
         img = restate.mm_projector(sd, feats)
         emb, labels, _ = restate.splice(sd, cfg, b["input_ids"], b["labels"], None, img)
         t1 = time.perf_counter()
@@ -251,7 +275,7 @@ def cpu_reference(c, T, distill, layers_sampled, repeats=1, warmup=0, budget_s=N
                   "model.mm_projector.2.bias"):
             sd[k].grad = None
     est = sum(times) / len(times)
-    desc = (f"B=1, T={T}: full CLIP tower fwd + mm_projector fwd/bwd + {layers_sampled}/{L} decoder layers "
+    desc = (f"B=1, T={T}: full {'ConvNeXt-XXL @768' if convnext else 'CLIP'} tower fwd + mm_projector fwd/bwd + {layers_sampled}/{L} decoder layers "
             f"fwd+dgrad (x{L / layers_sampled:.0f} extrapolated) + final norm + full-vocab lm_head/CE fwd+bwd; "
             f"fp32 torch on {cores} threads")
     return 1.0 / est, desc, times, cores
@@ -261,7 +285,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    c = model_cfg(args.model, args.layers)
+    c = model_cfg(args.model, args.layers, args.tower)
     distill = args.workload == "dsg"
     sps, desc, times, cores = cpu_reference(c, args.seq, distill, args.cpu_baseline_layers,
                                             repeats=max(1, args.steps), warmup=min(args.warmup, 1),
@@ -284,7 +308,8 @@ def run_reference(args):
 
 def workload_config(args, c, distill):
     return {"workload": ("BASELINE configs[1]: " if not distill else "BASELINE configs[2] per-GPU slice: ")
-            + f"{args.model} + CLIP-ViT-L/14-336, 336px, T={args.seq}, "
+            + f"{args.model} + " + ("CLIP-ConvNeXt-XXL, 768px" if c.get("tower") == "convnext" else "CLIP-ViT-L/14-336, 336px")
+            + f", T={args.seq}, "
             + ("NTP only" if not distill else "NTP + dsg distill heads (d18-20_s10-18_g12-20)")
             + (", depth (DINOv2-L) / seg (Swin-L @800) / gen (unCLIP ViT-H) targets from the on-GPU frozen teachers each step"
                if distill and getattr(args, "teachers", False) else "")
@@ -311,7 +336,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     distill = args.workload == "dsg"
-    c = model_cfg(args.model, args.layers)
+    c = model_cfg(args.model, args.layers, args.tower)
     cfg = presets.from_dict(c, distill=distill)
     fam = c["family"]
     cls = {("llama", True): pm.OlaLlavaLlamaForCausalLM, ("phi3", True): pm.OlaLlavaPhi3ForCausalLM,
@@ -435,6 +460,9 @@ def run_b200(args):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     flop_key = "dsg_adapter" if distill else ("ntp_full" if args.train == "full" else "ntp_adapter")
     full_model = args.model == "llama3-8b" and args.layers is None and T == 2048
+    step_flop = FLOPS[flop_key]
+    if c.get("tower") == "convnext":  # tower forward and the 3072-wide projector input replace the ViT-L terms
+        step_flop += (CONVNEXT_XXL_FLOP - 3.65e11) + 3 * (2 * 576 * (3072 - 1024) * 4096)
     line = {
         "metric": "train-step samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
@@ -457,7 +485,7 @@ def run_b200(args):
             "peak_source": peak_src, "launches": gemm_stats["launches"],
             "gemm_ms_per_step": gemm_stats["ms"] / args.steps,
             "gemm_share_of_step": gemm_stats["ms"] / ms_dev if ms_dev else None,
-            "step_model_flops_frac": (value / world * FLOPS[flop_key] / (peak_tf * 1e12)) if full_model else None,
+            "step_model_flops_frac": (value / world * step_flop / (peak_tf * 1e12)) if full_model else None,
         },
     }
     if world == 1 and not args.no_cpu_baseline:
