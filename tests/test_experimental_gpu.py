@@ -42,3 +42,22 @@ def test_one_pass_window_attention(B, H, S, nmask, variant):
     ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, W)
     assert ((o.float() - ref).norm() / ref.norm()).item() < 1.6e-2
     assert ((o.float() - base.float()).norm() / base.float().norm()).item() < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 5, 9, 64), (2, 24, 24, 128), (2, 48, 48, 1536)])
+def test_dwconv_packed_fma_is_bit_identical(B, H, W, C):
+    """VPB_OPT_DWCONV_FFMA2: fma.rn.f32x2 per channel pair == the validated scalar-FMA depthwise kernel, bit for bit."""
+    from visper_lm_b200 import ops
+
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B * H * W, C, generator=g).to(torch.bfloat16).cuda()
+    w49 = (torch.randn(49, C, generator=g) / 7).to(torch.bfloat16).cuda()
+    b = torch.randn(C, generator=g).to(torch.bfloat16).cuda()
+    base = ops.dwconv7x7(x, w49, b, B, H, W, C)
+    ops.set_option(ops.OPT_DWCONV_FFMA2, 1)
+    try:
+        got = ops.dwconv7x7(x, w49, b, B, H, W, C)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_DWCONV_FFMA2, 0)
+    assert torch.equal(got, base)

@@ -20,3 +20,10 @@ for v in 0 1; do
   VPB_ATTN_POLY_EXP2=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_poly_$v.json
   python -c "import json; d=json.load(open('gpurun_out/bench_poly_$v.json')); print('POLY=$v', d['ms_per_step'], d['value'], d['clocks'])"
 done
+# depthwise 7x7 of the ConvNeXt tower: scalar vs packed-FMA (FFMA2) variant, parity + alternating timings (no Python)
+timeout 60 tools/_bin/dwconv_check | tee gpurun_out/dwconv_ffma2_ab.jsonl | tail -n 20
+# ConvNeXt-XXL tower in the step (BASELINE configs[3] tower): first bench lines
+for v in 0 1; do
+  VPB_DWCONV_FFMA2=$v timeout 400 python bench.py --tower convnext-xxl --workload dsg --steps 6 --warmup 3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_convnext_dsg_ffma2_$v.json
+  python -c "import json; d=json.load(open('gpurun_out/bench_convnext_dsg_ffma2_$v.json')); print('convnext dsg FFMA2=$v', d['ms_per_step'], d['value'], d['clocks'])"
+done

@@ -21,7 +21,15 @@ namespace vpb {
 
 constexpr int DW_K = 7, DW_PAD = 3, DW_CH = 64;
 
-template <int TH, int TW>
+// acc += a * b on a channel pair as ONE packed instruction (IEEE fp32 FMA per half, so bit-identical to two fmaf)
+__device__ __forceinline__ void fma_pair(float2& acc, const float2& a, const float2& b) {
+  uint64_t ra = *reinterpret_cast<const uint64_t*>(&a), rb = *reinterpret_cast<const uint64_t*>(&b);
+  uint64_t rc = *reinterpret_cast<uint64_t*>(&acc);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  acc = *reinterpret_cast<float2*>(&rc);
+}
+
+template <int TH, int TW, bool PACKED>
 __global__ void __launch_bounds__(TH * 32)
 dwconv7x7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w49, const bf16* __restrict__ bias,
                  bf16* __restrict__ out, int H, int W, int C, int tiles_x) {
@@ -74,8 +82,12 @@ dwconv7x7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w49, cons
       const float2 wv = __bfloat1622float2(sw2[(ky * DW_K + kx) * (DW_CH / 2) + cp]);
 #pragma unroll
       for (int x = 0; x < TW; ++x) {
-        acc[x].x = fmaf(row[x + kx].x, wv.x, acc[x].x);
-        acc[x].y = fmaf(row[x + kx].y, wv.y, acc[x].y);
+        if constexpr (PACKED) {
+          fma_pair(acc[x], row[x + kx], wv);
+        } else {
+          acc[x].x = fmaf(row[x + kx].x, wv.x, acc[x].x);
+          acc[x].y = fmaf(row[x + kx].y, wv.y, acc[x].y);
+        }
       }
     }
   }
@@ -101,8 +113,12 @@ extern "C" int vpb_dwconv7x7_nhwc(const void* in, const void* w49, const void* b
   constexpr int TH = 8, TW = 16;
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
   dim3 grid(tiles_x * tiles_y, C / DW_CH, B);
-  dwconv7x7_kernel<TH, TW><<<grid, TH * 32, 0, ST(stream)>>>((const bf16*)in, (const bf16*)w49,
-                                                            (const bf16*)bias, (bf16*)out, H, W, C, tiles_x);
+  if (get_option(VPB_OPT_DWCONV_FFMA2))
+    dwconv7x7_kernel<TH, TW, true><<<grid, TH * 32, 0, ST(stream)>>>((const bf16*)in, (const bf16*)w49,
+                                                                    (const bf16*)bias, (bf16*)out, H, W, C, tiles_x);
+  else
+    dwconv7x7_kernel<TH, TW, false><<<grid, TH * 32, 0, ST(stream)>>>((const bf16*)in, (const bf16*)w49,
+                                                                     (const bf16*)bias, (bf16*)out, H, W, C, tiles_x);
   VPB_LAUNCH_OK();
   return 0;
 }
