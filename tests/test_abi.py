@@ -53,5 +53,18 @@ def test_reference_module_paths_resolve():
     for name in ("DAv2_Head", "TaskTokenGenHead", "TaskTokenDepthHead", "OneFormerTaskTokenSegHead", "OneFormerHead"):
         assert hasattr(a, name)
     assert hasattr(importlib.import_module("ola_vlm.model.aux_heads.depth_anything_v2.dpt"), "DepthAnythingV2")
+    b = importlib.import_module("ola_vlm.model.multimodal_encoder.builder")   # ola_arch.py:12 import
+    from types import SimpleNamespace
+
+    t = b.build_vision_tower(SimpleNamespace(mm_vision_tower="CLIP-convnext_xxlarge-res768", mm_vision_select_layer=-2),
+                             device="meta")
+    assert type(t).__name__ == "CLIPConvNextVisionTower" and t.hidden_size == 3072 and t.num_patches == 576
+    t = b.build_vision_tower(SimpleNamespace(mm_vision_tower="openai/clip-vit-large-patch14-336", mm_vision_select_layer=-2),
+                             device="meta")
+    assert type(t).__name__ == "CLIPVisionTower" and t.hidden_size == 1024 and t.num_patches == 576
+    import pytest
+
+    with pytest.raises(ValueError):
+        b.build_vision_tower(SimpleNamespace(mm_vision_tower="sam-vit"))
     for k in [k for k in sys.modules if k == "ola_vlm" or k.startswith("ola_vlm.")]:
         del sys.modules[k]
