@@ -27,3 +27,7 @@ for v in 0 1; do
   VPB_DWCONV_FFMA2=$v timeout 400 python bench.py --tower convnext-xxl --workload dsg --steps 6 --warmup 3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_convnext_dsg_ffma2_$v.json
   python -c "import json; d=json.load(open('gpurun_out/bench_convnext_dsg_ffma2_$v.json')); print('convnext dsg FFMA2=$v', d['ms_per_step'], d['value'], d['clocks'])"
 done
+# per-kernel split of the ConvNeXt-XXL tower (B = 8 @768) + one ncu capture of the depthwise kernel
+timeout 200 python tools/teacher_profile.py convnext 2>&1 | grep -v -i warn | head -14 | tee gpurun_out/convnext_tower_kernel_times.jsonl
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:dwconv7x7 -c 2 -o gpurun_out/dwconv7x7 tools/_bin/dwconv_check > /dev/null 2>&1; ls -la gpurun_out/dwconv7x7.ncu-rep
+timeout 400 python -m pytest tests/test_tower_convnext_gpu.py -m gpu -q -s -p no:cacheprovider 2>&1 | tail -n 15 | tee gpurun_out/convnext_gpu_tests.log

@@ -1,4 +1,5 @@
-"""Per-kernel device times of the three frozen teachers on one batch (torch profiler / CUPTI)."""
+"""Per-kernel device times of the three frozen teachers (and, with `convnext`, of the ConvNeXt-XXL tower) on one
+batch of 8 (torch profiler / CUPTI):  python tools/teacher_profile.py [seg|depth|gen|convnext ...]"""
 import json
 import sys
 from pathlib import Path
@@ -22,17 +23,29 @@ def init(m):
     return m
 
 
+def _convnext():
+    from types import SimpleNamespace
+
+    from visper_lm_b200.model.convnext import CLIPConvNextVisionTower
+
+    return CLIPConvNextVisionTower("CLIP-convnext_xxlarge-res768", args=SimpleNamespace(mm_vision_select_layer=-2), device=dev)
+
+
+# built lazily: only the requested models are allocated ("convnext" = the ConvNeXt-XXL vision tower, not a teacher)
 cases = {
-    "seg": (init(OneFormerHead(None, dev)), torch.randn(B, 3, 800, 800, device=dev).to(torch.bfloat16),
-            lambda m, x: m.seg_target_rows(x)),
-    "depth": (init(DepthAnythingV2("vitl", device=dev, with_depth_head=False)),
-              torch.randint(0, 256, (B, 336, 336, 3), dtype=torch.uint8, device=dev), lambda m, x: m.dsg_targets(x, 336)),
-    "gen": (init(CLIPVisionModelWithProjection(UNCLIP_VIT_H, dev)), torch.randn(B, 3, 224, 224, device=dev),
-            lambda m, x: m.image_embeds(x)),
+    "seg": lambda: (init(OneFormerHead(None, dev)), torch.randn(B, 3, 800, 800, device=dev).to(torch.bfloat16),
+                    lambda m, x: m.seg_target_rows(x)),
+    "depth": lambda: (init(DepthAnythingV2("vitl", device=dev, with_depth_head=False)),
+                      torch.randint(0, 256, (B, 336, 336, 3), dtype=torch.uint8, device=dev),
+                      lambda m, x: m.dsg_targets(x, 336)),
+    "gen": lambda: (init(CLIPVisionModelWithProjection(UNCLIP_VIT_H, dev)), torch.randn(B, 3, 224, 224, device=dev),
+                    lambda m, x: m.image_embeds(x)),
+    "convnext": lambda: (init(_convnext()), torch.randn(B, 3, 768, 768, device=dev).to(torch.bfloat16),
+                         lambda m, x: m(x)),
 }
-which = sys.argv[1:] or list(cases)
+which = sys.argv[1:] or ["seg", "depth", "gen"]
 for name in which:
-    m, x, fn = cases[name]
+    m, x, fn = cases[name]()
     for _ in range(2):
         fn(m, x)
     torch.cuda.synchronize()
