@@ -205,3 +205,28 @@ def test_config_selects_the_tower():
     assert isinstance(m.vision_tower, CLIPConvNextVisionTower)
     assert m.mm_projector[0].weight.shape == (64, 3072) and m.vision_tower.num_patches == 576
     assert "vision_tower.vision_tower.stages.2.blocks.29.mlp.fc2.weight" in dict(m.named_parameters())
+
+
+def test_image_processor_matches_torchvision():
+    """ProcessorWrapper(OpenClipEvalTransform) == open_clip's eval transform as the reference resizes it
+    (clip_convnext_encoder.py:113-115), spelled with torchvision here (open_clip is not installed)."""
+    tv = pytest.importorskip("torchvision.transforms")
+    import numpy as np
+    from PIL import Image
+
+    from visper_lm_b200.model.convnext import OPENAI_CLIP_MEAN, OPENAI_CLIP_STD, CLIPConvNextVisionTower
+
+    t = CLIPConvNextVisionTower("CLIP-convnext_xxlarge-res96", args=SimpleNamespace(mm_vision_select_layer=-2),
+                                device="meta", cfg=dict(MINI))
+    proc = t.image_processor
+    assert proc.crop_size == {"height": 96, "width": 96} and proc.image_mean == list(OPENAI_CLIP_MEAN)
+    ref = tv.Compose([tv.Resize(96, interpolation=tv.InterpolationMode.BICUBIC), tv.CenterCrop((96, 96)),
+                      lambda im: im.convert("RGB"), tv.ToTensor(), tv.Normalize(OPENAI_CLIP_MEAN, OPENAI_CLIP_STD)])
+    rng = np.random.default_rng(0)
+    for (w, h), mode in (((200, 131), "RGB"), ((77, 150), "RGB"), ((96, 96), "RGB"), ((40, 300), "L"), ((640, 480), "RGBA")):
+        arr = rng.integers(0, 256, (h, w, {"RGB": 3, "L": 1, "RGBA": 4}[mode]), dtype=np.uint8)
+        im = Image.fromarray(arr.squeeze(-1) if mode == "L" else arr, mode)
+        got = proc.preprocess(im, return_tensors="pt")["pixel_values"][0]
+        want = ref(im)
+        assert got.shape == (3, 96, 96) and torch.allclose(got, want, atol=1e-6), (w, h, mode)
+    assert torch.equal(proc([im])["pixel_values"][0], got)           # list input / __call__ (base_encoder.py:23-31)

@@ -78,6 +78,59 @@ def _read_checkpoint(path):
     return sd.get("state_dict", sd)
 
 
+OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+class OpenClipEvalTransform:
+    """open_clip's inference transform for these towers — Resize(shortest side → size, bicubic) → CenterCrop →
+    RGB → ToTensor → Normalize(CLIP mean/std) — with both sizes set to the tower's resolution as
+    clip_convnext_encoder.py:113-114 does.  Host-side PIL work (open_clip / torchvision are not required);
+    equal to the torchvision Compose on the same image (tests/test_convnext_cpu.py)."""
+
+    def __init__(self, size, mean=OPENAI_CLIP_MEAN, std=OPENAI_CLIP_STD):
+        self.size = int(size)
+        self.mean = torch.tensor(mean).view(3, 1, 1)
+        self.std = torch.tensor(std).view(3, 1, 1)
+
+    def __call__(self, image):
+        import numpy as np
+        from PIL import Image
+
+        w, h = image.size
+        s = self.size
+        short, long = (w, h) if w <= h else (h, w)
+        if short != s:                                   # torchvision Resize(int): shorter side → s, aspect kept
+            new_long = int(s * long / short)
+            nw, nh = (s, new_long) if w <= h else (new_long, s)
+            image = image.resize((nw, nh), Image.BICUBIC)
+            w, h = nw, nh
+        top, left = int(round((h - s) / 2.0)), int(round((w - s) / 2.0))   # torchvision CenterCrop
+        image = image.crop((left, top, left + s, top + s)).convert("RGB")
+        x = torch.from_numpy(np.asarray(image, dtype=np.uint8).copy()).permute(2, 0, 1).float().div_(255.0)
+        return (x - self.mean) / self.std
+
+
+class ProcessorWrapper:
+    """multimodal_encoder/base_encoder.py:8-40: what the dataset code sees as `image_processor`."""
+
+    def __init__(self, transform, height=378, width=378, image_mean=list(OPENAI_CLIP_MEAN)):
+        self._crop_size = {"height": height, "width": width}
+        self._transforms = transform
+        self.image_mean = image_mean
+
+    @property
+    def crop_size(self):
+        return self._crop_size
+
+    def preprocess(self, image, return_tensors="pt"):
+        if isinstance(image, list):
+            image = image[0]
+        return {"pixel_values": [self._transforms(image)]}
+
+    __call__ = preprocess
+
+
 class _Mlp(nn.Module):
     def __init__(self, C, device):
         super().__init__()
@@ -240,7 +293,9 @@ class CLIPConvNextVisionTower(nn.Module):
         self.cfg = dict(CONVNEXT_PRESETS[base] if cfg is None else cfg)
         self.vision_tower = ConvNeXtTrunk(self.cfg, device)
         self._hidden_size = self.cfg["dims"][-1]
-        self.image_processor = None
+        # clip_convnext_encoder.py:113-115
+        self.image_processor = ProcessorWrapper(OpenClipEvalTransform(self._image_size), height=self._image_size,
+                                                width=self._image_size)
         self.is_loaded = True
 
     def load_model(self, device_map=None, path=None):
