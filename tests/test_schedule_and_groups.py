@@ -45,3 +45,40 @@ def test_no_decay_names_match_hf_rule():
         if "layers.0.0" in n:   # an unnamed LayerNorm inside a Sequential: only the module TYPE identifies it
             continue            # (the product's norms all carry 'norm' in their reference names)
         assert _no_decay(n) == hf_no_decay, n
+
+
+def test_trainer_sampler_and_compute_loss_surface():
+    """LLaVATrainer._get_train_sampler (llava_trainer.py:219-232) and HF's compute_loss contract."""
+    import torch
+
+    from visper_lm_b200.train.data import LengthGroupedSampler
+    from visper_lm_b200.train.trainer import LLaVATrainer, TrainingArguments
+
+    class DS:
+        modality_lengths = [5, -3, 7, 9, -2, 4, 8, 6]
+
+        def __len__(self):
+            return len(self.modality_lengths)
+
+    t = LLaVATrainer(model=None, args=TrainingArguments(per_device_train_batch_size=2, group_by_modality_length=True,
+                                                        gradient_accumulation_steps=2), train_dataset=DS())
+    s = t._get_train_sampler()
+    assert isinstance(s, LengthGroupedSampler) and (s.batch_size, s.world_size, s.group_by_modality) == (2, 2, True)
+    assert sorted(s) == list(range(8))
+    t.args.group_by_modality_length = False
+    assert sorted(t._get_train_sampler()) == list(range(8))
+    assert LLaVATrainer(model=None, args=TrainingArguments())._get_train_sampler() is None
+
+    class Out:
+        loss = torch.tensor(1.5)
+
+    class M:
+        device = torch.device("cpu")
+
+        def __call__(self, **kw):
+            return (torch.tensor(2.5), None) if kw.get("return_dict") is False else Out()
+
+    t = LLaVATrainer(model=M(), args=TrainingArguments())
+    assert float(t.compute_loss(t.model, {"x": torch.zeros(1)})) == 1.5
+    loss, out = t.compute_loss(t.model, {"return_dict": False}, return_outputs=True)
+    assert float(loss) == 2.5 and isinstance(out, tuple)

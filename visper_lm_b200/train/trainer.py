@@ -238,6 +238,28 @@ class LLaVATrainer:
                 out[k] = v
         return out
 
+    def compute_loss(self, model, inputs, return_outputs=False, **_):
+        """HF Trainer.compute_loss as the reference relies on it: `model(**inputs)` and the
+        `loss` field (or element 0 of the tuple form)."""
+        out = model(**self._to_device(inputs))
+        loss = out[0] if isinstance(out, tuple) else out.loss
+        return (loss, out) if return_outputs else loss
+
+    def _get_train_sampler(self):
+        """llava_trainer.py:219-232: the modality-length-grouped sampler under --group_by_modality_length
+        (batch = per-device batch, world = world_size x grad-accum), else a seeded random sampler.  train()
+        consumes the same order through _index_order."""
+        ds = self.train_dataset
+        if ds is None or not hasattr(ds, "__len__"):
+            return None
+        a = self.args
+        if a.group_by_modality_length:
+            from .data import LengthGroupedSampler
+
+            return LengthGroupedSampler(a.per_device_train_batch_size, self.world * a.gradient_accumulation_steps,
+                                        lengths=ds.modality_lengths, group_by_modality=True)
+        return torch.utils.data.RandomSampler(ds, generator=torch.Generator().manual_seed(a.seed))
+
     def training_step(self, model, inputs):
         """HF Trainer.training_step semantics (llava_trainer.py:357-381 is a dead verbatim copy):
         forward → loss → backward; returns the detached loss tensor (no host sync)."""
