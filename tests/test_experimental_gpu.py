@@ -61,3 +61,28 @@ def test_dwconv_packed_fma_is_bit_identical(B, H, W, C):
     finally:
         ops.set_option(ops.OPT_DWCONV_FFMA2, 0)
     assert torch.equal(got, base)
+
+
+@pytest.mark.parametrize("B,H,S", [(2, 16, 577), (1, 16, 1370), (3, 4, 128), (2, 2, 70)])
+def test_vit_attention_on_tcgen05(B, H, S):
+    """VPB_OPT_ATTN_FWD_TC64: non-causal head_dim-64 attention forward (CLIP ViT-L: S = 577, DINOv2-L at 518 px:
+    S = 1370) on the tcgen05 kernel == torch fp32, and its LSE == the mma.sync kernel's."""
+    from visper_lm_b200 import ops
+
+    hd = 64
+    g = torch.Generator().manual_seed(S)
+    qkv = torch.randn(B * S, 3 * H * hd, generator=g).to(torch.bfloat16).cuda()
+    W = H * hd
+    base, lse0 = ops.attn_fwd(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, H, S, S, hd, hd ** -0.5, False)
+    ops.set_option(ops.OPT_ATTN_FWD_TC64, 1)
+    try:
+        o, lse = ops.attn_fwd(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, H, S, S, hd, hd ** -0.5, False)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_ATTN_FWD_TC64, 0)
+    q, k, v = (qkv.float()[:, i * W:(i + 1) * W].view(B, S, H, hd).transpose(1, 2) for i in range(3))
+    sc = q @ k.transpose(-1, -2) * hd ** -0.5
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, W)
+    assert ((o.float() - ref).norm() / ref.norm()).item() < 1.6e-2
+    assert ((o.float() - base.float()).norm() / base.float().norm()).item() < 1e-2
+    assert torch.allclose(lse, torch.logsumexp(sc, -1), atol=2e-2) and torch.allclose(lse, lse0, atol=2e-2)

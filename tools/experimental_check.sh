@@ -31,3 +31,11 @@ done
 timeout 200 python tools/teacher_profile.py convnext 2>&1 | grep -v -i warn | head -14 | tee gpurun_out/convnext_tower_kernel_times.jsonl
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:dwconv7x7 -c 2 -o gpurun_out/dwconv7x7 tools/_bin/dwconv_check > /dev/null 2>&1; ls -la gpurun_out/dwconv7x7.ncu-rep
 timeout 400 python -m pytest tests/test_tower_convnext_gpu.py -m gpu -q -s -p no:cacheprovider 2>&1 | tail -n 15 | tee gpurun_out/convnext_gpu_tests.log
+# ViT attention (head_dim 64, non-causal) on the tcgen05 forward kernel: depth teacher (DINOv2-L) per-kernel split and
+# the whole step (CLIP ViT-L tower), off vs on
+for v in 0 1; do
+  echo "{\"VPB_ATTN_FWD_TC64\": $v}" >> gpurun_out/attn_tc64_ab.jsonl
+  VPB_ATTN_FWD_TC64=$v timeout 120 python tools/teacher_profile.py depth 2>&1 | grep -v -i warn | head -5 >> gpurun_out/attn_tc64_ab.jsonl
+  VPB_ATTN_FWD_TC64=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_tc64_$v.json
+  python -c "import json; d=json.load(open('gpurun_out/bench_tc64_$v.json')); print('TC64=$v', d['ms_per_step'], d['value'], d['clocks'])"
+done; cat gpurun_out/attn_tc64_ab.jsonl

@@ -937,8 +937,11 @@ extern "C" int vpb_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t l
   p.scale = scale;
   if (check_attn(p, head_dim)) return -1;
   VPB_CHECK(!(causal && p.sk2 > 0), "attention: causal with a second key segment is not supported");
-  // tcgen05 path: head_dim 128 (Llama-3) and 96 (Phi-3); the 96 kernels need full 128-row tiles to exist
-  const bool tc_hd = (head_dim == 128 || head_dim == 96) && !(causal && sk < sq && (head_dim == 96 || p.window > 0));
+  // tcgen05 path: head_dim 128 (Llama-3) and 96 (Phi-3); the 96 kernels need full 128-row tiles to exist.
+  // head_dim 64, non-causal (the CLIP / DINOv2 ViT towers) rides the same forward kernel behind
+  // VPB_OPT_ATTN_FWD_TC64: written after the round's GPU budget was spent, off until validated on hardware.
+  const bool tc_hd = ((head_dim == 128 || head_dim == 96) && !(causal && sk < sq && (head_dim == 96 || p.window > 0))) ||
+                     (head_dim == 64 && !causal && get_option(VPB_OPT_ATTN_FWD_TC64));
   if (tc_hd && p.sk2 == 0 && !get_option(VPB_OPT_ATTN_LEGACY_FWD) &&
       (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(v) & 15) == 0)

@@ -117,28 +117,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      // head_dim 64 (ViT towers) is ONE 64-column chunk per tile; 96 / 128 add a second TMA box
+      constexpr uint32_t TX_BYTES = HD > 64 ? TILE_BYTES : CHUNK_BYTES;
+      mbar_arrive_expect_tx(q_full, TX_BYTES);
       tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * HD, b * p.sq + q0);
-      tma_load_2d(smem + OFF_Q + CHUNK_BYTES, &tmQ, q_full, h * HD + 64, b * p.sq + q0);
+      if constexpr (HD > 64) tma_load_2d(smem + OFF_Q + CHUNK_BYTES, &tmQ, q_full, h * HD + 64, b * p.sq + q0);
       auto load_k = [&](int j) {
         const int s = j % KST;
         mbar_wait(&k_empty[s], ((j / KST) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+        mbar_arrive_expect_tx(&k_full[s], TX_BYTES);
         uint8_t* sk = smem + OFF_K + s * TILE_BYTES;
         const int row = b * p.sk + (j + jb) * BN;
         tma_load_2d(sk, &tmK, &k_full[s], kvh * HD, row);
-        tma_load_2d(sk + CHUNK_BYTES, &tmK, &k_full[s], kvh * HD + 64, row);
+        if constexpr (HD > 64) tma_load_2d(sk + CHUNK_BYTES, &tmK, &k_full[s], kvh * HD + 64, row);
       };
       if (ntiles > 0) load_k(0);
       for (int j = 0; j < ntiles; ++j) {
         if (j + 1 < ntiles) load_k(j + 1);  // K runs one tile ahead of V
         const int s = j % VST;
         mbar_wait(&v_empty[s], ((j / VST) & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+        mbar_arrive_expect_tx(&v_full[s], TX_BYTES);
         uint8_t* sv = smem + OFF_V + s * TILE_BYTES;
         const int row = b * p.sk + (j + jb) * BN;
         tma_load_2d(sv, &tmV, &v_full[s], kvh * HD, row);
-        tma_load_2d(sv + CHUNK_BYTES, &tmV, &v_full[s], kvh * HD + 64, row);
+        if constexpr (HD > 64) tma_load_2d(sv + CHUNK_BYTES, &tmV, &v_full[s], kvh * HD + 64, row);
       }
     }
   } else if (warp == 1) {
@@ -2297,6 +2299,8 @@ int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
   p.ldo = ldo;
   p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk;
   p.scale = scale;
+  if (head_dim == 64)  // EXPERIMENTAL (VPB_OPT_ATTN_FWD_TC64): the ViT towers' non-causal attention
+    return launch_fwd_tc<false, 64>(q, ldq, k, ldk, v, ldv, p, st);
   if (head_dim == 96)
     return causal ? launch_fwd_tc<true, 96>(q, ldq, k, ldk, v, ldv, p, st)
                   : launch_fwd_tc<false, 96>(q, ldq, k, ldk, v, ldv, p, st);

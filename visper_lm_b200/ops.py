@@ -39,6 +39,7 @@ OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD, OPT_ATTN_TC_BWD_V1, OPT_GEMM_1CTA, OPT
 OPT_ATTN_BWD_SS, OPT_ATTN_FWD_V2, OPT_ATTN_BWD_PINGPONG, OPT_GEMM_L2_HINTS, OPT_ATTN_POLY_EXP2 = 5, 6, 7, 8, 9
 OPT_WIN_ATTN_V2 = 10
 OPT_DWCONV_FFMA2 = 11
+OPT_ATTN_FWD_TC64 = 12
 
 
 def set_option(key, value):
@@ -628,6 +629,6 @@ if os.environ.get("VPB_GEMM_PANEL_MB"):
 for _name, _key in (("VPB_ATTN_BWD_PINGPONG", OPT_ATTN_BWD_PINGPONG), ("VPB_ATTN_BWD_SS", OPT_ATTN_BWD_SS),
                     ("VPB_ATTN_FWD_V2", OPT_ATTN_FWD_V2), ("VPB_GEMM_1CTA", OPT_GEMM_1CTA),
                     ("VPB_GEMM_L2_HINTS", OPT_GEMM_L2_HINTS), ("VPB_ATTN_POLY_EXP2", OPT_ATTN_POLY_EXP2), ("VPB_WIN_ATTN_V2", OPT_WIN_ATTN_V2),
-                    ("VPB_DWCONV_FFMA2", OPT_DWCONV_FFMA2)):
+                    ("VPB_DWCONV_FFMA2", OPT_DWCONV_FFMA2), ("VPB_ATTN_FWD_TC64", OPT_ATTN_FWD_TC64)):
     if os.environ.get(_name):  # A/B switches for bench runs
         set_option(_key, int(os.environ[_name]))
