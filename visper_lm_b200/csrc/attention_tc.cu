@@ -677,7 +677,7 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   // thread then holds a 128-score row and the register file is split per SM sub-partition (three of
   // this CTA's ten warps share 16 K registers → 168 per thread), so the hot loop spills and it measures
   // 0.47 ms against 0.42 ms for the one-tile kernel at B=8,H=32,S=2048.
-  if (get_option(VPB_OPT_ATTN_FWD_V2) && nqt >= 2) {
+  if (HD > 64 && get_option(VPB_OPT_ATTN_FWD_V2) && nqt >= 2) {  // (the two-tile kernel always loads two chunks)
     auto kern = attn_fwd_tc2_kernel<CAUSAL, HD>;
     static bool cfg2 = false;
     if (!cfg2) {
