@@ -86,3 +86,29 @@ def test_vit_attention_on_tcgen05(B, H, S):
     assert ((o.float() - ref).norm() / ref.norm()).item() < 1.6e-2
     assert ((o.float() - base.float()).norm() / base.float().norm()).item() < 1e-2
     assert torch.allclose(lse, torch.logsumexp(sc, -1), atol=2e-2) and torch.allclose(lse, lse0, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K,act,res", [(20000, 768, 192, 1, False), (18432, 1536, 384, 0, True),
+                                           (8192, 520, 200, 1, True), (4096, 6144, 1024, 1, False)])
+def test_gemm_eight_epilogue_warps_is_bit_identical(M, N, K, act, res):
+    """VPB_OPT_GEMM_EPI8: the CTA-pair GEMM with eight epilogue warps (K <= 1024) == the default kernel bit for bit
+    (same MMAs, same per-element epilogue arithmetic; only which warp drains which columns changes)."""
+    from visper_lm_b200 import ops
+
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).to(torch.bfloat16).cuda()
+    r = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda() if res else None
+    base = ops.gemm(a, w, bias=b, act=act, residual=r)
+    ops.set_option(ops.OPT_GEMM_EPI8, 1)
+    try:
+        got = ops.gemm(a, w, bias=b, act=act, residual=r)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_GEMM_EPI8, 0)
+    assert torch.equal(got, base)
+    ref = a.float() @ w.float().t() + b.float()
+    ref = torch.nn.functional.gelu(ref) if act == 1 else ref
+    ref = ref + r.float() if res else ref
+    assert ((got.float() - ref).norm() / ref.norm()).item() < 1e-2

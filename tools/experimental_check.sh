@@ -39,3 +39,8 @@ for v in 0 1; do
   VPB_ATTN_FWD_TC64=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_tc64_$v.json
   python -c "import json; d=json.load(open('gpurun_out/bench_tc64_$v.json')); print('TC64=$v', d['ms_per_step'], d['value'], d['clocks'])"
 done; cat gpurun_out/attn_tc64_ab.jsonl
+# CTA-pair GEMM with eight epilogue warps for K <= 1024: seg teacher (Swin-L, K = 192..768 GEMMs) and the ConvNeXt tower, off vs on
+for v in 0 1; do
+  echo "{\"VPB_GEMM_EPI8\": $v}" >> gpurun_out/gemm_epi8_ab.jsonl
+  VPB_GEMM_EPI8=$v timeout 200 python tools/teacher_profile.py seg convnext 2>&1 | grep -v -i warn | grep -i "gpu_busy\|gemm" >> gpurun_out/gemm_epi8_ab.jsonl
+done; cat gpurun_out/gemm_epi8_ab.jsonl

@@ -78,8 +78,11 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 
 // Epilogue of one accumulator tile for one warp: thread `lane` owns output row `row` and walks
 // the BN fp32 accumulator columns at TMEM address `taddr` (lane quarter already applied).
+// [c_begin, c_end): the 32-column chunks of the tile this warp drains (EPI_STD only; the fused epilogues
+// always take the whole tile) — the 8-epilogue-warp variant gives each warp of a lane quarter one half.
 template <int BN, int EPI>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_t taddr, int row, int nb) {
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_t taddr, int row, int nb,
+                                                   int c_begin = 0, int c_end = BN / 32) {
   constexpr int BNO = (EPI == EPI_SWIGLU_FWD) ? BN / 2 : BN;
   const bool row_ok = row < args.M;
   bf16* crow = args.C + (int64_t)row * args.ldc;
@@ -223,7 +226,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmArgs& args, uint32_
     }
   } else {
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     const int n_base = nb * BN + c * 32;
     if (n_base >= args.N) break;  // warp-uniform
     uint32_t r[32];
@@ -429,8 +432,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 constexpr int PAIR_BN = 256;
 constexpr int PAIR_STAGES = 6;
 
-template <bool A_MN, bool B_MN, int EPI = EPI_STD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+// EW = epilogue warps per CTA: 4 (default), or 8 (EXPERIMENTAL, VPB_OPT_GEMM_EPI8, EPI_STD only, not yet
+// measured on hardware): two warps per TMEM lane quarter, each draining half of the 256 columns.  For K <= 1024 a
+// tile is <= 64 tcgen05.mma (~4.2 k tensor cycles at M = 256) while four warps need >= 6 k issue cycles for 256
+// columns of bias + exact-erf GELU + pack + store per thread, so the epilogue, not the tensor pipe, paces the kernel.
+template <bool A_MN, bool B_MN, int EPI = EPI_STD, int EW = 4>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                          const __grid_constant__ CUtensorMap tmB, const GemmArgs args) {
   constexpr int BN = PAIR_BN, STAGES = PAIR_STAGES;
@@ -470,7 +477,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], 2 * EW);  // the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -574,8 +581,16 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA,
       const uint32_t acc_ph = (tile_iter >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
-      gemm_epilogue_tile<BN, EPI>(args, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN,
-                                  mb * 2 * BM + (int)rank * BM + quarter * 32 + lane, nb);
+      if constexpr (EW == 8) {
+        static_assert(EW == 4 || EPI == EPI_STD, "8 epilogue warps: standard epilogue only");
+        const int part = (warp - 2) >> 2;  // warps 2-5 take columns [0,128), warps 6-9 [128,256)
+        gemm_epilogue_tile<BN, EPI>(args, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN,
+                                    mb * 2 * BM + (int)rank * BM + quarter * 32 + lane, nb, part * (BN / 64),
+                                    (part + 1) * (BN / 64));
+      } else {
+        gemm_epilogue_tile<BN, EPI>(args, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN,
+                                    mb * 2 * BM + (int)rank * BM + quarter * 32 + lane, nb);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
@@ -674,11 +689,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 }
 
 
-template <bool A_MN, bool B_MN, int EPI = EPI_STD>
+template <bool A_MN, bool B_MN, int EPI = EPI_STD, int EW = 4>
 static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& args,
                             cudaStream_t stream) {
+  if constexpr (EPI == EPI_STD && EW == 4) {
+    if (args.K <= 1024 && get_option(VPB_OPT_GEMM_EPI8))
+      return launch_gemm_pair<A_MN, B_MN, EPI, 8>(tmA, tmB, args, stream);
+  }
   constexpr int SMEM = PAIR_STAGES * (BM * BK * 2 + (PAIR_BN / 2) * BK * 2) + 256;
-  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN, EPI>;
+  auto kern = gemm_tcgen05_pair_kernel<A_MN, B_MN, EPI, EW>;
   static bool configured = false;
   if (!configured) {
     VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -691,7 +710,7 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   GemmArgs a2 = args;
   a2.group_m = panel_rows_for(args.K) / (2 * BM);
   a2.l2_hints = get_option(VPB_OPT_GEMM_L2_HINTS);
-  kern<<<grid, 192, SMEM, stream>>>(tmA, tmB, a2);
+  kern<<<grid, 64 + 32 * EW, SMEM, stream>>>(tmA, tmB, a2);
   VPB_LAUNCH_OK();
   return 0;
 }
