@@ -293,6 +293,7 @@ class CLIPConvNextVisionTower(nn.Module):
         self.cfg = dict(CONVNEXT_PRESETS[base] if cfg is None else cfg)
         self.vision_tower = ConvNeXtTrunk(self.cfg, device)
         self._hidden_size = self.cfg["dims"][-1]
+        self.vision_model = "convnext"                          # clip_convnext_encoder.py:110
         # clip_convnext_encoder.py:113-115
         self.image_processor = ProcessorWrapper(OpenClipEvalTransform(self._image_size), height=self._image_size,
                                                 width=self._image_size)
@@ -340,6 +341,11 @@ class CLIPConvNextVisionTower(nn.Module):
     @property
     def num_patches(self):
         return (self._image_size // self._reduction) ** 2 if self._interp_size is None else self._interp_size
+
+    @property
+    def dummy_feature(self):
+        """base_encoder.py:72-74"""
+        return torch.zeros(1, self.hidden_size, device=self.device, dtype=self.dtype)
 
     @property
     def dtype(self):
