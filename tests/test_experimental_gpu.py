@@ -112,3 +112,28 @@ def test_gemm_eight_epilogue_warps_is_bit_identical(M, N, K, act, res):
     ref = torch.nn.functional.gelu(ref) if act == 1 else ref
     ref = ref + r.float() if res else ref
     assert ((got.float() - ref).norm() / ref.norm()).item() < 1e-2
+
+
+@pytest.mark.parametrize("n,D,nsrc", [(5000, 192, 1), (333, 1536, 1), (1000, 64, 3), (7, 2048, 2)])
+def test_flat_gather_is_bit_identical(n, D, nsrc):
+    """VPB_OPT_GATHER_FLAT: grid-stride gather == the CTA-per-row kernel (zero rows, several sources, strided out)."""
+    from visper_lm_b200 import ops
+
+    g = torch.Generator().manual_seed(n + D)
+    srcs = [torch.randn(400 + 10 * i, D, generator=g).to(torch.bfloat16).cuda() for i in range(nsrc)]
+    index = torch.randint(-1, 400, (n,), generator=g, dtype=torch.int32).cuda()
+    kind = torch.randint(0, nsrc, (n,), generator=g, dtype=torch.int32).cuda() if nsrc > 1 else None
+    wide0 = torch.full((n, 2 * D), 7.0, dtype=torch.bfloat16, device="cuda")
+    wide1 = wide0.clone()
+    ops.gather_rows(index, srcs, D, kind=kind, out=wide0[:, D:])
+    ops.set_option(ops.OPT_GATHER_FLAT, 1)
+    try:
+        ops.gather_rows(index, srcs, D, kind=kind, out=wide1[:, D:])
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_GATHER_FLAT, 0)
+    assert torch.equal(wide0, wide1)
+    k = kind.long() if kind is not None else torch.zeros(n, dtype=torch.long, device="cuda")
+    ref = torch.stack([srcs[int(k[r])][int(index[r])] if index[r] >= 0 else torch.zeros(D, dtype=torch.bfloat16, device="cuda")
+                       for r in range(min(n, 300))])
+    assert torch.equal(wide1[:300, D:], ref)

@@ -44,3 +44,8 @@ for v in 0 1; do
   echo "{\"VPB_GEMM_EPI8\": $v}" >> gpurun_out/gemm_epi8_ab.jsonl
   VPB_GEMM_EPI8=$v timeout 200 python tools/teacher_profile.py seg convnext 2>&1 | grep -v -i warn | grep -i "gpu_busy\|gemm" >> gpurun_out/gemm_epi8_ab.jsonl
 done; cat gpurun_out/gemm_epi8_ab.jsonl
+# flat grid-stride gather (window partition / reverse / merges of the seg teacher and the ConvNeXt tower), off vs on
+for v in 0 1; do
+  echo "{\"VPB_GATHER_FLAT\": $v}" >> gpurun_out/gather_flat_ab.jsonl
+  VPB_GATHER_FLAT=$v timeout 200 python tools/teacher_profile.py seg 2>&1 | grep -v -i warn | grep -i "gpu_busy\|gather" >> gpurun_out/gather_flat_ab.jsonl
+done; cat gpurun_out/gather_flat_ab.jsonl

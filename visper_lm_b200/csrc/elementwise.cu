@@ -253,6 +253,24 @@ gather_rows_kernel(bf16* __restrict__ out, int64_t ldo, const int* __restrict__ 
   }
 }
 
+// EXPERIMENTAL (VPB_OPT_GATHER_FLAT, off until measured): the same gather as a flat grid-stride loop over
+// (row, 16-byte vector) pairs.  One CTA per row leaves 104 of 128 threads idle on a 192-wide Swin row and
+// launches 333 k CTAs per call (seg teacher gathers: 3.4 ms per batch against ~0.8 ms of HBM time).
+__global__ void __launch_bounds__(256)
+gather_rows_flat_kernel(bf16* __restrict__ out, int64_t ldo, const int* __restrict__ kind,
+                        const int* __restrict__ index, GatherSrc s, int D, int nrows) {
+  const int vec = D >> 3;
+  const int64_t total = (int64_t)nrows * vec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / vec), v = (int)(i - (int64_t)r * vec);
+    const int k = kind ? kind[r] : 0;
+    const int idx = index[r];
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (k >= 0 && idx >= 0) val = ldg16_stream(s.p[k] + (int64_t)idx * s.ld[k] + v * 8);
+    stg16(out + (int64_t)r * ldo + v * 8, val);
+  }
+}
+
 // out[s] = scale * sum_{c<cnt} src[index[s*cnt+c]]   (index < 0 skipped), fp32 accumulate
 __global__ void __launch_bounds__(128)
 gather_sum_rows_kernel(bf16* __restrict__ out, int64_t ldo, const int* __restrict__ index, int cnt,
@@ -476,6 +494,14 @@ extern "C" int vpb_gather_rows(void* out, int64_t ldo, int nrows, int D, const i
   s.p[1] = (const bf16*)src1; s.ld[1] = ld1;
   s.p[2] = (const bf16*)src2; s.ld[2] = ld2;
   s.p[3] = (const bf16*)src3; s.ld[3] = ld3;
+  if (get_option(VPB_OPT_GATHER_FLAT) && D <= 2048) {
+    const int64_t total = (int64_t)nrows * (D >> 3);
+    const int64_t want = (total + 255) / 256, cap = (int64_t)num_sms() * 16;
+    gather_rows_flat_kernel<<<(int)(want < cap ? want : cap), 256, 0, ST(stream)>>>((bf16*)out, ldo, kind, index, s,
+                                                                                   D, nrows);
+    VPB_LAUNCH_OK();
+    return 0;
+  }
   gather_rows_kernel<<<nrows, 128, 0, ST(stream)>>>((bf16*)out, ldo, kind, index, s, D);
   VPB_LAUNCH_OK();
   return 0;
