@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: validate the kernel variants that were written after round 1's GPU
 # budget ran out (all OFF by default) and A/B them on one box.  Results land in gpurun_out/.
-#   gpurun --timeout 900 -- 'bash tools/experimental_check.sh'
+#   gpurun --timeout 1500 -- 'bash tools/experimental_check.sh'   (≈ 18 GPU-minutes; every block is independent — split it if the budget is tight)
 mkdir -p gpurun_out
 VPB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py tests/test_ex2_poly.py -m gpu -q \
   -p no:cacheprovider > gpurun_out/experimental_tests.log 2>&1; echo "experimental tests exit $?"; tail -n 8 gpurun_out/experimental_tests.log
