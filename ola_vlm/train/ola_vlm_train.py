@@ -6,3 +6,8 @@ from visper_lm_b200.train.data import (DataArguments, DataCollatorForSupervisedD
                                        LazySupervisedDataset, make_supervised_data_module)
 from visper_lm_b200.train.prompts import (preprocess_llama_3, preprocess_multimodal,  # noqa: F401,E402
                                           preprocess_phi_3)
+from visper_lm_b200.train.entry import ModelArguments, train  # noqa: F401,E402  (ola_vlm_train.py:55-109, 977)
+from visper_lm_b200.train.trainer import TrainingArguments  # noqa: F401,E402
+
+if __name__ == "__main__":
+    train()

@@ -53,6 +53,10 @@ def test_reference_module_paths_resolve():
     for name in ("DAv2_Head", "TaskTokenGenHead", "TaskTokenDepthHead", "OneFormerTaskTokenSegHead", "OneFormerHead"):
         assert hasattr(a, name)
     assert hasattr(importlib.import_module("ola_vlm.model.aux_heads.depth_anything_v2.dpt"), "DepthAnythingV2")
+    tr = importlib.import_module("ola_vlm.train.ola_vlm_train")                # what pretrain.sh / finetune.sh launch
+    assert callable(tr.train) and hasattr(tr, "ModelArguments") and hasattr(tr, "TrainingArguments")
+    assert callable(importlib.import_module("ola_vlm.train.ola_vlm_train_mem").train)
+    assert callable(importlib.import_module("ola_vlm.train.train_mem").train)
     b = importlib.import_module("ola_vlm.model.multimodal_encoder.builder")   # ola_arch.py:12 import
     from types import SimpleNamespace
 

@@ -685,6 +685,13 @@ class VisperForCausalLM(nn.Module):
             if config.image_depth.get("output_dim") == 1024 and getattr(config, "depth_preds", True):
                 from .dpt import DAv2_Head
                 self.da_v2_head = DAv2_Head(dev)
+                path = getattr(config, "depth_estimator", None)
+                if path and __import__("os").path.exists(str(path)):   # base_ola_vlm.py:148 (strict=False)
+                    sd = torch.load(path, map_location="cpu")
+                    own = self.da_v2_head.state_dict()
+                    self.da_v2_head.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+                    self._da_v2_head_loaded = True
+                self.da_v2_head.requires_grad_(False)
         if "seg" in self.mode:
             self.seg_layer_indices, self.img_seg_loss_weight = self._layer_loss_weight(config.image_seg, "seg")
             self.seg_logit_scale = nn.Parameter(torch.tensor(2.0, device=dev)) if use_con else None
