@@ -230,3 +230,23 @@ def test_image_processor_matches_torchvision():
         want = ref(im)
         assert got.shape == (3, 96, 96) and torch.allclose(got, want, atol=1e-6), (w, h, mode)
     assert torch.equal(proc([im])["pixel_values"][0], got)           # list input / __call__ (base_encoder.py:23-31)
+
+
+def test_config_json_round_trip_keeps_the_tower():
+    """config.json as trainer._save writes it → from_pretrained's constructor call: the ConvNeXt tower survives."""
+    import json
+
+    from visper_lm_b200.model.convnext import CLIPConvNextVisionTower
+    from visper_lm_b200.model.vlm import VisperConfig, VisperModel
+    from visper_lm_b200.train.checkpoint import config_to_dict
+
+    cfg = VisperConfig(vocab_size=64, hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2,
+                       num_key_value_heads=2, mm_vision_tower="CLIP-convnext_xxlarge-res768")
+    d = json.loads(json.dumps(config_to_dict(cfg)))
+    for k in ("model_type", "family", "architectures"):
+        d.pop(k, None)
+    again = VisperConfig(**d)
+    assert again.mm_vision_tower == cfg.mm_vision_tower and again.mm_hidden_size == 3072
+    assert list(again.vision["dims"]) == [384, 768, 1536, 3072] and again.vision["eps"] == 1e-5
+    m = VisperModel(again, device="meta")
+    assert isinstance(m.vision_tower, CLIPConvNextVisionTower) and m.mm_projector[0].weight.shape == (64, 3072)
