@@ -1,5 +1,6 @@
 #!/bin/bash
-# Builds tools/_bin/dwconv_check (git-ignored, travels with gpurun) against the in-tree library.
+# Builds the stand-alone C-ABI checks tools/_bin/{dwconv_check,variants_check} (git-ignored, they travel with gpurun)
+# against the in-tree library.
 set -e
 cd "$(dirname "$0")/.."
 python -m visper_lm_b200.build > /dev/null
@@ -7,4 +8,6 @@ mkdir -p tools/_bin oracle/_ref
 gcc -O2 -c oracle/c/dwconv_ref.c -o tools/_bin/dwconv_ref.o
 nvcc -gencode arch=compute_100a,code=sm_100a -O2 -Iinclude tools/dwconv_check.cu tools/_bin/dwconv_ref.o \
   -o tools/_bin/dwconv_check -Lvisper_lm_b200 -l:libvisper_b200.so -Xlinker -rpath -Xlinker '$ORIGIN/../../visper_lm_b200'
-echo tools/_bin/dwconv_check
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -Iinclude tools/variants_check.cu \
+  -o tools/_bin/variants_check -Lvisper_lm_b200 -l:libvisper_b200.so -Xlinker -rpath -Xlinker '$ORIGIN/../../visper_lm_b200'
+echo tools/_bin/dwconv_check tools/_bin/variants_check

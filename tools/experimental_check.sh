@@ -3,6 +3,9 @@
 # budget ran out (all OFF by default) and A/B them on one box.  Results land in gpurun_out/.
 #   gpurun --timeout 1500 -- 'bash tools/experimental_check.sh'   (≈ 18 GPU-minutes; every block is independent — split it if the budget is tight)
 mkdir -p gpurun_out
+# fastest first: Python-free C-ABI A/B of the variants (bit identity / max diff + alternating timings), ~30 s of GPU.
+# Can be run on its own:  gpurun --timeout 120 -- 'tools/_bin/variants_check | tee gpurun_out/variants_check.jsonl'
+timeout 180 tools/_bin/variants_check | tee gpurun_out/variants_check.jsonl
 VPB_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_experimental_gpu.py tests/test_ex2_poly.py -m gpu -q \
   -p no:cacheprovider > gpurun_out/experimental_tests.log 2>&1; echo "experimental tests exit $?"; tail -n 8 gpurun_out/experimental_tests.log
 # polynomial exp2 in the tcgen05 attention kernels: isolated forward / backward times, off vs on (alternating)
