@@ -57,6 +57,7 @@ def test_reference_module_paths_resolve():
     assert callable(tr.train) and hasattr(tr, "ModelArguments") and hasattr(tr, "TrainingArguments")
     assert callable(importlib.import_module("ola_vlm.train.ola_vlm_train_mem").train)
     assert callable(importlib.import_module("ola_vlm.train.train_mem").train)
+    assert callable(importlib.import_module("ola_vlm.model.builder").load_pretrained_model)
     b = importlib.import_module("ola_vlm.model.multimodal_encoder.builder")   # ola_arch.py:12 import
     from types import SimpleNamespace
 

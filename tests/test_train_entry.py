@@ -159,3 +159,38 @@ def test_build_model_finetune_stage_and_convnext_tower(tmp_path, monkeypatch):
         build_model(*_args(tmp_path, mm_projector_type="linear"), _Tok(160, pad="<pad>"), device="cpu")
     with pytest.raises(ValueError):
         build_model(*_args(tmp_path, vision_tower=None), _Tok(160, pad="<pad>"), device="cpu")
+
+
+def test_builder_loads_what_the_trainer_saves(tmp_path):
+    """ola_vlm.model.builder.load_pretrained_model (builder.py:26-191) on a directory in the trainer's save
+    layout: class from config.json's model_type, the reference's 4-tuple, image-patch token added."""
+    from parity_utils import build_product, configs
+
+    from ola_vlm.model.builder import load_pretrained_model
+    from visper_lm_b200.model import OlaLlavaPhi3ForCausalLM
+    from visper_lm_b200.train import checkpoint as C
+
+    torch.manual_seed(5)
+    model = build_product(configs.TINY_PHI3, True, None)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(torch.randn(p.shape))
+    C.save_config(model.config, str(tmp_path))
+    C.save_pretrained_weights(model.state_dict(), str(tmp_path))
+    V = model.config.vocab_size
+    tok = _Tok(V, pad="<pad>")
+    tokenizer, again, image_processor, context_len = load_pretrained_model(str(tmp_path), None, "whatever-name",
+                                                                          device="cpu", tokenizer=tok)
+    assert type(again) is OlaLlavaPhi3ForCausalLM and tokenizer is tok and context_len == 4096
+    assert image_processor is again.get_vision_tower().image_processor
+    assert len(tok) == V + 1                                           # <im_patch> (mm_use_im_patch_token defaults True)
+    rows = again.get_input_embeddings().weight.shape[0]
+    assert rows >= V + 1 and rows % 8 == 0
+    a, b = model.state_dict(), again.state_dict()
+    for k in a:
+        if "embed_tokens" in k or "lm_head" in k:
+            assert torch.equal(a[k], b[k][:V]), k
+        else:
+            assert torch.equal(a[k], b[k]), k
+    with pytest.raises(NotImplementedError):
+        load_pretrained_model(str(tmp_path), "some/base", "lora-x", tokenizer=tok)
