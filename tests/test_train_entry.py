@@ -194,3 +194,18 @@ def test_builder_loads_what_the_trainer_saves(tmp_path):
             assert torch.equal(a[k], b[k]), k
     with pytest.raises(NotImplementedError):
         load_pretrained_model(str(tmp_path), "some/base", "lora-x", tokenizer=tok)
+
+
+def test_freeze_backbone_leaves_lm_head_trainable():
+    """--freeze_backbone = `model.model.requires_grad_(False)` (ola_vlm_train.py:1043-1044): decoder frozen,
+    lm_head and the later-created projector still train."""
+    from parity_utils import configs
+
+    from visper_lm_b200.model import LlavaLlamaForCausalLM, presets
+    from visper_lm_b200.train.policy import apply_freeze_policy
+
+    model = LlavaLlamaForCausalLM(presets.from_dict(configs.TINY_LLAMA, distill=False), device="meta")
+    names = apply_freeze_policy(model, freeze_backbone=True)
+    assert "lm_head.weight" in names and "model.mm_projector.0.weight" in names
+    assert not any(n.startswith("model.layers.") or n.startswith("model.embed_tokens") or n == "model.norm.weight" for n in names)
+    assert not any("vision_tower" in n for n in names)

@@ -27,7 +27,9 @@ def apply_freeze_policy(model, tune_mm_mlp_adapter=False, freeze_mm_mlp_adapter=
         elif any(t in n for t in ADDED_BY_DISTILLATION):
             on = True
         else:  # the language model itself (embed_tokens, layers, norm, lm_head)
-            on = not (tune_mm_mlp_adapter or freeze_backbone)
+            # --freeze_backbone is `model.model.requires_grad_(False)` (ola_vlm_train.py:1043-1044): the decoder
+            # under `model.`, not lm_head
+            on = not (tune_mm_mlp_adapter or (freeze_backbone and n.startswith("model.")))
         p.requires_grad_(on)
         if on:
             names.append(n)
