@@ -94,3 +94,20 @@ def test_expand2square():
     out = D.expand2square(im, (1, 2, 3))
     assert out.size == (6, 6) and out.getpixel((0, 0)) == (1, 2, 3) and out.getpixel((0, 2)) == (9, 9, 9)
     assert D.expand2square(Image.new("RGB", (4, 4)), (0, 0, 0)).size == (4, 4)
+
+
+def test_dataset_with_the_convnext_processor(tmp_path):
+    """The ConvNeXt tower's image_processor (ProcessorWrapper, base_encoder.py:8-40) through the dataset:
+    pad-to-square with its image_mean, 64x64 pixel tensors, black image of crop_size for the text-only sample."""
+    from visper_lm_b200.model.convnext import OpenClipEvalTransform, ProcessorWrapper
+
+    path, data = _write(tmp_path, False)
+    proc = ProcessorWrapper(OpenClipEvalTransform(64), height=64, width=64)
+    args = D.DataArguments(data_path=path, is_multimodal=True, image_folder=str(tmp_path), image_aspect_ratio="pad",
+                           image_processor=proc, version="llava_llama_3")
+    ds = D.make_supervised_data_module(MarkerTokenizer(), args)["train_dataset"]
+    items = [ds[i] for i in range(4)]
+    assert all(it["image"].shape == (3, 64, 64) and it["image"].dtype == torch.float32 for it in items)
+    assert float(items[1]["image"].abs().max()) == 0.0 and items[1]["seg_mask"] == 0       # text-only: black image
+    # padded-to-square wide image: top rows are the CLIP mean colour → ~0 after normalisation
+    assert float(items[0]["image"][:, :6].abs().max()) < 0.02 and float(items[0]["image"].abs().max()) > 0.5
