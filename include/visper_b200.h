@@ -51,6 +51,7 @@ void vpb_reset_launch_count(void);
 #define VPB_OPT_ATTN_FWD_TC64 12   /* 1: experimental — non-causal head_dim-64 attention forward (CLIP ViT-L, DINOv2-L towers) on the tcgen05 kernel (one 64-column chunk per tile) instead of the mma.sync kernel */
 #define VPB_OPT_GEMM_EPI8 13       /* 1: experimental — CTA-pair GEMM with EIGHT epilogue warps per CTA (two per TMEM lane quarter, half the columns each) for K <= 1024, where the bias/GELU/store epilogue outlasts the tile's MMAs */
 #define VPB_OPT_GATHER_FLAT 14     /* 1: experimental — vpb_gather_rows for rows of <= 2048 elements as a flat grid-stride loop instead of one CTA per row */
+#define VPB_OPT_ATTN_FWD_QTM 15    /* 1: experimental — head_dim-128 tcgen05 attention forward with Q resident in TMEM as the A operand of QK^T (no Q tile in shared memory); bit-identical results */
 #define VPB_OPT_DWCONV_FFMA2 11    /* 1: experimental — depthwise 7x7 with packed fp32 FMAs (fma.rn.f32x2 = SASS FFMA2, one per channel pair); bit-identical results, half the FMA instructions */
 #define VPB_OPT_WIN_ATTN_V2 10     /* experimental — vpb_attn_fwd_bias on the one-pass kernel for windows of <= 144 tokens: 1 = two CTAs per SM (96 registers, small spills), 2 = one CTA per SM (no spills) */
 int vpb_set_option(int key, int value);

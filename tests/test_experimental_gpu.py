@@ -137,3 +137,23 @@ def test_flat_gather_is_bit_identical(n, D, nsrc):
     ref = torch.stack([srcs[int(k[r])][int(index[r])] if index[r] >= 0 else torch.zeros(D, dtype=torch.bfloat16, device="cuda")
                        for r in range(min(n, 300))])
     assert torch.equal(wide1[:300, D:], ref)
+
+
+@pytest.mark.parametrize("B,H,KVH,S,causal", [(2, 8, 2, 1024, True), (1, 4, 4, 333, True), (2, 4, 1, 577, False)])
+def test_attention_forward_with_q_in_tmem_is_bit_identical(B, H, KVH, S, causal):
+    """VPB_OPT_ATTN_FWD_QTM: Q as the TMEM-resident A operand of QK^T == the default head_dim-128 forward, bit for
+    bit (same operands, same accumulation order), output and LSE; ragged last query / key tiles included."""
+    from visper_lm_b200 import ops
+
+    hd = 128
+    g = torch.Generator().manual_seed(S + H)
+    qkv = torch.randn(B * S, (H + 2 * KVH) * hd, generator=g).to(torch.bfloat16).cuda()
+    q, k, v = qkv[:, :H * hd], qkv[:, H * hd:(H + KVH) * hd], qkv[:, (H + KVH) * hd:]
+    base, lse0 = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, hd ** -0.5, causal)
+    ops.set_option(ops.OPT_ATTN_FWD_QTM, 1)
+    try:
+        o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, hd ** -0.5, causal)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_ATTN_FWD_QTM, 0)
+    assert torch.equal(o, base) and torch.equal(lse, lse0)

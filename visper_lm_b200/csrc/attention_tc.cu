@@ -25,6 +25,8 @@ struct AttnTcParams {
   int B, H, KVH, sq, sk;
   float scale;
   int window;  // causal sliding window: key j visible to query i iff 0 <= i + off - j <= window (0: off)
+  const bf16* q;  // QTM variant only: Q rows are read straight from global memory
+  int64_t ldq;
 };
 
 namespace tc {
@@ -48,7 +50,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // POLY (EXPERIMENTAL, VPB_OPT_ATTN_POLY_EXP2, off by default, not yet measured on hardware): every fourth
 // exponential of the softmax goes through ex2_poly on the FMA pipe instead of MUFU ex2.approx.
-template <bool CAUSAL, int HD, bool POLY = false>
+// QTM (EXPERIMENTAL, VPB_OPT_ATTN_FWD_QTM, head_dim 128, off by default, not yet measured on hardware): Q lives in
+// TMEM as the packed-bf16 A operand of S = Q.K^T (64 columns next to O) instead of shared memory.  Q is constant
+// for the CTA, so each softmax thread loads its own half row from global memory once and tcgen05.st's it exactly
+// like P; the QK^T MMAs then read only the K tile from shared memory (32 KB instead of 64 KB per key tile; the
+// kernel moves ~160 KB per tile through a 128 B/clk shared memory against 1024 tensor cycles).  Same operands,
+// same accumulation order: results are bit-identical to the default kernel.
+template <bool CAUSAL, int HD, bool POLY = false, bool QTM = false>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -93,7 +101,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
+    mbar_init(q_full, QTM ? 8 : 1);  // QTM: the eight softmax warps publish Q in TMEM
     for (int i = 0; i < KST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -114,14 +122,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t TM_S = tmem_base;        // S[0] at +0, S[1] at +128
   const uint32_t TM_O = tmem_base + 256;  // O accumulator
+  const uint32_t TM_Q = tmem_base + 384;  // QTM: Q as packed bf16 pairs, 64 columns
+  static_assert(!QTM || HD == 128, "Q-in-TMEM variant: head_dim 128 only");
 
   if (warp == 0) {
     if (lane == 0) {
       // head_dim 64 (ViT towers) is ONE 64-column chunk per tile; 96 / 128 add a second TMA box
       constexpr uint32_t TX_BYTES = HD > 64 ? TILE_BYTES : CHUNK_BYTES;
-      mbar_arrive_expect_tx(q_full, TX_BYTES);
-      tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * HD, b * p.sq + q0);
-      if constexpr (HD > 64) tma_load_2d(smem + OFF_Q + CHUNK_BYTES, &tmQ, q_full, h * HD + 64, b * p.sq + q0);
+      if constexpr (!QTM) {
+        mbar_arrive_expect_tx(q_full, TX_BYTES);
+        tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * HD, b * p.sq + q0);
+        if constexpr (HD > 64) tma_load_2d(smem + OFF_Q + CHUNK_BYTES, &tmQ, q_full, h * HD + 64, b * p.sq + q0);
+      }
       auto load_k = [&](int j) {
         const int s = j % KST;
         mbar_wait(&k_empty[s], ((j / KST) & 1) ^ 1);
@@ -160,7 +172,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
             const uint32_t o = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
-            umma_bf16(TM_S + sb * BN, desc_adv(q_desc, o), desc_adv(k_desc, o), idesc_s, k != 0);
+            if constexpr (QTM)
+              umma_bf16_ts(TM_S + sb * BN, TM_Q + k * 8, desc_adv(k_desc, o), idesc_s, k != 0);
+            else
+              umma_bf16(TM_S + sb * BN, desc_adv(q_desc, o), desc_adv(k_desc, o), idesc_s, k != 0);
           }
           umma_commit(&s_full[sb]);
           umma_commit(&k_empty[s]);
@@ -196,6 +211,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float sl2 = p.scale * LOG2E;
     float m_used = -INFINITY, l = 0.f;
     float* xchg = reinterpret_cast<float*>(smem + OFF_X);  // [2 parity][2 half][128 rows] + [2][128]
+    if constexpr (QTM) {
+      // this thread's half of its query row: 64 bf16 = 32 packed columns (zeros past the end of the sequence)
+      uint32_t w[32];
+      if (q0 + row < p.sq) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + ((int64_t)b * p.sq + q0 + row) * p.ldq + h * HD + half * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = __ldg(src + i);
+          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w[i] = 0;
+      }
+      tmem_st32(TM_Q + lane_addr + half * 32, w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_full);
+    }
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j & 1;
       mbar_wait_spin(&s_full[sb], (j >> 1) & 1);
@@ -700,6 +735,22 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
     kernp<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
     VPB_LAUNCH_OK();
     return 0;
+  }
+  if constexpr (HD == 128) {
+    if (get_option(VPB_OPT_ATTN_FWD_QTM) && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && ldq % 8 == 0) {
+      auto kernq = attn_fwd_tc_kernel<CAUSAL, HD, false, true>;
+      static bool cfgq = false;
+      if (!cfgq) {
+        VPB_CUDA(cudaFuncSetAttribute(kernq, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        cfgq = true;
+      }
+      AttnTcParams pq = p;
+      pq.q = static_cast<const bf16*>(q);
+      pq.ldq = ldq;
+      kernq<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, pq);
+      VPB_LAUNCH_OK();
+      return 0;
+    }
   }
   auto kern = attn_fwd_tc_kernel<CAUSAL, HD>;
   static bool cfg = false;
@@ -2299,6 +2350,8 @@ int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
   p.ldo = ldo;
   p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk;
   p.scale = scale;
+  p.q = nullptr;
+  p.ldq = 0;
   if (head_dim == 64)  // EXPERIMENTAL (VPB_OPT_ATTN_FWD_TC64): the ViT towers' non-causal attention
     return launch_fwd_tc<false, 64>(q, ldq, k, ldk, v, ldv, p, st);
   if (head_dim == 96)

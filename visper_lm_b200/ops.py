@@ -42,6 +42,7 @@ OPT_DWCONV_FFMA2 = 11
 OPT_ATTN_FWD_TC64 = 12
 OPT_GEMM_EPI8 = 13
 OPT_GATHER_FLAT = 14
+OPT_ATTN_FWD_QTM = 15
 
 
 def set_option(key, value):
@@ -632,6 +633,7 @@ for _name, _key in (("VPB_ATTN_BWD_PINGPONG", OPT_ATTN_BWD_PINGPONG), ("VPB_ATTN
                     ("VPB_ATTN_FWD_V2", OPT_ATTN_FWD_V2), ("VPB_GEMM_1CTA", OPT_GEMM_1CTA),
                     ("VPB_GEMM_L2_HINTS", OPT_GEMM_L2_HINTS), ("VPB_ATTN_POLY_EXP2", OPT_ATTN_POLY_EXP2), ("VPB_WIN_ATTN_V2", OPT_WIN_ATTN_V2),
                     ("VPB_DWCONV_FFMA2", OPT_DWCONV_FFMA2), ("VPB_ATTN_FWD_TC64", OPT_ATTN_FWD_TC64),
-                    ("VPB_GEMM_EPI8", OPT_GEMM_EPI8), ("VPB_GATHER_FLAT", OPT_GATHER_FLAT)):
+                    ("VPB_GEMM_EPI8", OPT_GEMM_EPI8), ("VPB_GATHER_FLAT", OPT_GATHER_FLAT),
+                    ("VPB_ATTN_FWD_QTM", OPT_ATTN_FWD_QTM)):
     if os.environ.get(_name):  # A/B switches for bench runs
         set_option(_key, int(os.environ[_name]))
