@@ -166,8 +166,10 @@ def test_builder_loads_what_the_trainer_saves(tmp_path):
     layout: class from config.json's model_type, the reference's 4-tuple, image-patch token added."""
     from parity_utils import build_product, configs
 
-    from ola_vlm.model.builder import load_pretrained_model
     from visper_lm_b200.model import OlaLlavaPhi3ForCausalLM
+    # (the implementation behind ola_vlm.model.builder; imported directly because the oracle tests of the same
+    # session may have pointed the `ola_vlm` namespace at the reference tree — oracle/ref_shim.py)
+    from visper_lm_b200.model.loader import load_pretrained_model
     from visper_lm_b200.train import checkpoint as C
 
     torch.manual_seed(5)
