@@ -52,3 +52,8 @@ for v in 0 1; do
   echo "{\"VPB_GATHER_FLAT\": $v}" >> gpurun_out/gather_flat_ab.jsonl
   VPB_GATHER_FLAT=$v timeout 200 python tools/teacher_profile.py seg 2>&1 | grep -v -i warn | grep -i "gpu_busy\|gather" >> gpurun_out/gather_flat_ab.jsonl
 done; cat gpurun_out/gather_flat_ab.jsonl
+# Q-in-TMEM attention forward in the whole step (kernel-level numbers come from variants_check above), off vs on
+for v in 0 1; do
+  VPB_ATTN_FWD_QTM=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_qtm_$v.json
+  python -c "import json; d=json.load(open('gpurun_out/bench_qtm_$v.json')); print('QTM=$v', d['ms_per_step'], d['value'], d['clocks'])"
+done
