@@ -141,7 +141,11 @@ static int gather_flat(int rows_src, int n, int D) {
 }
 
 // forward attention on the packed [B*S, 3*H*hd] projection: option `opt` off vs on
-static int attn_ab(const char* name, int opt, int B, int H, int KVH, int S, int hd, int causal, double tol) {
+static int attn_ab(const char* name, int opt, int B, int H, int KVH, int S, int hd, int causal, double tol, int opt2 = -1) {
+  auto set = [&](int v) {
+    vpb_set_option(opt, v);
+    if (opt2 >= 0) vpb_set_option(opt2, v);
+  };
   const int ld = (H + 2 * KVH) * hd;
   bf16* qkv = dev_rand((size_t)B * S * ld, 1.f);
   bf16 *o0, *o1;
@@ -155,9 +159,9 @@ static int attn_ab(const char* name, int opt, int B, int H, int KVH, int S, int 
     rc |= vpb_attn_fwd(qkv, ld, qkv + H * hd, ld, qkv + (H + KVH) * hd, ld, nullptr, 0, nullptr, 0, o, H * hd, l, B, H, KVH, S, S,
                        0, hd, 1.f / sqrtf((float)hd), causal, 0, nullptr);
   };
-  vpb_set_option(opt, 0);
+  set(0);
   run(o0, l0);
-  vpb_set_option(opt, 1);
+  set(1);
   run(o1, l1);
   cudaError_t e = cudaDeviceSynchronize();
   double mref = 0;
@@ -165,10 +169,10 @@ static int attn_ab(const char* name, int opt, int B, int H, int KVH, int S, int 
   float ms[2][2];
   for (int rep = 0; rep < 2; ++rep)
     for (int v = 0; v < 2; ++v) {
-      vpb_set_option(opt, v);
+      set(v);
       ms[rep][v] = time_ms([&] { run(o1, l1); }, 5);
     }
-  vpb_set_option(opt, 0);
+  set(0);
   const double fl = 4.0 * B * H * (double)S * S * hd * (causal ? 0.5 : 1.0);
   const bool ok = rc == 0 && e == cudaSuccess && d <= tol * mref;
   printf("{\"variant\": \"%s\", \"B\": %d, \"H\": %d, \"KVH\": %d, \"S\": %d, \"hd\": %d, \"causal\": %d, \"rc\": %d, \"cuda\": \"%s\", "
@@ -208,6 +212,8 @@ int main(int argc, char** argv) {
     fails += attn_ab("attn_poly", VPB_OPT_ATTN_POLY_EXP2, 8, 32, 8, 2048, 128, 1, 1e-2);  // Llama-3 decoder
     fails += attn_ab("attn_poly", VPB_OPT_ATTN_POLY_EXP2, 4, 32, 32, 2048, 96, 1, 1e-2);  // Phi-3 decoder
   }
+  if (want("attn_poly_qtm"))  // both: the MUFU relief and the shared-memory relief together
+    fails += attn_ab("attn_poly_qtm", VPB_OPT_ATTN_POLY_EXP2, 8, 32, 8, 2048, 128, 1, 1e-2, VPB_OPT_ATTN_FWD_QTM);
   if (want("attn_qtm")) {  // bit-identical by construction: tolerance 0
     fails += attn_ab("attn_qtm", VPB_OPT_ATTN_FWD_QTM, 8, 32, 8, 2048, 128, 1, 0.0);   // Llama-3 decoder
     fails += attn_ab("attn_qtm", VPB_OPT_ATTN_FWD_QTM, 2, 8, 2, 333, 128, 1, 0.0);     // ragged tiles

@@ -725,32 +725,30 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
     return 0;
   }
   dim3 grid((p.sq + tc::BM - 1) / tc::BM, p.H, p.B);
-  if (get_option(VPB_OPT_ATTN_POLY_EXP2)) {
-    auto kernp = attn_fwd_tc_kernel<CAUSAL, HD, true>;
-    static bool cfgp = false;
-    if (!cfgp) {
-      VPB_CUDA(cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-      cfgp = true;
-    }
-    kernp<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
-    VPB_LAUNCH_OK();
-    return 0;
-  }
-  if constexpr (HD == 128) {
-    if (get_option(VPB_OPT_ATTN_FWD_QTM) && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && ldq % 8 == 0) {
-      auto kernq = attn_fwd_tc_kernel<CAUSAL, HD, false, true>;
-      static bool cfgq = false;
-      if (!cfgq) {
-        VPB_CUDA(cudaFuncSetAttribute(kernq, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        cfgq = true;
+  // experimental variants (all off by default): POLY = polynomial exp2 for a quarter of the scores, QTM = Q in TMEM
+  // (head_dim 128); they combine
+  const bool poly = get_option(VPB_OPT_ATTN_POLY_EXP2) != 0;
+  const bool qtm = HD == 128 && get_option(VPB_OPT_ATTN_FWD_QTM) && (reinterpret_cast<uintptr_t>(q) & 15) == 0 &&
+                   ldq % 8 == 0;
+  if (poly || qtm) {
+    AttnTcParams pq = p;
+    pq.q = static_cast<const bf16*>(q);
+    pq.ldq = ldq;
+    auto launch_variant = [&](auto kernv, bool& configured) -> int {
+      if (!configured) {
+        VPB_CUDA(cudaFuncSetAttribute(kernv, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        configured = true;
       }
-      AttnTcParams pq = p;
-      pq.q = static_cast<const bf16*>(q);
-      pq.ldq = ldq;
-      kernq<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, pq);
+      kernv<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, pq);
       VPB_LAUNCH_OK();
       return 0;
+    };
+    static bool cfg_p = false, cfg_q = false, cfg_pq = false;
+    if constexpr (HD == 128) {
+      if (poly && qtm) return launch_variant(attn_fwd_tc_kernel<CAUSAL, HD, true, true>, cfg_pq);
+      if (qtm) return launch_variant(attn_fwd_tc_kernel<CAUSAL, HD, false, true>, cfg_q);
     }
+    return launch_variant(attn_fwd_tc_kernel<CAUSAL, HD, true, false>, cfg_p);
   }
   auto kern = attn_fwd_tc_kernel<CAUSAL, HD>;
   static bool cfg = false;
