@@ -114,10 +114,10 @@ class OpenClipEvalTransform:
 class ProcessorWrapper:
     """multimodal_encoder/base_encoder.py:8-40: what the dataset code sees as `image_processor`."""
 
-    def __init__(self, transform, height=378, width=378, image_mean=list(OPENAI_CLIP_MEAN)):
+    def __init__(self, transform, height=378, width=378, image_mean=None):
         self._crop_size = {"height": height, "width": width}
         self._transforms = transform
-        self.image_mean = image_mean
+        self.image_mean = list(OPENAI_CLIP_MEAN) if image_mean is None else image_mean
 
     @property
     def crop_size(self):
