@@ -108,7 +108,8 @@ def load():
     return out
 
 
-def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True, seed_fn=None):
+def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True, seed_fn=None,
+                          ntp_task_token_format=None):
     """Instantiate the reference's own OlaLlava*/Llava* class on a (tiny or full) config.
 
     cfg keys: see oracle.configs.  Weights are then overwritten *by name* from `seed_fn(name, shape)`
@@ -205,6 +206,16 @@ def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True
         config.depth_estimator = tmp.name
         config.image_generator = "none"
         config.image_segmentor = "none"
+    if not distill and ntp_task_token_format is not None:
+        # the VPT / IFT stages (scripts/train/vpt.sh, finetune.sh → train.py) load a distilled PT checkpoint into
+        # the NTP-only class: its config still carries the task-token keys, so LlavaMetaModel.__init__
+        # (llava_arch.py:50-51) creates the special tokens and append_special_tokens (:251-293) splices them
+        config.aux_mode = cfg.get("aux_mode", "gen-depth-seg")
+        config.num_task_tokens = 8
+        config.task_token_format = ntp_task_token_format
+        config.sample_tokens = False
+        config.image_seg = {"num_tokens": 576}
+        config.image_depth = {"num_tokens": 576}
     torch.manual_seed(0)
     model = Cls(config)
     model.steps = 1  # skip the `steps % 1000 == 0` wandb image logging

@@ -105,3 +105,29 @@ def test_oracle_matches_live_reference():
     assert torch.allclose(out.depth_embs[0][0][0], mine["depth_embs"][0][0], atol=3e-5)
     assert torch.allclose(out.seg_embs[1], mine["seg_embs"][1], atol=3e-5)
     assert torch.allclose(out.image_embs[0], mine["gen_embs"][0], atol=3e-5)
+
+
+@pytest.mark.parametrize("fmt", ["emb", "expand_emb"])
+def test_oracle_ntp_class_with_task_tokens_matches_live_reference(fmt):
+    """VPT / IFT stages (vpt.sh, finetune.sh → train.py:933-941): the NTP-only class on the config of a distilled
+    checkpoint keeps the task tokens — llava_arch.py:251-293 appends the RAW [576, D] parameters for
+    task_token_format "emb" and the 8 pooled rows for "expand_emb"."""
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("/root/reference not mounted")
+    cfg = dict(configs.TINY_LLAMA, max_pos=2048, tokenizer_model_max_length=2048)   # room for the 1775-token "emb" rows
+    model = ref_shim.build_reference_model(cfg, "llama", False, seed_fn=restate.seeded_param, ntp_task_token_format=fmt)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert sd["model.special_depth_tokens"].shape == (576, cfg["hidden"]) and sd["model.special_gen_tokens"].shape[0] == 8
+    batch = configs.synthetic_batch(cfg, 2, 40, distill=False, pad_rows=1)
+    with torch.no_grad():
+        out = model(input_ids=batch["input_ids"], labels=batch["labels"], attention_mask=batch["attention_mask"],
+                    images=batch["images"])
+        mine = restate.forward_step(sd, cfg, batch, distill=False, ntp_task_token_format=fmt)
+    extra = 576 + 576 + 8 if fmt == "emb" else 24
+    assert out.logits.shape[1] == 40 - 1 + 576 + extra == mine["logits"].shape[1]
+    assert torch.isfinite(out.loss)
+    assert abs(out.loss.item() - mine["loss"].item()) < 1e-5
+    real = mine["labels"][0] != -100
+    assert torch.allclose(out.logits[0][real], mine["logits"][0][real], atol=5e-5)

@@ -211,3 +211,31 @@ def test_freeze_backbone_leaves_lm_head_trainable():
     assert "lm_head.weight" in names and "model.mm_projector.0.weight" in names
     assert not any(n.startswith("model.layers.") or n.startswith("model.embed_tokens") or n == "model.norm.weight" for n in names)
     assert not any("vision_tower" in n for n in names)
+
+
+def test_ntp_class_loads_a_distilled_checkpoint_and_keeps_the_task_tokens(tmp_path):
+    """vpt.sh / finetune.sh: train.py loads the PT output into LlavaLlamaForCausalLM — heads are dropped like
+    HF drops unexpected keys, the task tokens stay (llava_arch.py:50-51) and, for task_token_format "emb", are
+    appended RAW (576 + 576 + 8 rows, llava_arch.py:259-260)."""
+    from parity_utils import build_product, configs
+
+    from visper_lm_b200.model import LlavaLlamaForCausalLM
+    from visper_lm_b200.train import checkpoint as C
+
+    torch.manual_seed(7)
+    pt = build_product(configs.TINY_LLAMA, True, None)
+    with torch.no_grad():
+        for p in pt.parameters():
+            p.copy_(torch.randn(p.shape))
+    C.save_config(pt.config, str(tmp_path))
+    C.save_pretrained_weights(pt.state_dict(), str(tmp_path))
+    m = LlavaLlamaForCausalLM.from_pretrained(str(tmp_path))
+    assert not hasattr(m, "image_depth_heads") and m.num_task_tokens == 8
+    assert torch.equal(m.model.special_seg_tokens, pt.model.special_seg_tokens)
+    assert torch.equal(m.model.layers[1].mlp.down_proj.weight, pt.model.layers[1].mlp.down_proj.weight)
+    rows = m._task_rows()                                   # "emb" → raw parameters, in token_order gen-depth-seg
+    assert rows.shape == (8 + 576 + 576, configs.TINY_LLAMA["hidden"])
+    assert torch.equal(rows[:8], m.model.special_gen_tokens) and torch.equal(rows[8:584], m.model.special_depth_tokens)
+    m.model.task_token_format = "text"
+    with pytest.raises(NotImplementedError):
+        m._task_rows()

@@ -451,7 +451,13 @@ class VisperForCausalLM(nn.Module):
         sd = load_pretrained_weights(model_dir)
         own = model.state_dict()
         missing = [k for k in own if k not in sd and not any(t in k for t in cls.NEW_MODULE_KEYS)]
-        unexpected = [k for k in sd if k not in own and not k.startswith(("dav2_backbone.", "oneformer."))]
+        # teachers are not part of the architecture; the NTP-only classes drop a distilled checkpoint's heads the way
+        # HF from_pretrained drops unexpected keys (vpt.sh / finetune.sh load the PT output into LlavaLlama*)
+        skip = ("dav2_backbone.", "oneformer.")
+        if not cls.distill:
+            skip += ("image_gen_heads.", "image_depth_heads.", "image_seg_heads.", "da_v2_head.", "gen_logit_scale",
+                     "depth_logit_scale", "seg_logit_scale")
+        unexpected = [k for k in sd if k not in own and not k.startswith(skip)]
         if missing or unexpected:
             raise KeyError(f"checkpoint does not match {cls.__name__}: missing {missing[:5]}, unexpected {unexpected[:5]}")
         model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
@@ -733,16 +739,24 @@ class VisperForCausalLM(nn.Module):
         return A.linear(h, pj[2].weight, pj[2].bias, ACT_NONE)
 
     def _task_rows(self):
-        """append_special_tokens (ola_arch.py:224-254): pooled rows in token_order."""
+        """append_special_tokens: rows appended after each image, in token_order.
+        Distillation classes (ola_arch.py:224-254): depth / seg parameters [576, D] pooled to num_task_tokens rows.
+        NTP-only classes (llava_arch.py:251-293) — reached when the VPT / IFT stages load a distilled checkpoint,
+        whose config still carries the task-token keys: the same pooling for task_token_format "expand_emb", the
+        RAW parameters (576 rows each) for "emb", exactly as published."""
         nt = self.num_task_tokens
-        if not (self.distill and nt):
+        if not nt:
             return None
+        fmt = getattr(self.model, "task_token_format", "emb")
+        if not self.distill and fmt not in ("emb", "expand_emb"):
+            raise NotImplementedError(f"task_token_format {fmt!r} (token-id task tokens) is not on the built path")
+        pool = self.distill or fmt == "expand_emb"
         rows = []
         for task in self.token_order:
             tok = {"depth": self.depth_tokens, "seg": self.seg_tokens, "gen": self.gen_tokens}[task]
             if tok is None or task not in self.model.aux_tokens:
                 continue
-            if task == "gen":
+            if task == "gen" or not pool:
                 rows.append(tok)
             else:
                 rows.append(A.GroupMeanFn.apply(tok, nt, tok.shape[0] // nt))
