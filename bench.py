@@ -307,7 +307,11 @@ def run_reference(args):
 
 
 def workload_config(args, c, distill):
-    return {"workload": ("BASELINE configs[1]: " if not distill else "BASELINE configs[2] per-GPU slice: ")
+    label = "BASELINE configs[1]: " if not distill else "BASELINE configs[2] per-GPU slice: "
+    if c.get("tower") == "convnext":
+        label = ("BASELINE configs[3] per-GPU slice under ZeRO-2: " if distill
+                 else "BASELINE configs[1] with configs[3]'s tower: ")
+    return {"workload": label
             + f"{args.model} + " + ("CLIP-ConvNeXt-XXL, 768px" if c.get("tower") == "convnext" else "CLIP-ViT-L/14-336, 336px")
             + f", T={args.seq}, "
             + ("NTP only" if not distill else "NTP + dsg distill heads (d18-20_s10-18_g12-20)")
