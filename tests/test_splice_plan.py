@@ -17,7 +17,7 @@ D, V, NIMG = 8, 50, 6  # tiny widths: 6 "image tokens" per image
 def batches(draw):
     B = draw(st.integers(1, 4))
     N = draw(st.integers(3, 24))
-    task_rows = draw(st.sampled_from([0, 3]))
+    task_rows = draw(st.sampled_from([0, 3, 17]))   # 17 > the image rows: the NTP-only "emb" case appends more task rows than image rows
     max_len = draw(st.sampled_from([None, 20, 64]))
     rng = np.random.default_rng(draw(st.integers(0, 2**31 - 1)))
     ids = rng.integers(0, V, (B, N))
