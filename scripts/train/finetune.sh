@@ -6,7 +6,6 @@ PT=${PT:-outputs/pretrain_dsg_VisPer-LM-CLIP-ViT-Llama3-8b}
 TOWER=${TOWER:-/ckpt/openai/clip-vit-large-patch14-336}
 torchrun --nnodes=1 --nproc-per-node ${GPUS:-8} --master-addr 127.0.0.1 --master-port ${PORT:-29500} \
     -m ola_vlm.train.train_mem \
-    --deepspeed ./scripts/zero2.json \
     --model_name_or_path $PT \
     --version llava_llama_3 \
     --data_path datasets/llava_v1_5_mix665k.json \

@@ -7,7 +7,6 @@ LLM=${LLM:-/ckpt/Meta-Llama-3-8B-Instruct}
 TOWER=${TOWER:-/ckpt/openai/clip-vit-large-patch14-336}
 torchrun --nnodes=1 --nproc-per-node ${GPUS:-8} --master-addr 127.0.0.1 --master-port ${PORT:-29500} \
     -m ola_vlm.train.ola_vlm_train_mem \
-    --deepspeed ./scripts/zero2.json \
     --model_name_or_path $LLM \
     --version llava_llama_3 \
     --mode gen-depth-seg \
