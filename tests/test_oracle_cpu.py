@@ -107,8 +107,8 @@ def test_oracle_matches_live_reference():
     assert torch.allclose(out.image_embs[0], mine["gen_embs"][0], atol=3e-5)
 
 
-@pytest.mark.parametrize("fmt", ["emb", "expand_emb"])
-def test_oracle_ntp_class_with_task_tokens_matches_live_reference(fmt):
+@pytest.mark.parametrize("fmt,family", [("emb", "llama"), ("expand_emb", "llama"), ("expand_emb", "phi3")])
+def test_oracle_ntp_class_with_task_tokens_matches_live_reference(fmt, family):
     """VPT / IFT stages (vpt.sh, finetune.sh → train.py:933-941): the NTP-only class on the config of a distilled
     checkpoint keeps the task tokens — llava_arch.py:251-293 appends the RAW [576, D] parameters for
     task_token_format "emb" and the 8 pooled rows for "expand_emb"."""
@@ -116,8 +116,9 @@ def test_oracle_ntp_class_with_task_tokens_matches_live_reference(fmt):
 
     if not ref_shim.available():
         pytest.skip("/root/reference not mounted")
-    cfg = dict(configs.TINY_LLAMA, max_pos=2048, tokenizer_model_max_length=2048)   # room for the 1775-token "emb" rows
-    model = ref_shim.build_reference_model(cfg, "llama", False, seed_fn=restate.seeded_param, ntp_task_token_format=fmt)
+    base = configs.TINY_LLAMA if family == "llama" else configs.TINY_PHI3
+    cfg = dict(base, max_pos=2048, tokenizer_model_max_length=2048)   # room for the 1775-token "emb" rows
+    model = ref_shim.build_reference_model(cfg, family, False, seed_fn=restate.seeded_param, ntp_task_token_format=fmt)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     assert sd["model.special_depth_tokens"].shape == (576, cfg["hidden"]) and sd["model.special_gen_tokens"].shape[0] == 8
     batch = configs.synthetic_batch(cfg, 2, 40, distill=False, pad_rows=1)
