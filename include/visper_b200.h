@@ -37,7 +37,8 @@ const char* vpb_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t vpb_launch_count(void);
 void vpb_reset_launch_count(void);
-/* process-wide kernel-selection switches (testing / A-B timing): key VPB_OPT_*, value 0/1 */
+/* process-wide kernel-selection switches (testing / A-B timing): key VPB_OPT_*, value 0/1.
+   Keys 10-14 default to 1 (measured faster on B200, round 2: profiles/r02_variants_ab.txt); all others to 0. */
 #define VPB_OPT_ATTN_LEGACY_FWD 0 /* 1: force the mma.sync attention forward */
 #define VPB_OPT_ATTN_LEGACY_BWD 1 /* 1: force the mma.sync attention backward */
 #define VPB_OPT_ATTN_TC_BWD_V1 2   /* 1: tcgen05 attention backward without the ping-pong groups */
@@ -47,13 +48,12 @@ void vpb_reset_launch_count(void);
 #define VPB_OPT_ATTN_BWD_SS 5      /* 1: attention backward stages P/dS through shared memory (not TMEM) */
 #define VPB_OPT_ATTN_BWD_PINGPONG 7 /* 1: attention backward with two softmax groups on alternate iterations (default: column split) */
 #define VPB_OPT_ATTN_FWD_V2 6      /* 1: experimental tcgen05 attention forward with two query tiles per CTA */
-#define VPB_OPT_ATTN_POLY_EXP2 9   /* 1: experimental — a quarter of the tcgen05 attention exponentials (forward, column-split backward) on the FMA pipe (degree-3 polynomial) instead of MUFU */
-#define VPB_OPT_ATTN_FWD_TC64 12   /* 1: experimental — non-causal head_dim-64 attention forward (CLIP ViT-L, DINOv2-L towers) on the tcgen05 kernel (one 64-column chunk per tile) instead of the mma.sync kernel */
-#define VPB_OPT_GEMM_EPI8 13       /* 1: experimental — CTA-pair GEMM with EIGHT epilogue warps per CTA (two per TMEM lane quarter, half the columns each) for K <= 1024, where the bias/GELU/store epilogue outlasts the tile's MMAs */
-#define VPB_OPT_GATHER_FLAT 14     /* 1: experimental — vpb_gather_rows for rows of <= 2048 elements as a flat grid-stride loop instead of one CTA per row */
-#define VPB_OPT_ATTN_FWD_QTM 15    /* 1: experimental — head_dim-128 tcgen05 attention forward with Q resident in TMEM as the A operand of QK^T (no Q tile in shared memory); bit-identical results */
-#define VPB_OPT_DWCONV_FFMA2 11    /* 1: experimental — depthwise 7x7 with packed fp32 FMAs (fma.rn.f32x2 = SASS FFMA2, one per channel pair); bit-identical results, half the FMA instructions */
-#define VPB_OPT_WIN_ATTN_V2 10     /* experimental — vpb_attn_fwd_bias on the one-pass kernel for windows of <= 144 tokens: 1 = two CTAs per SM (96 registers, small spills), 2 = one CTA per SM (no spills) */
+#define VPB_OPT_ATTN_FWD_TC64 12   /* default 1 — non-causal head_dim-64 attention forward (CLIP ViT-L, DINOv2-L towers) on the tcgen05 kernel (one 64-column chunk per tile) instead of the mma.sync kernel */
+#define VPB_OPT_GEMM_EPI8 13       /* default 1 — CTA-pair GEMM with EIGHT epilogue warps per CTA (two per TMEM lane quarter, half the columns each) for K <= 1024, where the bias/GELU/store epilogue outlasts the tile's MMAs */
+#define VPB_OPT_GATHER_FLAT 14     /* default 1 — vpb_gather_rows for rows of <= 2048 elements as a flat grid-stride loop instead of one CTA per row */
+#define VPB_OPT_NORM_LEGACY 15     /* 1: RMSNorm fwd/bwd on the CTA-per-row kernels of round 1 instead of the warp-per-row ones */
+#define VPB_OPT_DWCONV_FFMA2 11    /* default 1 — depthwise 7x7 with packed fp32 FMAs (fma.rn.f32x2 = SASS FFMA2, one per channel pair); bit-identical results, half the FMA instructions */
+#define VPB_OPT_WIN_ATTN_V2 10     /* default 1 — vpb_attn_fwd_bias on the one-pass kernel for windows of <= 144 tokens: 1 = two CTAs per SM (96 registers, small spills), 2 = one CTA per SM (no spills) */
 int vpb_set_option(int key, int value);
 /* profiling aid: device buffer of 16*512 int64 that CTA 0 of the attention dK/dV kernel fills with
  * clock64 stamps of its pipeline events (NULL = off, the default) */

@@ -1,8 +1,10 @@
-"""TEST INFRASTRUCTURE ONLY — imports the UNMODIFIED reference classes from /root/reference.
+"""TEST / BENCH INFRASTRUCTURE ONLY — imports the UNMODIFIED reference classes from /root/reference
+or, where that is not mounted (the GPU box), from the byte-identical copy oracle/build_ref.py placed under
+the git-ignored oracle/_ref/ (hashes in oracle/ref_manifest.json).
 
-Used in this container (where /root/reference exists) to (a) validate oracle/restate.py and
-(b) generate the golden vectors under tests/golden/ (oracle/make_golden.py).  It never travels to
-the GPU box and nothing in the product path imports it.
+Used (a) to validate oracle/restate.py, (b) to generate the golden vectors under tests/golden/
+(oracle/make_golden.py) and (c) by bench.py's reference / cpu_baseline legs (oracle/ref_run.py).
+Nothing in the product path imports it.
 
 The reference cannot be imported as-is here: its package __init__ eagerly imports
 open_clip / diffusers / diffdist / matplotlib (absent) and four private transformers names removed
@@ -19,7 +21,16 @@ import sys
 import types
 from unittest.mock import MagicMock
 
-REF_ROOT = os.environ.get("VISPER_REFERENCE_ROOT", "/root/reference")
+def _ref_root() -> str:
+    env = os.environ.get("VISPER_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/ola_vlm"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REF_ROOT = _ref_root()
 
 
 def available() -> bool:
@@ -109,11 +120,17 @@ def load():
 
 
 def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True, seed_fn=None,
-                          ntp_task_token_format=None):
+                          ntp_task_token_format=None, attn_implementation: str = "eager", device=None,
+                          dtype=None, fast_init: bool = False, train_mode: bool = False):
     """Instantiate the reference's own OlaLlava*/Llava* class on a (tiny or full) config.
 
     cfg keys: see oracle.configs.  Weights are then overwritten *by name* from `seed_fn(name, shape)`
     so the product can reproduce them through the state-dict ABI.
+
+    Timing runs (oracle/ref_run.py) pass `fast_init=True` (skip HF's per-module normal_ init of billions of
+    parameters; a cheap uniform fill of the same scale instead — values do not affect timing), `device` /
+    `dtype` (construction happens on that device) and `attn_implementation` ("sdpa" on CPU,
+    "flash_attention_2" on GPU as ola_vlm/train/ola_vlm_train_mem.py:5 selects it).
     """
     R = load()
     import tempfile
@@ -172,7 +189,7 @@ def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True
         vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], intermediate_size=cfg["inter"],
         num_hidden_layers=cfg["layers"], num_attention_heads=cfg["heads"],
         max_position_embeddings=cfg["max_pos"], rms_norm_eps=1e-5, tie_word_embeddings=False,
-        attn_implementation="eager", **lm_kwargs)
+        attn_implementation=attn_implementation, **lm_kwargs)
     config.mm_vision_tower = "synthetic-clip"
     config.mm_vision_select_layer = -2
     config.mm_vision_select_feature = "patch"
@@ -217,7 +234,17 @@ def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True
         config.image_seg = {"num_tokens": 576}
         config.image_depth = {"num_tokens": 576}
     torch.manual_seed(0)
-    model = Cls(config)
+    import contextlib
+
+    ctx = contextlib.ExitStack()
+    if fast_init:
+        from transformers.initialization import no_init_weights
+
+        ctx.enter_context(no_init_weights())
+    if device is not None:
+        ctx.enter_context(torch.device(device))
+    with ctx:
+        model = Cls(config)
     model.steps = 1  # skip the `steps % 1000 == 0` wandb image logging
     if distill:
         model.img_gen_loss_weight = 0.5
@@ -232,7 +259,24 @@ def build_reference_model(cfg: dict, family: str = "llama", distill: bool = True
                 return torch.zeros(f.shape[0], 336, 336, dtype=f.dtype, device=f.device)
 
         model.da_v2_head = _NoDPT()
-    model = model.float().eval()  # no dropout anywhere on the path; eval() only disables HF ckpt hooks
+    model = model.to(dtype or torch.float32)
+    # no dropout anywhere on the path; eval() only disables HF's gradient-checkpointing hooks
+    model = model.train() if train_mode else model.eval()
+    if fast_init:
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                if "da_v2_head" in name:
+                    continue
+                if p.dim() >= 2:
+                    p.uniform_(-0.0346, 0.0346)  # std 0.02
+                elif name.endswith("bias"):
+                    p.zero_()
+                elif "norm" in name and name.endswith("weight"):
+                    p.fill_(1.0)
+                elif name.endswith("logit_scale"):
+                    p.fill_(2.0)
+                else:
+                    p.uniform_(-0.0346, 0.0346)
     if seed_fn is not None:
         with torch.no_grad():
             for name, p in list(model.named_parameters()) + list(model.named_buffers()):

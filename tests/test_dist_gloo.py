@@ -67,7 +67,9 @@ def _zero2_worker(rank, world, port, ret):
     model = _Toy()
     groups = [(lambda n: not _no_decay(n), 1.0, 0.01), (lambda n: True, 1.0, 0.0)]
     opt = Zero2Optimizer(model.named_parameters(), 1e-2, (0.9, 0.999), 1e-8, 0.01, 1.0, groups)
-    assert opt.total % (world * 1024) == 0 and opt.shard * world == opt.total
+    # every bucket splits evenly (and 16-byte aligned) over the ranks; the shard is the sum of the rank's slices
+    assert opt.shard * world == opt.total and all((b.hi - b.lo) % (world * 8) == 0 for b in opt.buckets)
+    assert len({b.group for b in opt.buckets}) == 2   # decay / no-decay groups never share a bucket
     for step in range(3):
         opt.zero_grad()
         for n, p in opt.named:

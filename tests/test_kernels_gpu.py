@@ -174,7 +174,7 @@ def test_gemm_rope_fused(M, H, KVH, K, T):
 
 
 # ------------------------------------------------------------------------------------------- norms
-@pytest.mark.parametrize("M,D", [(37, 128), (512, 4096), (100, 3072), (64, 1024)])
+@pytest.mark.parametrize("M,D", [(37, 128), (512, 4096), (100, 3072), (64, 1024), (1003, 2048), (16384, 4096)])
 def test_rmsnorm(M, D):
     from visper_lm_b200 import ops
     x = rnd(M, D, seed=11).requires_grad_(False)
@@ -191,6 +191,30 @@ def test_rmsnorm(M, D):
     close(dx, xf.grad + dres.float(), name="rmsnorm bwd")
     dw = ops.colsum(dy, x, None, rstd, out_dtype=torch.float32)
     close(dw, wf.grad, rtol=2e-2, name="rmsnorm dw")
+
+
+def test_rmsnorm_warp_kernels_strided_rows_and_legacy_agreement():
+    """The warp-per-row RMSNorm kernels (round 2) on row views of a wider buffer (ld > D), against the
+    CTA-per-row kernels they replace (VPB_OPT_NORM_LEGACY): same values up to the order of the fp32 row sums."""
+    from visper_lm_b200 import ops
+    M, D = 777, 4096
+    big = rnd(M, 3 * D, seed=31)
+    x, dy, dres = big[:, :D], big[:, D:2 * D], big[:, 2 * D:]
+    w = (1 + 0.1 * rnd(D, seed=32).float()).to(BF)
+    out = torch.zeros(M, 2 * D, dtype=BF, device=dev())
+    y, rstd = ops.rmsnorm_fwd(x, w, 1e-5, out=out[:, D:])
+    dx = ops.rmsnorm_bwd(dy, x, w, rstd, dres)
+    ops.set_option(ops.OPT_NORM_LEGACY, 1)
+    try:
+        y0, rstd0 = ops.rmsnorm_fwd(x, w, 1e-5)
+        dx0 = ops.rmsnorm_bwd(dy, x, w, rstd0, dres)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_NORM_LEGACY, 0)
+    assert torch.equal(out[:, :D], torch.zeros_like(out[:, :D])), "wrote outside its row view"
+    assert torch.allclose(rstd, rstd0, rtol=1e-6)
+    assert (y.float() - y0.float()).abs().max().item() <= 2 ** -6 * y0.float().abs().max().item()
+    assert ((dx.float() - dx0.float()).norm() / dx0.float().norm()).item() < 2e-3
 
 
 @pytest.mark.parametrize("M,D", [(50, 64), (300, 1024), (77, 1536)])

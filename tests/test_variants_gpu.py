@@ -1,14 +1,26 @@
-"""Kernel variants that were written after the round's GPU budget was spent: compiled and shipped OFF by
-default, NOT yet run on hardware.  Skipped unless VPB_TEST_EXPERIMENTAL=1 — the first GPU call of the next
-round runs `VPB_TEST_EXPERIMENTAL=1 pytest tests/test_experimental_gpu.py tests/test_ex2_poly.py -m gpu`."""
-import os
+"""Kernel variants selected by vpb_set_option: each is checked against torch fp32 AND against the kernel it
+replaced (option value 0).  All ran on a B200 in round 2 (profiles/r02_variants_ab.txt); the five that won
+their A/B — one-pass window attention, packed-FMA depthwise, tcgen05 ViT attention, eight epilogue warps,
+flat gather — are now the library defaults (`DEFAULT` below mirrors csrc/api.cu)."""
+import contextlib
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("VPB_TEST_EXPERIMENTAL") != "1",
-                                 reason="experimental kernel variant, not yet validated on hardware")]
+pytestmark = pytest.mark.gpu
+DEFAULT = {10: 1, 11: 1, 12: 1, 13: 1, 14: 1}
+
+
+@contextlib.contextmanager
+def option(key, value):
+    from visper_lm_b200 import ops
+
+    ops.set_option(key, value)
+    try:
+        yield
+    finally:
+        torch.cuda.synchronize()
+        ops.set_option(key, DEFAULT.get(key, 0))
 
 
 @pytest.mark.parametrize("variant", [1, 2])
@@ -28,13 +40,10 @@ def test_one_pass_window_attention(B, H, S, nmask, variant):
         mask[:, torch.arange(S), torch.arange(S)] = 0.0
         mask = mask.contiguous().cuda()
     W = H * hd
-    base = ops.attn_fwd_bias(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, S, hd, hd ** -0.5, bias, mask)
-    ops.set_option(ops.OPT_WIN_ATTN_V2, variant)
-    try:
+    with option(ops.OPT_WIN_ATTN_V2, 0):
+        base = ops.attn_fwd_bias(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, S, hd, hd ** -0.5, bias, mask)
+    with option(ops.OPT_WIN_ATTN_V2, variant):
         o = ops.attn_fwd_bias(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, S, hd, hd ** -0.5, bias, mask)
-        torch.cuda.synchronize()
-    finally:
-        ops.set_option(ops.OPT_WIN_ATTN_V2, 0)
     q, k, v = (qkv.float()[:, i * W:(i + 1) * W].view(B, S, H, hd).transpose(1, 2) for i in range(3))
     sc = q @ k.transpose(-1, -2) * hd ** -0.5 + bias[None]
     if mask is not None:
@@ -53,13 +62,10 @@ def test_dwconv_packed_fma_is_bit_identical(B, H, W, C):
     x = torch.randn(B * H * W, C, generator=g).to(torch.bfloat16).cuda()
     w49 = (torch.randn(49, C, generator=g) / 7).to(torch.bfloat16).cuda()
     b = torch.randn(C, generator=g).to(torch.bfloat16).cuda()
-    base = ops.dwconv7x7(x, w49, b, B, H, W, C)
-    ops.set_option(ops.OPT_DWCONV_FFMA2, 1)
-    try:
+    with option(ops.OPT_DWCONV_FFMA2, 0):
+        base = ops.dwconv7x7(x, w49, b, B, H, W, C)
+    with option(ops.OPT_DWCONV_FFMA2, 1):
         got = ops.dwconv7x7(x, w49, b, B, H, W, C)
-        torch.cuda.synchronize()
-    finally:
-        ops.set_option(ops.OPT_DWCONV_FFMA2, 0)
     assert torch.equal(got, base)
 
 
@@ -73,13 +79,10 @@ def test_vit_attention_on_tcgen05(B, H, S):
     g = torch.Generator().manual_seed(S)
     qkv = torch.randn(B * S, 3 * H * hd, generator=g).to(torch.bfloat16).cuda()
     W = H * hd
-    base, lse0 = ops.attn_fwd(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, H, S, S, hd, hd ** -0.5, False)
-    ops.set_option(ops.OPT_ATTN_FWD_TC64, 1)
-    try:
+    with option(ops.OPT_ATTN_FWD_TC64, 0):
+        base, lse0 = ops.attn_fwd(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, H, S, S, hd, hd ** -0.5, False)
+    with option(ops.OPT_ATTN_FWD_TC64, 1):
         o, lse = ops.attn_fwd(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], B, H, H, S, S, hd, hd ** -0.5, False)
-        torch.cuda.synchronize()
-    finally:
-        ops.set_option(ops.OPT_ATTN_FWD_TC64, 0)
     q, k, v = (qkv.float()[:, i * W:(i + 1) * W].view(B, S, H, hd).transpose(1, 2) for i in range(3))
     sc = q @ k.transpose(-1, -2) * hd ** -0.5
     ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * S, W)
@@ -100,13 +103,10 @@ def test_gemm_eight_epilogue_warps_is_bit_identical(M, N, K, act, res):
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
     b = torch.randn(N, generator=g).to(torch.bfloat16).cuda()
     r = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda() if res else None
-    base = ops.gemm(a, w, bias=b, act=act, residual=r)
-    ops.set_option(ops.OPT_GEMM_EPI8, 1)
-    try:
+    with option(ops.OPT_GEMM_EPI8, 0):
+        base = ops.gemm(a, w, bias=b, act=act, residual=r)
+    with option(ops.OPT_GEMM_EPI8, 1):
         got = ops.gemm(a, w, bias=b, act=act, residual=r)
-        torch.cuda.synchronize()
-    finally:
-        ops.set_option(ops.OPT_GEMM_EPI8, 0)
     assert torch.equal(got, base)
     ref = a.float() @ w.float().t() + b.float()
     ref = torch.nn.functional.gelu(ref) if act == 1 else ref
@@ -125,35 +125,12 @@ def test_flat_gather_is_bit_identical(n, D, nsrc):
     kind = torch.randint(0, nsrc, (n,), generator=g, dtype=torch.int32).cuda() if nsrc > 1 else None
     wide0 = torch.full((n, 2 * D), 7.0, dtype=torch.bfloat16, device="cuda")
     wide1 = wide0.clone()
-    ops.gather_rows(index, srcs, D, kind=kind, out=wide0[:, D:])
-    ops.set_option(ops.OPT_GATHER_FLAT, 1)
-    try:
+    with option(ops.OPT_GATHER_FLAT, 0):
+        ops.gather_rows(index, srcs, D, kind=kind, out=wide0[:, D:])
+    with option(ops.OPT_GATHER_FLAT, 1):
         ops.gather_rows(index, srcs, D, kind=kind, out=wide1[:, D:])
-        torch.cuda.synchronize()
-    finally:
-        ops.set_option(ops.OPT_GATHER_FLAT, 0)
     assert torch.equal(wide0, wide1)
     k = kind.long() if kind is not None else torch.zeros(n, dtype=torch.long, device="cuda")
     ref = torch.stack([srcs[int(k[r])][int(index[r])] if index[r] >= 0 else torch.zeros(D, dtype=torch.bfloat16, device="cuda")
                        for r in range(min(n, 300))])
     assert torch.equal(wide1[:300, D:], ref)
-
-
-@pytest.mark.parametrize("B,H,KVH,S,causal", [(2, 8, 2, 1024, True), (1, 4, 4, 333, True), (2, 4, 1, 577, False)])
-def test_attention_forward_with_q_in_tmem_is_bit_identical(B, H, KVH, S, causal):
-    """VPB_OPT_ATTN_FWD_QTM: Q as the TMEM-resident A operand of QK^T == the default head_dim-128 forward, bit for
-    bit (same operands, same accumulation order), output and LSE; ragged last query / key tiles included."""
-    from visper_lm_b200 import ops
-
-    hd = 128
-    g = torch.Generator().manual_seed(S + H)
-    qkv = torch.randn(B * S, (H + 2 * KVH) * hd, generator=g).to(torch.bfloat16).cuda()
-    q, k, v = qkv[:, :H * hd], qkv[:, H * hd:(H + KVH) * hd], qkv[:, (H + KVH) * hd:]
-    base, lse0 = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, hd ** -0.5, causal)
-    ops.set_option(ops.OPT_ATTN_FWD_QTM, 1)
-    try:
-        o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, hd ** -0.5, causal)
-        torch.cuda.synchronize()
-    finally:
-        ops.set_option(ops.OPT_ATTN_FWD_QTM, 0)
-    assert torch.equal(o, base) and torch.equal(lse, lse0)

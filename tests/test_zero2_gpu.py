@@ -1,0 +1,99 @@
+"""ZeRO-2 optimizer on the GPU (world 1): the three gradient paths — wgrad GEMMs writing straight into the
+optimizer's buffer through LayerGradSink, autograd hooks, and the staging-pool / comm-stream path the NCCL
+run uses — must produce bit-identical parameters; and the fused q|k|v weights must be the optimizer's own
+storage."""
+import pytest
+import torch
+
+from parity_utils import build_product, configs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _trainer(overlap=True, sinks=True, bucket=64 * 1024 * 1024, distill=False, full=True):
+    from visper_lm_b200.train.trainer import LLaVATrainer, TrainingArguments, Zero2Optimizer
+
+    cfg = configs.TINY_LLAMA
+    model = build_product(cfg, distill, DEV)
+    for n, p in model.named_parameters():
+        p.requires_grad_(("vision_tower" not in n) and ("da_v2_head" not in n) if full else ("mm_projector" in n))
+    args = TrainingArguments(per_device_train_batch_size=2, learning_rate=1e-3, max_steps=100, zero_bucket_elems=bucket)
+    tr = LLaVATrainer(model=model, args=args)
+    if overlap != True:  # noqa: E712  (rebuild the optimizer with the requested mode)
+        tr.create_optimizer()
+        opt0 = tr.optimizer
+        for h in opt0._hooks:
+            h.remove()
+        from visper_lm_b200.model.modules import DecoderLayer, FusedRows
+
+        fused = [fr.params for m in model.modules() for fr in vars(m).values() if isinstance(fr, FusedRows)]
+        tr.optimizer = Zero2Optimizer(model.named_parameters(), 1e-3, max_grad_norm=1.0, groups=opt0.groups,
+                                      keep_together=fused, bucket_elems=bucket, overlap=overlap)
+        for m in model.modules():
+            if isinstance(m, DecoderLayer):
+                m._grad_sink = tr.optimizer.layer_sink(m.sink_params())
+        model._pre_trainable_hook = tr.optimizer.wait_params
+    else:
+        tr.create_optimizer()
+    tr.optimizer.sinks_enabled = sinks
+    tr.total_steps = 100
+    return model, tr
+
+
+def _batch(seed):
+    b = configs.synthetic_batch(configs.TINY_LLAMA, 2, 40, seed=seed, distill=False)
+    return dict(input_ids=b["input_ids"], labels=b["labels"], attention_mask=b["attention_mask"], images=b["images"])
+
+
+def _run(steps=3, **kw):
+    model, tr = _trainer(**kw)
+    losses = []
+    for s in range(steps):
+        loss, _ = tr.step(_batch(100 + s))
+        losses.append(float(loss))
+    torch.cuda.synchronize()
+    return model, tr, losses
+
+
+def test_sinks_hooks_and_staging_paths_are_bit_identical():
+    m1, t1, l1 = _run(sinks=True)
+    m2, t2, l2 = _run(sinks=False)
+    m3, t3, l3 = _run(sinks=True, overlap="force", bucket=150_000)     # several buckets through the pool
+    assert len(t3.optimizer.buckets) >= 4 and len(t3.optimizer.pool) >= 2
+    assert l1 == l2 == l3 and l1[-1] < l1[0] + 1.0
+    p1, p2, p3 = t1.optimizer.flat_params(), t2.optimizer.flat_params(), t3.optimizer.flat_params()
+    assert torch.equal(p1, p2), "sink path differs from the hook path"
+    n3 = {n: p for n, p in m3.named_parameters() if p.requires_grad}
+    for n, p in m1.named_parameters():
+        if p.requires_grad:
+            assert torch.equal(p, n3[n]), f"staging path differs in {n}"
+    # the decoder weight gradients never existed as p.grad
+    assert all(p.grad is None for p in m1.parameters())
+
+
+def test_fused_weights_are_the_optimizers_storage_and_train():
+    model, tr = _trainer()
+    opt = tr.optimizer
+    lo, hi = opt.flat_p.data_ptr(), opt.flat_p.data_ptr() + opt.flat_p.numel() * 2
+    layer = model.model.layers[1]
+    q, v, gate = layer.self_attn.q_proj.weight, layer.self_attn.v_proj.weight, layer.mlp.gate_proj.weight
+    before = {n: p.detach().clone() for n, p in (("q", q), ("v", v), ("gate", gate), ("o", layer.self_attn.o_proj.weight))}
+    tr.step(_batch(7))
+    tr.step(_batch(8))          # the second forward runs FusedRows.get() after the optimizer moved the storage
+    torch.cuda.synchronize()
+    for n, p in (("q", q), ("v", v), ("gate", gate), ("o", layer.self_attn.o_proj.weight)):
+        assert lo <= p.data_ptr() < hi, f"{n}_proj left the optimizer's flat buffer"
+        assert not torch.equal(p.detach(), before[n]), f"{n}_proj.weight did not train"
+    assert layer._qkv.get().data_ptr() == q.data_ptr() and layer._gu.get().data_ptr() == gate.data_ptr()
+
+
+def test_adapter_policy_unaffected():
+    """PT freeze policy: no decoder sink is registered (frozen weights), the projector trains."""
+    model, tr = _trainer(full=False)
+    assert all(l._grad_sink is None for l in model.model.layers)
+    w = model.model.mm_projector[0].weight
+    b4 = w.detach().clone()
+    tr.step(_batch(3))
+    torch.cuda.synchronize()
+    assert not torch.equal(w.detach(), b4)

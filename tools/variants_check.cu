@@ -3,8 +3,6 @@
 //   gemm_epi8   VPB_OPT_GEMM_EPI8      CTA-pair GEMM, eight epilogue warps (K <= 1024): bit identity + times
 //   gather_flat VPB_OPT_GATHER_FLAT    grid-stride row gather: bit identity + times
 //   attn_tc64   VPB_OPT_ATTN_FWD_TC64  ViT attention (head_dim 64, non-causal) on the tcgen05 forward: max diff + times
-//   attn_poly   VPB_OPT_ATTN_POLY_EXP2 quarter of the softmax exponentials on the FMA pipe: max diff + times
-//   attn_qtm    VPB_OPT_ATTN_FWD_QTM   Q resident in TMEM as the A operand of QK^T (head_dim 128): bit identity + times
 // Every timing alternates off / on inside one process (same box, same clocks) with an L2 flush before each launch.
 // Built by tools/build_dwconv_check.sh into tools/_bin/variants_check; prints JSON lines; exit code = failures.
 #include <cuda_runtime.h>
@@ -207,16 +205,6 @@ int main(int argc, char** argv) {
     fails += attn_ab("attn_tc64", VPB_OPT_ATTN_FWD_TC64, 8, 16, 16, 577, 64, 0, 2e-2);   // CLIP ViT-L/14-336
     fails += attn_ab("attn_tc64", VPB_OPT_ATTN_FWD_TC64, 8, 16, 16, 1370, 64, 0, 2e-2);  // DINOv2-L @518
     fails += attn_ab("attn_tc64", VPB_OPT_ATTN_FWD_TC64, 2, 4, 4, 70, 64, 0, 2e-2);      // shorter than one tile
-  }
-  if (want("attn_poly")) {
-    fails += attn_ab("attn_poly", VPB_OPT_ATTN_POLY_EXP2, 8, 32, 8, 2048, 128, 1, 1e-2);  // Llama-3 decoder
-    fails += attn_ab("attn_poly", VPB_OPT_ATTN_POLY_EXP2, 4, 32, 32, 2048, 96, 1, 1e-2);  // Phi-3 decoder
-  }
-  if (want("attn_poly_qtm"))  // both: the MUFU relief and the shared-memory relief together
-    fails += attn_ab("attn_poly_qtm", VPB_OPT_ATTN_POLY_EXP2, 8, 32, 8, 2048, 128, 1, 1e-2, VPB_OPT_ATTN_FWD_QTM);
-  if (want("attn_qtm")) {  // bit-identical by construction: tolerance 0
-    fails += attn_ab("attn_qtm", VPB_OPT_ATTN_FWD_QTM, 8, 32, 8, 2048, 128, 1, 0.0);   // Llama-3 decoder
-    fails += attn_ab("attn_qtm", VPB_OPT_ATTN_FWD_QTM, 2, 8, 2, 333, 128, 1, 0.0);     // ragged tiles
   }
   printf("{\"variants_check_failures\": %d}\n", fails);
   return fails;

@@ -129,10 +129,23 @@ class DecoderLayerFn(torch.autograd.Function):
         def dgrad(dy, w, wt):  # dY·W: K-major frozen copy Wᵀ when available, else MN-major descriptor
             return ops.gemm(dy, wt) if wt is not None else ops.gemm(dy, w, b_layout=1)
 
+        sink = getattr(meta, "grad_sink", None)
+
+        def wgrad(key, dy, xin):
+            """dYᵀ·X.  With a gradient sink (ZeRO-2 optimizer) the GEMM writes — or accumulates into — the
+            optimizer's gradient buffer and autograd gets None; otherwise the gradient tensor is returned."""
+            d = sink.dst(key) if sink is not None else None
+            if d is None:
+                return ops.gemm(dy, xin, a_layout=1, b_layout=1)
+            buf, acc = d
+            ops.gemm(dy, xin, a_layout=1, b_layout=1, out=buf, residual=buf if acc else None)
+            sink.done(key)
+            return None
+
         # ---- MLP: x3 = x2 + down(swiglu(gate_up(rmsnorm(x2)))) ----
         if nig[9]:
             hh = ops.swiglu_fwd(gu)
-            g[9] = ops.gemm(dx3, hh, a_layout=1, b_layout=1)
+            g[9] = wgrad("d", dx3, hh)
             del hh
         if ctx.gu_tiled:  # dgrad of down_proj with the SwiGLU derivative in its epilogue
             dgu = (ops.gemm_swiglu_bwd(dx3, meta.wdT, gu, b_layout=0, tiled=True, F=F)
@@ -145,9 +158,11 @@ class DecoderLayerFn(torch.autograd.Function):
         dn2 = dgrad(dgu, wgu, meta.wguT)
         if nig[7] or nig[8]:
             h2, _ = ops.rmsnorm_fwd(x2, n2, eps)
-            dwgu = ops.gemm(dgu, h2, a_layout=1, b_layout=1)
+            dwgu = wgrad("gu", dgu, h2)
             del h2
-            if ctx.split_gu:
+            if dwgu is None:
+                pass
+            elif ctx.split_gu:
                 g[7], g[8] = dwgu[:F], dwgu[F:]
             else:
                 g[7] = dwgu
@@ -160,7 +175,7 @@ class DecoderLayerFn(torch.autograd.Function):
         # ---- attention: x2 = x + o_proj(attn(rope(qkv(rmsnorm(x))))) ----
         do = dgrad(dx2, wo, meta.woT)
         if nig[5]:
-            g[5] = ops.gemm(dx2, o, a_layout=1, b_layout=1)
+            g[5] = wgrad("o", dx2, o)
         dqkv = torch.empty_like(qkv)
         if ops.FUSE_ROPE_BWD:  # inverse RoPE of dQ/dK in the backward epilogues (hd 128), else after
             ops.attn_bwd_rope(qkv[:, :qw], qkv[:, qw:qw + kw], qkv[:, qw + kw:], o, do, lse,
@@ -176,9 +191,11 @@ class DecoderLayerFn(torch.autograd.Function):
         dn1 = dgrad(dqkv, wqkv, meta.wqkvT)
         if nig[2] or nig[3] or nig[4]:
             h1, _ = ops.rmsnorm_fwd(x, n1, eps)
-            dwqkv = ops.gemm(dqkv, h1, a_layout=1, b_layout=1)
+            dwqkv = wgrad("qkv", dqkv, h1)
             del h1
-            if ctx.split_qkv:
+            if dwqkv is None:
+                pass
+            elif ctx.split_qkv:
                 g[2], g[3], g[4] = dwqkv[:qw], dwqkv[qw:qw + kw], dwqkv[qw + kw:]
             else:
                 g[2] = dwqkv

@@ -16,7 +16,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-static std::atomic<int> g_options[16];
+// defaults: the variants measured faster on B200 in round 2 (profiles/r02_variants_ab.txt) are ON —
+// WIN_ATTN_V2 (10) = 1, DWCONV_FFMA2 (11), ATTN_FWD_TC64 (12), GEMM_EPI8 (13), GATHER_FLAT (14); 0 selects the old kernel
+static std::atomic<int> g_options[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0};
 int get_option(int key) { return (key >= 0 && key < 16) ? g_options[key].load() : 0; }
 }  // namespace vpb
 

@@ -25,8 +25,6 @@ struct AttnTcParams {
   int B, H, KVH, sq, sk;
   float scale;
   int window;  // causal sliding window: key j visible to query i iff 0 <= i + off - j <= window (0: off)
-  const bf16* q;  // QTM variant only: Q rows are read straight from global memory
-  int64_t ldq;
 };
 
 namespace tc {
@@ -48,15 +46,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// POLY (EXPERIMENTAL, VPB_OPT_ATTN_POLY_EXP2, off by default, not yet measured on hardware): every fourth
-// exponential of the softmax goes through ex2_poly on the FMA pipe instead of MUFU ex2.approx.
-// QTM (EXPERIMENTAL, VPB_OPT_ATTN_FWD_QTM, head_dim 128, off by default, not yet measured on hardware): Q lives in
-// TMEM as the packed-bf16 A operand of S = Q.K^T (64 columns next to O) instead of shared memory.  Q is constant
-// for the CTA, so each softmax thread loads its own half row from global memory once and tcgen05.st's it exactly
-// like P; the QK^T MMAs then read only the K tile from shared memory (32 KB instead of 64 KB per key tile; the
-// kernel moves ~160 KB per tile through a 128 B/clk shared memory against 1024 tensor cycles).  Same operands,
-// same accumulation order: results are bit-identical to the default kernel.
-template <bool CAUSAL, int HD, bool POLY = false, bool QTM = false>
+// Two variants of this kernel were measured on B200 in round 2 and dropped (profiles/r02_variants_ab.txt): every
+// fourth exponential as a degree-3 polynomial on the FMA pipe (0.440 vs 0.427 ms — the softmax warps are bound by
+// instruction issue and latency, not by the MUFU rate) and Q resident in TMEM as the A operand of QK^T (0.450 ms).
+template <bool CAUSAL, int HD>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -101,7 +94,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, QTM ? 8 : 1);  // QTM: the eight softmax warps publish Q in TMEM
+    mbar_init(q_full, 1);
     for (int i = 0; i < KST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -122,18 +115,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t TM_S = tmem_base;        // S[0] at +0, S[1] at +128
   const uint32_t TM_O = tmem_base + 256;  // O accumulator
-  const uint32_t TM_Q = tmem_base + 384;  // QTM: Q as packed bf16 pairs, 64 columns
-  static_assert(!QTM || HD == 128, "Q-in-TMEM variant: head_dim 128 only");
 
   if (warp == 0) {
     if (lane == 0) {
       // head_dim 64 (ViT towers) is ONE 64-column chunk per tile; 96 / 128 add a second TMA box
       constexpr uint32_t TX_BYTES = HD > 64 ? TILE_BYTES : CHUNK_BYTES;
-      if constexpr (!QTM) {
-        mbar_arrive_expect_tx(q_full, TX_BYTES);
-        tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * HD, b * p.sq + q0);
-        if constexpr (HD > 64) tma_load_2d(smem + OFF_Q + CHUNK_BYTES, &tmQ, q_full, h * HD + 64, b * p.sq + q0);
-      }
+      mbar_arrive_expect_tx(q_full, TX_BYTES);
+      tma_load_2d(smem + OFF_Q, &tmQ, q_full, h * HD, b * p.sq + q0);
+      if constexpr (HD > 64) tma_load_2d(smem + OFF_Q + CHUNK_BYTES, &tmQ, q_full, h * HD + 64, b * p.sq + q0);
       auto load_k = [&](int j) {
         const int s = j % KST;
         mbar_wait(&k_empty[s], ((j / KST) & 1) ^ 1);
@@ -172,10 +161,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k) {
             const uint32_t o = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
-            if constexpr (QTM)
-              umma_bf16_ts(TM_S + sb * BN, TM_Q + k * 8, desc_adv(k_desc, o), idesc_s, k != 0);
-            else
-              umma_bf16(TM_S + sb * BN, desc_adv(q_desc, o), desc_adv(k_desc, o), idesc_s, k != 0);
+            umma_bf16(TM_S + sb * BN, desc_adv(q_desc, o), desc_adv(k_desc, o), idesc_s, k != 0);
           }
           umma_commit(&s_full[sb]);
           umma_commit(&k_empty[s]);
@@ -211,26 +197,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float sl2 = p.scale * LOG2E;
     float m_used = -INFINITY, l = 0.f;
     float* xchg = reinterpret_cast<float*>(smem + OFF_X);  // [2 parity][2 half][128 rows] + [2][128]
-    if constexpr (QTM) {
-      // this thread's half of its query row: 64 bf16 = 32 packed columns (zeros past the end of the sequence)
-      uint32_t w[32];
-      if (q0 + row < p.sq) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.q + ((int64_t)b * p.sq + q0 + row) * p.ldq + h * HD + half * 64);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 v = __ldg(src + i);
-          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) w[i] = 0;
-      }
-      tmem_st32(TM_Q + lane_addr + half * 32, w);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(q_full);
-    }
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j & 1;
       mbar_wait_spin(&s_full[sb], (j >> 1) & 1);
@@ -277,13 +243,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int c = 0; c < 64; c += 4) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float pv;
-          if constexpr (POLY) {
-            const float xs = fmaf(__uint_as_float(r[c + e]), sl2, -mb);
-            pv = (e == 3) ? ex2_poly(xs) : ex2_approx(xs);
-          } else {
-            pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
-          }
+          const float pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
           sum4[e] += pv;
           r[c + e] = __float_as_uint(pv);
         }
@@ -725,31 +685,6 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
     return 0;
   }
   dim3 grid((p.sq + tc::BM - 1) / tc::BM, p.H, p.B);
-  // experimental variants (all off by default): POLY = polynomial exp2 for a quarter of the scores, QTM = Q in TMEM
-  // (head_dim 128); they combine
-  const bool poly = get_option(VPB_OPT_ATTN_POLY_EXP2) != 0;
-  const bool qtm = HD == 128 && get_option(VPB_OPT_ATTN_FWD_QTM) && (reinterpret_cast<uintptr_t>(q) & 15) == 0 &&
-                   ldq % 8 == 0;
-  if (poly || qtm) {
-    AttnTcParams pq = p;
-    pq.q = static_cast<const bf16*>(q);
-    pq.ldq = ldq;
-    auto launch_variant = [&](auto kernv, bool& configured) -> int {
-      if (!configured) {
-        VPB_CUDA(cudaFuncSetAttribute(kernv, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        configured = true;
-      }
-      kernv<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(tmQ, tmK, tmV, pq);
-      VPB_LAUNCH_OK();
-      return 0;
-    };
-    static bool cfg_p = false, cfg_q = false, cfg_pq = false;
-    if constexpr (HD == 128) {
-      if (poly && qtm) return launch_variant(attn_fwd_tc_kernel<CAUSAL, HD, true, true>, cfg_pq);
-      if (qtm) return launch_variant(attn_fwd_tc_kernel<CAUSAL, HD, false, true>, cfg_q);
-    }
-    return launch_variant(attn_fwd_tc_kernel<CAUSAL, HD, true, false>, cfg_p);
-  }
   auto kern = attn_fwd_tc_kernel<CAUSAL, HD>;
   static bool cfg = false;
   if (!cfg) {
@@ -1350,8 +1285,7 @@ constexpr int B_SMEM = B_OFF_BAR + 256;
 // iteration, two per TMEM lane quarter splitting the 64 query columns — the exp / dS phase of one
 // group turned out to be the serial bottleneck (one warp per sub-partition issues ~0.26 IPC; the
 // timeline in profiles/r01_attn_dkdv_timeline_cta0.txt shows the two groups' phases do not overlap).
-// POLY: see attn_fwd_tc_kernel — every fourth exponential on the FMA pipe (column-split variant only).
-template <bool CAUSAL, int HD, bool TS, bool SPLIT, bool POLY = false>
+template <bool CAUSAL, int HD, bool TS, bool SPLIT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -1634,12 +1568,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = c4 * 4 + e;
-            if constexpr (POLY) {
-              const float xs = fmaf(__uint_as_float(s[c]), sl2, -lsv[e]);
-              s[c] = __float_as_uint(e == 3 ? ex2_poly(xs) : ex2_approx(xs));
-            } else {
-              s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e])));
-            }
+            s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e])));
             d[c] = __float_as_uint(__uint_as_float(d[c]) - dlv[e]);
           }
         }
@@ -1845,7 +1774,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 // dQ_i = scale * sum_j dS_ij K_j — two query tiles (heavy + light) per CTA, ping-pong groups
-template <bool CAUSAL, int HD, bool TS, bool SPLIT, bool POLY = false>
+template <bool CAUSAL, int HD, bool TS, bool SPLIT>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -2060,12 +1989,7 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          if constexpr (POLY) {
-            const float xs = fmaf(__uint_as_float(s[c]), sl2, -l2);
-            s[c] = __float_as_uint((c & 3) == 3 ? ex2_poly(xs) : ex2_approx(xs));
-          } else {
-            s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
-          }
+          s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -l2)));
         }
         if (need_mask) {  // one warp-uniform branch per tile, never one per score
           const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
@@ -2241,7 +2165,7 @@ static int launch_bwd_tc_v1(const void* q, int64_t ldq, const void* k, int64_t l
   return 0;
 }
 
-template <bool CAUSAL, int HD, bool TS, bool SPLIT, bool POLY = false>
+template <bool CAUSAL, int HD, bool TS, bool SPLIT>
 static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
                             cudaStream_t st) {
@@ -2254,7 +2178,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, A_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, A_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, A_BKV)) return -1;
-    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD, TS, SPLIT, POLY>;
+    auto kern = attn_bwd_dkdv_tc2_kernel<CAUSAL, HD, TS, SPLIT>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
@@ -2270,7 +2194,7 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, B_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, B_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, B_BKV)) return -1;
-    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS, SPLIT, POLY>;
+    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS, SPLIT>;
     static bool cfg = false;
     if (!cfg) {
       VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
@@ -2296,11 +2220,9 @@ static int launch_bwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   // for head_dim 96; head_dim 128 can still fall back to the v1 kernels)
   const bool ss = get_option(VPB_OPT_ATTN_BWD_SS) != 0;
   const bool pingpong = get_option(VPB_OPT_ATTN_BWD_PINGPONG) != 0;
-  const bool poly = get_option(VPB_OPT_ATTN_POLY_EXP2) != 0;  // experimental, see ex2_poly
 #define VPB_BWD_V2(HDv)                                                                              \
   (ss ? launch_bwd_tc_v2<CAUSAL, HDv, false, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)          \
       : pingpong ? launch_bwd_tc_v2<CAUSAL, HDv, true, false>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st) \
-      : poly ? launch_bwd_tc_v2<CAUSAL, HDv, true, true, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st)   \
              : launch_bwd_tc_v2<CAUSAL, HDv, true, true>(q, ldq, k, ldk, v, ldv, dO, lddo, p, st))
   // (a caller asking for the fused inverse RoPE only gets here with head_dim 128 on the v2 kernels:
   // attn_bwd_tc clears the request otherwise)
@@ -2348,9 +2270,7 @@ int attn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
   p.ldo = ldo;
   p.B = B; p.H = H; p.KVH = KVH; p.sq = sq; p.sk = sk;
   p.scale = scale;
-  p.q = nullptr;
-  p.ldq = 0;
-  if (head_dim == 64)  // EXPERIMENTAL (VPB_OPT_ATTN_FWD_TC64): the ViT towers' non-causal attention
+  if (head_dim == 64)  // the ViT towers' non-causal attention (VPB_OPT_ATTN_FWD_TC64, default on)
     return launch_fwd_tc<false, 64>(q, ldq, k, ldk, v, ldv, p, st);
   if (head_dim == 96)
     return causal ? launch_fwd_tc<true, 96>(q, ldq, k, ldk, v, ldv, p, st)

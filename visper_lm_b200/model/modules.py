@@ -55,31 +55,47 @@ class Seq(nn.Module):
 
 class FusedRows:
     """Keeps several [rows_i, K] parameters as row-slices of ONE contiguous buffer so a single GEMM
-    serves them (q|k|v, gate|up) while each keeps its reference name / requires_grad."""
+    serves them (q|k|v, gate|up) while each keeps its reference name / requires_grad.
+
+    Storage has ONE owner.  Before an optimizer exists, this object owns a concatenated buffer and the
+    parameters are views of it.  Once Zero2Optimizer has moved the parameters into its flat buffer (it
+    lays a fused group out adjacently for exactly this purpose) the group is ADOPTED in place: `fused`
+    becomes a view of that region, nothing is copied, and AdamW's writes are what the next GEMM reads."""
 
     def __init__(self, params):
         self.params = list(params)
         self.fused = None
 
+    def _adjacent(self):
+        ps = self.params
+        ptr = ps[0].data_ptr()
+        for p in ps:
+            if not p.is_contiguous() or p.data_ptr() != ptr or p.dtype != ps[0].dtype:
+                return False
+            ptr += p.numel() * p.element_size()
+        return ps[0].untyped_storage().data_ptr() == ps[-1].untyped_storage().data_ptr()
+
     def get(self):
         ps = self.params
-        ok = self.fused is not None
-        if ok:
-            off = 0
+        if self.fused is not None and self.fused.data_ptr() == ps[0].data_ptr() and self._adjacent():
+            return self.fused
+        with torch.no_grad():
+            if self._adjacent():
+                rows = sum(p.shape[0] for p in ps)
+                inner = tuple(ps[0].shape[1:])
+                stride = ps[0].data.stride()
+                self.fused = torch.as_strided(ps[0].data, (rows,) + inner, stride, ps[0].data.storage_offset())
+                return self.fused
+            if any(getattr(p, "_vpb_flat_owner", False) for p in ps):
+                raise RuntimeError("FusedRows: parameters live in an optimizer's flat buffer but are not adjacent "
+                                   "there; re-copying them would detach them from the optimizer")
+            fused = torch.cat([p.data.reshape(p.shape[0], -1) for p in ps], 0).contiguous()
+            r = 0
             for p in ps:
-                if p.data_ptr() != self.fused.data_ptr() + off * self.fused.element_size():
-                    ok = False
-                    break
-                off += p.numel()
-        if not ok:
-            with torch.no_grad():
-                fused = torch.cat([p.data.reshape(p.shape[0], -1) for p in ps], 0).contiguous()
-                r = 0
-                for p in ps:
-                    n = p.shape[0]
-                    p.data = fused[r:r + n].view(p.shape)
-                    r += n
-            self.fused = fused
+                n = p.shape[0]
+                p.data = fused[r:r + n].view(p.shape)
+                r += n
+        self.fused = fused
         return self.fused
 
 
@@ -142,9 +158,19 @@ class DecoderLayer(nn.Module):
             a, m = self.self_attn, self.mlp
             self._qkv = FusedRows([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight])
             self._gu = FusedRows([m.gate_proj.weight, m.up_proj.weight])
+        self._grad_sink = None   # set by Zero2Optimizer (trainer.create_optimizer): wgrads go straight to its buffer
         self._t = [FrozenTranspose() for _ in range(4)]
         # measured on B200: no gain inside the (power-capped) step, costs +14 GB → off by default
         self.use_frozen_transposes = False
+
+    def sink_params(self):
+        """{key: [parameters]} of the four weight gradients the hand-written backward produces."""
+        a, m = self.self_attn, self.mlp
+        if self.family == "phi3":
+            return {"qkv": [a.qkv_proj.weight], "o": [a.o_proj.weight], "gu": [m.gate_up_proj.weight],
+                    "d": [m.down_proj.weight]}
+        return {"qkv": [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], "o": [a.o_proj.weight],
+                "gu": [m.gate_proj.weight, m.up_proj.weight], "d": [m.down_proj.weight]}
 
     def run(self, x, meta_base):
         a, m = self.self_attn, self.mlp
@@ -157,6 +183,7 @@ class DecoderLayer(nn.Module):
             wg, wu = m.gate_proj.weight, m.up_proj.weight
         meta = SimpleNamespace(**vars(meta_base))
         meta.wqkv, meta.wgu = wqkv.detach(), wgu.detach()
+        meta.grad_sink = self._grad_sink
         meta.wqkvT = meta.woT = meta.wguT = meta.wdT = None
         if self.use_frozen_transposes and torch.is_grad_enabled():
             frozen_qkv = not (wq.requires_grad or (wk is not None and (wk.requires_grad or wv.requires_grad)))

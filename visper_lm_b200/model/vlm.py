@@ -407,6 +407,8 @@ class VisperForCausalLM(nn.Module):
     family = "llama"
     distill = True
     config_class = VisperConfig
+    supports_param_sync = True   # forward calls self._pre_trainable_hook() before its first trainable weight
+    _pre_trainable_hook = None
 
     def __init__(self, config, device=None):
         super().__init__()
@@ -734,6 +736,8 @@ class VisperForCausalLM(nn.Module):
     def encode_images(self, images):
         """ola_arch.py:187-190 — frozen tower (no grad) then the trainable mlp2x_gelu projector."""
         feats = self.get_vision_tower()(images)
+        if self._pre_trainable_hook is not None:   # ZeRO-2: the updated parameters must have arrived by now
+            self._pre_trainable_hook()
         pj = self.model.mm_projector
         h = A.linear(feats, pj[0].weight, pj[0].bias, ACT_GELU)
         return A.linear(h, pj[2].weight, pj[2].bias, ACT_NONE)
@@ -796,6 +800,8 @@ class VisperForCausalLM(nn.Module):
         B, T, D = inputs_embeds.shape
         H, KVH = cfg.num_attention_heads, cfg.num_key_value_heads
         hd = D // H
+        if self._pre_trainable_hook is not None:
+            self._pre_trainable_hook()
         cos, sin = ops.rope_tables(max(cfg.max_position_embeddings, T), hd, cfg.rope_theta, inputs_embeds.device)
         sw = getattr(cfg, "sliding_window", None)
         meta = SimpleNamespace(B=B, T=T, H=H, KVH=KVH, hd=hd, eps=cfg.rms_norm_eps, cos=cos, sin=sin,
@@ -977,6 +983,8 @@ class VisperForCausalLM(nn.Module):
                 pil_images=None, gen_mask=None, seg_mask=None, depth_mask=None, **kwargs):
         """Keyword surface of ola_llama.py:190-209 (llava_llama.py:73-91 for the NTP-only classes)."""
         distill_targets = kwargs.pop("distill_targets", None)
+        if images is None and self._pre_trainable_hook is not None:
+            self._pre_trainable_hook()   # no frozen tower to hide the parameter all-gather behind
         if inputs_embeds is None:
             (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds,
              labels) = self.prepare_inputs_labels_for_multimodal(

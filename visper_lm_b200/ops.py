@@ -36,13 +36,13 @@ def _rows(t: torch.Tensor):
 
 
 OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD, OPT_ATTN_TC_BWD_V1, OPT_GEMM_1CTA, OPT_GEMM_PANEL_MB = 0, 1, 2, 3, 4
-OPT_ATTN_BWD_SS, OPT_ATTN_FWD_V2, OPT_ATTN_BWD_PINGPONG, OPT_GEMM_L2_HINTS, OPT_ATTN_POLY_EXP2 = 5, 6, 7, 8, 9
+OPT_ATTN_BWD_SS, OPT_ATTN_FWD_V2, OPT_ATTN_BWD_PINGPONG, OPT_GEMM_L2_HINTS = 5, 6, 7, 8
 OPT_WIN_ATTN_V2 = 10
 OPT_DWCONV_FFMA2 = 11
 OPT_ATTN_FWD_TC64 = 12
 OPT_GEMM_EPI8 = 13
 OPT_GATHER_FLAT = 14
-OPT_ATTN_FWD_QTM = 15
+OPT_NORM_LEGACY = 15
 
 
 def set_option(key, value):
@@ -55,21 +55,44 @@ def _chk(status, what):
 
 
 # --------------------------------------------------------------------------------------------- GEMM
-class GemmTimer:
-    """CUDA-event timing of every GEMM launch on the launching stream (bench.py's live roofline)."""
+class KernelTimer:
+    """CUDA-event timing of the named hot kernels on the launching stream (bench.py's live rooflines):
+    every record is (start event, end event, category, algorithmic FLOPs, algorithmic bytes)."""
 
     def __init__(self):
         self.records = []
 
     def summary(self):
         torch.cuda.synchronize()
-        ms = sum(s.elapsed_time(e) for s, e, _ in self.records)
-        fl = sum(f for _, _, f in self.records)
-        return {"launches": len(self.records), "ms": ms, "flops": fl,
-                "tflops": (fl / ms / 1e9) if ms > 0 else None}
+        out = {}
+        for s, e, cat, fl, by in self.records:
+            d = out.setdefault(cat, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += by
+        for d in out.values():
+            d["tflops"] = (d["flops"] / d["ms"] / 1e9) if (d["ms"] > 0 and d["flops"]) else None
+        return out
 
 
-GEMM_TIMER = None
+KERNEL_TIMER = None
+
+
+def _timed(flops, cat="gemm", nbytes=0.0):
+    timer = KERNEL_TIMER
+    if timer is None:
+        return None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    return timer, ev0, ev1, cat, flops, nbytes
+
+
+def _timed_end(t):
+    if t is not None:
+        timer, ev0, ev1, cat, flops, nbytes = t
+        ev1.record()
+        timer.records.append((ev0, ev1, cat, flops, nbytes))
 
 
 def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None, out=None,
@@ -93,15 +116,10 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None
     pc, ldc = _rows(out)
     pr, ldr = _rows(residual) if residual is not None else (0, 0)
     px, ldx = _rows(pre) if pre is not None else (0, 0)
-    timer = GEMM_TIMER
-    if timer is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+    t = _timed(2.0 * M * N * K)
     _chk(_L().vpb_gemm_bf16(pa, lda, a_layout, pb, ldb, b_layout, pc, ldc, M, N, K, act, _p(bias),
                             pr, ldr, px, ldx, _stream()), "gemm")
-    if timer is not None:
-        ev1.record()
-        timer.records.append((ev0, ev1, 2.0 * M * N * K))
+    _timed_end(t)
     return (out, pre) if want_pre else out
 
 
@@ -111,22 +129,6 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, act=ACT_NONE, residual=None
 # per layer in isolation but is a wash inside the power-capped step, so it stays off by default.
 FUSE_SWIGLU = os.environ.get("VPB_FUSE_SWIGLU", "1") != "0"
 FUSE_SWIGLU_BWD = os.environ.get("VPB_FUSE_SWIGLU_BWD", "0") != "0"
-
-
-def _timed(flops):
-    timer = GEMM_TIMER
-    if timer is None:
-        return None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    return timer, ev0, ev1, flops
-
-
-def _timed_end(t):
-    if t is not None:
-        timer, ev0, ev1, flops = t
-        ev1.record()
-        timer.records.append((ev0, ev1, flops))
 
 
 def gemm_swiglu_fwd(a, wgu, want_gu=True, tiled=False):
@@ -207,8 +209,10 @@ def rmsnorm_fwd(x, w, eps, out=None):
     rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
     px, ldx = _rows(x)
     py, ldy = _rows(y)
+    t = _timed(0.0, "rmsnorm_fwd", 4.0 * M * D)  # read x + write y, bf16
     _chk(_L().vpb_rmsnorm_fwd(px, ldx, w.data_ptr(), py, ldy, rstd.data_ptr(), M, D, eps, _stream()),
          "rmsnorm_fwd")
+    _timed_end(t)
     return y, rstd
 
 
@@ -219,8 +223,10 @@ def rmsnorm_bwd(dy, x, w, rstd, dres=None, out=None):
     px, ldx = _rows(x)
     pr, ldr = _rows(dres) if dres is not None else (0, 0)
     pdx, lddx = _rows(dx)
+    t = _timed(0.0, "rmsnorm_bwd", (8.0 if dres is not None else 6.0) * M * D)  # dy, x (, dres) in; dx out
     _chk(_L().vpb_rmsnorm_bwd(pdy, lddy, px, ldx, w.data_ptr(), rstd.data_ptr(), pr, ldr,
                               pdx, lddx, M, D, _stream()), "rmsnorm_bwd")
+    _timed_end(t)
     return dx
 
 
@@ -307,7 +313,9 @@ def swiglu_bwd(gu, dh):
     dgu = torch.empty((M, F2), dtype=BF16, device=gu.device)
     pg, ldg = _rows(gu)
     pd, ldd = _rows(dh)
+    t = _timed(0.0, "swiglu_bwd", 10.0 * M * F)  # g|u (2F) + dh (F) in, d_gate|d_up (2F) out, bf16
     _chk(_L().vpb_swiglu_bwd(pg, ldg, pd, ldd, dgu.data_ptr(), F2, M, F, _stream()), "swiglu_bwd")
+    _timed_end(t)
     return dgu
 
 
@@ -477,6 +485,17 @@ def group_mean_bwd(dout, groups, gsize):
 
 
 # --------------------------------------------------------------------------------------------- attention
+def _attn_flops(B, H, sq, sk, hd, causal, window):
+    """QK^T + PV of the visible (query, key) pairs: causal = lower triangle, sliding window = band."""
+    pairs = float(sq) * sk
+    if causal:
+        pairs = sq * (sq + 1) / 2.0
+        if window and window < sq:
+            w = window + 1
+            pairs = w * (w + 1) / 2.0 + (sq - w) * float(w)
+    return 4.0 * B * H * pairs * hd
+
+
 def attn_fwd(q, k, v, B, H, KVH, sq, sk, head_dim, scale, causal, k2=None, v2=None, sk2=0, out=None,
              window=0):
     """q:[B*sq, >=H*hd] k,v:[B*sk, >=KVH*hd] row views (may alias one packed buffer)."""
@@ -489,9 +508,11 @@ def attn_fwd(q, k, v, B, H, KVH, sq, sk, head_dim, scale, causal, k2=None, v2=No
     pk2, ldk2 = _rows(k2) if k2 is not None else (0, 0)
     pv2, ldv2 = _rows(v2) if v2 is not None else (0, 0)
     po, ldo = _rows(o)
+    t = _timed(_attn_flops(B, H, sq, sk + sk2, head_dim, causal, window), f"attn_fwd_hd{head_dim}")
     _chk(_L().vpb_attn_fwd(pq, ldq, pk, ldk, pv, ldv, pk2, ldk2, pv2, ldv2, po, ldo, lse.data_ptr(),
                            B, H, KVH, sq, sk, sk2, head_dim, scale, 1 if causal else 0, int(window),
                            _stream()), "attn_fwd")
+    _timed_end(t)
     return o, lse
 
 
@@ -527,10 +548,12 @@ def attn_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, sq, sk, head_dim, scale
     pdv, lddv = _rows(dv)
     pdk2, lddk2 = _rows(dk2) if dk2 is not None else (0, 0)
     pdv2, lddv2 = _rows(dv2) if dv2 is not None else (0, 0)
+    t = _timed(2.5 * _attn_flops(B, H, sq, sk + sk2, head_dim, causal, window), f"attn_bwd_hd{head_dim}")
     _chk(_L().vpb_attn_bwd(pq, ldq, pk, ldk, pv, ldv, pk2, ldk2, pv2, ldv2, po, ldo, pdo, lddo,
                            lse.data_ptr(), delta.data_ptr(), pdq, lddq, pdk, lddk, pdv, lddv, pdk2,
                            lddk2, pdv2, lddv2, B, H, KVH, sq, sk, sk2, head_dim, scale,
                            1 if causal else 0, int(window), _stream()), "attn_bwd")
+    _timed_end(t)
 
 
 def attn_bwd_rope(q, k, v, o, do, lse, dq, dk, dv, B, H, KVH, T, head_dim, scale, causal, cos, sin,
@@ -563,9 +586,11 @@ def ce_count(labels, T, shift=True):
 def ce_fwd_bwd_(logits, labels, row0, T, row_loss, count, gscale=1.0, write_grad=True, shift=True):
     R, V = logits.shape
     pl, ld = _rows(logits)
+    t = _timed(0.0, "ce_fwd_bwd", (6.0 if write_grad else 2.0) * R * V)  # 2 reads (+1 write) of bf16 logits
     _chk(_L().vpb_ce_fwd_bwd(pl, ld, labels.data_ptr(), row0, R, V, T, 1 if shift else 0,
                              row_loss.data_ptr(), count.data_ptr(), gscale, 1 if write_grad else 0,
                              _stream()), "ce_fwd_bwd")
+    _timed_end(t)
 
 
 def ce_finalize(row_loss, count):
@@ -631,9 +656,9 @@ if os.environ.get("VPB_GEMM_PANEL_MB"):
     set_option(OPT_GEMM_PANEL_MB, int(os.environ["VPB_GEMM_PANEL_MB"]))
 for _name, _key in (("VPB_ATTN_BWD_PINGPONG", OPT_ATTN_BWD_PINGPONG), ("VPB_ATTN_BWD_SS", OPT_ATTN_BWD_SS),
                     ("VPB_ATTN_FWD_V2", OPT_ATTN_FWD_V2), ("VPB_GEMM_1CTA", OPT_GEMM_1CTA),
-                    ("VPB_GEMM_L2_HINTS", OPT_GEMM_L2_HINTS), ("VPB_ATTN_POLY_EXP2", OPT_ATTN_POLY_EXP2), ("VPB_WIN_ATTN_V2", OPT_WIN_ATTN_V2),
+                    ("VPB_GEMM_L2_HINTS", OPT_GEMM_L2_HINTS), ("VPB_WIN_ATTN_V2", OPT_WIN_ATTN_V2),
                     ("VPB_DWCONV_FFMA2", OPT_DWCONV_FFMA2), ("VPB_ATTN_FWD_TC64", OPT_ATTN_FWD_TC64),
                     ("VPB_GEMM_EPI8", OPT_GEMM_EPI8), ("VPB_GATHER_FLAT", OPT_GATHER_FLAT),
-                    ("VPB_ATTN_FWD_QTM", OPT_ATTN_FWD_QTM)):
+                    ("VPB_NORM_LEGACY", OPT_NORM_LEGACY)):
     if os.environ.get(_name):  # A/B switches for bench runs
         set_option(_key, int(os.environ[_name]))

@@ -44,6 +44,7 @@ class TrainingArguments:
     logging_steps: int = 1
     save_steps: int = 200
     save_total_limit: Optional[int] = None
+    zero_bucket_elems: int = 64 * 1024 * 1024   # ZeRO-2 reduce / gather bucket (scripts/zero2.json reduce_bucket_size)
     tune_mm_mlp_adapter: bool = False
     use_im_start_end: bool = False
     bf16: bool = True
@@ -65,105 +66,426 @@ def cosine_with_warmup(step, total, warmup):
     return max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 
 
+class _Bucket:
+    """A contiguous range [lo, hi) of the flat parameter space that is reduced / gathered as one collective.
+    hi - lo is a multiple of world·ALIGN; rank r owns [lo + r·slice, lo + (r+1)·slice)."""
+
+    __slots__ = ("idx", "lo", "hi", "slice", "shard_off", "group", "params", "pads", "pending", "buf", "buf_id",
+                 "ev_reduced", "ev_gathered", "launched", "touched")
+
+    def __init__(self, idx, lo, group):
+        self.idx, self.lo, self.hi, self.group = idx, lo, lo, group
+        self.slice = self.shard_off = 0
+        self.params, self.pads = [], []
+        self.pending = 0
+        self.buf = self.buf_id = self.ev_reduced = self.ev_gathered = None
+        self.launched = self.touched = False
+
+
+class LayerGradSink:
+    """Lets a hand-written backward write a weight gradient straight into the optimizer's gradient
+    buffer (no `p.grad` twin, no per-parameter copy): `dst(key)` → ([rows, K] view, accumulate?) or None
+    when that key is not (entirely) trainable; `done(key)` after the kernel that wrote it was launched."""
+
+    def __init__(self, opt, keys):
+        self.opt, self.keys = opt, keys          # key -> (first param index, [param indices], (rows, K))
+
+    def dst(self, key):
+        ent = self.keys.get(key)
+        if ent is None or not self.opt.sinks_enabled:
+            return None
+        first, idxs, shape = ent
+        buf, acc = self.opt._grad_dst(first, sum(self.opt.numels[i] for i in idxs), idxs)
+        return buf.view(shape), acc
+
+    def done(self, key):
+        for i in self.keys[key][1]:
+            self.opt._mark_written(i)
+
+
 class Zero2Optimizer:
-    """ZeRO-2: every rank holds all bf16 parameters (one flat buffer) and the full bf16 gradient
-    buffer; fp32 master weights and Adam moments exist only for the rank's 1/N shard.
+    """ZeRO-2 (scripts/zero2.json: contiguous gradients, bucketed reduce, overlap): every rank holds all
+    bf16 parameters in one flat buffer; gradients, fp32 master weights and Adam moments exist only for the
+    rank's 1/N share.
+
+    Layout.  Trainable parameters are laid out by optimizer group (decay / no-decay × lr scale), in
+    model order inside a group, and cut into BUCKETS of ~bucket_elems elements (a fused q|k|v or gate|up
+    group is never split and stays adjacent, so modules.FusedRows adopts its region of the flat buffer
+    instead of owning a copy).  Rank r owns slice r of every bucket; its shard (master, m, v, gradient)
+    is the concatenation of those slices in bucket order.
+
+    Gradients.  Producers write into the gradient space directly: the decoder backward through a
+    LayerGradSink (the wgrad GEMM's output pointer), everything else through a post-accumulate hook
+    that moves `p.grad` there and drops it.  With world > 1 a bucket's gradient space is a staging
+    buffer from a pool of `pool` buffers: when the bucket's last gradient is written — backward runs the
+    buckets in reverse order — the comm stream waits for that point and reduce-scatters the bucket into
+    the rank's gradient shard, so the transfer hides under the rest of backward and full-size gradient
+    memory never exists.  With world == 1 the gradient shard is the gradient space.
+
+    step(): wait for the reduces, global grad-norm (fp32 scalar all-reduce), clip coefficient on device,
+    fused AdamW on the shard (fp32 master → bf16 parameter slice), then the per-bucket parameter
+    all-gathers on the comm stream; the next forward waits for them only where it first touches a
+    trainable parameter (`wait_params`, after the frozen tower).
 
     groups: list of (predicate(name) -> bool, lr_scale, weight_decay); first match wins."""
 
     ALIGN = 8
 
     def __init__(self, named_params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 max_grad_norm=1.0, groups=None, process_group=None):
+                 max_grad_norm=1.0, groups=None, process_group=None, distributed=True,
+                 bucket_elems=64 * 1024 * 1024, keep_together=(), pool=3, overlap=True):
         self.named = [(n, p) for n, p in named_params if p.requires_grad]
         assert self.named, "no trainable parameters"
         self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
         self.pg = process_group
-        self.world = dist.get_world_size(self.pg) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(self.pg) if dist.is_initialized() else 0
+        use_dist = distributed and dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(self.pg) if use_dist else 1
+        self.rank = dist.get_rank(self.pg) if use_dist else 0
         dev = self.named[0][1].device
+        self.dev = dev
         groups = groups or [(lambda n: True, 1.0, weight_decay)]
-        # layout: parameters sorted by group so each group is one contiguous range
-        order = []
+        self.groups = groups
+        # ---- order: by group, model order inside a group ------------------------------------------------
+        order, seen = [], set()
         for gi, (pred, _, _) in enumerate(groups):
             for n, p in self.named:
-                if not any(n == o[0] for o in order) and pred(n) and \
-                        not any(g[0](n) for g in groups[:gi]):
+                if n not in seen and pred(n):
+                    seen.add(n)
                     order.append((n, p, gi))
         self.named = [(n, p) for n, p, _ in order]
-        offs, off = [], 0
-        self.group_ranges = []
-        cur_g, g_start = order[0][2], 0
-        for n, p, gi in order:
-            if gi != cur_g:
-                self.group_ranges.append((g_start, off, cur_g))
-                cur_g, g_start = gi, off
+        self.index = {id(p): i for i, (_, p) in enumerate(self.named)}
+        self.numels = [p.numel() for _, p in self.named]
+        together = {}
+        for grp in keep_together:  # parameters that must stay adjacent and in one bucket (FusedRows groups)
+            ids = [self.index[id(p)] for p in grp if id(p) in self.index]
+            if len(ids) == len(list(grp)) and ids == list(range(ids[0], ids[0] + len(ids))) \
+                    and all(self.numels[i] % self.ALIGN == 0 for i in ids):
+                for k in ids[1:]:
+                    together[k] = ids[0]
+        # ---- buckets ----------------------------------------------------------------------------------
+        unit = self.world * self.ALIGN
+        offs, off, buckets, cur = [], 0, [], None
+
+        def close(b, off):
+            end = (off + unit - 1) // unit * unit
+            if end > off:
+                b.pads.append((off, end))
+            b.hi = end
+            return end
+
+        for i, (n, p, gi) in enumerate(order):
+            if cur is None or gi != cur.group or (cur.hi - cur.lo >= bucket_elems and i not in together):
+                if cur is not None:
+                    off = close(cur, off)
+                cur = _Bucket(len(buckets), off, gi)
+                buckets.append(cur)
             offs.append(off)
-            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        self.group_ranges.append((g_start, off, cur_g))
-        self.groups = groups
-        chunk = self.world * 1024
-        self.total = (off + chunk - 1) // chunk * chunk
+            cur.params.append(i)
+            nxt = off + (self.numels[i] + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            if nxt > off + self.numels[i]:
+                cur.pads.append((off + self.numels[i], nxt))
+            off = nxt
+            cur.hi = off
+        off = close(cur, off)
+        self.total = off
         self.offsets = offs
+        self.buckets = buckets
+        self.bucket_of = [None] * len(order)
+        shard_off = 0
+        for b in buckets:
+            b.slice = (b.hi - b.lo) // self.world
+            b.shard_off = shard_off
+            shard_off += b.slice
+            for i in b.params:
+                self.bucket_of[i] = b
+        self.shard = shard_off
+        assert self.shard * self.world == self.total
+        # ---- storage ----------------------------------------------------------------------------------
         self.flat_p = torch.zeros(self.total, dtype=BF16, device=dev)
-        self.flat_g = torch.zeros(self.total, dtype=BF16, device=dev)
         with torch.no_grad():
             for (n, p), o in zip(self.named, offs):
                 view = self.flat_p[o:o + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view  # parameters now live in the flat buffer (dtype becomes bf16)
-        self.shard = self.total // self.world
-        s0 = self.rank * self.shard
-        self.s0, self.s1 = s0, s0 + self.shard
-        self.master = self.flat_p[s0:s0 + self.shard].float()
+                p._vpb_flat_owner = True
+        self.master = torch.cat([self.flat_p[b.lo + self.rank * b.slice: b.lo + (self.rank + 1) * b.slice]
+                                 for b in buckets]).float()
         self.m = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.shard, dtype=torch.float32, device=dev)
-        self.g_shard = torch.zeros(self.shard, dtype=BF16, device=dev) if self.world > 1 else None
+        self.g_shard = torch.zeros(self.shard, dtype=BF16, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
         self.last_grad_norm = None
+        # AdamW runs: contiguous in shard space AND in parameter space, one optimizer group each
+        runs = []
+        for b in buckets:
+            plo = b.lo + self.rank * b.slice
+            if runs and runs[-1][3] == b.group and runs[-1][1] == b.shard_off and runs[-1][2] + (runs[-1][1] - runs[-1][0]) == plo:
+                runs[-1][1] = b.shard_off + b.slice
+            else:
+                runs.append([b.shard_off, b.shard_off + b.slice, plo, b.group])
+        self.update_runs = [tuple(r) for r in runs]
+        # ---- gradient plumbing --------------------------------------------------------------------------
+        self.cuda = dev.type == "cuda"
+        # overlap="force": exercise the staging pool / comm-stream path on ONE GPU (tests): the "reduce-scatter"
+        # of world 1 is a copy of the bucket into the gradient shard on the comm stream
+        self.force_staging = overlap == "force" and self.cuda and self.world == 1
+        self.overlap = bool(overlap and (self.world > 1 or self.force_staging) and self.cuda)
+        self.sinks_enabled = self.cuda
+        self.accumulating = False
+        self.flat_g = None                     # full-size gradient space: only world > 1 without overlap
+        self.comm = torch.cuda.Stream(device=dev) if (self.cuda and (self.world > 1 or self.force_staging)) else None
+        self.pool_n = max(2, int(pool))
+        self.pool = []                         # staging buffers (overlap mode), each the size of the largest bucket
+        self.pool_last = []                    # bucket that last used each staging buffer
+        self.written = [False] * len(order)
+        self._pending_gather = []
+        self._events = {}
+        self._hooks = []
+        if hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
+            for _, p in self.named:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self._reset_step_state()
+
+    # ---- layout helpers -----------------------------------------------------------------------------------
+    def flat_params(self):
+        """All bf16 parameters as one flat tensor (waits for a pending parameter all-gather)."""
+        self.wait_params()
+        return self.flat_p
+
+    def layer_sink(self, keyed_params):
+        """keyed_params: {key: [Parameter, ...]} (adjacent rows of one fused weight).  Keys whose parameters
+        are not all trainable and adjacent are left out (their gradients take the hook path)."""
+        keys = {}
+        for key, ps in keyed_params.items():
+            idxs = [self.index.get(id(p)) for p in ps]
+            if any(i is None for i in idxs) or idxs != list(range(idxs[0], idxs[0] + len(idxs))):
+                continue
+            if any(self.offsets[i + 1] != self.offsets[i] + self.numels[i] for i in idxs[:-1]):
+                continue
+            if len({self.bucket_of[i].idx for i in idxs}) != 1:
+                continue
+            rows = sum(self.named[i][1].shape[0] for i in idxs)
+            keys[key] = (idxs[0], idxs, (rows, self.named[idxs[0]][1].shape[1]))
+        return LayerGradSink(self, keys) if keys else None
+
+    # ---- per-step gradient collection ---------------------------------------------------------------------
+    def _reset_step_state(self):
+        self.written = [False] * len(self.named)
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.launched = b.touched = False
+            b.buf = b.buf_id = None
 
     def zero_grad(self):
         for _, p in self.named:
             p.grad = None
+        self._reset_step_state()
+        self.accumulating = False
 
-    def _pack_grads(self):
-        for (n, p), o in zip(self.named, self.offsets):
-            dst = self.flat_g[o:o + p.numel()]
-            if p.grad is None:
-                dst.zero_()
-                continue
-            g = p.grad
-            if g.dtype == BF16 and g.is_contiguous() and g.numel() % 8 == 0:
-                ops.axpby(g.reshape(-1), None, 1.0, 0.0, out=dst)
+    def set_accumulating(self, flag=True):
+        """gradient_accumulation_steps > 1: gradients add up over several backward passes before step();
+        the bucketed overlap (one reduce per bucket per backward) is switched off for such steps."""
+        self.accumulating = bool(flag)
+
+    def _use_staging(self):
+        return self.overlap and not self.accumulating
+
+    def _grad_space(self, b):
+        """The tensor that holds bucket b's gradient space [b.lo, b.hi) for this step."""
+        if self.world == 1 and not (self.force_staging and self._use_staging()):
+            return self.g_shard[b.shard_off: b.shard_off + b.slice]
+        if not self._use_staging():
+            if self.flat_g is None:
+                self.flat_g = torch.zeros(self.total, dtype=BF16, device=self.dev)
+            return self.flat_g[b.lo:b.hi]
+        if b.buf is None:
+            if not self.pool:
+                big = max(x.hi - x.lo for x in self.buckets)
+                self.pool = [torch.zeros(big, dtype=BF16, device=self.dev) for _ in range(self.pool_n)]
+                self.pool_last = [None] * self.pool_n
+            k = (len(self.buckets) - 1 - b.idx) % self.pool_n     # backward visits buckets in reverse order
+            prev = self.pool_last[k]
+            if prev is not None and prev is not b and prev.ev_reduced is not None:
+                torch.cuda.current_stream().wait_event(prev.ev_reduced)   # its reduce must have read the buffer
+            self.pool_last[k] = b
+            b.buf_id = k
+            b.buf = self.pool[k][: b.hi - b.lo]
+        return b.buf
+
+    def _touch(self, b):
+        space = self._grad_space(b)
+        if not b.touched:
+            b.touched = True
+            if self._use_staging():
+                for lo, hi in b.pads:          # padding never receives a gradient: keep it zero for the norm
+                    space[lo - b.lo: hi - b.lo].zero_()
+        return space
+
+    def _grad_dst(self, first, n, idxs):
+        b = self.bucket_of[first]
+        space = self._touch(b)
+        o = self.offsets[first] - b.lo
+        acc = all(self.written[i] for i in idxs)
+        if not acc:
+            for i in idxs:
+                if self.written[i]:           # partially written group: cannot happen with whole-group sinks
+                    raise RuntimeError("gradient sink: group written piecewise")
+        return space[o:o + n], acc
+
+    def _mark_written(self, i):
+        if self.written[i]:
+            return
+        self.written[i] = True
+        b = self.bucket_of[i]
+        b.pending -= 1
+        if b.pending == 0 and self._use_staging() and not b.launched:
+            self._reduce_bucket(b)
+
+    def _collect(self, i, g):
+        """Move one parameter's gradient into the gradient space (generic path)."""
+        n = self.numels[i]
+        dst, acc = self._grad_dst(i, n, [i])
+        g = g.reshape(-1)
+        if g.dtype == BF16 and g.is_contiguous() and n % 8 == 0:
+            ops.axpby(g, dst if acc else None, 1.0, 1.0 if acc else 0.0, out=dst)
+        elif acc:
+            dst.add_(g.to(dst.dtype))
+        else:
+            dst.copy_(g)
+        self._mark_written(i)
+
+    def _on_grad(self, p):
+        i = self.index.get(id(p))
+        if i is None or p.grad is None:
+            return
+        self._collect(i, p.grad)
+        p.grad = None
+
+    def _reduce_bucket(self, b):
+        b.launched = True
+        if self.world == 1 and not (self.force_staging and self._use_staging()):
+            return
+        src = self._grad_space(b)
+        out = self.g_shard[b.shard_off: b.shard_off + b.slice]
+        if self.comm is None:                 # CPU (gloo) path of the tests: synchronous
+            self._reduce_scatter_cpu(out, src)
+            return
+        ready = torch.cuda.Event()
+        ready.record()
+        self.comm.wait_event(ready)
+        with torch.cuda.stream(self.comm):
+            if self.world == 1:
+                out.copy_(src)
             else:
-                dst.copy_(g.reshape(-1))
+                dist.reduce_scatter_tensor(out, src, op=dist.ReduceOp.SUM, group=self.pg)
+            b.ev_reduced = torch.cuda.Event()
+            b.ev_reduced.record()
+
+    def _reduce_scatter_cpu(self, out, src):
+        # gloo has no reduce_scatter: all-reduce the bucket (fp32 sum rounded to bf16, as NCCL's bf16 sum) and slice
+        t = src.clone()
+        dist.all_reduce(t, group=self.pg)
+        out.copy_(t[self.rank * out.numel():(self.rank + 1) * out.numel()])
+
+    def _finish_gradients(self):
+        """Collect stragglers (p.grad set without the hook, parameters that got no gradient) and launch
+        the reduces that are still outstanding."""
+        for i, (_, p) in enumerate(self.named):
+            if p.grad is not None:
+                self._collect(i, p.grad)
+                p.grad = None
+        for b in self.buckets:
+            if b.pending:
+                space = self._touch(b)
+                for i in b.params:
+                    if not self.written[i]:   # no gradient this step (e.g. linear_2/3 of the depth heads)
+                        o = self.offsets[i] - b.lo
+                        space[o:o + self.numels[i]].zero_()
+                        self.written[i] = True
+                b.pending = 0
+            if not b.launched:
+                self._reduce_bucket(b)
+        if self.comm is not None:
+            cur = torch.cuda.current_stream()
+            for b in self.buckets:
+                if b.ev_reduced is not None:
+                    cur.wait_event(b.ev_reduced)
 
     def step(self, lr_mult=1.0):
         self.step_count += 1
-        self._pack_grads()
-        if self.world > 1:
-            dist.reduce_scatter_tensor(self.g_shard, self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-            g = self.g_shard
-        else:
-            g = self.flat_g
+        timing = self.cuda and self.world > 1
+        if timing:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self._finish_gradients()
+        if timing:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self._events["reduce_wait"] = (e0, e1)
+        g = self.g_shard
         ops.grad_sumsq(g, out=self.sumsq)
         if self.world > 1:
             dist.all_reduce(self.sumsq, group=self.pg)
         # gradients are SUMS over ranks here → average with 1/world inside the clip coefficient
         coef, norm = ops.clip_coef(self.sumsq, self.max_grad_norm or 0.0, 1.0 / self.world)
         self.last_grad_norm = norm
-        for (a, b, gi) in self.group_ranges:
-            lo, hi = max(a, self.s0), min(b, self.s1)
-            if lo >= hi:
-                continue
+        for (slo, shi, plo, gi) in self.update_runs:
             _, lr_scale, wd = self.groups[gi]
-            sl = slice(lo - self.s0, hi - self.s0)
-            ops.adamw_step_(self.master[sl], self.m[sl], self.v[sl], g[sl], self.flat_p[lo:hi],
+            sl = slice(slo, shi)
+            ops.adamw_step_(self.master[sl], self.m[sl], self.v[sl], g[sl], self.flat_p[plo:plo + (shi - slo)],
                             self.lr * lr_scale * lr_mult, self.betas[0], self.betas[1], self.eps, wd,
                             self.step_count, grad_scale=coef)
         if self.world > 1:
-            dist.all_gather_into_tensor(self.flat_p, self.flat_p[self.s0:self.s1], group=self.pg)
+            self._gather_params()
+        self._reset_step_state()
+
+    def _gather_params(self):
+        if self.comm is None:                 # gloo tests
+            for b in self.buckets:
+                full = self.flat_p[b.lo:b.hi]
+                mine = full[self.rank * b.slice:(self.rank + 1) * b.slice].clone()
+                parts = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(parts, mine, group=self.pg)
+                full.copy_(torch.cat(parts))
+            return
+        upd = torch.cuda.Event()
+        upd.record()
+        self.comm.wait_event(upd)
+        with torch.cuda.stream(self.comm):
+            for b in self.buckets:            # forward order: the first layers' weights arrive first
+                full = self.flat_p[b.lo:b.hi]
+                dist.all_gather_into_tensor(full, full[self.rank * b.slice:(self.rank + 1) * b.slice], group=self.pg)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._pending_gather = [ev]
+
+    def wait_params(self):
+        """The compute stream waits for the updated parameters (no-op when nothing is pending)."""
+        if self._pending_gather:
+            cur = torch.cuda.current_stream()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for ev in self._pending_gather:
+                cur.wait_event(ev)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self._events["gather_wait"] = (e0, e1)
+            self._pending_gather = []
+
+    def comm_summary(self):
+        """Exposed communication of the LAST step: how long the compute stream sat in the two waits
+        (after backward for the outstanding reduce-scatters; before the first trainable weight of the
+        next forward for the parameter all-gathers).  Synchronises."""
+        if not (self.cuda and self.world > 1):
+            return None
+        torch.cuda.synchronize()
+        out = {"buckets": len(self.buckets), "bucket_mb": round(max(b.hi - b.lo for b in self.buckets) * 2 / 2**20, 1),
+               "grad_bytes_per_step": self.total * 2, "overlap": self.overlap,
+               "staging_buffers": len(self.pool)}
+        for k, (a, b) in self._events.items():
+            out[f"exposed_{k}_ms"] = round(a.elapsed_time(b), 3)
+        return out
 
     def state_dict(self):
         return {"step": self.step_count, "master": self.master, "m": self.m, "v": self.v,
@@ -178,7 +500,7 @@ class LLaVATrainer:
     """Constructor and entry points of ola_vlm/train/llava_trainer.py:217 (HF Trainer subclass)."""
 
     def __init__(self, model=None, tokenizer=None, args: TrainingArguments = None, train_dataset=None,
-                 eval_dataset=None, data_collator=None, **kwargs):
+                 eval_dataset=None, data_collator=None, distributed=True, **kwargs):
         self.model = model
         self.tokenizer = tokenizer
         self.args = args or TrainingArguments()
@@ -188,7 +510,7 @@ class LLaVATrainer:
         self.deepspeed = None
         self.optimizer = None
         self.state = {"global_step": 0, "log_history": []}
-        self.is_dist = dist.is_available() and dist.is_initialized()
+        self.is_dist = bool(distributed) and dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size() if self.is_dist else 1
         self.rank = dist.get_rank() if self.is_dist else 0
         self.total_steps = None
@@ -206,9 +528,20 @@ class LLaVATrainer:
             groups.append((lambda n: "mm_projector" in n and _no_decay(n), scale, 0.0))
         groups.append((lambda n: not _no_decay(n), 1.0, a.weight_decay))
         groups.append((lambda n: True, 1.0, 0.0))
+        from ..model.modules import DecoderLayer, FusedRows
+
+        fused = [fr.params for m in self.model.modules() for fr in vars(m).values() if isinstance(fr, FusedRows)]
         self.optimizer = Zero2Optimizer(self.model.named_parameters(), a.learning_rate,
                                         (a.adam_beta1, a.adam_beta2), a.adam_epsilon, a.weight_decay,
-                                        a.max_grad_norm, groups)
+                                        a.max_grad_norm, groups, distributed=self.is_dist, keep_together=fused,
+                                        bucket_elems=int(getattr(a, "zero_bucket_elems", 64 * 1024 * 1024)))
+        for m in self.model.modules():   # decoder weight gradients are written straight into the optimizer's buffer
+            if isinstance(m, DecoderLayer):
+                m._grad_sink = self.optimizer.layer_sink(m.sink_params())
+        if getattr(self.model, "supports_param_sync", False):
+            # the parameter all-gather of step k overlaps the frozen tower of step k+1: the model calls this
+            # where it first touches a trainable weight
+            self.model._pre_trainable_hook = self.optimizer.wait_params
         return self.optimizer
 
     # -- one optimisation step on a HOST batch (collator output) ------------------------------------
@@ -264,6 +597,8 @@ class LLaVATrainer:
         """HF Trainer.training_step semantics (llava_trainer.py:357-381 is a dead verbatim copy):
         forward → loss → backward; returns the detached loss tensor (no host sync)."""
         inputs = self._to_device(inputs)
+        if self.optimizer is not None and not getattr(model, "supports_param_sync", False):
+            self.optimizer.wait_params()
         out = model(**inputs)
         loss = out.loss
         loss.backward()
@@ -288,6 +623,8 @@ class LLaVATrainer:
         the number of micro-batches before backward, gradients add up in p.grad, one optimizer step."""
         opt = self.create_optimizer()
         opt.zero_grad()
+        opt.set_accumulating(True)
+        opt.wait_params()
         k = len(micro_batches)
         total = None
         for mb in micro_batches:
@@ -437,6 +774,8 @@ class LLaVATrainer:
         if self.rank == 0:
             from . import checkpoint as ckpt
 
+            if self.optimizer is not None:
+                self.optimizer.wait_params()
             sd = state_dict if state_dict is not None else {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
             ckpt.save_config(self.model.config, output_dir)
             # HF save_pretrained layout (safetensors, 5 GB shards + index) so builder.py / from_pretrained load it
