@@ -85,6 +85,9 @@ def parse():
     ap.add_argument("--no-reference-gpu", action="store_true", help="reference arm: skip the GPU leg")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed device leg with cudaProfilerStart/Stop (ncu --profile-from-start off)")
+    ap.add_argument("--cpu-config", default="configs0", choices=["configs0", "tiny"],
+                    help="workload of the CPU reference legs: BASELINE configs[0] (default) or the tiny debug model "
+                         "(contract tests)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0,
                     help="wall budget of the CPU reference legs (whole steps only; at least 3 are timed)")
     return ap.parse_args()
@@ -221,14 +224,17 @@ CFG0_DESC = ("BASELINE configs[0]: Phi-3-mini-4k + CLIP-ViT-L/14-336, one 336 px
              "(forward, backward, clip, AdamW) of the unmodified reference classes, no extrapolation")
 
 
-def reference_cpu(budget_s, steps, warmup=1):
+def reference_cpu(budget_s, steps, warmup=1, which="configs0"):
     """The unmodified reference (oracle/_ref under oracle/ref_shim) on the host cores at BASELINE configs[0]."""
     from oracle import ref_run
     from visper_lm_b200.model import presets
 
-    c = dict(presets.PHI3_MINI, num_sys_tokens=13)
-    r = ref_run.time_cpu(c, distill=True, n_text=128, B=1, steps=max(3, steps), warmup=warmup, budget_s=budget_s)
-    sample = (f"{CFG0_DESC}; {len(r['step_s'])} timed steps after {r['warmup']} warm-up on {r['cores']} threads: "
+    if which == "tiny":
+        c, n_text, desc = dict(TINY, num_sys_tokens=26), 60, "tiny debug model (4 layers, hidden 128), 60 text tokens, batch 1"
+    else:
+        c, n_text, desc = dict(presets.PHI3_MINI, num_sys_tokens=13), 128, CFG0_DESC
+    r = ref_run.time_cpu(c, distill=True, n_text=n_text, B=1, steps=max(3, steps), warmup=warmup, budget_s=budget_s)
+    sample = (f"{desc}; {len(r['step_s'])} timed steps after {r['warmup']} warm-up on {r['cores']} threads: "
               f"mean {r['step_s_mean']:.2f} s, min {r['step_s_min']:.2f}, max {r['step_s_max']:.2f} "
               f"(model construction {r['build_s']:.0f} s not timed)")
     return r, {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "reference",
@@ -243,7 +249,7 @@ def run_reference(args):
         return
     c = model_cfg(args.model, args.layers, args.tower)
     distill = args.workload == "dsg"
-    r, cpu = reference_cpu(args.cpu_budget_s, args.steps, warmup=min(max(args.warmup, 1), 1))
+    r, cpu = reference_cpu(args.cpu_budget_s, args.steps, warmup=min(max(args.warmup, 1), 1), which=args.cpu_config)
     n_timed = len(r["step_s"])
     ms = 1000.0 * r["step_s_mean"]
     cfgd = workload_config(args, c, distill)
@@ -603,7 +609,7 @@ def run_b200(args):
         line["dp_check"] = check
     if world == 1 and not args.no_cpu_baseline:
         try:
-            _, line["cpu_baseline"] = reference_cpu(args.cpu_budget_s, 3, warmup=1)
+            _, line["cpu_baseline"] = reference_cpu(args.cpu_budget_s, 3, warmup=1, which=args.cpu_config)
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"failed: {type(ex).__name__}: {ex}"}

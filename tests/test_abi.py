@@ -73,3 +73,19 @@ def test_reference_module_paths_resolve():
         b.build_vision_tower(SimpleNamespace(mm_vision_tower="sam-vit"))
     for k in [k for k in sys.modules if k == "ola_vlm" or k.startswith("ola_vlm.")]:
         del sys.modules[k]
+
+
+def test_auto_factories_know_the_model_types():
+    """ola_llama.py:246-247 / llava_llama.py:174-175: the four model_type strings resolve through transformers'
+    Auto* factories to this package's classes."""
+    from transformers import AutoConfig, AutoModelForCausalLM
+
+    from visper_lm_b200.model import vlm
+
+    for mt, cfg, cls in (("ola_llama", vlm.OlaLlavaLlamaConfig, vlm.OlaLlavaLlamaForCausalLM),
+                         ("ola_phi3", vlm.OlaLlavaPhi3Config, vlm.OlaLlavaPhi3ForCausalLM),
+                         ("llava_llama", vlm.LlavaConfig, vlm.LlavaLlamaForCausalLM),
+                         ("llava_phi3", vlm.LlavaPhi3Config, vlm.LlavaPhi3ForCausalLM)):
+        c = AutoConfig.for_model(mt, hidden_size=128, num_hidden_layers=2)
+        assert type(c) is cfg and c.model_type == mt and c.hidden_size == 128
+        assert AutoModelForCausalLM._model_mapping[cfg] is cls

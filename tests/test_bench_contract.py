@@ -10,8 +10,8 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def test_reference_arm_line():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--model", "tiny",
-                        "--seq", "700", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
-                       timeout=600)
+                        "--cpu-config", "tiny", "--seq", "700", "--steps", "4", "--warmup", "1"], capture_output=True,
+                       text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -22,7 +22,10 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # the reference arm runs the UNMODIFIED reference classes (oracle/_ref or /root/reference), whole steps only
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["steps"] == len(cb["step_s"]) == 4 and d["steps_requested"] == 4 and "extrapolat" not in cb["sample"].replace("no extrapolation", "")
+    assert abs(sum(cb["step_s"]) / len(cb["step_s"]) * 1000 - d["ms_per_step"]) < 1.0
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert abs(d["ms_per_step"] * d["value"] - 1000.0) < 1e-6 * 1000
 

@@ -239,3 +239,44 @@ def test_ntp_class_loads_a_distilled_checkpoint_and_keeps_the_task_tokens(tmp_pa
     m.model.task_token_format = "text"
     with pytest.raises(NotImplementedError):
         m._task_rows()
+
+
+def test_stage_chaining_keeps_trained_projector_and_pt_output_is_loadable(tmp_path, monkeypatch):
+    """(a) the PT stage's end-of-run save also writes the FULL model (the reference falls through to
+    trainer.save_model under DeepSpeed, ola_vlm_train.py:249-251), so the next stage can from_pretrained() it;
+    (b) loading such a multimodal checkpoint must keep its projector (llava_arch.py:126-127 builds one only if
+    missing) instead of re-initialising it; (c) a tower that is neither a local directory nor in the checkpoint
+    raises instead of training on uninitialised memory."""
+    import types
+
+    from visper_lm_b200.model import LlavaLlamaForCausalLM, OlaLlavaLlamaForCausalLM
+    from visper_lm_b200.train.checkpoint import safe_save_model_for_hf_trainer
+    from visper_lm_b200.train.entry import build_model
+
+    llm = tmp_path / "llm"
+    _tiny_llm(llm)
+    monkeypatch.setattr(OlaLlavaLlamaForCausalLM, "init_target_models", lambda self, cfg: None)
+    vis = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=3, num_attention_heads=2, image_size=28, patch_size=14)
+    m_args, d_args, t_args = _args(llm, tune_mm_mlp_adapter=True)
+    model, _ = build_model(m_args, d_args, t_args, _Tok(160, pad="<pad>"), device="cpu", config_overrides={"vision": vis})
+    with torch.no_grad():   # "training": make the projector and a task token recognisable
+        model.model.mm_projector[0].weight.fill_(0.125)
+        model.model.special_gen_tokens.fill_(-0.5)
+    out = tmp_path / "pretrain_out"
+    tr = types.SimpleNamespace(args=t_args, model=model, rank=0, optimizer=None)
+    from visper_lm_b200.train.trainer import LLaVATrainer
+    tr._save = lambda d, state_dict=None: LLaVATrainer._save(tr, d, state_dict)
+    safe_save_model_for_hf_trainer(trainer=tr, output_dir=str(out))
+    assert (out / "mm_projector.bin").exists() and (out / "config.json").exists()
+    assert (out / "model.safetensors").exists() or (out / "model.safetensors.index.json").exists()
+    # next stage (finetune.sh → train.py): NTP-only class on the PT output, no --pretrain_mm_mlp_adapter
+    m2, d2, t2 = _args(out, tune_mm_mlp_adapter=False, random_init_teachers=False)
+    nxt, _ = build_model(m2, d2, t2, _Tok(160, pad="<pad>"), device="cpu", distill=False, config_overrides={"vision": vis})
+    assert type(nxt) is LlavaLlamaForCausalLM
+    assert torch.equal(nxt.model.mm_projector[0].weight, torch.full_like(nxt.model.mm_projector[0].weight, 0.125)), \
+        "the trained projector was re-initialised"
+    assert torch.equal(nxt.model.special_gen_tokens, torch.full_like(nxt.model.special_gen_tokens, -0.5))
+    # (c) base LLM + hub id for the tower, no random-init flag → loud failure
+    m3, d3, t3 = _args(llm, random_init_teachers=False)
+    with pytest.raises(FileNotFoundError, match="vision tower"):
+        build_model(m3, d3, t3, _Tok(160, pad="<pad>"), device="cpu", config_overrides={"vision": vis})

@@ -463,6 +463,9 @@ class VisperForCausalLM(nn.Module):
         if missing or unexpected:
             raise KeyError(f"checkpoint does not match {cls.__name__}: missing {missing[:5]}, unexpected {unexpected[:5]}")
         model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+        # what the checkpoint did NOT carry (fresh modules the caller must initialise or load): a plain LLM
+        # checkpoint lacks tower / projector / heads, a multimodal one (PT / VPT output) brings them
+        model._missing_from_checkpoint = [k for k in own if k not in sd]
         return model
 
     # ---- reference accessors ---------------------------------------------------------------
@@ -1013,7 +1016,9 @@ class VisperForCausalLM(nn.Module):
             text_loss = A.LMHeadCEFn.apply(hidden, self.lm_head.weight, labels, T, chunk, wt, compact)
         if labels is None or self.config.materialize_logits:
             with torch.no_grad():
-                logits = A.lm_head_logits(hidden.detach(), self.lm_head.weight).view(B, T, -1)
+                # bf16 GEMM, then upcast — the reference's `logits = self.lm_head(h); logits = logits.float()`
+                # (ola_llama.py:121-122): fp32 [B,T,V] whenever the field is produced
+                logits = A.lm_head_logits(hidden.detach(), self.lm_head.weight).view(B, T, -1).float()
         d = None
         if self.distill and hasattr(self, "mode"):
             d = self._distill(states, B, T, pil_images,
@@ -1047,3 +1052,23 @@ class LlavaLlamaForCausalLM(VisperForCausalLM):
 
 class LlavaPhi3ForCausalLM(VisperForCausalLM):
     family, distill, config_class = "phi3", False, LlavaPhi3Config
+
+
+def _register_with_transformers():
+    """AutoConfig.register / AutoModelForCausalLM.register as the reference does at import time
+    (ola_llama.py:246-247, ola_phi3.py, llava_llama.py:174-175, llava_phi3.py), so `model_type` strings in a saved
+    config.json resolve to these classes through the Auto* factories."""
+    try:
+        from transformers import AutoConfig, AutoModelForCausalLM
+    except Exception:  # transformers absent: the classes work without the factories
+        return
+    for cfg, cls in ((OlaLlavaLlamaConfig, OlaLlavaLlamaForCausalLM), (OlaLlavaPhi3Config, OlaLlavaPhi3ForCausalLM),
+                     (LlavaConfig, LlavaLlamaForCausalLM), (LlavaPhi3Config, LlavaPhi3ForCausalLM)):
+        try:
+            AutoConfig.register(cfg.model_type, cfg, exist_ok=True)
+            AutoModelForCausalLM.register(cfg, cls, exist_ok=True)
+        except Exception:  # a different class already owns the name in this process (the shimmed reference in tests)
+            pass
+
+
+_register_with_transformers()

@@ -146,7 +146,9 @@ def safe_save_model_for_hf_trainer(trainer, output_dir: str):
                 torch.save(weights, os.path.join(folder, f"{current}.bin"))
             else:
                 torch.save(weights, os.path.join(output_dir, "mm_projector.bin"))
-        return
+        # no `return` here in the reference either (ola_vlm_train.py:249-251): under DeepSpeed — every shipped
+        # script — it falls through to trainer.save_model(output_dir), so the PT output directory also holds the
+        # FULL model (trained heads, task tokens, logit scales) that finetune.sh / vpt.sh load with from_pretrained
     if trainer.rank == 0:
         trainer._save(output_dir, state_dict={k: v.detach().cpu() for k, v in trainer.model.state_dict().items()})
 

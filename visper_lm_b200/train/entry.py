@@ -197,14 +197,27 @@ def build_model(model_args: ModelArguments, data_args: DataArguments, training_a
         model.resize_token_embeddings(len(tokenizer))
         if n_new > 0:   # smart_tokenizer_and_embedding_resize (:939-975): new rows ~ N(mean, std) of the table
             with torch.no_grad():
+                n_tok = len(tokenizer)   # rows past len(tokenizer) are kernel padding (vocab rounded up to 8), not tokens
                 for emb in (model.get_input_embeddings().weight, model.get_output_embeddings().weight):
-                    old = emb[:-n_new].float()
-                    emb[-n_new:] = torch.normal(old.mean().item(), old.std().item(), size=emb[-n_new:].shape).to(emb.dtype)
+                    old = emb[:n_tok - n_new].float()
+                    emb[n_tok - n_new:n_tok] = torch.normal(old.mean().item(), old.std().item(),
+                                                            size=emb[n_tok - n_new:n_tok].shape).to(emb.dtype)
     # vision tower + projector (:1099-1121): built with the model; a fresh projector needs initial values
     tower = model.get_vision_tower()
-    if model_args.vision_tower and os.path.exists(model_args.vision_tower):
+    missing = getattr(model, "_missing_from_checkpoint", [])
+    if model_args.vision_tower and os.path.isdir(str(model_args.vision_tower)):
         tower.load_model(path=model_args.vision_tower)
-    model.init_weights(only=("model.mm_projector.",))
+    elif any(k.startswith("model.vision_tower.") for k in missing):
+        # neither a local tower directory nor a checkpoint that carries the tower: the parameters are uninitialised
+        # memory (the reference would download the hub id here; there is no network)
+        if not model_args.random_init_teachers:
+            raise FileNotFoundError(f"vision tower weights not found: --vision_tower {model_args.vision_tower!r} is not a "
+                                    "local directory and the loaded checkpoint has no model.vision_tower.* tensors")
+        model.init_weights(only=("model.vision_tower.",))
+    # initialize_vision_modules builds a projector only if the model has none (llava_arch.py:126-127): a projector that
+    # came with a multimodal checkpoint (finetune.sh / vpt.sh load the PT output) is kept
+    if any(k.startswith("model.mm_projector.") for k in missing):
+        model.init_weights(only=("model.mm_projector.",))
     data_args.image_processor = getattr(tower, "image_processor", None) or data_args.image_processor
     data_args.is_multimodal = True
     data_args.version = model_args.version

@@ -711,6 +711,9 @@ class LLaVATrainer:
         from . import checkpoint as ckpt
 
         a = self.args
+        if self.train_dataset is not None and self.steps_per_epoch() == 0:
+            raise ValueError(f"dataset of {len(self.train_dataset)} samples is smaller than one global batch "
+                             f"({a.per_device_train_batch_size} x {self.world} ranks x {a.gradient_accumulation_steps} accumulation)")
         per_epoch = max(1, self.steps_per_epoch())
         self.total_steps = a.max_steps if a.max_steps > 0 else int(per_epoch * a.num_train_epochs)
         self.create_optimizer()
