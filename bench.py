@@ -249,7 +249,12 @@ def run_reference(args):
         return
     c = model_cfg(args.model, args.layers, args.tower)
     distill = args.workload == "dsg"
-    r, cpu = reference_cpu(args.cpu_budget_s, args.steps, warmup=min(max(args.warmup, 1), 1), which=args.cpu_config)
+    import contextlib
+
+    # the reference prints from its constructors ("Number of System Tokens: 38", ola_llama.py:69): keep stdout for
+    # the ONE JSON line
+    with contextlib.redirect_stdout(sys.stderr):
+        r, cpu = reference_cpu(args.cpu_budget_s, args.steps, warmup=min(max(args.warmup, 1), 1), which=args.cpu_config)
     n_timed = len(r["step_s"])
     ms = 1000.0 * r["step_s_mean"]
     cfgd = workload_config(args, c, distill)
@@ -273,8 +278,9 @@ def run_reference(args):
         try:
             n_text = args.seq - 575 - (24 if distill else 0)
             cc = dict(c, num_sys_tokens=n_sys(c))
-            g = ref_run.time_gpu(cc, distill=distill, B=args.batch, n_text=n_text, steps=min(max(args.steps, 3), 8),
-                                 warmup=3, train=args.train)
+            with contextlib.redirect_stdout(sys.stderr):
+                g = ref_run.time_gpu(cc, distill=distill, B=args.batch, n_text=n_text, steps=min(max(args.steps, 3), 8),
+                                     warmup=3, train=args.train)
             line["reference_gpu"] = {
                 "value": g["samples_per_s"], "unit": "samples/s", "n_gpus": 1, "ms_per_step": g["ms_per_step"],
                 "ms_min": g["ms_min"], "ms_max": g["ms_max"], "steps": g["steps"], "warmup": g["warmup"],
@@ -609,7 +615,10 @@ def run_b200(args):
         line["dp_check"] = check
     if world == 1 and not args.no_cpu_baseline:
         try:
-            _, line["cpu_baseline"] = reference_cpu(args.cpu_budget_s, 3, warmup=1, which=args.cpu_config)
+            import contextlib
+
+            with contextlib.redirect_stdout(sys.stderr):
+                _, line["cpu_baseline"] = reference_cpu(args.cpu_budget_s, 3, warmup=1, which=args.cpu_config)
         except Exception as ex:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"failed: {type(ex).__name__}: {ex}"}

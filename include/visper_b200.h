@@ -47,11 +47,10 @@ void vpb_reset_launch_count(void);
 #define VPB_OPT_GEMM_PANEL_MB 4    /* >0: MB of the A operand kept L2-resident per tile-order group (default 32) */
 #define VPB_OPT_ATTN_BWD_SS 5      /* 1: attention backward stages P/dS through shared memory (not TMEM) */
 #define VPB_OPT_ATTN_BWD_PINGPONG 7 /* 1: attention backward with two softmax groups on alternate iterations (default: column split) */
-#define VPB_OPT_ATTN_FWD_V2 6      /* 1: experimental tcgen05 attention forward with two query tiles per CTA */
+#define VPB_OPT_ATTN_FWD_NS2 9     /* 1: tcgen05 attention forward with one work item per CTA (round 1) instead of the persistent kernel */
 #define VPB_OPT_ATTN_FWD_TC64 12   /* default 1 — non-causal head_dim-64 attention forward (CLIP ViT-L, DINOv2-L towers) on the tcgen05 kernel (one 64-column chunk per tile) instead of the mma.sync kernel */
 #define VPB_OPT_GEMM_EPI8 13       /* default 1 — CTA-pair GEMM with EIGHT epilogue warps per CTA (two per TMEM lane quarter, half the columns each) for K <= 1024, where the bias/GELU/store epilogue outlasts the tile's MMAs */
 #define VPB_OPT_GATHER_FLAT 14     /* default 1 — vpb_gather_rows for rows of <= 2048 elements as a flat grid-stride loop instead of one CTA per row */
-#define VPB_OPT_NORM_LEGACY 15     /* 1: RMSNorm fwd/bwd on the CTA-per-row kernels of round 1 instead of the warp-per-row ones */
 #define VPB_OPT_DWCONV_FFMA2 11    /* default 1 — depthwise 7x7 with packed fp32 FMAs (fma.rn.f32x2 = SASS FFMA2, one per channel pair); bit-identical results, half the FMA instructions */
 #define VPB_OPT_WIN_ATTN_V2 10     /* default 1 — vpb_attn_fwd_bias on the one-pass kernel for windows of <= 144 tokens: 1 = two CTAs per SM (96 registers, small spills), 2 = one CTA per SM (no spills) */
 int vpb_set_option(int key, int value);

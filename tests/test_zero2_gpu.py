@@ -60,8 +60,10 @@ def test_sinks_hooks_and_staging_paths_are_bit_identical():
     m1, t1, l1 = _run(sinks=True)
     m2, t2, l2 = _run(sinks=False)
     m3, t3, l3 = _run(sinks=True, overlap="force", bucket=150_000)     # several buckets through the pool
-    assert len(t3.optimizer.buckets) >= 4 and len(t3.optimizer.pool) >= 2
-    assert l1 == l2 == l3 and l1[-1] < l1[0] + 1.0
+    assert len(t3.optimizer.buckets) >= 4 and 0 < t3.optimizer.staging_peak < t3.optimizer.total * 2
+    assert l1 == l2, f"sink path vs hook path losses: {l1} vs {l2}"
+    assert l1 == l3, f"direct vs staged gradient space losses: {l1} vs {l3}"
+    assert l1[-1] < l1[0] + 1.0
     p1, p2, p3 = t1.optimizer.flat_params(), t2.optimizer.flat_params(), t3.optimizer.flat_params()
     assert torch.equal(p1, p2), "sink path differs from the hook path"
     n3 = {n: p for n, p in m3.named_parameters() if p.requires_grad}

@@ -235,12 +235,10 @@ if __name__ == "__main__":
         print(json.dumps({"variant": "tc backward v2, ping-pong groups, P/dS in TMEM"}), flush=True)
         attn_profile()
         ops.set_option(ops.OPT_ATTN_BWD_PINGPONG, 0)
-        ops.set_option(ops.OPT_ATTN_FWD_V2, 1)
         ops.set_option(ops.OPT_ATTN_BWD_SS, 1)
-        print(json.dumps({"variant": "fwd v2 (experimental, two query tiles per CTA); tc backward v2, P/dS through shared memory (SS)"}), flush=True)
+        print(json.dumps({"variant": "tc backward v2, P/dS through shared memory (SS)"}), flush=True)
         attn_profile()
         ops.set_option(ops.OPT_ATTN_BWD_SS, 0)
-        ops.set_option(ops.OPT_ATTN_FWD_V2, 0)
         ops.set_option(ops.OPT_ATTN_TC_BWD_V1, 1)
         print(json.dumps({"variant": "tc backward v1"}), flush=True)
         attn_profile()

@@ -36,8 +36,8 @@ constexpr int KST = 3, VST = 2;                      // K ring runs ahead of the
 constexpr int OFF_K = TILE_BYTES;                    // K stage s at OFF_K + s*TILE
 constexpr int OFF_V = OFF_K + KST * TILE_BYTES;      // V stage s at OFF_V + s*TILE
 constexpr int OFF_BAR = OFF_V + VST * TILE_BYTES;
-constexpr int OFF_X = OFF_BAR + 256;  // softmax exchange: 768 floats
-constexpr int SMEM_BYTES = OFF_X + 3072 + 1024;
+constexpr int OFF_X = OFF_BAR + 256;  // softmax exchange: [2][NS][128] maxima + [NS][128] sums, NS <= 4: 1536 floats
+constexpr int SMEM_BYTES = OFF_X + 6144 + 1024;
 constexpr int THREADS = 320;  // TMA warp + MMA warp + 8 softmax warps
 constexpr float LOG2E = 1.4426950408889634f;
 }  // namespace tc
@@ -49,8 +49,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // Two variants of this kernel were measured on B200 in round 2 and dropped (profiles/r02_variants_ab.txt): every
 // fourth exponential as a degree-3 polynomial on the FMA pipe (0.440 vs 0.427 ms — the softmax warps are bound by
 // instruction issue and latency, not by the MUFU rate) and Q resident in TMEM as the A operand of QK^T (0.450 ms).
-template <bool CAUSAL, int HD>
-__global__ void __launch_bounds__(320, 1)
+// NS = softmax warps per TMEM lane quarter (they split the 128 key columns): 2 → 8 softmax warps.  NS = 4 (16 warps,
+// 32 scores per thread) is supported by the code below and was measured no faster (0.447 vs 0.431 ms,
+// profiles/r02_attn_fwd_experiments.txt), like two other restructurings of this one-work-item-per-CTA kernel (three
+// score buffers with software-pipelined TMEM reads: 0.497 ms; two co-resident CTAs per SM: 0.453 ms).  What they all
+// share is the per-CTA fixed cost — see attn_fwd_tc_persist_kernel below, which is the default.
+template <bool CAUSAL, int HD, int NS>
+__global__ void __launch_bounds__(64 + 128 * NS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using namespace tc;
@@ -104,7 +109,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_full, 8);
+    mbar_init(p_full, 4 * NS);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -188,25 +193,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    // 8 softmax warps: warp pair (w, w+4) shares the 32 TMEM lanes of quarter w&3 and splits the
-    // 128 key columns in two halves, so every SM sub-partition runs two softmax warps.
+    // 4*NS softmax warps: warps w, w+4, ... share the 32 TMEM lanes of quarter w&3 and split the 128 key
+    // columns into NS parts of CW, so every SM sub-partition runs NS softmax warps.
+    constexpr int CW = 128 / NS;          // score columns per thread
+    constexpr int OC = 4 / NS;            // 32-column chunks of O per thread (rescale / epilogue)
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;     // part index 0..NS-1
     const int row = quarter * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
     float m_used = -INFINITY, l = 0.f;
-    float* xchg = reinterpret_cast<float*>(smem + OFF_X);  // [2 parity][2 half][128 rows] + [2][128]
+    float* xchg = reinterpret_cast<float*>(smem + OFF_X);  // [2 parity][NS parts][128 rows] + [NS][128]
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j & 1;
       mbar_wait_spin(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t r[64];
-      tmem_ld32(TM_S + lane_addr + sb * BN + half * 64, r);
-      tmem_ld32(TM_S + lane_addr + sb * BN + half * 64 + 32, r + 32);
+      uint32_t r[CW];
+      tmem_ld32(TM_S + lane_addr + sb * BN + half * CW, r);
+      if constexpr (CW == 64) tmem_ld32(TM_S + lane_addr + sb * BN + half * CW + 32, r + 32);
       tmem_ld_wait();
       const int jt0 = (j + jb) * BN;  // first key of this tile
-      const int j0 = jt0 + half * 64;
+      const int j0 = jt0 + half * CW;
       const bool win = CAUSAL && p.window > 0;
       const bool need_mask = (jt0 + BN > p.sk) || (CAUSAL && (jt0 + BN - 1 > q0 + off)) ||
                              (win && jt0 < q0 + BM - 1 + off - p.window);
@@ -214,20 +221,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;  // last visible key
         const int lo = win ? q0 + row + off - p.window : 0;                 // first visible key
 #pragma unroll
-        for (int c = 0; c < 64; ++c)
+        for (int c = 0; c < CW; ++c)
           if (j0 + c > lim || j0 + c < lo) r[c] = 0xff800000u;  // -inf
       }
       // max of the RAW scores (scaled once, scale > 0); four independent chains for ILP
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
+      for (int c = 0; c < CW; c += 4) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(r[c + e]));
       }
       float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      xchg[(sb * 2 + half) * 128 + row] = mx;
-      named_bar_sync(1, 256);
-      mx = fmaxf(mx, xchg[(sb * 2 + (half ^ 1)) * 128 + row]) * sl2;
+      xchg[(sb * NS + half) * 128 + row] = mx;
+      named_bar_sync(1, 128 * NS);
+#pragma unroll
+      for (int o = 1; o < NS; ++o) mx = fmaxf(mx, xchg[(sb * NS + ((half + o) % NS)) * 128 + row]);
+      mx *= sl2;
       // lazy rescale: keep the old reference max unless the new one is > 2^8 larger
       const bool upd = mx > m_used + 8.f;
       float alpha = 1.f;
@@ -240,7 +249,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float mb = (m_used == -INFINITY) ? 0.f : m_used;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
+      for (int c = 0; c < CW; c += 4) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
@@ -253,22 +262,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} finished: O may be rescaled
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          if (half * 64 + c * 32 >= HD) break;  // head_dim 96: the second half owns one chunk
+        for (int c = 0; c < OC; ++c) {
+          const int oc = (half * OC + c) * 32;  // this thread's 32-column chunk of O
+          if (oc >= HD) break;                  // head_dim 96 / 64: the last parts own fewer chunks
           uint32_t o[32];
-          tmem_ld32(TM_O + lane_addr + half * 64 + c * 32, o);
+          tmem_ld32(TM_O + lane_addr + oc, o);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(TM_O + lane_addr + half * 64 + c * 32, o);
+          tmem_st32(TM_O + lane_addr + oc, o);
         }
       }
-      // P_j (bf16 pairs) overwrites this thread pair's own scores in TMEM: columns [0,64) of S[sb]
+      // P_j (bf16 pairs) overwrites the row's own scores in TMEM: packed columns [0,64) of S[sb]
       {
-        uint32_t w[32];
+        uint32_t w[CW / 2];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) w[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-        tmem_st32(TM_S + lane_addr + sb * BN + half * 32, w);
+        for (int i = 0; i < CW / 2; ++i) w[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+        if constexpr (CW == 64) tmem_st32(TM_S + lane_addr + sb * BN + half * 32, w);
+        else tmem_st16(TM_S + lane_addr + sb * BN + half * 16, w);
         tmem_st_wait();
       }
       l += sum;
@@ -276,24 +287,25 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: combine the two half-row sums, O / l → bf16 → global, LSE
-    float* lx = xchg + 512;
+    // epilogue: combine the NS partial row sums, O / l → bf16 → global, LSE
+    float* lx = xchg + 2 * NS * 128;
     lx[half * 128 + row] = l;
-    named_bar_sync(1, 256);
-    l += lx[(half ^ 1) * 128 + row];
+    named_bar_sync(1, 128 * NS);
+#pragma unroll
+    for (int o = 1; o < NS; ++o) l += lx[((half + o) % NS) * 128 + row];
     const bool row_ok = q0 + row < p.sq;
     if (ntiles > 0) {
       mbar_wait(pv_done, (ntiles - 1) & 1);
       tc_fence_after();
     }
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    bf16* orow = p.o + ((int64_t)b * p.sq + q0 + row) * p.ldo + h * HD + half * 64;
+    bf16* orow = p.o + ((int64_t)b * p.sq + q0 + row) * p.ldo + h * HD + half * OC * 32;
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      if (half * 64 + c * 32 >= HD) break;
+    for (int c = 0; c < OC; ++c) {
+      if ((half * OC + c) * 32 >= HD) break;
       uint32_t o[32];
       if (ntiles > 0) {
-        tmem_ld32(TM_O + lane_addr + half * 64 + c * 32, o);
+        tmem_ld32(TM_O + lane_addr + (half * OC + c) * 32, o);
         tmem_ld_wait();
       } else {
 #pragma unroll
@@ -318,6 +330,379 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// =============================================================================================
+// forward, persistent (default)
+// =============================================================================================
+// tools/attn_overhead_probe.py (profiles/r02_attn_overhead_probe.jsonl) fits the kernel above as
+//     time per CTA = 6.07 us + 1.10 us x key tiles
+// on B200: a 128-query work item pays ~11 500 cycles that are not tile work — CTA launch behind the previous CTA's
+// exit (192 KB of shared memory, 512 TMEM columns: nothing co-resides), barrier init + TMEM allocation, tensor-map
+// fetch and the Q / K_0 round trip, the first Q·Kᵀ, the pipeline ramp, the O epilogue, deallocation.  A causal
+// S = 2048 item has 8.5 key tiles on average, so 39 % of the 0.427 ms was that fixed cost (27.7 items per SM x 6 us).
+// Here ONE CTA per SM stays resident and walks a heavy-first list of work items.  Its TMA warp runs ahead across item
+// boundaries (Q double-buffered, the K / V rings never drain), its MMA warp issues the first Q·Kᵀ of item n+1 before
+// it waits for the last P of item n, O is double-buffered in TMEM so that P·V of item n+1 does not wait for the
+// epilogue of item n, and barriers / TMEM are set up once.  Same arithmetic in the same order as the kernel above:
+// bit-identical output and LSE.
+namespace tcp {
+constexpr int KST = 2, VST = 2;
+constexpr int OFF_Q = 0;                                   // Q[2]
+constexpr int OFF_K = 2 * tc::TILE_BYTES;                  // K[2]
+constexpr int OFF_V = OFF_K + KST * tc::TILE_BYTES;        // V[2]
+constexpr int OFF_BAR = OFF_V + VST * tc::TILE_BYTES;      // 6 x 32 KB of tiles
+constexpr int OFF_X = OFF_BAR + 256;                       // softmax exchange: 768 floats
+constexpr int SMEM_BYTES = OFF_X + 3072 + 1024;
+}  // namespace tcp
+
+struct FwdItem {
+  int h, b, kvh, q0, jb, ntiles;
+};
+
+// work item w of the heavy-first list: query tiles in descending order (causal: most key tiles first), the heads of
+// one batch entry adjacent (a GQA group's CTAs read the same K / V tiles while they are hot in L2)
+template <bool CAUSAL>
+__device__ __forceinline__ bool fwd_item(const AttnTcParams& p, int w, int nqt, FwdItem& it) {
+  const int per = p.H * p.B;
+  if (w >= nqt * per) return false;
+  const int qi = w / per, r = w - qi * per;
+  const int qt = CAUSAL ? nqt - 1 - qi : qi;
+  it.h = r % p.H;
+  it.b = r / p.H;
+  it.kvh = it.h / (p.H / p.KVH);
+  it.q0 = qt * tc::BM;
+  const int off = p.sk - p.sq;
+  int kv_end = p.sk;
+  if (CAUSAL) {
+    kv_end = it.q0 + tc::BM + off;
+    if (kv_end > p.sk) kv_end = p.sk;
+  }
+  it.jb = 0;
+  if (CAUSAL && p.window > 0) {  // sliding window: first key tile any row of this query tile can see
+    const int lo = it.q0 + off - p.window;
+    it.jb = lo > 0 ? lo / tc::BN : 0;
+    if (it.jb * tc::BN > kv_end) it.jb = kv_end / tc::BN;
+  }
+  it.ntiles = (kv_end + tc::BN - 1) / tc::BN - it.jb;  // >= 1: the launcher only takes shapes with sk >= sq
+  return true;
+}
+
+template <bool CAUSAL, int HD>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                           const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  using namespace tc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tcp::OFF_BAR);
+  uint64_t* q_full = bars + 0;    // [2]
+  uint64_t* q_empty = bars + 2;   // [2] every Q·Kᵀ of the item that used the buffer has completed
+  uint64_t* k_full = bars + 4;    // [2]
+  uint64_t* k_empty = bars + 6;   // [2]
+  uint64_t* v_full = bars + 8;    // [2]
+  uint64_t* v_empty = bars + 10;  // [2]
+  uint64_t* s_full = bars + 12;   // [2]
+  // p_full / pv_done are indexed by tile parity as well: a waiter is never more than two tiles behind the arriving
+  // side (the scores of tile g+2 are only issued after P·V of tile g), so with two barriers a phase can not be
+  // observed one wrap late whatever the TMA latency does to the relative timing
+  uint64_t* p_full = bars + 14;   // [2]
+  uint64_t* pv_done = bars + 16;  // [2]
+  uint64_t* o_free = bars + 18;   // [2] the epilogue has O[n&1] in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqt = (p.sq + BM - 1) / BM;
+  const int off = p.sk - p.sq;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&o_free[i], 8);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t TM_S = tmem_base;        // S[0] at +0, S[1] at +128
+  const uint32_t TM_O = tmem_base + 256;  // O[0] at +256, O[1] at +384
+  constexpr uint32_t TX_BYTES = HD > 64 ? TILE_BYTES : CHUNK_BYTES;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // global tile sequence (item 0 tile 0, item 0 tile 1, ..., item 1 tile 0, ...); g counts tiles, K is requested
+      // one tile ahead of V, and the Q of an item right before its first K
+      auto load_q = [&](int n, const FwdItem& it) {
+        const int s = n & 1;
+        mbar_wait(&q_empty[s], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[s], TX_BYTES);
+        uint8_t* sq_ = smem + tcp::OFF_Q + s * TILE_BYTES;
+        tma_load_2d(sq_, &tmQ, &q_full[s], it.h * HD, it.b * p.sq + it.q0);
+        if constexpr (HD > 64) tma_load_2d(sq_ + CHUNK_BYTES, &tmQ, &q_full[s], it.h * HD + 64, it.b * p.sq + it.q0);
+      };
+      auto load_k = [&](int g, const FwdItem& it, int j) {
+        const int s = g % tcp::KST;
+        mbar_wait(&k_empty[s], ((g / tcp::KST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], TX_BYTES);
+        uint8_t* sk_ = smem + tcp::OFF_K + s * TILE_BYTES;
+        const int row = it.b * p.sk + (j + it.jb) * BN;
+        tma_load_2d(sk_, &tmK, &k_full[s], it.kvh * HD, row);
+        if constexpr (HD > 64) tma_load_2d(sk_ + CHUNK_BYTES, &tmK, &k_full[s], it.kvh * HD + 64, row);
+      };
+      auto load_v = [&](int g, const FwdItem& it, int j) {
+        const int s = g % tcp::VST;
+        mbar_wait(&v_empty[s], ((g / tcp::VST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], TX_BYTES);
+        uint8_t* sv_ = smem + tcp::OFF_V + s * TILE_BYTES;
+        const int row = it.b * p.sk + (j + it.jb) * BN;
+        tma_load_2d(sv_, &tmV, &v_full[s], it.kvh * HD, row);
+        if constexpr (HD > 64) tma_load_2d(sv_ + CHUNK_BYTES, &tmV, &v_full[s], it.kvh * HD + 64, row);
+      };
+      FwdItem cur, nxt;
+      int n = 0, g = 0;
+      bool have = fwd_item<CAUSAL>(p, blockIdx.x, nqt, cur);
+      if (have) {
+        load_q(0, cur);
+        load_k(0, cur, 0);
+      }
+      while (have) {
+        bool have_next = false;
+        for (int j = 0; j < cur.ntiles; ++j, ++g) {
+          if (j + 1 < cur.ntiles) {
+            load_k(g + 1, cur, j + 1);
+          } else {  // the tile after this item's last one is the next item's first
+            have_next = fwd_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nxt);
+            if (have_next) {
+              load_q(n + 1, nxt);
+              load_k(g + 1, nxt, 0);
+            }
+          }
+          load_v(g, cur, j);
+        }
+        cur = nxt;
+        have = have_next;
+        ++n;
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();  // warp-uniform loops, one elected lane issues (descriptors stay uniform)
+    constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(BM, HD, 0, 1);
+    const uint64_t q_desc0 = make_smem_desc(smem_u32(smem + tcp::OFF_Q), 16, 1024);
+    const uint64_t k_desc0 = make_smem_desc(smem_u32(smem + tcp::OFF_K), 16, 1024);
+    const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + tcp::OFF_V), CHUNK_BYTES, 1024);  // MN-major
+    // S of global tile g (item n): Q[n&1] · K[g%2]ᵀ → S[g&1]; `last` = the item's last tile (its Q buffer is then free)
+    auto issue_s = [&](int g, int n, bool last) {
+      const int s = g % tcp::KST, sb = g & 1;
+      mbar_wait_spin(&k_full[s], (g / tcp::KST) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint64_t q_desc = desc_adv(q_desc0, (n & 1) * TILE_BYTES);
+        const uint64_t k_desc = desc_adv(k_desc0, s * TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t o = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
+          umma_bf16(TM_S + sb * BN, desc_adv(q_desc, o), desc_adv(k_desc, o), idesc_s, k != 0);
+        }
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[s]);
+        if (last) umma_commit(&q_empty[n & 1]);
+      }
+    };
+    FwdItem cur, nxt;
+    int n = 0, g = 0;
+    bool have = fwd_item<CAUSAL>(p, blockIdx.x, nqt, cur);
+    if (have) {
+      mbar_wait(&q_full[0], 0);
+      issue_s(0, 0, cur.ntiles == 1);
+    }
+    while (have) {
+      bool have_next = false;
+      for (int j = 0; j < cur.ntiles; ++j, ++g) {
+        // the next tile's scores are issued before this tile's P is awaited: Q·Kᵀ overlaps the softmax, also across
+        // the boundary between two work items
+        if (j + 1 < cur.ntiles) {
+          issue_s(g + 1, n, j + 2 == cur.ntiles);
+        } else {
+          have_next = fwd_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nxt);
+          if (have_next) {
+            mbar_wait_spin(&q_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+            issue_s(g + 1, n + 1, nxt.ntiles == 1);
+          }
+        }
+        mbar_wait_spin(&v_full[g % tcp::VST], (g / tcp::VST) & 1);
+        mbar_wait_spin(&p_full[g & 1], (g >> 1) & 1);
+        if (j == 0) mbar_wait_spin(&o_free[n & 1], ((n >> 1) & 1) ^ 1);  // the epilogue of item n-2 has read O[n&1]
+        tc_fence_after();
+        if (leader) {
+          const uint64_t v_desc = desc_adv(v_desc0, (g % tcp::VST) * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BN / 16; ++k) {
+            // A = P in TMEM, written by the softmax warps over the first 64 columns of S[g&1]
+            umma_bf16_ts(TM_O + (n & 1) * 128, TM_S + (g & 1) * BN + k * 8, desc_adv(v_desc, k * 2048), idesc_pv,
+                         (j | k) != 0);
+          }
+          umma_commit(&pv_done[g & 1]);
+          umma_commit(&v_empty[g % tcp::VST]);
+        }
+      }
+      cur = nxt;
+      have = have_next;
+      ++n;
+    }
+  } else {
+    // 8 softmax warps: warp pair (w, w+4) shares the 32 TMEM lanes of quarter w&3 and splits the 128 key columns
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    float* xchg = reinterpret_cast<float*>(smem + tcp::OFF_X);  // [2 parity][2 half][128 rows] + [2][128]
+    const bool win = CAUSAL && p.window > 0;
+    FwdItem it;
+    int g = 0;
+    for (int n = 0; fwd_item<CAUSAL>(p, blockIdx.x + n * gridDim.x, nqt, it); ++n) {
+      const int q0 = it.q0;
+      float m_used = -INFINITY, l = 0.f;
+      const uint32_t tm_o = TM_O + (n & 1) * 128;
+      for (int j = 0; j < it.ntiles; ++j, ++g) {
+        const int sb = g & 1;
+        mbar_wait_spin(&s_full[sb], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t r[64];
+        tmem_ld32(TM_S + lane_addr + sb * BN + half * 64, r);
+        tmem_ld32(TM_S + lane_addr + sb * BN + half * 64 + 32, r + 32);
+        tmem_ld_wait();
+        const int jt0 = (j + it.jb) * BN;  // first key of this tile
+        const int j0 = jt0 + half * 64;
+        const bool need_mask = (jt0 + BN > p.sk) || (CAUSAL && (jt0 + BN - 1 > q0 + off)) ||
+                               (win && jt0 < q0 + BM - 1 + off - p.window);
+        if (need_mask) {
+          const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;  // last visible key
+          const int lo = win ? q0 + row + off - p.window : 0;                 // first visible key
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (j0 + c > lim || j0 + c < lo) r[c] = 0xff800000u;  // -inf
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(r[c + e]));
+        }
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        xchg[(sb * 2 + half) * 128 + row] = mx;
+        named_bar_sync(1, 256);
+        mx = fmaxf(mx, xchg[(sb * 2 + (half ^ 1)) * 128 + row]) * sl2;
+        const bool upd = mx > m_used + 8.f;  // lazy rescale: keep the reference max unless it moved by > 2^8
+        float alpha = 1.f;
+        if (upd) {
+          alpha = exp2f(m_used - mx);  // m_used = -inf → 0
+          m_used = mx;
+          l *= alpha;
+        }
+        const float mb = (m_used == -INFINITY) ? 0.f : m_used;
+        float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
+            sum4[e] += pv;
+            r[c + e] = __float_as_uint(pv);
+          }
+        }
+        const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        if (j > 0 && __any_sync(0xffffffffu, upd)) {
+          mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);  // P·V of the previous tile finished: O may be rescaled
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            if (half * 64 + c * 32 >= HD) break;  // head_dim 96 / 64: the second half owns fewer chunks
+            uint32_t o[32];
+            tmem_ld32(tm_o + lane_addr + half * 64 + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tm_o + lane_addr + half * 64 + c * 32, o);
+          }
+        }
+        {
+          uint32_t w[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          tmem_st32(TM_S + lane_addr + sb * BN + half * 32, w);
+          tmem_st_wait();
+        }
+        l += sum;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[sb]);
+      }
+      // epilogue of this work item: combine the two half-row sums, O / l → bf16 → global, LSE.  The accumulator is
+      // handed back (o_free) as soon as it is in registers.
+      float* lx = xchg + 512;
+      lx[half * 128 + row] = l;
+      named_bar_sync(1, 256);
+      l += lx[(half ^ 1) * 128 + row];
+      const bool row_ok = q0 + row < p.sq;
+      mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+      tc_fence_after();
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* orow = p.o + ((int64_t)it.b * p.sq + q0 + row) * p.ldo + it.h * HD + half * 64;
+      uint32_t o0[32], o1[32];
+      const bool two = half * 64 + 32 < HD;
+      const bool one = half * 64 < HD;
+      if (one) tmem_ld32(tm_o + lane_addr + half * 64, o0);
+      if (two) tmem_ld32(tm_o + lane_addr + half * 64 + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[n & 1]);
+      if (row_ok) {
+        if (one) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o0[q * 8 + i]) * inv;
+            stg16(orow + q * 8, pack8(v));
+          }
+        }
+        if (two) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o1[q * 8 + i]) * inv;
+            stg16(orow + 32 + q * 8, pack8(v));
+          }
+        }
+      }
+      if (p.lse && row_ok && half == 0)
+        p.lse[((int64_t)it.b * p.H + it.h) * p.sq + q0 + row] =
+            l > 0.f ? m_used * 0.6931471805599453f + logf(l) : -INFINITY;
+      // the l-exchange slots are rewritten at the end of the next item, after at least one more exchange barrier
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // bounded polling for the MMA issuers that watch several barriers (a broken invariant traps)
 __device__ __forceinline__ void poll_guard(uint32_t& spins, bool did) {
   if (did) {
@@ -328,338 +713,6 @@ __device__ __forceinline__ void poll_guard(uint32_t& spins, bool did) {
   }
 }
 
-// =============================================================================================
-// forward v2: TWO 128-query tiles per CTA, one softmax group (4 warps) per tile
-// =============================================================================================
-// v1 (above) runs one query tile per CTA: its softmax is MUFU-bound at about the same 1024 cycles
-// per key tile as the two MMAs, the two phases of ONE tile depend on each other, and a causal CTA
-// lives for only ~8 key tiles, so the tensor pipe was 37 % active (profiles/r01_ncu_attn_tc_v2.csv).
-// v2 pairs two adjacent query tiles: while one tile's rows are in exp2, the tensor pipe works on
-// the other tile's S / PV; every K/V tile is fetched once for 256 query rows; each softmax thread
-// owns a whole 128-column score row (no cross-warp max exchange); the MMA warp polls for whichever
-// of {S_A, S_B, PV_A, PV_B} is ready.  TMEM: S_A | S_B | O_A | O_B (4 x 128 columns), P over S.
-namespace tc2 {
-constexpr int BM = 128, BN = 128;
-constexpr int TILE_BYTES = 128 * 128 * 2, CHUNK_BYTES = 16384;
-constexpr int KST = 3, VST = 2;
-constexpr int OFF_Q = 0;                             // Q_A, Q_B
-constexpr int OFF_K = 2 * TILE_BYTES;
-constexpr int OFF_V = OFF_K + KST * TILE_BYTES;
-constexpr int OFF_BAR = OFF_V + VST * TILE_BYTES;    // 7 x 32 KB = 224 KB of tiles
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-constexpr float LOG2E = 1.4426950408889634f;
-}  // namespace tc2
-
-template <bool CAUSAL, int HD>
-__global__ void __launch_bounds__(384, 1)
-attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
-  using namespace tc2;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_full = bars + 0;    // [2] per query tile
-  uint64_t* k_full = bars + 2;    // [3]
-  uint64_t* k_empty = bars + 5;   // [3]
-  uint64_t* v_full = bars + 8;    // [2]
-  uint64_t* v_empty = bars + 10;  // [2]
-  uint64_t* s_full = bars + 12;   // [2] per query tile: S_t complete
-  uint64_t* p_full = bars + 14;   // [2] per query tile: P_t written (4 warps)
-  uint64_t* pv_done = bars + 16;  // [2] per query tile: PV_t retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pr = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy pairs first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int kvh = h / (p.H / p.KVH);
-  const int off = p.sk - p.sq;
-  const int nqt = (p.sq + BM - 1) / BM;
-  const bool win = CAUSAL && p.window > 0;
-  // per query tile: first query row, first / one-past-last visible key tile
-  int q0[2], jb[2], je[2];
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int qt = 2 * pr + t;
-    q0[t] = qt * BM;
-    jb[t] = je[t] = 0;
-    if (qt < nqt) {
-      int kv_end = p.sk;
-      if (CAUSAL) {
-        kv_end = q0[t] + BM + off;
-        if (kv_end > p.sk) kv_end = p.sk;
-        if (kv_end < 0) kv_end = 0;
-      }
-      je[t] = (kv_end + BN - 1) / BN;
-      if (win) {
-        const int lo = q0[t] + off - p.window;
-        jb[t] = lo > 0 ? lo / BN : 0;
-        if (jb[t] > je[t]) jb[t] = je[t];
-      }
-    }
-  }
-  const int cnt0 = je[0] - jb[0], cnt1 = je[1] - jb[1];
-  int jmin = jb[0], jmax = je[0];
-  if (cnt1 > 0) {
-    if (cnt0 == 0 || jb[1] < jmin) jmin = jb[1];
-    if (cnt0 == 0 || je[1] > jmax) jmax = je[1];
-  }
-  const int nkv = (cnt0 > 0 || cnt1 > 0) ? jmax - jmin : 0;  // key tiles this CTA streams
-
-  if (warp == 0 && lane == 0) {
-    if (smem_u32(smem) & 1023) {
-      printf("[vpb] dynamic shared memory base is not 1024-byte aligned\n");
-      __trap();
-    }
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&pv_done[i], 1);
-    }
-    for (int i = 0; i < KST; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t TM_S = tmem_base;        // S_t at + t*128 (P_t over its first 64 columns)
-  const uint32_t TM_O = tmem_base + 256;  // O_t at + t*128
-
-  // 384 threads = three warpgroups: {TMA warp, MMA warp, two idle warps} and one softmax warpgroup per
-  // query tile.  Registers are partitioned per SM sub-partition (16 K each, three warps of this CTA
-  // on each), so 168 is what every thread gets at launch; the data-movement warpgroup then hands
-  // registers to the softmax warpgroups, whose threads each keep a 128-score row in registers.
-  // (the setmaxnreg sits INSIDE each role's branch: ptxas budgets registers per region only when no
-  // control-flow merge separates the instruction from the code it governs)
-  if (warp < 4) {
-  setmaxnreg_dec<80>();
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int t = 0; t < 2; ++t) {
-        if ((t ? cnt1 : cnt0) == 0) continue;
-        mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
-        tma_load_2d(smem + OFF_Q + t * TILE_BYTES, &tmQ, &q_full[t], h * HD, b * p.sq + q0[t]);
-        tma_load_2d(smem + OFF_Q + t * TILE_BYTES + CHUNK_BYTES, &tmQ, &q_full[t], h * HD + 64, b * p.sq + q0[t]);
-      }
-      auto load_k = [&](int i) {
-        const int s = i % KST;
-        mbar_wait(&k_empty[s], ((i / KST) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-        uint8_t* sk = smem + OFF_K + s * TILE_BYTES;
-        const int row = b * p.sk + (jmin + i) * BN;
-        tma_load_2d(sk, &tmK, &k_full[s], kvh * HD, row);
-        tma_load_2d(sk + CHUNK_BYTES, &tmK, &k_full[s], kvh * HD + 64, row);
-      };
-      if (nkv > 0) load_k(0);
-      for (int i = 0; i < nkv; ++i) {
-        if (i + 1 < nkv) load_k(i + 1);  // K runs one tile ahead of V
-        const int s = i % VST;
-        mbar_wait(&v_empty[s], ((i / VST) & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-        uint8_t* sv = smem + OFF_V + s * TILE_BYTES;
-        const int row = b * p.sk + (jmin + i) * BN;
-        tma_load_2d(sv, &tmV, &v_full[s], kvh * HD, row);
-        tma_load_2d(sv + CHUNK_BYTES, &tmV, &v_full[s], kvh * HD + 64, row);
-      }
-    }
-  } else if (warp == 1) {
-    if (nkv > 0) {  // warp-uniform polling loop, one elected lane issues
-      const bool leader = elect_one();
-      constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BM, HD, 0, 1);
-      const uint64_t q_desc0 = make_smem_desc(smem_u32(smem + OFF_Q), 16, 1024);
-      const uint64_t k_desc0 = make_smem_desc(smem_u32(smem + OFF_K), 16, 1024);
-      const uint64_t v_desc0 = make_smem_desc(smem_u32(smem + OFF_V), CHUNK_BYTES, 1024);  // MN-major
-      int ns[2] = {0, 0}, npv[2] = {0, 0};  // next S / PV iteration of each query tile
-      const int cnt[2] = {cnt0, cnt1};
-      const int kb[2] = {jb[0] - jmin, jb[1] - jmin};  // tile-local iteration i uses K/V ring entry kb+i
-      int k_rel = 0, v_rel = 0;
-      bool q_ready[2] = {false, false};
-      uint32_t spins = 0;
-      while (npv[0] < cnt[0] || npv[1] < cnt[1]) {
-        bool did = false;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          // S_t(i): the score buffer doubles as P_t(i-1), so PV_t(i-1) must have been issued
-          if (ns[t] < cnt[t] && npv[t] >= ns[t]) {
-            const int e = kb[t] + ns[t];
-            bool ok = mbar_test(&k_full[e % KST], (e / KST) & 1);
-            if (ok && !q_ready[t]) ok = q_ready[t] = mbar_test(&q_full[t], 0);
-            if (ok) {
-              tc_fence_after();
-              if (leader) {
-                const uint64_t q_desc = desc_adv(q_desc0, t * TILE_BYTES);
-                const uint64_t k_desc = desc_adv(k_desc0, (e % KST) * TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                  const uint32_t o = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
-                  umma_bf16(TM_S + t * BN, desc_adv(q_desc, o), desc_adv(k_desc, o), idesc_s, k != 0);
-                }
-                umma_commit(&s_full[t]);
-              }
-              ++ns[t];
-              did = true;
-              // K ring entries no tile still needs
-              int lim = nkv;
-              if (ns[0] < cnt[0]) lim = kb[0] + ns[0];
-              if (ns[1] < cnt[1] && kb[1] + ns[1] < lim) lim = kb[1] + ns[1];
-              for (; k_rel < lim; ++k_rel)
-                if (leader) umma_commit(&k_empty[k_rel % KST]);
-            }
-          }
-          if (npv[t] < ns[t]) {
-            const int e = kb[t] + npv[t];
-            if (mbar_test(&p_full[t], npv[t] & 1) && mbar_test(&v_full[e % VST], (e / VST) & 1)) {
-              tc_fence_after();
-              if (leader) {
-                const uint64_t v_desc = desc_adv(v_desc0, (e % VST) * TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < BN / 16; ++k)
-                  umma_bf16_ts(TM_O + t * 128, TM_S + t * BN + k * 8, desc_adv(v_desc, k * 2048), idesc_pv,
-                               (npv[t] | k) != 0);
-                umma_commit(&pv_done[t]);
-              }
-              ++npv[t];
-              did = true;
-              int lim = nkv;
-              if (npv[0] < cnt[0]) lim = kb[0] + npv[0];
-              if (npv[1] < cnt[1] && kb[1] + npv[1] < lim) lim = kb[1] + npv[1];
-              for (; v_rel < lim; ++v_rel)
-                if (leader) umma_commit(&v_empty[v_rel % VST]);
-            }
-          }
-        }
-        poll_guard(spins, did);
-      }
-    }
-  }
-  } else {
-    setmaxnreg_inc<208>();
-    const int quarter = warp & 3;
-    const int t = (warp - 4) >> 2;        // query tile of this softmax warpgroup
-    const int row = quarter * 32 + lane;  // query row within the tile == TMEM lane
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const float sl2 = p.scale * LOG2E;
-    const int cnt = t ? cnt1 : cnt0;
-    const int q0t = t ? q0[1] : q0[0], jbt = t ? jb[1] : jb[0];
-    const uint32_t tS = TM_S + lane_addr + t * BN, tO = TM_O + lane_addr + t * 128;
-    float m_used = -INFINITY, l = 0.f;
-    for (int i = 0; i < cnt; ++i) {
-      mbar_wait_spin(&s_full[t], i & 1);
-      tc_fence_after();
-      uint32_t r[128];
-      tmem_ld32(tS, r);
-      tmem_ld32(tS + 32, r + 32);
-      tmem_ld32(tS + 64, r + 64);
-      tmem_ld32(tS + 96, r + 96);
-      tmem_ld_wait();
-      const int j0 = (jbt + i) * BN;  // first key of this tile
-      const bool need_mask = (j0 + BN > p.sk) || (CAUSAL && (j0 + BN - 1 > q0t + off)) ||
-                             (win && j0 < q0t + BM - 1 + off - p.window);
-      if (need_mask) {
-        const int lim = CAUSAL ? min(p.sk - 1, q0t + row + off) : p.sk - 1;  // last visible key
-        const int lo = win ? q0t + row + off - p.window : 0;                 // first visible key
-#pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (j0 + c > lim || j0 + c < lo) r[c] = 0xff800000u;  // -inf
-      }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int c = 0; c < 128; c += 4) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(r[c + e]));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
-      // lazy rescale: keep the old reference max unless the new one is > 2^8 larger
-      const bool upd = mx > m_used + 8.f;
-      float alpha = 1.f;
-      if (upd) {
-        alpha = exp2f(m_used - mx);  // m_used = -inf → 0
-        m_used = mx;
-        l *= alpha;
-      }
-      const float mb = (m_used == -INFINITY) ? 0.f : m_used;
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 128; c += 4) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float pv = ex2_approx(fmaf(__uint_as_float(r[c + e]), sl2, -mb));
-          sum4[e] += pv;
-          r[c + e] = __float_as_uint(pv);
-        }
-      }
-      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      if (i > 0 && __any_sync(0xffffffffu, upd)) {
-        mbar_wait(&pv_done[t], (i - 1) & 1);  // PV_{i-1} finished: O may be rescaled
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < HD / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-          tmem_st32(tO + c * 32, o);
-        }
-      }
-      // P (bf16 pairs) overwrites this thread's own scores: columns [0,64) of S_t
-#pragma unroll
-      for (int c = 0; c < 64; ++c) r[c] = pack2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1]));
-      tmem_st32(tS, r);
-      tmem_st32(tS + 32, r + 32);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
-    }
-    if (2 * pr + t < nqt) {
-      const bool row_ok = q0t + row < p.sq;
-      if (cnt > 0) {
-        mbar_wait(&pv_done[t], (cnt - 1) & 1);
-        tc_fence_after();
-      }
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      bf16* orow = p.o + ((int64_t)b * p.sq + q0t + row) * p.ldo + h * HD;
-#pragma unroll 1
-      for (int c = 0; c < HD / 32; ++c) {
-        uint32_t o[32];
-        if (cnt > 0) {
-          tmem_ld32(tO + c * 32, o);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) o[k] = 0;
-        }
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(o[g * 8 + k]) * inv;
-            stg16(orow + c * 32 + g * 8, pack8(v));
-          }
-        }
-      }
-      if (p.lse && row_ok)
-        p.lse[((int64_t)b * p.H + h) * p.sq + q0t + row] =
-            l > 0.f ? m_used * 0.6931471805599453f + logf(l) : -INFINITY;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
-}
-
 template <bool CAUSAL, int HD>
 static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, const AttnTcParams& p, cudaStream_t st) {
@@ -667,25 +720,30 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   if (make_tmap_2d(&tmQ, q, (uint64_t)p.H * HD, (uint64_t)p.B * p.sq, (uint64_t)ldq, 64, 128)) return -1;
   if (make_tmap_2d(&tmK, k, (uint64_t)p.KVH * HD, (uint64_t)p.B * p.sk, (uint64_t)ldk, 64, 128)) return -1;
   if (make_tmap_2d(&tmV, v, (uint64_t)p.KVH * HD, (uint64_t)p.B * p.sk, (uint64_t)ldv, 64, 128)) return -1;
-  const int nqt = (p.sq + 127) / 128;
-  // EXPERIMENTAL (off by default): two query tiles per CTA.  Correct (tests run it), but each softmax
-  // thread then holds a 128-score row and the register file is split per SM sub-partition (three of
-  // this CTA's ten warps share 16 K registers → 168 per thread), so the hot loop spills and it measures
-  // 0.47 ms against 0.42 ms for the one-tile kernel at B=8,H=32,S=2048.
-  if (HD > 64 && get_option(VPB_OPT_ATTN_FWD_V2) && nqt >= 2) {  // (the two-tile kernel always loads two chunks)
-    auto kern = attn_fwd_tc2_kernel<CAUSAL, HD>;
-    static bool cfg2 = false;
-    if (!cfg2) {
-      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-      cfg2 = true;
+  dim3 grid((p.sq + tc::BM - 1) / tc::BM, p.H, p.B);
+  // default: persistent kernel (every work item needs at least one key tile: sk >= sq, the self-attention shapes);
+  // VPB_OPT_ATTN_FWD_NS2 = 1 selects the one-work-item-per-CTA kernel
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    VPB_CUDA(cudaGetDevice(&dev));
+    VPB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int items = (int)grid.x * p.H * p.B;
+  // with only a few work items per SM (the ViT towers: 640 items of 5 key tiles) the static round-robin of the
+  // persistent kernel loses more to its ragged last round than it saves: 0.061 vs 0.053 ms at B=8, S=577
+  if (!get_option(VPB_OPT_ATTN_FWD_NS2) && p.sk >= p.sq && p.sk > 0 && items >= 8 * n_sm) {
+    auto kernp = attn_fwd_tc_persist_kernel<CAUSAL, HD>;
+    static bool cfgp = false;
+    if (!cfgp) {
+      VPB_CUDA(cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::SMEM_BYTES));
+      cfgp = true;
     }
-    dim3 grid((nqt + 1) / 2, p.H, p.B);
-    kern<<<grid, 384, tc2::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    kernp<<<n_sm, tc::THREADS, tcp::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
     VPB_LAUNCH_OK();
     return 0;
   }
-  dim3 grid((p.sq + tc::BM - 1) / tc::BM, p.H, p.B);
-  auto kern = attn_fwd_tc_kernel<CAUSAL, HD>;
+  auto kern = attn_fwd_tc_kernel<CAUSAL, HD, 2>;
   static bool cfg = false;
   if (!cfg) {
     VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));

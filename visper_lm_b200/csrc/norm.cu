@@ -146,95 +146,6 @@ layernorm_fwd_warp_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* _
   }
 }
 
-// RMSNorm of the decoder (D = 1024 … 4096, M = batch·seq rows): ONE WARP PER ROW, eight rows per CTA.
-// A lane owns NV 16-byte vectors of its row (NV = D / 256) and issues all of their loads before it touches
-// the first one — 256 B in flight per lane, 64 KB per CTA — keeps the row as packed bf16 in registers across
-// the reduction (shuffles only: no shared memory, no block barrier between the load and the store phase, which
-// is what left the CTA-per-row kernel at 0.48 of HBM inside the power-capped step), then streams the result.
-template <int NV>
-__global__ void __launch_bounds__(256)
-rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w,
-                        bf16* __restrict__ y, int64_t ldy, float* __restrict__ rstd_out, int M, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= M) return;
-  constexpr int D = NV * 256;
-  const bf16* xr = x + (int64_t)row * ldx + lane * 8;
-  uint4 xv[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) xv[k] = ldg16_stream(xr + k * 256);
-  float ss = 0.f;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    float v[8];
-    unpack8(xv[k], v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
-  if (lane == 0 && rstd_out) rstd_out[row] = rstd;
-  bf16* yr = y + (int64_t)row * ldy + lane * 8;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    float v[8], wv[8], o[8];
-    unpack8(xv[k], v);
-    unpack8(ldg16(w + lane * 8 + k * 256), wv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = wv[j] * __bfloat162float(__float2bfloat16(v[j] * rstd));  // HF rounding order
-    stg16(yr + k * 256, pack8(o));
-  }
-}
-
-// dx = rstd * (g - xhat * mean(g * xhat)) (+ dres),  g = dy * w,  xhat = x * rstd — same layout as the forward.
-template <int NV>
-__global__ void __launch_bounds__(256)
-rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
-                        const bf16* __restrict__ w, const float* __restrict__ rstd_in,
-                        const bf16* __restrict__ dres, int64_t lddres, bf16* __restrict__ dx, int64_t lddx, int M) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= M) return;
-  constexpr int D = NV * 256;
-  const bf16* xr = x + (int64_t)row * ldx + lane * 8;
-  const bf16* dyr = dy + (int64_t)row * lddy + lane * 8;
-  uint4 xv[NV], gv[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    xv[k] = ldg16_stream(xr + k * 256);
-    gv[k] = ldg16_stream(dyr + k * 256);
-  }
-  const float rstd = rstd_in[row];
-  float sgx = 0.f;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    float xh[8], g[8], wv[8];
-    unpack8(xv[k], xh);
-    unpack8(gv[k], g);
-    unpack8(ldg16(w + lane * 8 + k * 256), wv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sgx = fmaf(g[j] * wv[j], xh[j] * rstd, sgx);
-  }
-  sgx = warp_sum(sgx) / D;
-  bf16* dxr = dx + (int64_t)row * lddx + lane * 8;
-  const bf16* rr = dres ? dres + (int64_t)row * lddres + lane * 8 : nullptr;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    float xh[8], g[8], wv[8], o[8];
-    unpack8(xv[k], xh);
-    unpack8(gv[k], g);
-    unpack8(ldg16(w + lane * 8 + k * 256), wv);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * wv[j] - (xh[j] * rstd) * sgx);
-    if (rr) {
-      float r[8];
-      unpack8(ldg16_stream(rr + k * 256), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += r[j];
-    }
-    stg16(dxr + k * 256, pack8(o));
-  }
-}
-
 // dx = rstd * (g - [mean(g)] - xhat * mean(g*xhat)),  g = dy * w ;  dx (+)= dres if given
 template <bool RMS>
 __global__ void __launch_bounds__(NORM_THREADS)
@@ -345,21 +256,6 @@ static int check_norm(int M, int D) {
 extern "C" int vpb_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy,
                                float* rstd, int M, int D, float eps, void* stream) {
   if (check_norm(M, D)) return -1;
-  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) == 0 &&
-                  ldx % 8 == 0 && ldy % 8 == 0;
-  if (al && M >= 64 && !get_option(VPB_OPT_NORM_LEGACY)) {
-#define VPB_RMS_FWD(NV)                                                                                          \
-  case NV:                                                                                                       \
-    rmsnorm_fwd_warp_kernel<NV><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(                                  \
-        (const bf16*)x, ldx, (const bf16*)w, (bf16*)y, ldy, rstd, M, eps);                                       \
-    VPB_LAUNCH_OK();                                                                                             \
-    return 0;
-    if (D % 256 == 0) switch (D / 256) {
-      VPB_RMS_FWD(4) VPB_RMS_FWD(8) VPB_RMS_FWD(12) VPB_RMS_FWD(16)
-      default: break;
-    }
-#undef VPB_RMS_FWD
-  }
   norm_fwd_kernel<true><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, ldx, (const bf16*)w, nullptr, (bf16*)y, ldy, nullptr, rstd, D, eps);
   VPB_LAUNCH_OK();
@@ -370,23 +266,6 @@ extern "C" int vpb_rmsnorm_bwd(const void* dy, int64_t lddy, const void* x, int6
                                const void* w, const float* rstd, const void* dres, int64_t lddres,
                                void* dx, int64_t lddx, int M, int D, void* stream) {
   if (check_norm(M, D)) return -1;
-  const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(w) |
-                    reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0 &&
-                  ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && lddres % 8 == 0;
-  if (al && M >= 64 && !get_option(VPB_OPT_NORM_LEGACY)) {
-#define VPB_RMS_BWD(NV)                                                                                          \
-  case NV:                                                                                                       \
-    rmsnorm_bwd_warp_kernel<NV><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(                                  \
-        (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)w, rstd, (const bf16*)dres, lddres, (bf16*)dx,  \
-        lddx, M);                                                                                                \
-    VPB_LAUNCH_OK();                                                                                             \
-    return 0;
-    if (D % 256 == 0) switch (D / 256) {
-      VPB_RMS_BWD(4) VPB_RMS_BWD(8) VPB_RMS_BWD(12) VPB_RMS_BWD(16)
-      default: break;
-    }
-#undef VPB_RMS_BWD
-  }
   norm_bwd_kernel<true><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)w, nullptr, rstd, (const bf16*)dres,
       lddres, (bf16*)dx, lddx, D);

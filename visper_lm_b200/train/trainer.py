@@ -70,7 +70,7 @@ class _Bucket:
     """A contiguous range [lo, hi) of the flat parameter space that is reduced / gathered as one collective.
     hi - lo is a multiple of world·ALIGN; rank r owns [lo + r·slice, lo + (r+1)·slice)."""
 
-    __slots__ = ("idx", "lo", "hi", "slice", "shard_off", "group", "params", "pads", "pending", "buf", "buf_id",
+    __slots__ = ("idx", "lo", "hi", "slice", "shard_off", "group", "params", "pads", "pending", "buf",
                  "ev_reduced", "ev_gathered", "launched", "touched")
 
     def __init__(self, idx, lo, group):
@@ -78,7 +78,7 @@ class _Bucket:
         self.slice = self.shard_off = 0
         self.params, self.pads = [], []
         self.pending = 0
-        self.buf = self.buf_id = self.ev_reduced = self.ev_gathered = None
+        self.buf = self.ev_reduced = self.ev_gathered = None
         self.launched = self.touched = False
 
 
@@ -117,10 +117,11 @@ class Zero2Optimizer:
     Gradients.  Producers write into the gradient space directly: the decoder backward through a
     LayerGradSink (the wgrad GEMM's output pointer), everything else through a post-accumulate hook
     that moves `p.grad` there and drops it.  With world > 1 a bucket's gradient space is a staging
-    buffer from a pool of `pool` buffers: when the bucket's last gradient is written — backward runs the
+    buffer allocated at its first gradient: when the bucket's last gradient is written — backward runs the
     buckets in reverse order — the comm stream waits for that point and reduce-scatters the bucket into
     the rank's gradient shard, so the transfer hides under the rest of backward and full-size gradient
-    memory never exists.  With world == 1 the gradient shard is the gradient space.
+    memory never exists (a staging buffer is freed to the caching allocator as soon as its reduce is launched).
+    With world == 1 the gradient shard is the gradient space.
 
     step(): wait for the reduces, global grad-norm (fp32 scalar all-reduce), clip coefficient on device,
     fused AdamW on the shard (fp32 master → bf16 parameter slice), then the per-bucket parameter
@@ -133,7 +134,7 @@ class Zero2Optimizer:
 
     def __init__(self, named_params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  max_grad_norm=1.0, groups=None, process_group=None, distributed=True,
-                 bucket_elems=64 * 1024 * 1024, keep_together=(), pool=3, overlap=True):
+                 bucket_elems=64 * 1024 * 1024, keep_together=(), overlap=True):
         self.named = [(n, p) for n, p in named_params if p.requires_grad]
         assert self.named, "no trainable parameters"
         self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
@@ -235,9 +236,7 @@ class Zero2Optimizer:
         self.accumulating = False
         self.flat_g = None                     # full-size gradient space: only world > 1 without overlap
         self.comm = torch.cuda.Stream(device=dev) if (self.cuda and (self.world > 1 or self.force_staging)) else None
-        self.pool_n = max(2, int(pool))
-        self.pool = []                         # staging buffers (overlap mode), each the size of the largest bucket
-        self.pool_last = []                    # bucket that last used each staging buffer
+        self.staging_peak = 0                  # most gradient-staging bytes alive at one time (overlap mode)
         self.written = [False] * len(order)
         self._pending_gather = []
         self._events = {}
@@ -275,7 +274,7 @@ class Zero2Optimizer:
         for b in self.buckets:
             b.pending = len(b.params)
             b.launched = b.touched = False
-            b.buf = b.buf_id = None
+            b.buf = None
 
     def zero_grad(self):
         for _, p in self.named:
@@ -300,18 +299,15 @@ class Zero2Optimizer:
                 self.flat_g = torch.zeros(self.total, dtype=BF16, device=self.dev)
             return self.flat_g[b.lo:b.hi]
         if b.buf is None:
-            if not self.pool:
-                big = max(x.hi - x.lo for x in self.buckets)
-                self.pool = [torch.zeros(big, dtype=BF16, device=self.dev) for _ in range(self.pool_n)]
-                self.pool_last = [None] * self.pool_n
-            k = (len(self.buckets) - 1 - b.idx) % self.pool_n     # backward visits buckets in reverse order
-            prev = self.pool_last[k]
-            if prev is not None and prev is not b and prev.ev_reduced is not None:
-                torch.cuda.current_stream().wait_event(prev.ev_reduced)   # its reduce must have read the buffer
-            self.pool_last[k] = b
-            b.buf_id = k
-            b.buf = self.pool[k][: b.hi - b.lo]
+            # a staging buffer lives from the bucket's first gradient to the launch of its reduce-scatter; the
+            # caching allocator hands the block to a later bucket only after the comm stream is done with it
+            # (record_stream in _reduce_bucket), so gradient memory is bounded by the buckets open at one time
+            b.buf = torch.empty(b.hi - b.lo, dtype=BF16, device=self.dev)
+            self.staging_peak = max(self.staging_peak, self._staging_live() )
         return b.buf
+
+    def _staging_live(self):
+        return sum((x.hi - x.lo) * 2 for x in self.buckets if x.buf is not None)
 
     def _touch(self, b):
         space = self._grad_space(b)
@@ -381,6 +377,9 @@ class Zero2Optimizer:
                 dist.reduce_scatter_tensor(out, src, op=dist.ReduceOp.SUM, group=self.pg)
             b.ev_reduced = torch.cuda.Event()
             b.ev_reduced.record()
+        if b.buf is not None:
+            b.buf.record_stream(self.comm)
+            b.buf = None                      # the block returns to the allocator once the comm stream has read it
 
     def _reduce_scatter_cpu(self, out, src):
         # gloo has no reduce_scatter: all-reduce the bucket (fp32 sum rounded to bf16, as NCCL's bf16 sum) and slice
@@ -482,7 +481,7 @@ class Zero2Optimizer:
         torch.cuda.synchronize()
         out = {"buckets": len(self.buckets), "bucket_mb": round(max(b.hi - b.lo for b in self.buckets) * 2 / 2**20, 1),
                "grad_bytes_per_step": self.total * 2, "overlap": self.overlap,
-               "staging_buffers": len(self.pool)}
+               "staging_peak_mb": round(self.staging_peak / 2**20, 1)}
         for k, (a, b) in self._events.items():
             out[f"exposed_{k}_ms"] = round(a.elapsed_time(b), 3)
         return out
