@@ -174,7 +174,8 @@ def test_gemm_rope_fused(M, H, KVH, K, T):
 
 
 # ------------------------------------------------------------------------------------------- norms
-@pytest.mark.parametrize("M,D", [(37, 128), (512, 4096), (100, 3072), (64, 1024), (1003, 2048), (16384, 4096)])
+@pytest.mark.parametrize("M,D", [(37, 128), (512, 4096), (100, 3072), (64, 1024), (1003, 2048), (16384, 4096), (5001, 3072),
+                                 (2048, 1024), (1500, 4096)])
 def test_rmsnorm(M, D):
     from visper_lm_b200 import ops
     x = rnd(M, D, seed=11).requires_grad_(False)
@@ -208,6 +209,26 @@ def test_rmsnorm_strided_row_views():
     torch.cuda.synchronize()
     assert torch.equal(out[:, :D], torch.zeros_like(out[:, :D])), "wrote outside its row view"
     assert torch.equal(y, y0) and torch.equal(rstd, rstd0) and torch.equal(dx, dx0)
+    # M >= 1024 takes the cp.async-pipelined kernels: same values as the CTA-per-row kernels up to the order of the
+    # fp32 row sums, also on strided views and without the residual-gradient input
+    M = 3000
+    big = rnd(M, 3 * D, seed=33)
+    x, dy, dres = big[:, :D], big[:, D:2 * D], big[:, 2 * D:]
+    y, rstd = ops.rmsnorm_fwd(x, w, 1e-5)
+    dx = ops.rmsnorm_bwd(dy, x, w, rstd, dres)
+    dxn = ops.rmsnorm_bwd(dy, x, w, rstd, None)
+    ops.set_option(ops.OPT_NORM_R1, 1)
+    try:
+        y0, rstd0 = ops.rmsnorm_fwd(x, w, 1e-5)
+        dx0 = ops.rmsnorm_bwd(dy, x, w, rstd0, dres)
+        dxn0 = ops.rmsnorm_bwd(dy, x, w, rstd0, None)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option(ops.OPT_NORM_R1, 0)
+    assert torch.allclose(rstd, rstd0, rtol=1e-6)
+    assert (y.float() - y0.float()).abs().max().item() <= 2 ** -6 * y0.float().abs().max().item()
+    assert ((dx.float() - dx0.float()).norm() / dx0.float().norm()).item() < 2e-3
+    assert ((dxn.float() - dxn0.float()).norm() / dxn0.float().norm()).item() < 2e-3
 
 
 @pytest.mark.parametrize("M,D", [(50, 64), (300, 1024), (77, 1536)])

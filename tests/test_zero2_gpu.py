@@ -96,6 +96,7 @@ def test_adapter_policy_unaffected():
     assert all(l._grad_sink is None for l in model.model.layers)
     w = model.model.mm_projector[0].weight
     b4 = w.detach().clone()
-    tr.step(_batch(3))
+    tr.step(_batch(3))      # step 0 of the warm-up has lr 0
+    tr.step(_batch(4))
     torch.cuda.synchronize()
     assert not torch.equal(w.detach(), b4)

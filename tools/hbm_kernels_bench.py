@@ -65,7 +65,12 @@ def main():
     _, rstd = ops.rmsnorm_fwd(x, w, 1e-5, out=y)
     report("rmsnorm_fwd", timeit(lambda: ops.rmsnorm_fwd(x, w, 1e-5, out=y)), 4.0 * M * D, M=M, D=D)
     report("rmsnorm_bwd(+dres)", timeit(lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dres, out=y)), 8.0 * M * D, M=M, D=D)
-    # context for the two numbers above: what a plain copy of the SAME size reaches (the 6.55 TB/s peak in
+    ops.set_option(ops.OPT_NORM_R1, 1)
+    report("rmsnorm_fwd[CTA-per-row, round 1]", timeit(lambda: ops.rmsnorm_fwd(x, w, 1e-5, out=y)), 4.0 * M * D, M=M, D=D)
+    report("rmsnorm_bwd(+dres)[CTA-per-row, round 1]", timeit(lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dres, out=y)),
+           8.0 * M * D, M=M, D=D)
+    ops.set_option(ops.OPT_NORM_R1, 0)
+    # context for the numbers above: what a plain copy of the SAME size reaches (the 6.55 TB/s peak in
     # MEASURED_PEAKS.json is a 4 GiB copy; a 134 MB -> 134 MB pass lasts ~60 us, ramp and tail included)
     report("torch copy_, same size as rmsnorm_fwd", timeit(lambda: y.copy_(x)), 4.0 * M * D, M=M, D=D)
     big_a = torch.empty(1 << 30, dtype=BF, device=dev)

@@ -146,6 +146,114 @@ layernorm_fwd_warp_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// RMSNorm of the decoder rows, high-occupancy variants of the CTA-per-row kernels.
+// ncu on norm_fwd_kernel<true> at M = 16384, D = 4096 (profiles/r02_ncu_hbm_kernels.csv): 58 registers → 4 CTAs =
+// 4 rows = 32 KB of loads in flight per SM, DRAM 44 % busy, 0.63 of the HBM copy rate where a plain copy of the
+// same 268 MB reaches 0.83: the kernel is bound by the memory latency it can cover, not by bandwidth.  These
+// variants keep the row PACKED (bf16, 16 B per vector) in registers across the block reduction and unpack it twice
+// instead, which fits 32 (forward) / 40 (backward) registers: 8 / 6 resident CTAs per SM, twice the bytes in flight.
+// (Two other designs were measured and dropped — one warp per row with the row in registers: 243 registers, and a
+// persistent cp.async ring of rows in shared memory: no faster, ALU-latency-bound with 8 warps per SM —
+// profiles/r02_norm_experiments.txt.)
+// ---------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(NORM_THREADS, 8)
+rmsnorm_fwd_packed_kernel(const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w,
+                          bf16* __restrict__ y, int64_t ldy, float* __restrict__ rstd_out, int D, float eps) {
+  __shared__ float red[33];
+  const int row = blockIdx.x;
+  const int nvec = D >> 3;
+  const bf16* xr = x + (int64_t)row * ldx;
+  uint4 xv[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = threadIdx.x + k * NORM_THREADS;
+    xv[k] = i < nvec ? ldg16_stream(xr + i * 8) : make_uint4(0, 0, 0, 0);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    float v[8];
+    unpack8(xv[k], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss = fmaf(v[j], v[j], ss);
+  }
+  ss = block_sum(ss, red);
+  const float rstd = rsqrtf(ss / D + eps);
+  if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+  bf16* yr = y + (int64_t)row * ldy;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = threadIdx.x + k * NORM_THREADS;
+    if (i < nvec) {
+      asm volatile("" : "+r"(xv[k].x), "+r"(xv[k].y), "+r"(xv[k].z), "+r"(xv[k].w));  // re-unpack, do not keep floats
+      float v[8], wv[8], o[8];
+      unpack8(xv[k], v);
+      unpack8(ldg16(w + i * 8), wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = wv[j] * __bfloat162float(__float2bfloat16(v[j] * rstd));  // HF rounding order
+      stg16(yr + i * 8, pack8(o));
+    }
+  }
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(NORM_THREADS, 6)
+rmsnorm_bwd_packed_kernel(const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
+                          const bf16* __restrict__ w, const float* __restrict__ rstd_in,
+                          const bf16* __restrict__ dres, int64_t lddres, bf16* __restrict__ dx, int64_t lddx, int D) {
+  __shared__ float red[33];
+  const int row = blockIdx.x;
+  const int nvec = D >> 3;
+  const bf16* xr = x + (int64_t)row * ldx;
+  const bf16* dyr = dy + (int64_t)row * lddy;
+  uint4 xv[MAXV], gv[MAXV];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = threadIdx.x + k * NORM_THREADS;
+    xv[k] = i < nvec ? ldg16_stream(xr + i * 8) : make_uint4(0, 0, 0, 0);
+    gv[k] = i < nvec ? ldg16_stream(dyr + i * 8) : make_uint4(0, 0, 0, 0);
+  }
+  const float rstd = rstd_in[row];
+  float sgx = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = threadIdx.x + k * NORM_THREADS;
+    if (i < nvec) {
+      float xh[8], g[8], wv[8];
+      unpack8(xv[k], xh);
+      unpack8(gv[k], g);
+      unpack8(ldg16(w + i * 8), wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sgx = fmaf(g[j] * wv[j], xh[j] * rstd, sgx);
+    }
+  }
+  sgx = block_sum(sgx, red) / D;
+  bf16* dxr = dx + (int64_t)row * lddx;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = threadIdx.x + k * NORM_THREADS;
+    if (i < nvec) {
+      asm volatile("" : "+r"(xv[k].x), "+r"(xv[k].y), "+r"(xv[k].z), "+r"(xv[k].w));
+      asm volatile("" : "+r"(gv[k].x), "+r"(gv[k].y), "+r"(gv[k].z), "+r"(gv[k].w));
+      float xh[8], g[8], wv[8], o[8];
+      unpack8(xv[k], xh);
+      unpack8(gv[k], g);
+      unpack8(ldg16(w + i * 8), wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[j] * wv[j] - (xh[j] * rstd) * sgx);
+      if (dres) {
+        float r[8];
+        unpack8(ldg16_stream(dres + (int64_t)row * lddres + i * 8), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      stg16(dxr + i * 8, pack8(o));
+    }
+  }
+}
+
 // dx = rstd * (g - [mean(g)] - xhat * mean(g*xhat)),  g = dy * w ;  dx (+)= dres if given
 template <bool RMS>
 __global__ void __launch_bounds__(NORM_THREADS)
@@ -256,6 +364,16 @@ static int check_norm(int M, int D) {
 extern "C" int vpb_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy,
                                float* rstd, int M, int D, float eps, void* stream) {
   if (check_norm(M, D)) return -1;
+  if (!get_option(VPB_OPT_NORM_R1)) {
+    if (D <= 8 * NORM_THREADS * 2)
+      rmsnorm_fwd_packed_kernel<2><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w,
+                                                                                (bf16*)y, ldy, rstd, D, eps);
+    else
+      rmsnorm_fwd_packed_kernel<4><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)w,
+                                                                                (bf16*)y, ldy, rstd, D, eps);
+    VPB_LAUNCH_OK();
+    return 0;
+  }
   norm_fwd_kernel<true><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, ldx, (const bf16*)w, nullptr, (bf16*)y, ldy, nullptr, rstd, D, eps);
   VPB_LAUNCH_OK();
@@ -266,6 +384,16 @@ extern "C" int vpb_rmsnorm_bwd(const void* dy, int64_t lddy, const void* x, int6
                                const void* w, const float* rstd, const void* dres, int64_t lddres,
                                void* dx, int64_t lddx, int M, int D, void* stream) {
   if (check_norm(M, D)) return -1;
+  if (!get_option(VPB_OPT_NORM_R1)) {
+    if (D <= 8 * NORM_THREADS * 2)
+      rmsnorm_bwd_packed_kernel<2><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>(
+          (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)w, rstd, (const bf16*)dres, lddres, (bf16*)dx, lddx, D);
+    else
+      rmsnorm_bwd_packed_kernel<4><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>(
+          (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)w, rstd, (const bf16*)dres, lddres, (bf16*)dx, lddx, D);
+    VPB_LAUNCH_OK();
+    return 0;
+  }
   norm_bwd_kernel<true><<<M, NORM_THREADS, 0, (cudaStream_t)stream>>>(
       (const bf16*)dy, lddy, (const bf16*)x, ldx, (const bf16*)w, nullptr, rstd, (const bf16*)dres,
       lddres, (bf16*)dx, lddx, D);
