@@ -11,8 +11,7 @@ mm_projector → splice → 32 decoder layers → lm_head+CE → six distillatio
 
 Default workload = the configuration `north_star`'s target sentence names ("with all dsg distill heads
 active"): BASELINE.json configs[2]'s per-GPU slice — it fits one GPU, so it is also the N=1 line.  The
-same run adds, as extra keys, `ntp` (configs[1]: NTP only, PT freeze policy) and, at N>1 or with
---extras all, `ift` (full fine-tune of the LLM as finetune.sh does: the 16 GB gradient reduce-scatter /
+same run adds, as extra keys, `ntp` (configs[1]: NTP only, PT freeze policy) and `ift` (full fine-tune of the LLM as finetune.sh does: the 16 GB gradient reduce-scatter /
 parameter all-gather of ZeRO-2).  `--workload ntp` makes configs[1] the main line instead.
 
 Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = same step through the public
@@ -71,8 +70,8 @@ def parse():
                          "CLIP-ConvNeXt-XXL at 768 px of BASELINE configs[3] (576 image tokens of width 3072)")
     ap.add_argument("--layers", type=int, default=None, help="override decoder depth (debug only; reported)")
     ap.add_argument("--extras", default="auto", choices=["auto", "none", "ntp", "all"],
-                    help="extra workloads measured after the main one and reported as keys of the same line: "
-                         "auto = ntp at N=1, ntp + ift at N>1")
+                    help="extra workloads measured after the main one and reported as keys of the same line "
+                         "(auto = all = ntp + ift)")
     ap.add_argument("--ift-batch", type=int, default=4, help="per-GPU batch of the `ift` extra (full fine-tune)")
     ap.add_argument("--torch-profile", action="store_true",
                     help="diagnostic: torch.profiler over 2 device-leg steps, prints kernel totals and busy time")
@@ -257,8 +256,7 @@ def run_reference(args):
         r, cpu = reference_cpu(args.cpu_budget_s, args.steps, warmup=min(max(args.warmup, 1), 1), which=args.cpu_config)
     n_timed = len(r["step_s"])
     ms = 1000.0 * r["step_s_mean"]
-    cfgd = workload_config(args, c, distill)
-    cfgd["reference_cpu_workload"] = CFG0_DESC
+    cfgd = workload_config(args, c, distill)   # identical to the B200 arm's config (the driver compares them)
     line = {
         "impl": "reference", "metric": "train-step samples/sec", "value": r["samples_per_s"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": n_timed, "steps_requested": args.steps, "warmup": r["warmup"],
@@ -336,7 +334,7 @@ class Env:
         torch.cuda.synchronize()
 
 
-def build_trainer(env, c, distill, train, batch, teachers=False, distributed=True, lr=1e-3):
+def build_trainer(env, c, distill, train, batch, teachers=False, distributed=True, lr=1e-3, warmup_ratio=0.03):
     from visper_lm_b200 import model as pm
     from visper_lm_b200.model import presets
     from visper_lm_b200.train.trainer import LLaVATrainer, TrainingArguments
@@ -356,7 +354,8 @@ def build_trainer(env, c, distill, train, batch, teachers=False, distributed=Tru
                              and ("oneformer" not in n))
         else:  # PT freeze policy
             p.requires_grad_(("mm_projector" in n) or ("_heads." in n) or ("special_" in n) or n.endswith("logit_scale"))
-    targs = TrainingArguments(per_device_train_batch_size=batch, learning_rate=lr, max_steps=10_000)
+    targs = TrainingArguments(per_device_train_batch_size=batch, learning_rate=lr, max_steps=10_000,
+                              warmup_ratio=warmup_ratio)
     trainer = LLaVATrainer(model=model, args=targs, distributed=distributed)
     trainer.total_steps = 10_000
     trainer.create_optimizer()
@@ -466,48 +465,58 @@ def brief(res, world):
 
 
 def dp_check(env):
-    """NCCL ZeRO-2 + cross-rank InfoNCE numerics on hardware: a tiny dsg model steps data-parallel on per-rank
-    batches; rank 0 re-runs the concatenated GLOBAL batch single-process (no collectives) from the same
-    initial weights.  DP semantics to match: loss = mean of rank-local means, gradients averaged over ranks,
-    InfoNCE negatives all-gathered with labels offset by rank·B (ola_utils.py:96-125), one AdamW step
-    (llava_trainer.py:890-995)."""
+    """NCCL ZeRO-2 + cross-rank InfoNCE numerics on hardware: a tiny dsg model takes two optimizer steps
+    data-parallel on per-rank batches; rank 0 re-runs the concatenated GLOBAL batches single-process (no
+    collectives) from the same initial weights.  DP semantics to match: loss = mean of rank-local means, gradients
+    averaged over ranks, InfoNCE negatives all-gathered with labels offset by rank·B (ola_utils.py:96-125), AdamW
+    on the rank's shard then parameter all-gather (llava_trainer.py:890-995, scripts/zero2.json)."""
     c = dict(TINY)
-    B, n_text = 2, 40
+    B, n_text, steps = 2, 40, 2
     T = n_text - 1 + 576 + 24
-    model, trainer = build_trainer(env, c, True, "adapter", B)
-    hb = host_batch(c, B, T, True, 4321 + env.rank, n_text=n_text)
-    p0 = trainer.optimizer.flat_params().clone()
-    loss, _ = trainer.step(fresh(hb))
+
+    def snapshot(model):
+        return {n: p.detach().float().clone() for n, p in model.named_parameters() if p.requires_grad}
+
+    model, trainer = build_trainer(env, c, True, "adapter", B, warmup_ratio=0.0)
+    p0 = snapshot(model)
+    losses, norms = [], []
+    for s_ in range(steps):
+        loss, _ = trainer.step(fresh(host_batch(c, B, T, True, 4321 + 10 * s_ + env.rank, n_text=n_text)))
+        lt = loss.detach().float().reshape(1).clone()
+        dist.all_reduce(lt)
+        losses.append(lt.item() / env.world)
+        norms.append(float(trainer.optimizer.last_grad_norm))
+    trainer.optimizer.wait_params()
     env.sync_all()
-    loss_t = loss.detach().float().reshape(1).clone()
-    dist.all_reduce(loss_t)
-    loss_dp = loss_t.item() / env.world
-    gn_dp = float(trainer.optimizer.last_grad_norm)
-    p_dp = trainer.optimizer.flat_params().clone()
-    names = [n for n, _ in trainer.optimizer.named]
+    p_dp = snapshot(model)
     out = None
     if env.rank == 0:
-        model1, trainer1 = build_trainer(env, c, True, "adapter", B * env.world, distributed=False)
-        assert [n for n, _ in trainer1.optimizer.named] == names
-        model1._gather_targets = lambda t: (t, 0)     # single process: the global batch holds every target
-        gb = cat_batches([host_batch(c, B, T, True, 4321 + r, n_text=n_text) for r in range(env.world)])
-        q0 = trainer1.optimizer.flat_params().clone()
-        loss1, _ = trainer1.step(fresh(gb))
+        model1, trainer1 = build_trainer(env, c, True, "adapter", B * env.world, distributed=False, warmup_ratio=0.0)
+        model1._gather_targets = lambda t: (t, 0, None)     # single process: the global batch holds every target
+        q0 = snapshot(model1)
+        losses1, norms1 = [], []
+        for s_ in range(steps):
+            gb = cat_batches([host_batch(c, B, T, True, 4321 + 10 * s_ + r, n_text=n_text) for r in range(env.world)])
+            loss1, _ = trainer1.step(fresh(gb))
+            losses1.append(float(loss1))
+            norms1.append(float(trainer1.optimizer.last_grad_norm))
         torch.cuda.synchronize()
-        gn1 = float(trainer1.optimizer.last_grad_norm)
-        p1 = trainer1.optimizer.flat_params()
-        n = min(p1.numel(), p_dp.numel())
-        up_dp, up_1 = (p_dp[:n].float() - p0[:n].float()), (p1[:n].float() - q0[:n].float())
-        cos = float((up_dp @ up_1) / (up_dp.norm() * up_1.norm()).clamp_min(1e-30))
-        out = {"world": env.world, "config": "tiny Llama (4 layers, hidden 128) + dsg heads, B=2/rank, T=639, PT freeze policy",
-               "loss_dp": loss_dp, "loss_single": float(loss1),
-               "loss_rel": abs(loss_dp - float(loss1)) / abs(float(loss1)),
-               "grad_norm_dp": gn_dp, "grad_norm_single": gn1, "grad_norm_rel": abs(gn_dp - gn1) / max(gn1, 1e-30),
-               "init_params_equal": bool(torch.equal(p0[:n], q0[:n])),
-               "param_after_step_max_abs": float((p_dp[:n].float() - p1[:n].float()).abs().max()),
-               "param_update_cos": cos, "lr": 1e-3,
-               "note": "first AdamW step moves every weight by ±lr·sign(g): max_abs is 0 or 2·lr where a near-zero "
-                       "gradient changed sign under bf16 rounding; update_cos is the aggregate"}
+        p1 = snapshot(model1)
+        up_dp = torch.cat([(p_dp[n] - p0[n]).flatten() for n in p0])
+        up_1 = torch.cat([(p1[n] - q0[n]).flatten() for n in p0])
+        out = {"world": env.world, "steps": steps,
+               "config": "tiny Llama (4 layers, hidden 128) + dsg heads, B=2/rank, T=639, PT freeze policy, lr 1e-3, no warm-up",
+               "loss_dp": losses, "loss_single": losses1,
+               "loss_rel": max(abs(a - b) / abs(b) for a, b in zip(losses, losses1)),
+               "grad_norm_dp": norms, "grad_norm_single": norms1,
+               "grad_norm_rel": max(abs(a - b) / max(b, 1e-30) for a, b in zip(norms, norms1)),
+               "init_params_equal": all(torch.equal(p0[n], q0[n]) for n in p0),
+               "param_after_step_max_abs": max(float((p_dp[n] - p1[n]).abs().max()) for n in p0),
+               "param_update_cos": float((up_dp @ up_1) / (up_dp.norm() * up_1.norm()).clamp_min(1e-30)),
+               "param_update_norm_rel": float((up_dp.norm() - up_1.norm()).abs() / up_1.norm().clamp_min(1e-30)),
+               "trainable_tensors": len(p0),
+               "note": "AdamW's first steps move a weight by about lr*sign(g): max_abs is at most 2*lr per step where a "
+                       "near-zero gradient changes sign under bf16 rounding; update_cos / update_norm_rel are the aggregates"}
         del model1, trainer1
     del model, trainer
     gc.collect()
@@ -543,7 +552,7 @@ def run_b200(args):
         return
 
     extras = {}
-    want = {"auto": (["ntp"] if world == 1 else ["ntp", "ift"]), "none": [], "ntp": ["ntp"], "all": ["ntp", "ift"]}[args.extras]
+    want = {"auto": ["ntp", "ift"], "none": [], "ntp": ["ntp"], "all": ["ntp", "ift"]}[args.extras]
     full_model = args.model == "llama3-8b" and args.layers is None and args.seq == 2048 and args.tower == "clip-vit-l"
     if not (args.train == "adapter" and not teachers):
         want = []

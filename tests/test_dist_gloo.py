@@ -120,7 +120,8 @@ def _infonce_worker(rank, world, port, ret):
     preds = torch.randn(world * B, n, generator=g)
     tgts = torch.randn(world * B, n, generator=g)
     mine_p = preds[rank * B:(rank + 1) * B].clone().requires_grad_(True)
-    tall, off = gather_targets(tgts[rank * B:(rank + 1) * B].clone())
+    tall, off, ev = gather_targets(tgts[rank * B:(rank + 1) * B].clone())
+    assert ev is None   # CPU tensors: synchronous collective
     assert off == rank * B and torch.equal(tall, tgts)
     tau = torch.tensor(2.0)
     ce = restate.calculate_contrastive_loss(mine_p, tall, tau, rank=rank)

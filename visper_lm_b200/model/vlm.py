@@ -332,17 +332,37 @@ def tile_targets(tgt, mask, B):
     return tgt, mask
 
 
+_TARGET_STREAMS = {}
+
+
 def gather_targets(tgt_flat, group=None):
     """dist_collect (ola_utils.py:96-106) for the InfoNCE negatives: all-gather of the rank-local
-    targets [B, n] → ([world·B, n], offset of the local rows = rank·B, cf. ola_utils.py:111).
-    Targets carry no gradient, so a plain collective suffices (no backward collective)."""
+    targets [B, n] → ([world·B, n], offset of the local rows = rank·B (ola_utils.py:111), event or None).
+    Targets carry no gradient, so a plain collective suffices (no backward collective).  On the GPU the
+    collective runs on a side stream — the forward pass gets no extra point at which the ranks wait for each
+    other — and the consumer waits for the returned event right before the loss kernel reads the targets."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         world = dist.get_world_size(group)
-        out = torch.empty((world * tgt_flat.shape[0], tgt_flat.shape[1]), dtype=tgt_flat.dtype,
-                          device=tgt_flat.device)
-        dist.all_gather_into_tensor(out, tgt_flat.contiguous(), group=group)
-        return out, dist.get_rank(group) * tgt_flat.shape[0]
-    return tgt_flat, 0
+        src = tgt_flat.contiguous()
+        out = torch.empty((world * src.shape[0], src.shape[1]), dtype=src.dtype, device=src.device)
+        off = dist.get_rank(group) * src.shape[0]
+        if src.is_cuda:
+            st = _TARGET_STREAMS.get(src.device)
+            if st is None:
+                st = _TARGET_STREAMS[src.device] = torch.cuda.Stream(device=src.device)
+            ready = torch.cuda.Event()
+            ready.record()
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                dist.all_gather_into_tensor(out, src, group=group)
+                done = torch.cuda.Event()
+                done.record()
+            src.record_stream(st)
+            out.record_stream(st)
+            return out, off, done
+        dist.all_gather_into_tensor(out, src, group=group)
+        return out, off, None
+    return tgt_flat, 0, None
 
 
 # ------------------------------------------------------------------------------------------------ model
@@ -739,8 +759,8 @@ class VisperForCausalLM(nn.Module):
     def encode_images(self, images):
         """ola_arch.py:187-190 — frozen tower (no grad) then the trainable mlp2x_gelu projector."""
         feats = self.get_vision_tower()(images)
-        if self._pre_trainable_hook is not None:   # ZeRO-2: the updated parameters must have arrived by now
-            self._pre_trainable_hook()
+        if self._pre_trainable_hook is not None:   # ZeRO-2: the updated projector must have arrived by now
+            self._pre_trainable_hook(0)
         pj = self.model.mm_projector
         h = A.linear(feats, pj[0].weight, pj[0].bias, ACT_GELU)
         return A.linear(h, pj[2].weight, pj[2].bias, ACT_NONE)
@@ -779,6 +799,8 @@ class VisperForCausalLM(nn.Module):
         dev = self.device
         image_features = self.encode_images(images.to(dev, non_blocking=True))  # [n_img*576, D]
         n_tok = self.get_vision_tower().num_patches
+        if self._pre_trainable_hook is not None:
+            self._pre_trainable_hook(1)   # embedding table and task tokens
         task_rows = self._task_rows()
         cpu = lambda t: None if t is None else (t.cpu() if t.is_cuda else t)
         plan = SplicePlan(cpu(input_ids), cpu(labels), cpu(attention_mask), n_tok,
@@ -803,8 +825,7 @@ class VisperForCausalLM(nn.Module):
         B, T, D = inputs_embeds.shape
         H, KVH = cfg.num_attention_heads, cfg.num_key_value_heads
         hd = D // H
-        if self._pre_trainable_hook is not None:
-            self._pre_trainable_hook()
+        hook = self._pre_trainable_hook
         cos, sin = ops.rope_tables(max(cfg.max_position_embeddings, T), hd, cfg.rope_theta, inputs_embeds.device)
         sw = getattr(cfg, "sliding_window", None)
         meta = SimpleNamespace(B=B, T=T, H=H, KVH=KVH, hd=hd, eps=cfg.rms_norm_eps, cos=cos, sin=sin,
@@ -813,9 +834,13 @@ class VisperForCausalLM(nn.Module):
         if x.dtype != BF16:
             x = x.to(BF16)
         states = [x]
-        for layer in self.model.layers:
+        for li, layer in enumerate(self.model.layers):
+            if hook is not None:
+                hook(2 + li)        # ZeRO-2: wait only for the all-gathers up to this layer's weights
             x = layer.run(x, meta)
             states.append(x)
+        if hook is not None:
+            hook(None)              # final norm, lm_head, heads: everything
         states[-1] = A.RMSNormFn.apply(x, self.model.norm.weight, cfg.rms_norm_eps)
         return states
 
@@ -928,7 +953,7 @@ class VisperForCausalLM(nn.Module):
             heads = getattr(self, heads_name)
             weight = getattr(self, w_name)
             tgt = self._targets(task, pil_images, distill_targets, dev)
-            tgt_all = off = None
+            tgt_all = off = tgt_ev = None
             if tgt is not None:
                 tgt, masks[task] = tile_targets(tgt, masks.get(task), B)
                 tgt = tgt.to(dev, BF16)
@@ -941,7 +966,7 @@ class VisperForCausalLM(nn.Module):
                     tgt_flat = tflat
                 else:
                     tgt_flat = tgt.reshape(tgt.shape[0], -1).contiguous()
-                tgt_all, off = self._gather_targets(tgt_flat)
+                tgt_all, off, tgt_ev = self._gather_targets(tgt_flat)
             mask = masks.get(task)
             if tgt is not None and tgt.shape[0] != B:
                 raise ValueError(f"{task} targets: {tgt.shape[0]} rows cannot be tiled to a batch of {B}")
@@ -973,6 +998,9 @@ class VisperForCausalLM(nn.Module):
                 if mask is not None and cfg.zero_masks_like_reference:
                     mask.zero_()  # base_ola_vlm.py:472-473, 498-499, 525-526
                 if tgt_all is not None:
+                    if tgt_ev is not None:      # the side-stream all-gather of the targets must have landed
+                        torch.cuda.current_stream().wait_event(tgt_ev)
+                        tgt_ev = None
                     l3 = self._emb_loss(pred.reshape(B, -1), mask, tgt_all, off, getattr(self, scale_name))
                     out["terms"].setdefault(task, []).append(l3)
                     total = l3[0] * weight if total is None else total + l3[0] * weight
@@ -987,7 +1015,7 @@ class VisperForCausalLM(nn.Module):
         """Keyword surface of ola_llama.py:190-209 (llava_llama.py:73-91 for the NTP-only classes)."""
         distill_targets = kwargs.pop("distill_targets", None)
         if images is None and self._pre_trainable_hook is not None:
-            self._pre_trainable_hook()   # no frozen tower to hide the parameter all-gather behind
+            self._pre_trainable_hook(1)  # no frozen tower to hide the parameter all-gather behind
         if inputs_embeds is None:
             (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds,
              labels) = self.prepare_inputs_labels_for_multimodal(

@@ -134,7 +134,7 @@ class Zero2Optimizer:
 
     def __init__(self, named_params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  max_grad_norm=1.0, groups=None, process_group=None, distributed=True,
-                 bucket_elems=64 * 1024 * 1024, keep_together=(), overlap=True):
+                 bucket_elems=64 * 1024 * 1024, keep_together=(), overlap=True, use_order=None):
         self.named = [(n, p) for n, p in named_params if p.requires_grad]
         assert self.named, "no trainable parameters"
         self.lr, self.betas, self.eps, self.max_grad_norm = lr, betas, eps, max_grad_norm
@@ -238,8 +238,23 @@ class Zero2Optimizer:
         self.comm = torch.cuda.Stream(device=dev) if (self.cuda and (self.world > 1 or self.force_staging)) else None
         self.staging_peak = 0                  # most gradient-staging bytes alive at one time (overlap mode)
         self.written = [False] * len(order)
+        # parameters that received no gradient in the previous step (e.g. linear_2/3 of the depth heads, which the
+        # reference's loss never reaches): they are not waited for, so their buckets can be reduced during backward
+        self.expected_missing = set()
         self._pending_gather = []
+        # use_order(name) -> rank of first use in the forward pass: the parameter all-gathers are issued in that
+        # order and a consumer waits only for the buckets up to its own (wait_params(upto=...))
+        key = use_order or (lambda n: 0)
+        self.gather_order = sorted(self.buckets, key=lambda b: (min(key(self.named[i][0]) for i in b.params), b.idx))
+        self.gather_pos = {b.idx: k for k, b in enumerate(self.gather_order)}
+        self.use_rank = sorted({key(self.named[i][0]) for i in range(len(self.named))})
+        self._rank_last_pos = {}
+        for r in self.use_rank:   # position (in issue order) of the last bucket holding a parameter used at rank <= r
+            self._rank_last_pos[r] = max(self.gather_pos[self.bucket_of[i].idx] for i in range(len(self.named))
+                                         if key(self.named[i][0]) <= r)
         self._events = {}
+        self._gather_waited = 0
+        self._gather_wait_pairs = []
         self._hooks = []
         if hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
             for _, p in self.named:
@@ -271,8 +286,9 @@ class Zero2Optimizer:
     # ---- per-step gradient collection ---------------------------------------------------------------------
     def _reset_step_state(self):
         self.written = [False] * len(self.named)
+        miss = self.expected_missing
         for b in self.buckets:
-            b.pending = len(b.params)
+            b.pending = sum(1 for i in b.params if i not in miss)
             b.launched = b.touched = False
             b.buf = None
 
@@ -316,6 +332,10 @@ class Zero2Optimizer:
             if self._use_staging():
                 for lo, hi in b.pads:          # padding never receives a gradient: keep it zero for the norm
                     space[lo - b.lo: hi - b.lo].zero_()
+            for i in b.params:                 # predicted to get no gradient: zero now, the bucket does not wait for it
+                if i in self.expected_missing:
+                    o = self.offsets[i] - b.lo
+                    space[o:o + self.numels[i]].zero_()
         return space
 
     def _grad_dst(self, first, n, idxs):
@@ -334,6 +354,12 @@ class Zero2Optimizer:
             return
         self.written[i] = True
         b = self.bucket_of[i]
+        if i in self.expected_missing:
+            if b.launched:
+                raise RuntimeError(f"gradient of {self.named[i][0]} arrived after its bucket was reduced: the set of "
+                                   "parameters that receive gradients changed between steps (call "
+                                   "optimizer.expected_missing.clear() when switching workloads)")
+            return                             # pre-zeroed at first touch, now overwritten; it was never counted
         b.pending -= 1
         if b.pending == 0 and self._use_staging() and not b.launched:
             self._reduce_bucket(b)
@@ -394,17 +420,22 @@ class Zero2Optimizer:
             if p.grad is not None:
                 self._collect(i, p.grad)
                 p.grad = None
+        missing = set()
         for b in self.buckets:
-            if b.pending:
+            if not b.launched:
                 space = self._touch(b)
                 for i in b.params:
                     if not self.written[i]:   # no gradient this step (e.g. linear_2/3 of the depth heads)
-                        o = self.offsets[i] - b.lo
-                        space[o:o + self.numels[i]].zero_()
-                        self.written[i] = True
+                        missing.add(i)
+                        if i not in self.expected_missing:   # (predicted ones were zeroed at first touch)
+                            o = self.offsets[i] - b.lo
+                            space[o:o + self.numels[i]].zero_()
                 b.pending = 0
-            if not b.launched:
                 self._reduce_bucket(b)
+            else:
+                missing.update(i for i in b.params if not self.written[i])
+        if not self.accumulating:
+            self.expected_missing = missing
         if self.comm is not None:
             cur = torch.cuda.current_stream()
             for b in self.buckets:
@@ -451,25 +482,39 @@ class Zero2Optimizer:
         upd = torch.cuda.Event()
         upd.record()
         self.comm.wait_event(upd)
+        evs = []
         with torch.cuda.stream(self.comm):
-            for b in self.buckets:            # forward order: the first layers' weights arrive first
+            for b in self.gather_order:       # order of first use in the forward pass
                 full = self.flat_p[b.lo:b.hi]
                 dist.all_gather_into_tensor(full, full[self.rank * b.slice:(self.rank + 1) * b.slice], group=self.pg)
-            ev = torch.cuda.Event()
-            ev.record()
-        self._pending_gather = [ev]
+                ev = torch.cuda.Event()
+                ev.record()
+                evs.append(ev)
+        self._pending_gather = evs
+        self._gather_waited = 0
+        self._events.pop("gather_wait", None)
+        self._gather_wait_pairs = []
 
-    def wait_params(self):
-        """The compute stream waits for the updated parameters (no-op when nothing is pending)."""
-        if self._pending_gather:
-            cur = torch.cuda.current_stream()
-            e0 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for ev in self._pending_gather:
-                cur.wait_event(ev)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record()
-            self._events["gather_wait"] = (e0, e1)
+    def wait_params(self, upto=None):
+        """The compute stream waits for the updated parameters: all of them (upto=None), or only the buckets that
+        hold parameters whose use_order rank is <= upto.  No-op when nothing (more) is pending."""
+        if not self._pending_gather:
+            return
+        n = len(self._pending_gather)
+        if upto is not None:
+            ranks = [r for r in self.use_rank if r <= upto]
+            n = (self._rank_last_pos[ranks[-1]] + 1) if ranks else 0
+        if n <= self._gather_waited:
+            return
+        cur = torch.cuda.current_stream()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cur.wait_event(self._pending_gather[n - 1])   # issued in order on one stream: the last one covers the rest
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self._gather_wait_pairs.append((e0, e1))
+        self._gather_waited = n
+        if n == len(self._pending_gather):
             self._pending_gather = []
 
     def comm_summary(self):
@@ -484,11 +529,36 @@ class Zero2Optimizer:
                "staging_peak_mb": round(self.staging_peak / 2**20, 1)}
         for k, (a, b) in self._events.items():
             out[f"exposed_{k}_ms"] = round(a.elapsed_time(b), 3)
+        out["exposed_gather_wait_ms"] = round(sum(a.elapsed_time(b) for a, b in getattr(self, "_gather_wait_pairs", [])), 3)
+        # a rank also waits in a collective for the OTHER ranks to arrive (clock / power-cap skew between GPUs):
+        # the minimum over ranks is what the communication itself costs, the maximum includes the skew
+        t = torch.tensor([out.get("exposed_reduce_wait_ms", 0.0), out["exposed_gather_wait_ms"]], device=self.dev)
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.pg)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.pg)
+        out["exposed_reduce_wait_ms_min_max_over_ranks"] = [round(lo[0].item(), 3), round(hi[0].item(), 3)]
+        out["exposed_gather_wait_ms_min_max_over_ranks"] = [round(lo[1].item(), 3), round(hi[1].item(), 3)]
         return out
 
     def state_dict(self):
         return {"step": self.step_count, "master": self.master, "m": self.m, "v": self.v,
                 "rank": self.rank, "world": self.world}
+
+
+def forward_use_rank(name):
+    """Rank of a parameter's first use in the forward pass (ola_llama.py:79-188): projector → embedding / task
+    tokens (splice) → decoder layer i → final norm, lm_head, heads.  The model passes the same ranks to
+    `_pre_trainable_hook`, so layer i waits only for the all-gathers up to its own weights."""
+    import re
+
+    if "mm_projector" in name:
+        return 0
+    if "embed_tokens" in name or "special_" in name:
+        return 1
+    m = re.search(r"model\.layers\.(\d+)\.", name)
+    if m:
+        return 2 + int(m.group(1))
+    return 1000
 
 
 def _no_decay(name):
@@ -533,7 +603,8 @@ class LLaVATrainer:
         self.optimizer = Zero2Optimizer(self.model.named_parameters(), a.learning_rate,
                                         (a.adam_beta1, a.adam_beta2), a.adam_epsilon, a.weight_decay,
                                         a.max_grad_norm, groups, distributed=self.is_dist, keep_together=fused,
-                                        bucket_elems=int(getattr(a, "zero_bucket_elems", 64 * 1024 * 1024)))
+                                        bucket_elems=int(getattr(a, "zero_bucket_elems", 64 * 1024 * 1024)),
+                                        use_order=forward_use_rank)
         for m in self.model.modules():   # decoder weight gradients are written straight into the optimizer's buffer
             if isinstance(m, DecoderLayer):
                 m._grad_sink = self.optimizer.layer_sink(m.sink_params())
