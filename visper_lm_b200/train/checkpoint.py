@@ -86,6 +86,7 @@ def save_checkpoint(trainer, output_dir: str):
     opt = trainer.optimizer
     rank, world = trainer.rank, trainer.world
     if opt is not None:
+        opt.wait_params()   # a parameter all-gather of the last step may still be in flight on the comm stream
         torch.save({"step": opt.step_count, "master": opt.master.cpu(), "m": opt.m.cpu(), "v": opt.v.cpu(),
                     "rank": rank, "world": world, "total": opt.total,
                     "names": [n for n, _ in opt.named]},
