@@ -606,11 +606,13 @@ def run_b200(args):
             "kernel": "gemm_tcgen05_pair_kernel / gemm_tcgen05_kernel (all GEMM launches of the timed steps)",
             "achieved": gemm["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
             "frac": gemm["tflops"] / peak_tf if gemm["tflops"] else None,
-            # ncu --set full, dominant launch shape (down_proj dgrad, M=16384 N=14336 K=4096): dram read+write per
-            # launch vs its algorithmic bytes (operands + output) — profiles/r01_ncu_gemm_pair_shapes.csv
-            "traffic": 1.51e9 if full_model else None,
-            "traffic_algorithmic": 0.72e9 if full_model else None,
-            "traffic_source": "profiles/r01_ncu_gemm_pair_shapes.csv (one --set full capture, per launch)" if full_model else None,
+            # ncu --set full inside the dsg step (profiles/r02_ncu_gemm_instep.csv), the launch that moves the most DRAM
+            # bytes: gate|up dgrad, M=16384 N=4096 K=28672 — 7.41 GB read + 0.13 GB written per launch against 1.31 GB of
+            # operands + output (A panels of 32 MB stay L2-resident, B streams once per panel; tensor pipe 99.4 % active,
+            # 2.75 ms).  The other three decoder dgrad shapes of the same capture: 1.35 / 0.45 / 0.91 GB per launch.
+            "traffic": 7.55e9 if full_model else None,
+            "traffic_algorithmic": 1.31e9 if full_model else None,
+            "traffic_source": "profiles/r02_ncu_gemm_instep.csv (one --set full capture, per launch)" if full_model else None,
             "peak_source": peak_src, "launches": gemm["launches"],
             "gemm_ms_per_step": gemm["ms"] / args.steps,
             "gemm_share_of_step": gemm["ms"] / res["ms_dev"] if res["ms_dev"] else None,
