@@ -630,7 +630,10 @@ def run_b200(args):
 
             with contextlib.redirect_stdout(sys.stderr):
                 _, line["cpu_baseline"] = reference_cpu(args.cpu_budget_s, 3, warmup=1, which=args.cpu_config)
-        except Exception as ex:  # the baseline is reported, never required for the GPU number
+        except Exception as ex:  # the baseline is reported, never required for the GPU number — but never silently lost
+            import traceback
+
+            traceback.print_exc(file=sys.stderr)
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "reference",
                                     "sample": f"failed: {type(ex).__name__}: {ex}"}
     print(json.dumps(line), flush=True)
