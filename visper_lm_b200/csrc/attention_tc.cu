@@ -341,8 +341,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // S = 2048 item has 8.5 key tiles on average, so 39 % of the 0.427 ms was that fixed cost (27.7 items per SM x 6 us).
 // Here ONE CTA per SM stays resident and walks a heavy-first list of work items.  Its TMA warp runs ahead across item
 // boundaries (Q double-buffered, the K / V rings never drain), its MMA warp issues the first Q·Kᵀ of item n+1 before
-// it waits for the last P of item n, O is double-buffered in TMEM so that P·V of item n+1 does not wait for the
-// epilogue of item n, and barriers / TMEM are set up once.  Same arithmetic in the same order as the kernel above:
+// it waits for the last P of item n, O is double-buffered in TMEM and a separate EPILOGUE warpgroup writes item n out
+// while the softmax warps are already on item n+1, and barriers / TMEM are set up once.  Same arithmetic in the same order as the kernel above:
 // bit-identical output and LSE.
 namespace tcp {
 constexpr int KST = 2, VST = 2;
@@ -350,8 +350,9 @@ constexpr int OFF_Q = 0;                                   // Q[2]
 constexpr int OFF_K = 2 * tc::TILE_BYTES;                  // K[2]
 constexpr int OFF_V = OFF_K + KST * tc::TILE_BYTES;        // V[2]
 constexpr int OFF_BAR = OFF_V + VST * tc::TILE_BYTES;      // 6 x 32 KB of tiles
-constexpr int OFF_X = OFF_BAR + 256;                       // softmax exchange: 768 floats
-constexpr int SMEM_BYTES = OFF_X + 3072 + 1024;
+constexpr int OFF_X = OFF_BAR + 256;                       // max exchange [2][2][128] + per-item [2][l0|l1|m][128]: 1280 floats
+constexpr int SMEM_BYTES = OFF_X + 5120 + 1024;
+constexpr int THREADS = 512;
 }  // namespace tcp
 
 struct FwdItem {
@@ -387,13 +388,14 @@ __device__ __forceinline__ bool fwd_item(const AttnTcParams& p, int w, int nqt, 
 }
 
 template <bool CAUSAL, int HD>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(512, 1)
 attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                            const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by OFFSET on the __shared__ array (not through an integer cast): the compiler keeps the
+  // shared address space, so the softmax exchange slots are LDS / STS instead of generic loads through L1TEX
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tcp::OFF_BAR);
   uint64_t* q_full = bars + 0;    // [2]
   uint64_t* q_empty = bars + 2;   // [2] every Q·Kᵀ of the item that used the buffer has completed
@@ -407,8 +409,10 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   // observed one wrap late whatever the TMA latency does to the relative timing
   uint64_t* p_full = bars + 14;   // [2]
   uint64_t* pv_done = bars + 16;  // [2]
-  uint64_t* o_free = bars + 18;   // [2] the epilogue has O[n&1] in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* o_free = bars + 18;   // [2] the epilogue warps have read O[n&1] and the row sums of item n
+  uint64_t* o_ready = bars + 20;  // [2] every P·V of item n has completed (committed after its last tile)
+  uint64_t* l_ready = bars + 22;  // [2] the softmax warps have published the row sums / maxima of item n
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqt = (p.sq + BM - 1) / BM;
@@ -426,7 +430,9 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&o_free[i], 8);
+      mbar_init(&o_free[i], 4);
+      mbar_init(&o_ready[i], 1);
+      mbar_init(&l_ready[i], 8);
       mbar_init(&p_full[i], 8);
       mbar_init(&pv_done[i], 1);
     }
@@ -441,6 +447,11 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
   const uint32_t TM_O = tmem_base + 256;  // O[0] at +256, O[1] at +384
   constexpr uint32_t TX_BYTES = HD > 64 ? TILE_BYTES : CHUNK_BYTES;
 
+  // 512 threads = four warpgroups: {TMA warp, MMA warp, two idle warps}, two softmax warpgroups, one epilogue
+  // warpgroup.  128 registers per thread at launch; the data-movement and epilogue groups hand registers to the
+  // softmax groups (setmaxnreg INSIDE each role's branch, so that ptxas budgets each region separately).
+  if (warp < 4) {
+  setmaxnreg_dec<96>();
   if (warp == 0) {
     if (lane == 0) {
       // global tile sequence (item 0 tile 0, item 0 tile 1, ..., item 1 tile 0, ...); g counts tiles, K is requested
@@ -479,18 +490,19 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         load_k(0, cur, 0);
       }
       while (have) {
-        bool have_next = false;
+        const bool have_next = fwd_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nxt);
+        // Q of the NEXT item is requested as soon as its buffer can be free (the previous item's last Q·Kᵀ was issued
+        // two producer tiles ago): Q rows are read once, so this is a DRAM round trip that must not sit in front of
+        // the next item's first MMA
+        const int jq = cur.ntiles > 1 ? 1 : 0;
         for (int j = 0; j < cur.ntiles; ++j, ++g) {
           if (j + 1 < cur.ntiles) {
             load_k(g + 1, cur, j + 1);
-          } else {  // the tile after this item's last one is the next item's first
-            have_next = fwd_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nxt);
-            if (have_next) {
-              load_q(n + 1, nxt);
-              load_k(g + 1, nxt, 0);
-            }
+          } else if (have_next) {  // the tile after this item's last one is the next item's first
+            load_k(g + 1, nxt, 0);
           }
           load_v(g, cur, j);
+          if (j == jq && have_next) load_q(n + 1, nxt);
         }
         cur = nxt;
         have = have_next;
@@ -545,7 +557,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         }
         mbar_wait_spin(&v_full[g % tcp::VST], (g / tcp::VST) & 1);
         mbar_wait_spin(&p_full[g & 1], (g >> 1) & 1);
-        if (j == 0) mbar_wait_spin(&o_free[n & 1], ((n >> 1) & 1) ^ 1);  // the epilogue of item n-2 has read O[n&1]
+        if (j == 0) mbar_wait_spin(&o_free[n & 1], ((n >> 1) & 1) ^ 1);  // the epilogue warps are done with O[n&1] (item n-2)
         tc_fence_after();
         if (leader) {
           const uint64_t v_desc = desc_adv(v_desc0, (g % tcp::VST) * TILE_BYTES);
@@ -557,16 +569,19 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           }
           umma_commit(&pv_done[g & 1]);
           umma_commit(&v_empty[g % tcp::VST]);
+          if (j + 1 == cur.ntiles) umma_commit(&o_ready[n & 1]);  // O of this work item is complete
         }
       }
       cur = nxt;
       have = have_next;
       ++n;
     }
-  } else {
+  }
+  } else if (warp < 12) {
+    setmaxnreg_inc<168>();
     // 8 softmax warps: warp pair (w, w+4) shares the 32 TMEM lanes of quarter w&3 and splits the 128 key columns
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 4) >> 2;
     const int row = quarter * 32 + lane;  // query row within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
@@ -627,7 +642,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         }
         const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
         if (j > 0 && __any_sync(0xffffffffu, upd)) {
-          mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);  // P·V of the previous tile finished: O may be rescaled
+          mbar_wait_spin(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);  // P·V of the previous tile finished: O may be rescaled
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -652,50 +667,58 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[sb]);
       }
-      // epilogue of this work item: combine the two half-row sums, O / l → bf16 → global, LSE.  The accumulator is
-      // handed back (o_free) as soon as it is in registers.
-      float* lx = xchg + 512;
-      lx[half * 128 + row] = l;
-      named_bar_sync(1, 256);
-      l += lx[(half ^ 1) * 128 + row];
-      const bool row_ok = q0 + row < p.sq;
-      mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
-      tc_fence_after();
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      bf16* orow = p.o + ((int64_t)it.b * p.sq + q0 + row) * p.ldo + it.h * HD + half * 64;
-      uint32_t o0[32], o1[32];
-      const bool two = half * 64 + 32 < HD;
-      const bool one = half * 64 < HD;
-      if (one) tmem_ld32(tm_o + lane_addr + half * 64, o0);
-      if (two) tmem_ld32(tm_o + lane_addr + half * 64 + 32, o1);
-      tmem_ld_wait();
-      tc_fence_before();
+      // end of this work item: publish the half-row sums and the reference maximum for the epilogue warps and go on
+      // with the next item.  The slot of item n-2 must have been read (o_free is arrived after that read).
+      mbar_wait(&o_free[n & 1], ((n >> 1) & 1) ^ 1);
+      float* lm = xchg + 512 + (n & 1) * 384;  // [l half 0 | l half 1 | m] x 128 rows
+      lm[half * 128 + row] = l;
+      if (half == 0) lm[256 + row] = m_used;
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[n & 1]);
-      if (row_ok) {
-        if (one) {
+      if (lane == 0) mbar_arrive(&l_ready[n & 1]);
+    }
+  } else {
+    // epilogue warpgroup: one thread per query row; O / l → bf16 → global and the LSE of work item n while the
+    // softmax warps are already on item n+1 (the per-item code was 23 % of the softmax warps' time — TMEM read of O,
+    // 8 KB of global stores per warp, logf — in the ncu source view of the kernel that did it in line)
+    setmaxnreg_dec<72>();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float* xchg = reinterpret_cast<const float*>(smem + tcp::OFF_X);
+    FwdItem it;
+    for (int n = 0; fwd_item<CAUSAL>(p, blockIdx.x + n * gridDim.x, nqt, it); ++n) {
+      mbar_wait(&l_ready[n & 1], (n >> 1) & 1);
+      const float* lm = xchg + 512 + (n & 1) * 384;
+      const float l = lm[row] + lm[128 + row];
+      const float m = lm[256 + row];
+      mbar_wait(&o_ready[n & 1], (n >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tm_o = TM_O + (n & 1) * 128 + lane_addr;
+      const bool row_ok = it.q0 + row < p.sq;
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* orow = p.o + ((int64_t)it.b * p.sq + it.q0 + row) * p.ldo + it.h * HD;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o0[q * 8 + i]) * inv;
-            stg16(orow + q * 8, pack8(v));
-          }
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tm_o + c * 32, o);
+        tmem_ld_wait();
+        if (c == HD / 32 - 1) {  // the accumulator (and the row sums) have been read: hand the buffers back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_free[n & 1]);
         }
-        if (two) {
+        if (row_ok) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o1[q * 8 + i]) * inv;
-            stg16(orow + 32 + q * 8, pack8(v));
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o[q * 8 + i]) * inv;
+            stg16(orow + c * 32 + q * 8, pack8(v));
           }
         }
       }
-      if (p.lse && row_ok && half == 0)
-        p.lse[((int64_t)it.b * p.H + it.h) * p.sq + q0 + row] =
-            l > 0.f ? m_used * 0.6931471805599453f + logf(l) : -INFINITY;
-      // the l-exchange slots are rewritten at the end of the next item, after at least one more exchange barrier
+      if (p.lse && row_ok)
+        p.lse[((int64_t)it.b * p.H + it.h) * p.sq + it.q0 + row] = l > 0.f ? m * 0.6931471805599453f + logf(l) : -INFINITY;
     }
   }
   tc_fence_before();
@@ -739,7 +762,7 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
       VPB_CUDA(cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::SMEM_BYTES));
       cfgp = true;
     }
-    kernp<<<n_sm, tc::THREADS, tcp::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
+    kernp<<<n_sm, tcp::THREADS, tcp::SMEM_BYTES, st>>>(tmQ, tmK, tmV, p);
     VPB_LAUNCH_OK();
     return 0;
   }
