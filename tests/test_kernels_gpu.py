@@ -744,3 +744,45 @@ def test_layernorm_many_short_rows(M, D):
     close(y, torch.nn.functional.layer_norm(xf, (D,), w.float(), b.float(), 1e-5), name="ln fwd (warp rows)")
     assert torch.allclose(mean, xf.mean(1), atol=1e-5)
     assert torch.allclose(rstd, (xf.var(1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,H,KVH,S,hd,window", [(8, 32, 8, 2048, 128, 0), (8, 32, 8, 1000, 128, 0), (4, 32, 32, 2048, 96, 0),
+                                                 (4, 32, 32, 1500, 96, 600), (2, 64, 8, 1333, 128, 0)])
+def test_persistent_dq_kernel_is_bit_identical(B, H, KVH, S, hd, window):
+    """The persistent dQ kernel (one CTA per SM, Q / dO and dQ double-buffered, epilogue warpgroup) against the
+    round-1 kernel it replaces (VPB_OPT_ATTN_BWD_DQ_R1): same MMAs in the same order → dq, dk, dv bit for bit; both
+    against torch fp32 on a sub-sample."""
+    from visper_lm_b200 import ops
+    g = torch.Generator().manual_seed(S + hd)
+    qkv = torch.randn(B * S, (H + 2 * KVH) * hd, generator=g).to(BF).to(dev())
+    q, k, v = qkv[:, :H * hd], qkv[:, H * hd:(H + KVH) * hd], qkv[:, (H + KVH) * hd:]
+    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, hd ** -0.5, True, window=window)
+    do = torch.randn(B * S, H * hd, generator=g).to(BF).to(dev())
+    outs = []
+    for r1 in (1, 0):
+        d = torch.zeros_like(qkv)
+        ops.set_option(ops.OPT_ATTN_BWD_DQ_R1, r1)
+        try:
+            ops.attn_bwd(q, k, v, o, do, lse, d[:, :H * hd], d[:, H * hd:(H + KVH) * hd], d[:, (H + KVH) * hd:], B, H, KVH, S, S,
+                         hd, hd ** -0.5, True, window=window)
+            torch.cuda.synchronize()
+        finally:
+            ops.set_option(ops.OPT_ATTN_BWD_DQ_R1, 0)
+        outs.append(d)
+    assert torch.equal(outs[0], outs[1]), f"max diff {(outs[0].float() - outs[1].float()).abs().max().item()}"
+    # torch fp32 reference for batch entry 0, two heads
+    b0 = slice(0, S)
+    for h in (0, H - 1):
+        kvh = h // (H // KVH)
+        qh = q[b0, h * hd:(h + 1) * hd].float().requires_grad_(True)
+        kh = k[b0, kvh * hd:(kvh + 1) * hd].float()
+        vh = v[b0, kvh * hd:(kvh + 1) * hd].float()
+        sc = qh @ kh.t() * hd ** -0.5
+        i = torch.arange(S, device=sc.device)
+        vis = i[None, :] <= i[:, None]
+        if window:
+            vis = vis & (i[:, None] - i[None, :] <= window)
+        pr = torch.softmax(sc.masked_fill(~vis, float("-inf")), -1)
+        (pr @ vh).backward(do[b0, h * hd:(h + 1) * hd].float())
+        got = outs[1][b0, h * hd:(h + 1) * hd].float()
+        assert ((got - qh.grad).norm() / qh.grad.norm()).item() < 2e-2

@@ -2204,6 +2204,344 @@ attn_bwd_dq_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// =============================================================================================
+// dQ, persistent (default for self-attention shapes without the fused inverse RoPE)
+// =============================================================================================
+// The same two measures that took the forward from 0.430 to 0.330 ms (profiles/r02_attn_fwd_experiments.txt), applied
+// to the dQ kernel above, whose 2048 CTAs at B=8,H=32,S=2048 (13.8 per SM) each pay the per-CTA fixed cost, reload
+// Q / dO between their two query tiles with the tensor pipe drained, and write 64 KB of dQ from the softmax warps:
+// one CTA per SM walks a heavy-first list of 128-query work items; Q / dO are double-buffered in shared memory and
+// requested one item ahead, the K/V ring never drains, lse / delta of the next item are prefetched into registers,
+// dQ is double-buffered in TMEM and written out by a separate EPILOGUE warpgroup while the softmax warps and the
+// tensor pipe are already on the next item.  Same MMAs, same order: bit-identical to the kernel above.
+namespace tcq {
+constexpr int BQ = 128, BKV = 64, ST = 3;
+constexpr int OFF_QD = 0;                       // [2] x (Q 32 KB | dO 32 KB)
+constexpr int OFF_KV = 2 * 65536;               // stage s: K (16 KB) then V (16 KB)
+constexpr int OFF_BAR = OFF_KV + ST * 32768;    // 224 KB of tiles
+constexpr int SMEM = OFF_BAR + 512;
+constexpr int THREADS = 512;
+constexpr float LOG2E = 1.4426950408889634f;
+}  // namespace tcq
+
+struct DqItem {
+  int h, b, kvh, q0, jb, nit;
+};
+
+template <bool CAUSAL>
+__device__ __forceinline__ bool dq_item(const AttnTcBwdParams& p, int w, int nqt, DqItem& it) {
+  const int per = p.H * p.B;
+  if (w >= nqt * per) return false;
+  const int qi = w / per, r = w - qi * per;
+  const int qt = CAUSAL ? nqt - 1 - qi : qi;  // heavy query tiles first
+  it.h = r % p.H;
+  it.b = r / p.H;
+  it.kvh = it.h / (p.H / p.KVH);
+  it.q0 = qt * tcq::BQ;
+  const int off = p.sk - p.sq;
+  int kv_end = p.sk;
+  if (CAUSAL) {
+    kv_end = it.q0 + tcq::BQ + off;
+    if (kv_end > p.sk) kv_end = p.sk;
+  }
+  it.jb = 0;
+  if (CAUSAL && p.window > 0) {
+    const int lo = it.q0 + off - p.window;
+    it.jb = lo > 0 ? lo / tcq::BKV : 0;
+  }
+  it.nit = (kv_end + tcq::BKV - 1) / tcq::BKV - it.jb;  // >= 1: the launcher guarantees sk >= sq
+  return true;
+}
+
+template <bool CAUSAL, int HD>
+__global__ void __launch_bounds__(512, 1)
+attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                           const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                           const AttnTcBwdParams p) {
+  using namespace tcq;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;     // [2] Q / dO of item n landed in buffer n&1
+  uint64_t* q_empty = bars + 2;    // [2] every S / dP MMA of the item in that buffer has completed
+  uint64_t* kv_full = bars + 4;    // [ST]
+  uint64_t* kv_empty = bars + 7;   // [ST]
+  uint64_t* sd_full = bars + 10;   // [2] S / dP of iteration x (buffer x&1) complete
+  uint64_t* ds_full = bars + 12;   // [2] the softmax warps wrote dS of iteration x
+  uint64_t* dq_ready = bars + 14;  // [2] every dQ MMA of item n has completed
+  uint64_t* dq_free = bars + 16;   // [2] the epilogue warps have read dQ[n&1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int off = p.sk - p.sq;
+  const int nqt = (p.sq + BQ - 1) / BQ;
+  const bool win = CAUSAL && p.window > 0;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_u32(smem) & 1023) {
+      printf("[vpb] dynamic shared memory base is not 1024-byte aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&sd_full[i], 1);
+      mbar_init(&ds_full[i], 8);
+      mbar_init(&dq_ready[i], 1);
+      mbar_init(&dq_free[i], 4);
+    }
+    for (int i = 0; i < ST; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t TM_S = tmem_base;         // S[2]  : 2 x 64
+  const uint32_t TM_DP = tmem_base + 128;  // dP[2] : 2 x 64
+  const uint32_t TM_DQ = tmem_base + 256;  // dQ[2] : 2 x 128 (item n in half n&1)
+
+  if (warp < 4) {
+  setmaxnreg_dec<96>();
+  if (warp == 0) {
+    if (lane == 0) {
+      auto load_q = [&](int n, const DqItem& it) {
+        const int s_ = n & 1;
+        mbar_wait(&q_empty[s_], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[s_], 65536);
+        uint8_t* sq_ = smem + OFF_QD + s_ * 65536;
+        const int qrow = it.b * p.sq + it.q0;
+        tma_load_2d(sq_, &tmQ, &q_full[s_], it.h * HD, qrow);
+        tma_load_2d(sq_ + 16384, &tmQ, &q_full[s_], it.h * HD + 64, qrow);
+        tma_load_2d(sq_ + 32768, &tmDO, &q_full[s_], it.h * HD, qrow);
+        tma_load_2d(sq_ + 49152, &tmDO, &q_full[s_], it.h * HD + 64, qrow);
+      };
+      DqItem cur, nxt;
+      int n = 0, x = 0;
+      bool have = dq_item<CAUSAL>(p, blockIdx.x, nqt, cur);
+      if (have) load_q(0, cur);
+      while (have) {
+        const bool have_next = dq_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nxt);
+        const int iq = cur.nit > 1 ? 1 : 0;  // the next item's Q / dO are requested after this item's first K/V tiles
+        for (int i = 0; i < cur.nit; ++i, ++x) {
+          const int st = x % ST;
+          const int krow = cur.b * p.sk + (i + cur.jb) * BKV;
+          mbar_wait(&kv_empty[st], ((x / ST) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[st], 32768);
+          uint8_t* sk_ = smem + OFF_KV + st * 32768;
+          tma_load_2d(sk_, &tmK, &kv_full[st], cur.kvh * HD, krow);
+          tma_load_2d(sk_ + 8192, &tmK, &kv_full[st], cur.kvh * HD + 64, krow);
+          tma_load_2d(sk_ + 16384, &tmV, &kv_full[st], cur.kvh * HD, krow);
+          tma_load_2d(sk_ + 24576, &tmV, &kv_full[st], cur.kvh * HD + 64, krow);
+          if (i == iq && have_next) load_q(n + 1, nxt);
+        }
+        cur = nxt;
+        have = have_next;
+        ++n;
+      }
+    }
+  } else if (warp == 1) {
+    // warp-uniform issue loop, one elected lane issues; S / dP of iteration x+1 and dQ of iteration x are issued in
+    // whichever order their inputs become ready (mbarrier.test_wait polling), also across work-item boundaries
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_sd = make_idesc_bf16(128, BKV, 0, 0);  // [128 queries x 64 keys]
+    constexpr uint32_t idesc_dq = make_idesc_bf16(128, HD, 0, 1);
+    const uint64_t q_desc0 = make_smem_desc(smem_u32(smem + OFF_QD), 16, 1024);
+    const uint64_t kv_desc0 = make_smem_desc(smem_u32(smem + OFF_KV), 16, 1024);   // K-major view
+    const uint64_t kv_mn0 = make_smem_desc(smem_u32(smem + OFF_KV), 8192, 1024);  // MN-major view
+    DqItem si, di;                 // work items of the next S/dP issue and of the next dQ issue
+    int sn = 0, dn = 0;            // their indices in this CTA's list
+    int s_i = 0, d_i = 0;          // iteration inside the item
+    bool s_have = dq_item<CAUSAL>(p, blockIdx.x, nqt, si);
+    bool d_have = s_have;
+    di = si;
+    int n_sd = 0, n_dq = 0;
+    uint32_t spins = 0;
+    while (d_have) {
+      bool did = false;
+      if (s_have) {
+        const int sb = n_sd & 1, st = n_sd % ST;
+        // a score buffer is free when the dQ MMAs of iteration n_sd-2 have been ISSUED (they read dS in place and
+        // the tensor pipe executes one thread's MMAs in order)
+        bool ok = (n_sd < 2) || (n_dq >= n_sd - 1);
+        ok = ok && mbar_test(&kv_full[st], (n_sd / ST) & 1);
+        if (ok && s_i == 0) ok = mbar_test(&q_full[sn & 1], (sn >> 1) & 1);
+        if (ok) {
+          tc_fence_after();
+          if (leader) {
+            const uint64_t q_desc = desc_adv(q_desc0, (sn & 1) * 65536);
+            const uint64_t do_desc = desc_adv(q_desc, 32768);
+            const uint64_t k_desc = desc_adv(kv_desc0, st * 32768);
+            const uint64_t v_desc = desc_adv(k_desc, 16384);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+              const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;
+              const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;
+              umma_bf16(TM_S + sb * BKV, desc_adv(q_desc, oa), desc_adv(k_desc, ob), idesc_sd, k != 0);
+            }
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) {
+              const uint32_t oa = (k >> 2) * 16384 + (k & 3) * 32;
+              const uint32_t ob = (k >> 2) * 8192 + (k & 3) * 32;
+              umma_bf16(TM_DP + sb * BKV, desc_adv(do_desc, oa), desc_adv(v_desc, ob), idesc_sd, k != 0);
+            }
+            umma_commit(&sd_full[sb]);
+            if (s_i == si.nit - 1) umma_commit(&q_empty[sn & 1]);  // last reader of this item's Q / dO
+          }
+          ++n_sd;
+          if (++s_i == si.nit) {
+            s_i = 0;
+            ++sn;
+            s_have = dq_item<CAUSAL>(p, blockIdx.x + sn * gridDim.x, nqt, si);
+          }
+          did = true;
+        }
+      }
+      if (n_dq < n_sd && mbar_test(&ds_full[n_dq & 1], (n_dq >> 1) & 1) &&
+          (d_i != 0 || mbar_test(&dq_free[dn & 1], ((dn >> 1) & 1) ^ 1))) {
+        tc_fence_after();
+        const int st = n_dq % ST;
+        if (leader) {
+          const uint64_t k_mn = desc_adv(kv_mn0, st * 32768);
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {  // contraction over the 64 keys; A = dS in TMEM over dP (column-split halves)
+            umma_bf16_ts(TM_DQ + (dn & 1) * 128, TM_DP + (n_dq & 1) * BKV + (k >> 1) * 32 + (k & 1) * 8,
+                         desc_adv(k_mn, k * 2048), idesc_dq, (d_i | k) != 0);
+          }
+          umma_commit(&kv_empty[st]);
+          if (d_i == di.nit - 1) umma_commit(&dq_ready[dn & 1]);
+        }
+        ++n_dq;
+        if (++d_i == di.nit) {
+          d_i = 0;
+          ++dn;
+          d_have = dq_item<CAUSAL>(p, blockIdx.x + dn * gridDim.x, nqt, di);
+        }
+        did = true;
+      }
+      poll_guard(spins, did);
+    }
+  }
+  } else if (warp < 12) {
+    setmaxnreg_inc<152>();
+    // 8 softmax warps, two per TMEM lane quarter splitting the 64 key columns of a tile
+    const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale * LOG2E;
+    DqItem it, nx;
+    bool have = dq_item<CAUSAL>(p, blockIdx.x, nqt, it);
+    float l2 = 0.f, dlt = 0.f;
+    bool rok = false;
+    if (have) {
+      rok = it.q0 + row < p.sq;
+      if (rok) {
+        const int64_t li = ((int64_t)it.b * p.H + it.h) * p.sq + it.q0 + row;
+        l2 = p.lse[li] * LOG2E;
+        dlt = p.delta[li];
+      }
+    }
+    int x = 0;
+    for (int n = 0; have; ++n) {
+      // lse / delta of the NEXT item: in flight during this item's iterations
+      const bool have_next = dq_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nx);
+      float l2n = 0.f, dln = 0.f;
+      bool rokn = false;
+      if (have_next) {
+        rokn = nx.q0 + row < p.sq;
+        if (rokn) {
+          const int64_t li = ((int64_t)nx.b * p.H + nx.h) * p.sq + nx.q0 + row;
+          l2n = p.lse[li] * LOG2E;
+          dln = p.delta[li];
+        }
+      }
+      const int q0 = it.q0;
+      for (int i = 0; i < it.nit; ++i, ++x) {
+        const int sb = x & 1;
+        const int j0 = (i + it.jb) * BKV;
+        const bool need_mask = !rok || (j0 + BKV > p.sk) || (CAUSAL && (j0 + BKV - 1 > q0 + off)) ||
+                               (win && j0 < q0 + BQ - 1 + off - p.window);
+        mbar_wait_spin(&sd_full[sb], (x >> 1) & 1);
+        tc_fence_after();
+        uint32_t s_[32], d[32];
+        tmem_ld32(TM_S + lane_addr + sb * BKV + half * 32, s_);
+        tmem_ld32(TM_DP + lane_addr + sb * BKV + half * 32, d);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s_[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s_[c]), sl2, -l2)));
+        if (need_mask) {  // one warp-uniform branch per tile, never one per score
+          const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
+          const int vis = rok ? lim - (j0 + half * 32) : -1;                      // last visible column
+          const int lov = win ? q0 + row + off - p.window - (j0 + half * 32) : 0;  // first visible column
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c > vis || c < lov) s_[c] = 0u;
+        }
+        uint32_t wd[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          wd[c] = pack2(__uint_as_float(s_[2 * c]) * (__uint_as_float(d[2 * c]) - dlt),
+                        __uint_as_float(s_[2 * c + 1]) * (__uint_as_float(d[2 * c + 1]) - dlt));
+        tmem_st16(TM_DP + lane_addr + sb * BKV + half * 32, wd);  // over this warp's own dP columns
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ds_full[sb]);
+      }
+      it = nx;
+      have = have_next;
+      l2 = l2n;
+      dlt = dln;
+      rok = rokn;
+    }
+  } else {
+    // epilogue warpgroup: one thread per query row writes dQ of item n (scaled, bf16) while the others are on n+1
+    setmaxnreg_dec<112>();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    DqItem it;
+    for (int n = 0; dq_item<CAUSAL>(p, blockIdx.x + n * gridDim.x, nqt, it); ++n) {
+      mbar_wait(&dq_ready[n & 1], (n >> 1) & 1);
+      tc_fence_after();
+      const bool rok = it.q0 + row < p.sq;
+      bf16* dqrow = p.dq + ((int64_t)it.b * p.sq + it.q0 + row) * p.lddq + it.h * HD;
+      const uint32_t tm = TM_DQ + (n & 1) * 128 + lane_addr;
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t a[32];
+        tmem_ld32(tm + c * 32, a);
+        tmem_ld_wait();
+        if (c == HD / 32 - 1) {  // the accumulator has been read: the MMA warp may start item n+2 in it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dq_free[n & 1]);
+        }
+        if (rok) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(a[q * 8 + i]) * p.scale;
+            stg16(dqrow + c * 32 + q * 8, pack8(v));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 template <bool CAUSAL>
 static int launch_bwd_tc_v1(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                          int64_t ldv, const void* dO, int64_t lddo, const AttnTcBwdParams& p,
@@ -2275,16 +2613,41 @@ static int launch_bwd_tc_v2(const void* q, int64_t ldq, const void* k, int64_t l
     if (make_tmap_2d(&tmDO, dO, qcols, qrows, (uint64_t)lddo, 64, B_BQ)) return -1;
     if (make_tmap_2d(&tmK, k, kcols, krows, (uint64_t)ldk, 64, B_BKV)) return -1;
     if (make_tmap_2d(&tmV, v, kcols, krows, (uint64_t)ldv, 64, B_BKV)) return -1;
-    auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS, SPLIT>;
-    static bool cfg = false;
-    if (!cfg) {
-      VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
-      cfg = true;
-    }
     const int nqt = (p.sq + B_BQ - 1) / B_BQ;
-    dim3 grid((nqt + 1) / 2, p.H, p.B);
-    kern<<<grid, 320, B_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
-    VPB_LAUNCH_OK();
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      VPB_CUDA(cudaGetDevice(&dev));
+      VPB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    bool persistent = false;
+    if constexpr (TS && SPLIT) {
+      // persistent dQ kernel: self-attention shapes (every work item sees at least one key tile), no fused inverse
+      // RoPE, enough work items per SM for the static round-robin to balance
+      persistent = !get_option(VPB_OPT_ATTN_BWD_DQ_R1) && p.rope_cos == nullptr && p.sk >= p.sq && p.sk > 0 &&
+                   nqt * p.H * p.B >= 8 * n_sm;
+      if (persistent) {
+        auto kernp = attn_bwd_dq_persist_kernel<CAUSAL, HD>;
+        static bool cfgp = false;
+        if (!cfgp) {
+          VPB_CUDA(cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, tcq::SMEM));
+          cfgp = true;
+        }
+        kernp<<<n_sm, tcq::THREADS, tcq::SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
+        VPB_LAUNCH_OK();
+      }
+    }
+    if (!persistent) {
+      auto kern = attn_bwd_dq_tc2_kernel<CAUSAL, HD, TS, SPLIT>;
+      static bool cfg = false;
+      if (!cfg) {
+        VPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM));
+        cfg = true;
+      }
+      dim3 grid((nqt + 1) / 2, p.H, p.B);
+      kern<<<grid, 320, B_SMEM, st>>>(tmQ, tmDO, tmK, tmV, p);
+      VPB_LAUNCH_OK();
+    }
   }
   return 0;
 }

@@ -37,6 +37,7 @@ def _rows(t: torch.Tensor):
 
 OPT_ATTN_LEGACY_FWD, OPT_ATTN_LEGACY_BWD, OPT_ATTN_TC_BWD_V1, OPT_GEMM_1CTA, OPT_GEMM_PANEL_MB = 0, 1, 2, 3, 4
 OPT_ATTN_BWD_SS, OPT_ATTN_BWD_PINGPONG, OPT_GEMM_L2_HINTS = 5, 7, 8
+OPT_ATTN_BWD_DQ_R1 = 6
 OPT_ATTN_FWD_NS2 = 9
 OPT_NORM_R1 = 15
 OPT_WIN_ATTN_V2 = 10
@@ -660,6 +661,6 @@ for _name, _key in (("VPB_ATTN_BWD_PINGPONG", OPT_ATTN_BWD_PINGPONG), ("VPB_ATTN
                     ("VPB_GEMM_L2_HINTS", OPT_GEMM_L2_HINTS), ("VPB_WIN_ATTN_V2", OPT_WIN_ATTN_V2),
                     ("VPB_DWCONV_FFMA2", OPT_DWCONV_FFMA2), ("VPB_ATTN_FWD_TC64", OPT_ATTN_FWD_TC64),
                     ("VPB_GEMM_EPI8", OPT_GEMM_EPI8), ("VPB_GATHER_FLAT", OPT_GATHER_FLAT),
-                    ("VPB_ATTN_FWD_NS2", OPT_ATTN_FWD_NS2), ("VPB_NORM_R1", OPT_NORM_R1)):
+                    ("VPB_ATTN_FWD_NS2", OPT_ATTN_FWD_NS2), ("VPB_ATTN_BWD_DQ_R1", OPT_ATTN_BWD_DQ_R1), ("VPB_NORM_R1", OPT_NORM_R1)):
     if os.environ.get(_name):  # A/B switches for bench runs
         set_option(_key, int(os.environ[_name]))
