@@ -1384,6 +1384,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint64_t* pds_empty = bars + 17;  // [2] SS mode: dV/dK MMAs reading smem buffer b retired
   uint64_t* all_done = bars + 19;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* ld_full = bars + 22;    // [3] SPLIT mode: lse / delta of an iteration staged in ld_buf[it % 3]
   float* ld_buf = reinterpret_cast<float*>(smem + A_OFF_LD);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1436,6 +1437,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_init(&pds_empty[i], 1);
     }
     mbar_init(all_done, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(&ld_full[i], 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -1607,8 +1609,14 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int64_t li = ((int64_t)b * p.H + hq) * p.sq + q;
         return tid < 64 ? p.lse[li] * LOG2E : p.delta[li];
       };
-      // lse/delta of iteration it+1 are staged at the END of iteration it (store + barrier sit in the
-      // shadow of the wait for the next S/dP), those of it+2 are in flight in a register meanwhile
+      // lse / delta staging without a block barrier.  Round 1 staged iteration it+1 at the end of iteration it behind
+      // a 256-thread bar.sync and fetched it+2 into a register meanwhile; the ncu source view
+      // (profiles/r02_ncu_attn_baseline.csv) put 19 % of the softmax warps' samples on that barrier and another 8 %
+      // on the global load arriving late.  Now: three staging buffers, the four writer warps arrive on ld_full[it % 3]
+      // after their stores (readers wait on it — written an iteration earlier, so the wait is free), and two fetches
+      // are in flight (iterations it+2 and it+3).  Buffer (it+1) % 3 is rewritten at the end of iteration it: its last
+      // readers were in iteration it-2, and S/dP of iteration it — which this warp has seen complete — is only issued
+      // after every warp handed over P/dS of it-2.
       int hq_n = kvh * G, qi_n = 0;  // (head, query tile) of the iteration whose values are fetched next
       auto step = [&]() {
         if (++qi_n == nper) {
@@ -1616,17 +1624,26 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           ++hq_n;
         }
       };
+      auto publish = [&](int it_, float val) {  // writer warps (tid < 128 = the first four softmax warps)
+        if (tid < 128) {
+          ld_buf[(it_ % 3) * 128 + tid] = val;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ld_full[it_ % 3]);
+        }
+      };
       int qi_c = 0;  // query tile of the current iteration
+      float pre_a = 0.f, pre_b = 0.f;
       if (nit > 0) {
-        if (tid < 128) ld_buf[tid] = fetch8(hq_n, qi_n);
+        publish(0, fetch8(hq_n, qi_n));
         step();
       }
-      float pre8 = nit > 1 ? fetch8(hq_n, qi_n) : 0.f;  // iteration 1
+      if (nit > 1) pre_a = fetch8(hq_n, qi_n);  // iteration 1
       step();
-      named_bar_sync(1, 256);
+      if (nit > 2) pre_b = fetch8(hq_n, qi_n);  // iteration 2
+      step();
       for (int it = 0; it < nit; ++it) {
         const int sb = it & 1;
-        float* lbuf = ld_buf + sb * 128;
+        float* lbuf = ld_buf + (it % 3) * 128;
         const int q0 = (qt_begin + qi_c) * A_BQ;
         if (++qi_c == nper) qi_c = 0;
         const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
@@ -1634,6 +1651,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
                                (win && (q0 + A_BQ - 1 + off - p.window > kv0));
         if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(3, it);
         mbar_wait_spin(&sd_full[sb], (it >> 1) & 1);
+        mbar_wait_spin(&ld_full[it % 3], (it / 3) & 1);
         if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(4, it);
         tc_fence_after();
         uint32_t s[32], d[32];
@@ -1679,14 +1697,11 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&pds_full[sb]);
         if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(7, it);
-        // stage iteration it+1 (buffer sb^1: its last readers finished iteration it-1 before the
-        // previous barrier), fetch it+2
-        if (it + 1 < nit) {
-          if (tid < 128) ld_buf[(sb ^ 1) * 128 + tid] = pre8;
-          if (it + 2 < nit) pre8 = fetch8(hq_n, qi_n);
-          step();
-          named_bar_sync(1, 256);
-        }
+        // stage iteration it+1, keep it+2 in a register, fetch it+3
+        if (it + 1 < nit) publish(it + 1, pre_a);
+        pre_a = pre_b;
+        if (it + 3 < nit) pre_b = fetch8(hq_n, qi_n);
+        step();
       }
     } else {
     int hq_c = kvh * G, qi_c = 0;
