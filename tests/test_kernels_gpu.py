@@ -786,3 +786,20 @@ def test_persistent_dq_kernel_is_bit_identical(B, H, KVH, S, hd, window):
         (pr @ vh).backward(do[b0, h * hd:(h + 1) * hd].float())
         got = outs[1][b0, h * hd:(h + 1) * hd].float()
         assert ((got - qh.grad).norm() / qh.grad.norm()).item() < 2e-2
+
+
+@pytest.mark.parametrize("B,H,W,C,stride,relu", [(2, 12, 12, 64, 1, False), (3, 24, 24, 256, 2, False), (2, 9, 13, 128, 1, True),
+                                                 (1, 48, 48, 256, 1, True), (1, 7, 5, 8, 2, False)])
+def test_im2col3x3_matches_torch_unfold(B, H, W, C, stride, relu):
+    """vpb_im2col3x3_nhwc (3x3, pad 1, K order (ky, kx, c), optional ReLU on load) against F.unfold."""
+    from visper_lm_b200 import ops
+    x = rnd(B * H * W, C, seed=H * W + C)
+    col, Ho, Wo = ops.im2col3x3(x, B, H, W, C, stride, relu)
+    torch.cuda.synchronize()
+    xi = x.float().view(B, H, W, C).permute(0, 3, 1, 2)
+    if relu:
+        xi = xi.relu()
+    u = torch.nn.functional.unfold(xi, 3, padding=1, stride=stride)          # [B, C*9, Ho*Wo], K order (c, ky, kx)
+    ref = u.view(B, C, 9, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, 9 * C)
+    assert (Ho, Wo) == ((H - 1) // stride + 1, (W - 1) // stride + 1)
+    assert torch.equal(col.float(), ref)
