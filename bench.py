@@ -540,12 +540,16 @@ def run_b200(args):
             check = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
             env.sync_all()
 
-    clocks = ClockSampler(env.local)
-    if rank == 0:
-        clocks.start()
+    clocks = ClockSampler(env.local)  # every rank samples its own GPU: synchronous DP runs at the slowest one's clock
+    clocks.start()
     res = measure(env, args, c, distill=distill, train=args.train, batch=args.batch, steps=args.steps,
                   warmup=args.warmup, teachers=teachers, want_e2e=not args.no_e2e, main=True)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop()
+    if world > 1:
+        every = [None] * world
+        dist.all_gather_object(every, clk)
+        clk = dict(every[0], sm_mhz_per_rank=[e.get("sm_mhz") for e in every],
+                   reasons=sorted({r for e in every for r in e.get("reasons", [])}))
     if res is None:  # --torch-profile
         if world > 1:
             dist.destroy_process_group()
