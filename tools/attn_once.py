@@ -1,6 +1,7 @@
 """One attention forward + backward at the decoder's shape (B=8, H=32, KVH=8, S=2048, hd=128, causal) after one
-warm-up pair — the target of the per-kernel `ncu --set full --import-source on -k regex:<kernel> -s 1 -c 1` captures
-under profiles/ (tools/gpu_validation.sh shows the command)."""
+warm-up pair — the target of the per-kernel captures under profiles/ (r02_ncu_final_attn_*.csv):
+    ncu --set full --import-source on --clock-control none -k regex:attn_bwd_dkdv_tc2 -s 1 -c 1 -o rep python tools/attn_once.py
+    ncu -i rep.ncu-rep --page raw --csv ; ncu -i rep.ncu-rep --page source --csv"""
 import sys
 from pathlib import Path
 
