@@ -13,6 +13,7 @@
 //             max / sum in the log2 domain with LAZY rescaling (O in TMEM is only multiplied when the
 //             running max moved by more than 2^8), P_j → bf16 → swizzled shared memory for the PV MMA.
 // Saves LSE [B,H,sq] in natural-log units, same contract as the mma.sync kernels in attention.cu.
+#include <type_traits>
 #include "common.cuh"
 #include "visper_b200.h"
 
@@ -1609,7 +1610,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const int q = (qt_begin + qi) * A_BQ + (tid & 63);
         if (tid >= 128 || q >= p.sq) return 0.f;
         const int64_t li = ((int64_t)b * p.H + hq) * p.sq + q;
-        return tid < 64 ? p.lse[li] * LOG2E : p.delta[li];
+        return tid < 64 ? p.lse[li] : p.delta[li];  // raw: a multiply here would make the warp wait for the load at once
       };
       // lse / delta staging without a block barrier.  Round 1 staged iteration it+1 at the end of iteration it behind
       // a 256-thread bar.sync and fetched it+2 into a register meanwhile; the ncu source view
@@ -1628,7 +1629,7 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       };
       auto publish = [&](int it_, float val) {  // writer warps (tid < 128 = the first four softmax warps)
         if (tid < 128) {
-          ld_buf[(it_ % 3) * 128 + tid] = val;
+          ld_buf[(it_ % 3) * 128 + tid] = tid < 64 ? val * LOG2E : val;  // lse in log2 units | delta
           __syncwarp();
           if (lane == 0) mbar_arrive(&ld_full[it_ % 3]);
         }
@@ -1648,7 +1649,9 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         float* lbuf = ld_buf + (it % 3) * 128;
         const int q0 = (qt_begin + qi_c) * A_BQ;
         if (++qi_c == nper) qi_c = 0;
-        const bool need_mask = (q0 + A_BQ > p.sq) || !key_ok ||
+        // tile-level, hence warp-uniform: the two bodies below hold .sync.aligned TMEM stores (a per-row test such as
+        // !key_ok would split the warp between them)
+        const bool need_mask = (q0 + A_BQ > p.sq) || (kv0 + A_BKV > p.sk) ||
                                (CAUSAL && (kv0 + A_BKV - 1 > q0 + off)) ||
                                (win && (q0 + A_BQ - 1 + off - p.window > kv0));
         if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(3, it);
@@ -1662,37 +1665,44 @@ attn_bwd_dkdv_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tmem_ld_wait();
         if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(5, it);
         const float4* l4 = reinterpret_cast<const float4*>(lbuf) + half * 8;
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 ls = l4[c4], dl4 = l4[16 + c4];
-          const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c4 * 4 + e;
-            s[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e])));
-            d[c] = __float_as_uint(__uint_as_float(d[c]) - dlv[e]);
-          }
-        }
-        if (need_mask) {  // one warp-uniform branch per tile, never one per score
+        // Two straight-line chunks of sixteen query columns, each stored to TMEM as soon as it is packed: ptxas then
+        // mixes the FFMA / FADD / FMUL / pack / LDS work into the MUFU stream (one 32-long MUFU burst per warp, with both
+        // warps of a scheduler in that phase at the same time, left the other pipes idle).  MASK is a compile-time
+        // copy of the body: a branch inside it would fence the two kinds of work into separate blocks again.
+        auto body = [&](auto mask_c) {
+          constexpr bool MASK = decltype(mask_c)::value;
           const int first_q = key_ok ? (CAUSAL ? kv0 + row - off : 0) : 0x7fffffff;
           const int last_q = win ? min(p.sq - 1, kv0 + row - off + p.window) : p.sq - 1;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int qc = q0 + half * 32 + c;
-            if (qc < first_q || qc > last_q) s[c] = 0u;
-          }
-        }
-        uint32_t wp[16], wd[16];
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t wp[8], wd[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float d0 = __uint_as_float(s[2 * i]) * __uint_as_float(d[2 * i]);
-          const float d1 = __uint_as_float(s[2 * i + 1]) * __uint_as_float(d[2 * i + 1]);
-          wp[i] = pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
-          wd[i] = pack2(d0, d1);
-        }
-        // bf16 pairs back over this warp's OWN score columns: packed columns [32*half, 32*half+16)
-        tmem_st16(TM_S + lane_addr + sb * A_BQ + half * 32, wp);
-        tmem_st16(TM_DP + lane_addr + sb * A_BQ + half * 32, wd);
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 ls = l4[ch * 4 + c4], dl4 = l4[16 + ch * 4 + c4];
+              const float lsv[4] = {ls.x, ls.y, ls.z, ls.w}, dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+              float pv[4], dv[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = ch * 16 + c4 * 4 + e;
+                pv[e] = ex2_approx(fmaf(__uint_as_float(s[c]), sl2, -lsv[e]));
+                if (MASK) {
+                  const int qc = q0 + half * 32 + c;
+                  if (qc < first_q || qc > last_q) pv[e] = 0.f;
+                }
+                dv[e] = pv[e] * (__uint_as_float(d[c]) - dlv[e]);
+              }
+              wp[c4 * 2] = pack2(pv[0], pv[1]);
+              wp[c4 * 2 + 1] = pack2(pv[2], pv[3]);
+              wd[c4 * 2] = pack2(dv[0], dv[1]);
+              wd[c4 * 2 + 1] = pack2(dv[2], dv[3]);
+            }
+            // bf16 pairs back over this warp's OWN score columns: packed columns [32*half, 32*half+16)
+            tmem_st8(TM_S + lane_addr + sb * A_BQ + half * 32 + ch * 8, wp);
+            tmem_st8(TM_DP + lane_addr + sb * A_BQ + half * 32 + ch * 8, wd);
+          }
+        };
+        if (need_mask) body(std::true_type{});  // one warp-uniform branch per tile, never one per score
+        else body(std::false_type{});
         if (quarter == 0 && lane == 0 && half == 0) VPB_TRACE(6, it);
         tmem_st_wait();
         tc_fence_before();
@@ -2476,7 +2486,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         rokn = nx.q0 + row < p.sq;
         if (rokn) {
           const int64_t li = ((int64_t)nx.b * p.H + nx.h) * p.sq + nx.q0 + row;
-          l2n = p.lse[li] * LOG2E;
+          l2n = p.lse[li];  // raw, scaled when the item becomes current: a multiply here would wait for the load
           dln = p.delta[li];
         }
       }
@@ -2484,7 +2494,8 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       for (int i = 0; i < it.nit; ++i, ++x) {
         const int sb = x & 1;
         const int j0 = (i + it.jb) * BKV;
-        const bool need_mask = !rok || (j0 + BKV > p.sk) || (CAUSAL && (j0 + BKV - 1 > q0 + off)) ||
+        // tile-level, hence warp-uniform (the bodies below hold .sync.aligned TMEM stores)
+        const bool need_mask = (q0 + BQ > p.sq) || (j0 + BKV > p.sk) || (CAUSAL && (j0 + BKV - 1 > q0 + off)) ||
                                (win && j0 < q0 + BQ - 1 + off - p.window);
         mbar_wait_spin(&sd_full[sb], (x >> 1) & 1);
         tc_fence_after();
@@ -2492,22 +2503,31 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         tmem_ld32(TM_S + lane_addr + sb * BKV + half * 32, s_);
         tmem_ld32(TM_DP + lane_addr + sb * BKV + half * 32, d);
         tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) s_[c] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(s_[c]), sl2, -l2)));
-        if (need_mask) {  // one warp-uniform branch per tile, never one per score
+        // two straight-line chunks of sixteen key columns (see attn_bwd_dkdv_tc2_kernel): MUFU mixed with the FMA-pipe work
+        auto body = [&](auto mask_c) {
+          constexpr bool MASK = decltype(mask_c)::value;
           const int lim = CAUSAL ? min(p.sk - 1, q0 + row + off) : p.sk - 1;
           const int vis = rok ? lim - (j0 + half * 32) : -1;                      // last visible column
           const int lov = win ? q0 + row + off - p.window - (j0 + half * 32) : 0;  // first visible column
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c > vis || c < lov) s_[c] = 0u;
-        }
-        uint32_t wd[16];
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t wd[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
-          wd[c] = pack2(__uint_as_float(s_[2 * c]) * (__uint_as_float(d[2 * c]) - dlt),
-                        __uint_as_float(s_[2 * c + 1]) * (__uint_as_float(d[2 * c + 1]) - dlt));
-        tmem_st16(TM_DP + lane_addr + sb * BKV + half * 32, wd);  // over this warp's own dP columns
+            for (int i = 0; i < 8; ++i) {
+              const int c = ch * 16 + 2 * i;
+              float p0 = ex2_approx(fmaf(__uint_as_float(s_[c]), sl2, -l2));
+              float p1 = ex2_approx(fmaf(__uint_as_float(s_[c + 1]), sl2, -l2));
+              if (MASK) {
+                if (c > vis || c < lov) p0 = 0.f;
+                if (c + 1 > vis || c + 1 < lov) p1 = 0.f;
+              }
+              wd[i] = pack2(p0 * (__uint_as_float(d[c]) - dlt), p1 * (__uint_as_float(d[c + 1]) - dlt));
+            }
+            tmem_st8(TM_DP + lane_addr + sb * BKV + half * 32 + ch * 8, wd);  // over this warp's own dP columns
+          }
+        };
+        if (need_mask) body(std::true_type{});  // one warp-uniform branch per tile, never one per score
+        else body(std::false_type{});
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -2515,7 +2535,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       }
       it = nx;
       have = have_next;
-      l2 = l2n;
+      l2 = l2n * LOG2E;
       dlt = dln;
       rok = rokn;
     }
