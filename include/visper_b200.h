@@ -48,7 +48,7 @@ void vpb_reset_launch_count(void);
 #define VPB_OPT_ATTN_BWD_SS 5      /* 1: attention backward stages P/dS through shared memory (not TMEM) */
 #define VPB_OPT_ATTN_BWD_PINGPONG 7 /* 1: attention backward with two softmax groups on alternate iterations (default: column split) */
 #define VPB_OPT_ATTN_BWD_DQ_R1 6  /* 1: dQ backward on the round-1 kernel (one CTA per query-tile pair) instead of the persistent kernel */
-#define VPB_OPT_ATTN_FWD_NS2 9     /* 1: tcgen05 attention forward with one work item per CTA (round 1) instead of the persistent kernel */
+#define VPB_OPT_ATTN_FWD_NS2 9     /* 1: tcgen05 attention forward with one work item per CTA (round 1) instead of the persistent kernel; 2: the persistent kernel also for launches with few work items (tests) */
 #define VPB_OPT_NORM_R1 15          /* 1: RMSNorm fwd/bwd on the round-1 kernels (row as fp32 in registers, 4 / 3 CTAs per SM) instead of the packed high-occupancy ones */
 #define VPB_OPT_ATTN_FWD_TC64 12   /* default 1 — non-causal head_dim-64 attention forward (CLIP ViT-L, DINOv2-L towers) on the tcgen05 kernel (one 64-column chunk per tile) instead of the mma.sync kernel */
 #define VPB_OPT_GEMM_EPI8 13       /* default 1 — CTA-pair GEMM with EIGHT epilogue warps per CTA (two per TMEM lane quarter, half the columns each) for K <= 1024, where the bias/GELU/store epilogue outlasts the tile's MMAs */

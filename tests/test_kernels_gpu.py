@@ -465,15 +465,52 @@ def test_attention_tcgen05_matches_legacy(B, H, KVH, sq, sk, causal):
     torch.cuda.synchronize()
     close(o, o_ref, name="tc fwd vs legacy")
     assert (lse - lse_ref).abs().max().item() < 2e-2
-    # the default is the persistent kernel; the one-work-item-per-CTA kernel does the same arithmetic in the same
-    # order: bit-identical output and LSE
-    ops.set_option(ops.OPT_ATTN_FWD_NS2, 1)
-    try:
-        o2, lse2 = ops.attn_fwd(q, k, v, B, H, KVH, sq, sk, hd, hd ** -0.5, causal)
-        torch.cuda.synchronize()
-    finally:
-        ops.set_option(ops.OPT_ATTN_FWD_NS2, 0)
-    assert torch.equal(o2, o) and torch.equal(lse2, lse), "persistent forward differs from the one-item-per-CTA kernel"
+    # the persistent kernel (the default for launches with many work items, forced here for the small ones) against
+    # the one-work-item-per-CTA kernel: same MMAs, row sums accumulated per tile parity instead of per column half
+    outs = []
+    for mode in (1, 2):
+        ops.set_option(ops.OPT_ATTN_FWD_NS2, mode)
+        try:
+            outs.append(ops.attn_fwd(q, k, v, B, H, KVH, sq, sk, hd, hd ** -0.5, causal))
+            torch.cuda.synchronize()
+        finally:
+            ops.set_option(ops.OPT_ATTN_FWD_NS2, 0)
+    (o1, lse1), (o2, lse2) = outs
+    if sk >= sq:
+        close(o2, o1, rtol=4e-3, name="persistent forward vs one-item-per-CTA kernel")
+        assert (lse2 - lse1).abs().max().item() < 2e-4
+        close(o2, o_ref, name="persistent tc fwd vs legacy")
+        assert (lse2 - lse_ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("B,H,KVH,S,hd,causal,window", [(2, 32, 8, 2560, 128, True, 0), (4, 32, 32, 1500, 96, True, 600),
+                                                        (8, 20, 4, 1100, 128, False, 0), (16, 16, 16, 577, 64, False, 0)])
+def test_persistent_forward_kernel_vs_torch(B, H, KVH, S, hd, causal, window):
+    """Launches with >= 8 work items per SM take the persistent forward kernel by default (the decoder's shapes):
+    output and LSE against torch fp32 for the first and the last batch entry."""
+    from visper_lm_b200 import ops
+    g = torch.Generator().manual_seed(S + hd + B)
+    qkv = torch.randn(B * S, (H + 2 * KVH) * hd, generator=g).to(BF).to(dev())
+    q, k, v = qkv[:, :H * hd], qkv[:, H * hd:(H + KVH) * hd], qkv[:, (H + KVH) * hd:]
+    o, lse = ops.attn_fwd(q, k, v, B, H, KVH, S, S, hd, hd ** -0.5, causal, window=window)
+    torch.cuda.synchronize()
+    i = torch.arange(S, device=q.device)
+    vis = torch.ones(S, S, dtype=torch.bool, device=q.device)
+    if causal:
+        vis = i[None, :] <= i[:, None]
+        if window:
+            vis = vis & (i[:, None] - i[None, :] <= window)
+    for b in (0, B - 1):
+        rows = slice(b * S, (b + 1) * S)
+        qf = q[rows].float().view(S, H, hd).transpose(0, 1)
+        kf = k[rows].float().view(S, KVH, hd).transpose(0, 1).repeat_interleave(H // KVH, 0)
+        vf = v[rows].float().view(S, KVH, hd).transpose(0, 1).repeat_interleave(H // KVH, 0)
+        sc = (qf @ kf.transpose(1, 2) * hd ** -0.5).masked_fill(~vis[None], float("-inf"))
+        ref = (torch.softmax(sc, -1) @ vf).transpose(0, 1).reshape(S, H * hd)
+        got = o[rows].float()
+        assert ((got - ref).norm() / ref.norm()).item() < 1e-2, (b, ((got - ref).norm() / ref.norm()).item())
+        assert (got - ref).abs().max().item() < 3e-2
+        assert (lse.view(B, H, S)[b] - torch.logsumexp(sc, -1)).abs().max().item() < 2e-2
 
 
 @pytest.mark.parametrize("B,H,KVH,sq,sk,causal", [

@@ -632,6 +632,11 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         }
         const float mb = (m_used == -INFINITY) ? 0.f : m_used;
         float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+        // (Measured after this change and dropped, profiles/r02_attn_fwd_experiments.txt: the next tile's scores read
+        // from TMEM and reduced to their maximum under this tile's exponentials — 0.42 ms, the wait for S of tile g+1
+        // serialises the softmax behind P·V(g-1) + Q·Kᵀ(g+1) on the in-order tensor pipe; the two warps of a lane quarter
+        // on ALTERNATE tiles with all 128 columns per thread — 0.342 ms, the per-tile chain S -> softmax -> P·V -> S(g+2)
+        // gets longer with twice the columns per thread; every fourth exponential as a polynomial — 0.301 ms.)
         // sixteen columns at a time, each chunk packed and stored to TMEM before the next one's exponentials: with the
         // stores as ordering points ptxas mixes the FFMA / FADD / pack work into the MUFU stream.  (Written as one loop
         // of 64 exponentials followed by the packing, the SASS was 64 back-to-back MUFU.EX2 — 8 issue cycles each, the
@@ -758,7 +763,8 @@ static int launch_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk,
   const int items = (int)grid.x * p.H * p.B;
   // with only a few work items per SM (the ViT towers: 640 items of 5 key tiles) the static round-robin of the
   // persistent kernel loses more to its ragged last round than it saves: 0.061 vs 0.053 ms at B=8, S=577
-  if (!get_option(VPB_OPT_ATTN_FWD_NS2) && p.sk >= p.sq && p.sk > 0 && items >= 8 * n_sm) {
+  const int fwd_mode = get_option(VPB_OPT_ATTN_FWD_NS2);  // 1: never persistent, 2: persistent whatever the item count (tests)
+  if (fwd_mode != 1 && p.sk >= p.sq && p.sk > 0 && (fwd_mode == 2 || items >= 8 * n_sm)) {
     auto kernp = attn_fwd_tc_persist_kernel<CAUSAL, HD>;
     static bool cfgp = false;
     if (!cfgp) {
