@@ -687,6 +687,20 @@ def test_adamw_and_clip():
     assert torch.equal(param, master.to(BF))
 
 
+@pytest.mark.parametrize("n,offset", [(1, 0), (7, 1), (8, 0), (9, 3), (2055, 5), (10007, 0), (1 << 20, 2), (5_000_003, 7),
+                                      (40_000_000, 0)])
+def test_grad_sumsq_alignment_and_sizes(n, offset):
+    """vpb_grad_sumsq reads 16 bytes per load: unaligned starts (bucket slices), tails shorter than a vector, sizes from
+    one element to more than one pass of the grid."""
+    from visper_lm_b200 import ops
+    g = torch.Generator().manual_seed(n + offset)
+    buf = (torch.randn(n + offset, generator=g) * 0.5).to(BF).to(dev())
+    x = buf[offset:]
+    got = ops.grad_sumsq(x).item()
+    ref = x.double().pow(2).sum().item()
+    assert abs(got - ref) <= 2e-5 * ref + 1e-12, (got, ref)
+
+
 @pytest.mark.parametrize("B,H,KVH,S,hd,window,use_pos,mode", [
     (2, 8, 2, 1024, 128, 0, False, "v2"), (1, 4, 4, 333, 128, 0, True, "v2"),
     (2, 4, 1, 777, 128, 0, True, "v2"), (1, 4, 2, 1300, 128, 500, False, "v2"),

@@ -324,12 +324,13 @@ colsum_kernel(const bf16* __restrict__ a, int64_t lda, const bf16* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (n0 + 8 <= N) {
-    for (int m = m_begin + wid; m < m_end; m += 8) {
+    // two rows per warp in flight (four 16-byte loads): one row at a time reached 0.57 of the HBM rate
+    auto row = [&](int m, const uint4& ua, const uint4& ub) {
       float av[8];
-      unpack8(ldg16_stream(a + (int64_t)m * lda + n0), av);
+      unpack8(ua, av);
       if (b) {
         float bv[8];
-        unpack8(ldg16_stream(b + (int64_t)m * ldb + n0), bv);
+        unpack8(ub, bv);
         const float mu = mean ? mean[m] : 0.f;
         const float rs = rstd ? rstd[m] : 1.f;
 #pragma unroll
@@ -338,6 +339,23 @@ colsum_kernel(const bf16* __restrict__ a, int64_t lda, const bf16* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += av[j];
       }
+    };
+    int m = m_begin + wid;
+    for (; m + 8 < m_end; m += 16) {
+      const uint4 a0 = ldg16_stream(a + (int64_t)m * lda + n0);
+      const uint4 a1 = ldg16_stream(a + (int64_t)(m + 8) * lda + n0);
+      uint4 b0 = a0, b1 = a1;
+      if (b) {
+        b0 = ldg16_stream(b + (int64_t)m * ldb + n0);
+        b1 = ldg16_stream(b + (int64_t)(m + 8) * ldb + n0);
+      }
+      row(m, a0, b0);
+      row(m + 8, a1, b1);
+    }
+    if (m < m_end) {
+      const uint4 a0 = ldg16_stream(a + (int64_t)m * lda + n0);
+      const uint4 b0 = b ? ldg16_stream(b + (int64_t)m * ldb + n0) : a0;
+      row(m, a0, b0);
     }
   }
 #pragma unroll
