@@ -621,7 +621,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         }
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         xchg[(sb * 2 + half) * 128 + row] = mx;
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + quarter, 64);  // only the two warps of this lane quarter exchange (and overwrite each other's S columns with P)
         mx = fmaxf(mx, xchg[(sb * 2 + (half ^ 1)) * 128 + row]) * sl2;
         const bool upd = mx > m_used + 8.f;  // lazy rescale: keep the reference max unless it moved by > 2^8
         float alpha = 1.f;
