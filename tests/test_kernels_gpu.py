@@ -476,8 +476,9 @@ def test_attention_tcgen05_matches_legacy(B, H, KVH, sq, sk, causal):
         finally:
             ops.set_option(ops.OPT_ATTN_FWD_NS2, 0)
     (o1, lse1), (o2, lse2) = outs
-    if sk >= sq:  # same arithmetic in the same order: bit-identical output and LSE
-        assert torch.equal(o2, o1) and torch.equal(lse2, lse1), "persistent forward differs from the one-item-per-CTA kernel"
+    if sk >= sq:  # same MMAs and softmax; the epilogues differ in rounding only
+        close(o2, o1, rtol=4e-3, name="persistent forward vs one-item-per-CTA kernel")
+        assert (lse2 - lse1).abs().max().item() < 2e-4
         close(o2, o_ref, name="persistent tc fwd vs legacy")
         assert (lse2 - lse_ref).abs().max().item() < 2e-2
 
