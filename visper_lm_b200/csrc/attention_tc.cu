@@ -356,6 +356,14 @@ constexpr int SMEM_BYTES = OFF_X + 5120 + 1024;
 constexpr int THREADS = 512;
 }  // namespace tcp
 
+// n-th work item of this CTA in a persistent kernel.  The work lists are sorted heavy-first and dealt round by round; dealing
+// every second round in reverse CTA order ("snake") evens out who gets the heavier side of the rounds in which the item size
+// steps down: the busiest CTA is 0.6 % above the mean instead of 2.6 % (forward, B=8, H=32, S=2048), 1.2 % instead of 4.7 % at
+// Phi-3's B=4.  Neighbouring CTAs still hold neighbouring items (the heads of a GQA group share K/V in L2).
+__device__ __forceinline__ int persist_item(int n) {
+  return n * (int)gridDim.x + ((n & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
+}
+
 struct FwdItem {
   int h, b, kvh, q0, jb, ntiles;
 };
@@ -485,13 +493,13 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       };
       FwdItem cur, nxt;
       int n = 0, g = 0;
-      bool have = fwd_item<CAUSAL>(p, blockIdx.x, nqt, cur);
+      bool have = fwd_item<CAUSAL>(p, persist_item(0), nqt, cur);
       if (have) {
         load_q(0, cur);
         load_k(0, cur, 0);
       }
       while (have) {
-        const bool have_next = fwd_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nxt);
+        const bool have_next = fwd_item<CAUSAL>(p, persist_item(n + 1), nqt, nxt);
         // Q of the NEXT item is requested as soon as its buffer can be free (the previous item's last Q·Kᵀ was issued
         // two producer tiles ago): Q rows are read once, so this is a DRAM round trip that must not sit in front of
         // the next item's first MMA
@@ -537,7 +545,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     };
     FwdItem cur, nxt;
     int n = 0, g = 0;
-    bool have = fwd_item<CAUSAL>(p, blockIdx.x, nqt, cur);
+    bool have = fwd_item<CAUSAL>(p, persist_item(0), nqt, cur);
     if (have) {
       mbar_wait(&q_full[0], 0);
       issue_s(0, 0, cur.ntiles == 1);
@@ -550,7 +558,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         if (j + 1 < cur.ntiles) {
           issue_s(g + 1, n, j + 2 == cur.ntiles);
         } else {
-          have_next = fwd_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nxt);
+          have_next = fwd_item<CAUSAL>(p, persist_item(n + 1), nqt, nxt);
           if (have_next) {
             mbar_wait_spin(&q_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
             issue_s(g + 1, n + 1, nxt.ntiles == 1);
@@ -590,7 +598,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const bool win = CAUSAL && p.window > 0;
     FwdItem it;
     int g = 0;
-    for (int n = 0; fwd_item<CAUSAL>(p, blockIdx.x + n * gridDim.x, nqt, it); ++n) {
+    for (int n = 0; fwd_item<CAUSAL>(p, persist_item(n), nqt, it); ++n) {
       const int q0 = it.q0;
       float m_used = -INFINITY, l = 0.f;
       const uint32_t tm_o = TM_O + (n & 1) * 128;
@@ -694,7 +702,7 @@ attn_fwd_tc_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float* xchg = reinterpret_cast<const float*>(smem + tcp::OFF_X);
     FwdItem it;
-    for (int n = 0; fwd_item<CAUSAL>(p, blockIdx.x + n * gridDim.x, nqt, it); ++n) {
+    for (int n = 0; fwd_item<CAUSAL>(p, persist_item(n), nqt, it); ++n) {
       mbar_wait(&l_ready[n & 1], (n >> 1) & 1);
       const float* lm = xchg + 512 + (n & 1) * 384;
       const float l = lm[row] + lm[128 + row];
@@ -2358,10 +2366,10 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
       };
       DqItem cur, nxt;
       int n = 0, x = 0;
-      bool have = dq_item<CAUSAL>(p, blockIdx.x, nqt, cur);
+      bool have = dq_item<CAUSAL>(p, persist_item(0), nqt, cur);
       if (have) load_q(0, cur);
       while (have) {
-        const bool have_next = dq_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nxt);
+        const bool have_next = dq_item<CAUSAL>(p, persist_item(n + 1), nqt, nxt);
         const int iq = cur.nit > 1 ? 1 : 0;  // the next item's Q / dO are requested after this item's first K/V tiles
         for (int i = 0; i < cur.nit; ++i, ++x) {
           const int st = x % ST;
@@ -2392,7 +2400,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     DqItem si, di;                 // work items of the next S/dP issue and of the next dQ issue
     int sn = 0, dn = 0;            // their indices in this CTA's list
     int s_i = 0, d_i = 0;          // iteration inside the item
-    bool s_have = dq_item<CAUSAL>(p, blockIdx.x, nqt, si);
+    bool s_have = dq_item<CAUSAL>(p, persist_item(0), nqt, si);
     bool d_have = s_have;
     di = si;
     int n_sd = 0, n_dq = 0;
@@ -2432,7 +2440,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
           if (++s_i == si.nit) {
             s_i = 0;
             ++sn;
-            s_have = dq_item<CAUSAL>(p, blockIdx.x + sn * gridDim.x, nqt, si);
+            s_have = dq_item<CAUSAL>(p, persist_item(sn), nqt, si);
           }
           did = true;
         }
@@ -2455,7 +2463,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
         if (++d_i == di.nit) {
           d_i = 0;
           ++dn;
-          d_have = dq_item<CAUSAL>(p, blockIdx.x + dn * gridDim.x, nqt, di);
+          d_have = dq_item<CAUSAL>(p, persist_item(dn), nqt, di);
         }
         did = true;
       }
@@ -2471,7 +2479,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale * LOG2E;
     DqItem it, nx;
-    bool have = dq_item<CAUSAL>(p, blockIdx.x, nqt, it);
+    bool have = dq_item<CAUSAL>(p, persist_item(0), nqt, it);
     float l2 = 0.f, dlt = 0.f;
     bool rok = false;
     if (have) {
@@ -2485,7 +2493,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     int x = 0;
     for (int n = 0; have; ++n) {
       // lse / delta of the NEXT item: in flight during this item's iterations
-      const bool have_next = dq_item<CAUSAL>(p, blockIdx.x + (n + 1) * gridDim.x, nqt, nx);
+      const bool have_next = dq_item<CAUSAL>(p, persist_item(n + 1), nqt, nx);
       float l2n = 0.f, dln = 0.f;
       bool rokn = false;
       if (have_next) {
@@ -2552,7 +2560,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     DqItem it;
-    for (int n = 0; dq_item<CAUSAL>(p, blockIdx.x + n * gridDim.x, nqt, it); ++n) {
+    for (int n = 0; dq_item<CAUSAL>(p, persist_item(n), nqt, it); ++n) {
       mbar_wait(&dq_ready[n & 1], (n >> 1) & 1);
       tc_fence_after();
       const bool rok = it.q0 + row < p.sq;
