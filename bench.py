@@ -668,8 +668,19 @@ def kernel_rooflines(ks, steps, peak_tf, hbm_gbs):
         elif st.get("bytes"):
             gbs = st["bytes"] / st["ms"] / 1e6
             d.update(bound="hbm", achieved=gbs, unit="GB/s", frac=gbs / hbm_gbs)
+        if name in KERNEL_NOTES:
+            d["note"] = KERNEL_NOTES[name]
         out[name] = d
     return out
+
+
+# context for the small-problem entries: their fraction of a tensor peak says how small the launches are, not how the kernel runs
+KERNEL_NOTES = {
+    "attn_fwd_hd64": "CLIP ViT-L tower: 23 launches per step of B*16 heads x 5 query tiles at S=577 (tcgen05, one work item per CTA); "
+                     "latency-bound at 4-5 key tiles per CTA",
+    "attn_fwd_hd32": "Perceiver cross-attention of the six task-token heads (mma.sync): 576 keys + a few latents per sample, microseconds per launch",
+    "attn_bwd_hd32": "backward of the same cross-attention (mma.sync), microseconds per launch",
+}
 
 
 if __name__ == "__main__":
